@@ -1,0 +1,173 @@
+/*
+ * magvit2_b200.h -- C ABI of libmagvit2_b200.so, the sm_100a compute library behind
+ * the VideoTokenizer forward path (tokenize / decode_from_code_indices / forward).
+ *
+ * The reference (lucidrains/magvit2-pytorch @ a00519fa) has NO native / FFI layer of
+ * its own: its boundary is the Python class magvit2_pytorch.VideoTokenizer
+ * (magvit2_pytorch/magvit2_pytorch.py:1045) whose forward dispatches ~730 ATen calls.
+ * Each entry point below replaces the ATen call sequence of one reference module
+ * (cited as M:line = magvit2_pytorch.py, A:line = attend.py).  The Python host class
+ * magvit2_pytorch_b200.VideoTokenizer binds them with ctypes.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no torch / C++ types cross the boundary.
+ *   - every call returns 0 on success or a negative MV2_E_* code; mv2_last_error()
+ *     returns a thread-local message.  Nothing throws across the boundary.
+ *   - all device pointers are borrowed for the duration of the call; the library
+ *     never allocates device memory: the caller supplies workspaces.
+ *   - stream ordered, no implicit synchronisation; `stream` is a cudaStream_t passed
+ *     as void*.
+ *   - activations are channels-last ("NDHWC"): x[b][t][h][w][c], dtype MV2_F32 or
+ *     MV2_BF16; accumulation is always fp32; biases / gammas / tiny SE + quantiser
+ *     weights are fp32.
+ *   - there is NO CPU fallback: every function launches sm_100a kernels.
+ */
+#ifndef MAGVIT2_B200_H
+#define MAGVIT2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MV2_ABI_VERSION 1
+
+enum { MV2_F32 = 0, MV2_BF16 = 1 };
+enum { MV2_ACT_NONE = 0, MV2_ACT_ELU = 1, MV2_ACT_SILU = 2 };
+enum { MV2_SHUFFLE_NONE = 0, MV2_SHUFFLE_SPACE = 1, MV2_SHUFFLE_TIME = 2 };
+enum {
+  MV2_OK = 0,
+  MV2_E_ARG = -1,       /* bad argument / unsupported shape */
+  MV2_E_CUDA = -2,      /* CUDA runtime / driver error (see mv2_last_error) */
+  MV2_E_UNSUPPORTED = -3
+};
+
+int mv2_abi_version(void);
+const char* mv2_last_error(void);
+/* Compute capability of the current device as major*10+minor (100 on B200), <0 on error. */
+int mv2_device_arch(void);
+
+/* ---- layout: torch (B,C,T,H,W) <-> channels-last activations ------------------
+ * mv2_to_channels_last : video ingest.  Replaces pad_at_dim (M:86-89, use M:1537) +
+ *   the implicit layout of every later conv: dst[b][t+t_pad][h][w][c] = src[b][c][t][h][w],
+ *   frames [0,t_pad) of dst are zero-filled.
+ * mv2_to_channels_first: replaces the frame crop at M:1646-1647 and the layout return:
+ *   dst[b][c][t][h][w] = src[b][t+t_crop][h][w][c],  dst has T - t_crop frames.            */
+int mv2_to_channels_last(const void* src, int src_dtype, void* dst, int dst_dtype,
+                         int B, int C, int T, int H, int W, int t_pad, void* stream);
+int mv2_to_channels_first(const void* src, int src_dtype, void* dst, int dst_dtype,
+                          int B, int C, int T, int H, int W, int t_crop, void* stream);
+
+/* ---- convolution family (CUDA-core fp32-accumulate path; any shape) -----------
+ * One generic strided N-d convolution over channels-last activations with a fused
+ * epilogue  y = shuffle(act(conv(x) + bias)) + res.   Replaces
+ *   CausalConv3d.forward           F.pad + nn.Conv3d            M:924-928  (pt = kt-1, ph = kh/2, pw = kw/2)
+ *   nn.Conv3d 1x1x1 / nn.Linear    M:939, M:352, M:367, M:493-495
+ *   SpatialDownsample2x.forward    Conv2d k3 s2 p1 per frame    M:770-780
+ *   TimeDownsample2x.forward       F.pad(2,0) + Conv1d k3 s2    M:796-807
+ *   SpatialUpsample2x / TimeUpsample2x  1x1 conv + SiLU + depth-to-space/time  M:838-846, M:875-883
+ *   Residual.forward               "+ x"                         M:173-174 (res)
+ *   TokenShift.forward             half-channel one-frame delay  M:250-254 (x_token_shift)
+ * Weights are packed by the host as w[tap][ci][co] (tap = (dt*kh + dh)*kw + dw) in the
+ * activation dtype; bias is fp32[Co] or NULL.                                            */
+typedef struct mv2_conv_args {
+  const void* x;       /* (B, Ti, Hi, Wi, Ci) */
+  const void* w;       /* [kt*kh*kw][Ci][Co]  */
+  const float* bias;   /* [Co] or NULL */
+  const void* res;     /* same shape as y, or NULL */
+  void* y;             /* (B, To, Ho, Wo, Co) or its depth-to-space/time shuffle */
+  int32_t dtype;
+  int32_t B, Ti, Hi, Wi, Ci;
+  int32_t To, Ho, Wo, Co;
+  int32_t kt, kh, kw;
+  int32_t st, sh, sw;
+  int32_t pt, ph, pw;        /* leading zero padding; trailing padding is implied by To/Ho/Wo */
+  int32_t act;               /* MV2_ACT_* */
+  int32_t shuffle;           /* MV2_SHUFFLE_*: SPACE: y (B,To,2Ho,2Wo,Co/4), co=(c,p1,p2); TIME: y (B,2To,Ho,Wo,Co/2), co=(c,p) */
+  int32_t x_token_shift;     /* 1: input channels >= Ci/2 are read from frame t-1 (zero at t = 0) */
+} mv2_conv_args;
+int mv2_conv_forward(const mv2_conv_args* a, void* stream);
+
+/* ---- SqueezeExcite (M:221-240) --------------------------------------------------
+ * se_pool  : per frame f (F = B*T frames of P = H*W positions, C channels):
+ *            logit[n] = <y[f,n,:], wk> + bk; a = softmax_n(logit); pooled[f,c] = sum_n a[n] y[f,n,c]
+ *            done as chunk partials (online softmax) + a combine fused into se_gate.
+ * se_gate  : gate[f,:] = sigmoid(W2 leaky_relu_0.1(W1 pooled + b1) + b2)   (fp32 [F][C])
+ * gate_residual : out = gate[f(m), c] * y[m, c] + x[m, c]                    (M:240 + M:174)
+ * workspace for se_pool: mv2_se_workspace_bytes(F, P, C).                                   */
+size_t mv2_se_workspace_bytes(int F, int P, int C);
+int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, float bk,
+                void* workspace, void* stream);
+int mv2_se_gate(const void* workspace, int F, int P, int C, int Hd,
+                const float* w1, const float* b1, const float* w2, const float* b2,
+                float* gates, void* stream);
+int mv2_gate_residual(const void* y, const void* x, const float* gates, void* out, int dtype,
+                      int F, int P, int C, void* stream);
+
+/* ---- RMSNorm (M:275-276): out = x / max(||x||_2, 1e-12) * sqrt(C) * gamma over the channel
+ * axis of channels-last tokens; token_shift as in mv2_conv_args (M:250-254).               */
+int mv2_rmsnorm(const void* x, void* out, int dtype, const float* gamma,
+                int B, int T, int P, int C, int token_shift, void* stream);
+
+/* ---- axial softmax attention core (Attention.forward M:379-388 + Attend A:186-243) ------
+ * qkv: [Ntok][3*heads*dim_head] laid out '(qkv h d)' (M:353); out: [Ntok][heads*dim_head] '(h d)'.
+ * Sequence s = (o, n): token(i) = o*outer_stride + n*inner_stride + i*tok_stride, i in [0, L).
+ *   space attention (M:444-454): n_outer = B*T, n_inner = 1, outer_stride = H*W, tok_stride = 1, L = H*W
+ *   time  attention (M:456-464): n_outer = B, outer_stride = T*H*W, n_inner = H*W, inner_stride = 1,
+ *                                tok_stride = H*W, L = T, causal = 1
+ * n_mem learned key/values (mem_kv fp32 [2][heads][n_mem][dim_head], M:357, M:383-385) are
+ * prepended; causal masking is right aligned (A:46-47, A:123-129): query i sees mem + keys <= i;
+ * it is disabled when L == 1 (A:209-210).  dim_head must be a multiple of 32, <= 96.           */
+typedef struct mv2_attn_args {
+  const void* qkv; void* out; const float* mem_kv;
+  int32_t dtype, heads, dim_head, n_mem, causal;
+  int32_t n_outer, n_inner, L;
+  int64_t outer_stride, inner_stride, tok_stride;
+} mv2_attn_args;
+int mv2_attention(const mv2_attn_args* a, void* stream);
+
+/* ---- Taylor-series linear attention core (TaylorSeriesLinearAttn, un-vendored dependency;
+ * SURVEY.md Appendix A.3; called at M:430).  q: [Ntok][heads*8], kv: [Ntok][2*heads*8] '(kv h d)',
+ * out: [Ntok][heads*8]; sequences are n_seq contiguous runs of L tokens.  dim_head must be 8.
+ * workspace: mv2_linattn_workspace_bytes(n_seq, heads, L).                                    */
+size_t mv2_linattn_workspace_bytes(int n_seq, int heads, int L);
+int mv2_linear_attention(const void* q, const void* kv, void* out, int dtype,
+                         int n_seq, int L, int heads, int dim_head, void* workspace, void* stream);
+
+/* ---- GEGLU (M:466-469): out[n][i] = gelu_erf(in[n][I + i]) * in[n][i] ------------------------- */
+int mv2_geglu(const void* in, void* out, int dtype, int64_t N, int I, void* stream);
+
+/* ---- quantisers (un-vendored vector-quantize-pytorch LFQ / FSQ; SURVEY.md Appendix A.1/A.2;
+ * reference call sites M:1576, M:1593, M:1700, M:1705) ---------------------------------------
+ * lfq_forward : x [N][C] -> p = tanh((Win x + bin)/clamp)*clamp (fp32), bit_i = p_i > 0,
+ *               index = sum bit_i << (d-1-i) (int64), quantized [N][C] = Wout (+-1) + bout.
+ *               presign (fp32 [N][d]) is optional (diagnostics / training losses).
+ * lfq_decode  : indices -> quantized (LFQ.indices_to_codes).
+ * fsq_*       : same with tanh-bound + round-half-even + mixed-radix int32 index.
+ * win [d][C], bin [d], wout [C][d], bout [C] are fp32.                                         */
+int mv2_lfq_forward(const void* x, int dtype, int64_t N, int C, int d,
+                    const float* win, const float* bin, const float* wout, const float* bout,
+                    float clamp, int64_t* indices, void* quantized, float* presign, void* stream);
+int mv2_lfq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d,
+                   const float* wout, const float* bout, void* quantized, int dtype, void* stream);
+int mv2_fsq_forward(const void* x, int dtype, int64_t N, int C, int d, const int32_t* levels /* host */,
+                    const float* win, const float* bin, const float* wout, const float* bout,
+                    int32_t* indices, void* quantized, float* bounded, void* stream);
+int mv2_fsq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d, const int32_t* levels /* host */,
+                   const float* wout, const float* bout, void* quantized, int dtype, void* stream);
+
+/* ---- LFQ training-mode auxiliary terms (A.1 steps 7-8; the one collective on the path) -------
+ * lfq_entropy_partials: from presign [N][d] (d <= 12) accumulates, for this rank,
+ *   stats[0] = sum_tokens H(softmax_K(2*inv_temp*<p, code_k>)), stats[1] = sum (p - sign p)^2,
+ *   avg_prob[K] += sum_tokens prob (un-normalised; caller divides by the global token count after
+ *   the cross-rank SUM all-reduce of avg_prob -- the 4 KiB NCCL all-reduce of cfg 3).
+ * stats and avg_prob must be zeroed by the caller.                                             */
+int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, float inv_temperature,
+                             float* avg_prob, float* stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGVIT2_B200_H */

@@ -1,0 +1,71 @@
+// Shared helpers for libmagvit2_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/magvit2_b200.h"
+
+namespace mv2 {
+
+void set_error(const char* fmt, ...);
+
+#define MV2_CHECK_ARG(cond, ...)                                  \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      mv2::set_error("%s:%d: argument check failed: %s", __FILE__, __LINE__, #cond); \
+      return MV2_E_ARG;                                           \
+    }                                                             \
+  } while (0)
+
+#define MV2_CHECK_LAUNCH()                                        \
+  do {                                                            \
+    cudaError_t e__ = cudaGetLastError();                         \
+    if (e__ != cudaSuccess) {                                     \
+      mv2::set_error("%s:%d: CUDA launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return MV2_E_CUDA;                                          \
+    }                                                             \
+  } while (0)
+
+#define MV2_CHECK_CUDA(expr)                                      \
+  do {                                                            \
+    cudaError_t e__ = (expr);                                     \
+    if (e__ != cudaSuccess) {                                     \
+      mv2::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return MV2_E_CUDA;                                          \
+    }                                                             \
+  } while (0)
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Activations.  expm1f / expf (not the fast intrinsics): the fp32 path must track the
+// reference's libm-based CPU results to ~1 ulp.
+__device__ __forceinline__ float act_elu(float v) { return v > 0.f ? v : expm1f(v); }
+__device__ __forceinline__ float act_silu(float v) { return v / (1.f + expf(-v)); }
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == MV2_ACT_ELU) return act_elu(v);
+  if (act == MV2_ACT_SILU) return act_silu(v);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace mv2

@@ -1,0 +1,1014 @@
+// CUDA-core (fp32-accumulate) kernels of libmagvit2_b200.so.
+//
+// These cover every operator of the VideoTokenizer forward path for ANY shape and for both
+// activation dtypes.  They are (a) the whole fp32 parity path (fp32 storage + fp32 FMA, no
+// TF32), (b) the memory-bound operators of the bf16 path (SqueezeExcite, norms, attention
+// cores, GEGLU, quantisers, layout), and (c) the on-device cross-check for the tcgen05
+// implicit-GEMM kernels in tc_conv.cu, which take over the dense contractions in bf16.
+//
+// Reference semantics are cited per entry point in include/magvit2_b200.h.
+#include "common.cuh"
+#include <math.h>
+#include <mutex>
+
+namespace mv2 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------
+// src [B][R][S] -> dst [B][S_dst][R]  (R = channels rows, S = positions), dst position = s + s_off_dst,
+// src position = s + s_off_src.  Classic 32x32 smem tile transpose.
+template <typename TS, typename TD>
+__global__ void transpose_rs_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int64_t S,
+                                    int64_t src_S_total, int64_t dst_S_total, int64_t s_off_src,
+                                    int64_t s_off_dst, bool src_is_rs) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int64_t s0 = (int64_t)blockIdx.x * 32;
+  const int r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (src_is_rs) {
+    // src [B][R][S_total] -> dst [B][S_total'][R]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = r0 + ty + 8 * j;
+      int64_t s = s0 + tx;
+      float v = 0.f;
+      if (r < R && s < S) v = to_f32<TS>(src[((int64_t)b * R + r) * src_S_total + s + s_off_src]);
+      tile[ty + 8 * j][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t s = s0 + ty + 8 * j;
+      int r = r0 + tx;
+      if (r < R && s < S) dst[((int64_t)b * dst_S_total + s + s_off_dst) * R + r] = from_f32<TD>(tile[tx][ty + 8 * j]);
+    }
+  } else {
+    // src [B][S_total][R] -> dst [B][R][S_total']
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t s = s0 + ty + 8 * j;
+      int r = r0 + tx;
+      float v = 0.f;
+      if (r < R && s < S) v = to_f32<TS>(src[((int64_t)b * src_S_total + s + s_off_src) * R + r]);
+      tile[ty + 8 * j][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = r0 + ty + 8 * j;
+      int64_t s = s0 + tx;
+      if (r < R && s < S) dst[((int64_t)b * R + r) * dst_S_total + s + s_off_dst] = from_f32<TD>(tile[tx][ty + 8 * j]);
+    }
+  }
+}
+
+template <typename TS, typename TD>
+static int launch_transpose(const void* src, void* dst, int B, int R, int64_t S, int64_t src_S_total,
+                            int64_t dst_S_total, int64_t s_off_src, int64_t s_off_dst, bool src_is_rs,
+                            cudaStream_t st) {
+  dim3 grid(ceil_div(S, 32), ceil_div(R, 32), B), block(32, 8);
+  transpose_rs_kernel<TS, TD><<<grid, block, 0, st>>>((const TS*)src, (TD*)dst, R, S, src_S_total, dst_S_total,
+                                                      s_off_src, s_off_dst, src_is_rs);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+static int dispatch_transpose(const void* src, int sd, void* dst, int dd, int B, int R, int64_t S,
+                              int64_t src_S_total, int64_t dst_S_total, int64_t s_off_src, int64_t s_off_dst,
+                              bool src_is_rs, cudaStream_t st) {
+  if (sd == MV2_F32 && dd == MV2_F32)
+    return launch_transpose<float, float>(src, dst, B, R, S, src_S_total, dst_S_total, s_off_src, s_off_dst, src_is_rs, st);
+  if (sd == MV2_F32 && dd == MV2_BF16)
+    return launch_transpose<float, __nv_bfloat16>(src, dst, B, R, S, src_S_total, dst_S_total, s_off_src, s_off_dst, src_is_rs, st);
+  if (sd == MV2_BF16 && dd == MV2_F32)
+    return launch_transpose<__nv_bfloat16, float>(src, dst, B, R, S, src_S_total, dst_S_total, s_off_src, s_off_dst, src_is_rs, st);
+  if (sd == MV2_BF16 && dd == MV2_BF16)
+    return launch_transpose<__nv_bfloat16, __nv_bfloat16>(src, dst, B, R, S, src_S_total, dst_S_total, s_off_src, s_off_dst, src_is_rs, st);
+  set_error("unsupported dtype pair %d -> %d", sd, dd);
+  return MV2_E_ARG;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic convolution (implicit GEMM on CUDA cores)
+// ------------------------------------------------------------------------------------------
+constexpr int CBM = 64, CBN = 64, CBK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const mv2_conv_args a) {
+  __shared__ float As[CBK][CBM + 4];
+  __shared__ float Bs[CBK][CBN + 4];
+  const T* __restrict__ x = (const T*)a.x;
+  const T* __restrict__ w = (const T*)a.w;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t M = (int64_t)a.B * a.To * a.Ho * a.Wo;
+  const int64_t m0 = (int64_t)blockIdx.x * CBM;
+  const int n0 = blockIdx.y * CBN;
+
+  // loader role: position lp (0..63), 4 consecutive channels at (tid & 3) * 4
+  const int lp = tid >> 2, lk = (tid & 3) * 4;
+  const int64_t lm = m0 + lp;
+  const bool lvalid = lm < M;
+  int lb = 0, lto = 0, lho = 0, lwo = 0;
+  if (lvalid) {
+    int64_t r = lm;
+    lwo = (int)(r % a.Wo); r /= a.Wo;
+    lho = (int)(r % a.Ho); r /= a.Ho;
+    lto = (int)(r % a.To); r /= a.To;
+    lb = (int)r;
+  }
+  // weight loader role: k row = tid >> 4, 4 columns at (tid & 15) * 4
+  const int wk = tid >> 4, wn = (tid & 15) * 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int ntaps = a.kt * a.kh * a.kw;
+  const int half_c = a.Ci >> 1;
+  for (int tap = 0; tap < ntaps; ++tap) {
+    const int dw = tap % a.kw, dh = (tap / a.kw) % a.kh, dt = tap / (a.kw * a.kh);
+    const int ti = lto * a.st - a.pt + dt;
+    const int hi = lho * a.sh - a.ph + dh;
+    const int wi = lwo * a.sw - a.pw + dw;
+    const bool sp_ok = lvalid && hi >= 0 && hi < a.Hi && wi >= 0 && wi < a.Wi;
+    for (int c0 = 0; c0 < a.Ci; c0 += CBK) {
+      // ---- stage A (im2col gather) ----
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + lk + j;
+        float v = 0.f;
+        if (sp_ok && c < a.Ci) {
+          int tt = ti;
+          if (a.x_token_shift && c >= half_c) tt -= 1;
+          if (tt >= 0 && tt < a.Ti)
+            v = to_f32<T>(x[((((int64_t)lb * a.Ti + tt) * a.Hi + hi) * a.Wi + wi) * a.Ci + c]);
+        }
+        As[lk + j][lp] = v;
+      }
+      // ---- stage B (weights) ----
+      {
+        const int c = c0 + wk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + wn + j;
+          float v = 0.f;
+          if (c < a.Ci && n < a.Co) v = to_f32<T>(w[((int64_t)tap * a.Ci + c) * a.Co + n]);
+          Bs[wk][wn + j] = v;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < CBK; ++k) {
+        float av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue: bias, activation, depth-to-space/time shuffle, residual ----
+  T* __restrict__ y = (T*)a.y;
+  const T* __restrict__ res = (const T*)a.res;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    int64_t r = m;
+    const int wo = (int)(r % a.Wo); r /= a.Wo;
+    const int ho = (int)(r % a.Ho); r /= a.Ho;
+    const int to = (int)(r % a.To); r /= a.To;
+    const int b = (int)r;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.Co) continue;
+      float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
+      v = apply_act(v, a.act);
+      int64_t off;
+      if (a.shuffle == MV2_SHUFFLE_SPACE) {
+        const int cy = a.Co >> 2, c = n >> 2, p1 = (n >> 1) & 1, p2 = n & 1;
+        off = ((((int64_t)b * a.To + to) * (2 * a.Ho) + (2 * ho + p1)) * (2 * a.Wo) + (2 * wo + p2)) * cy + c;
+      } else if (a.shuffle == MV2_SHUFFLE_TIME) {
+        const int cy = a.Co >> 1, c = n >> 1, p = n & 1;
+        off = ((((int64_t)b * (2 * a.To) + (2 * to + p)) * a.Ho + ho) * a.Wo + wo) * cy + c;
+      } else {
+        off = m * a.Co + n;
+      }
+      if (res) v += to_f32<T>(res[off]);
+      y[off] = from_f32<T>(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SqueezeExcite
+// ------------------------------------------------------------------------------------------
+constexpr int SE_CHUNK = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(256) se_pool_kernel(const T* __restrict__ y, int P, int C,
+                                                      const float* __restrict__ wk, float bk,
+                                                      float* __restrict__ ws, int n_chunks) {
+  __shared__ float e[SE_CHUNK];
+  __shared__ float red[8];
+  __shared__ float bcast[2];
+  const int f = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p0 = chunk * SE_CHUNK;
+  const T* yf = y + (int64_t)f * P * C;
+  for (int n = warp; n < SE_CHUNK; n += 8) {
+    const int p = p0 + n;
+    float s = 0.f;
+    if (p < P) {
+      const T* row = yf + (int64_t)p * C;
+      for (int c = lane; c < C; c += 32) s = fmaf(to_f32<T>(row[c]), wk[c], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) e[n] = (p < P) ? s + bk : -INFINITY;
+  }
+  __syncthreads();
+  float v = (tid < SE_CHUNK) ? e[tid] : -INFINITY;
+  float mx = warp_max(v);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bcast[0] = m;
+  }
+  __syncthreads();
+  const float m = bcast[0];
+  float ev = (tid < SE_CHUNK && v > -INFINITY) ? expf(v - m) : 0.f;
+  __syncthreads();
+  if (tid < SE_CHUNK) e[tid] = ev;
+  float sm = warp_sum(ev);
+  if (lane == 0) red[warp] = sm;
+  __syncthreads();
+  float* out = ws + ((int64_t)f * n_chunks + chunk) * (C + 2);
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    out[0] = m;
+    out[1] = s;
+  }
+  const int cnt = min(SE_CHUNK, P - p0);
+  for (int c = tid; c < C; c += 256) {
+    float acc = 0.f;
+    for (int n = 0; n < cnt; ++n) acc = fmaf(e[n], to_f32<T>(yf[(int64_t)(p0 + n) * C + c]), acc);
+    out[2 + c] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ ws, int n_chunks, int C, int Hd,
+                                                      const float* __restrict__ w1, const float* __restrict__ b1,
+                                                      const float* __restrict__ w2, const float* __restrict__ b2,
+                                                      float* __restrict__ gates) {
+  extern __shared__ float sm[];
+  float* pooled = sm;          // [C]
+  float* hidden = sm + C;      // [Hd]
+  float* coef = hidden + Hd;   // [n_chunks]
+  __shared__ float s_inv;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* wf = ws + (int64_t)f * n_chunks * (C + 2);
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int k = lane; k < n_chunks; k += 32) m = fmaxf(m, wf[(int64_t)k * (C + 2)]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int k = lane; k < n_chunks; k += 32) {
+      float cf = expf(wf[(int64_t)k * (C + 2)] - m);
+      coef[k] = cf;
+      s += cf * wf[(int64_t)k * (C + 2) + 1];
+    }
+    s = warp_sum(s);
+    if (lane == 0) s_inv = 1.f / s;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    float acc = 0.f;
+    for (int k = 0; k < n_chunks; ++k) acc = fmaf(coef[k], wf[(int64_t)k * (C + 2) + 2 + c], acc);
+    pooled[c] = acc * s_inv;
+  }
+  __syncthreads();
+  for (int j = warp; j < Hd; j += 8) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(w1[(int64_t)j * C + c], pooled[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float h = acc + b1[j];
+      hidden[j] = h > 0.f ? h : 0.1f * h;
+    }
+  }
+  __syncthreads();
+  for (int c = warp; c < C; c += 8) {
+    float acc = 0.f;
+    for (int j = lane; j < Hd; j += 32) acc = fmaf(w2[(int64_t)c * Hd + j], hidden[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) gates[(int64_t)f * C + c] = 1.f / (1.f + expf(-(acc + b2[c])));
+  }
+}
+
+template <typename T>
+__global__ void gate_residual_kernel(const T* __restrict__ y, const T* __restrict__ x,
+                                     const float* __restrict__ gates, T* __restrict__ out,
+                                     int64_t total, int64_t PC, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / PC;
+    const int c = (int)(i % C);
+    out[i] = from_f32<T>(fmaf(gates[f * C + c], to_f32<T>(y[i]), to_f32<T>(x[i])));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// RMSNorm (+ token shift addressing)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, T* __restrict__ out,
+                                                      const float* __restrict__ gamma, int64_t n_tok, int T_,
+                                                      int P, int C, int token_shift) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= n_tok) return;
+  const int t = (int)((tok / P) % T_);
+  const int half = C >> 1;
+  const T* row = x + tok * C;
+  const T* prow = row - (int64_t)P * C;
+  const bool has_prev = t > 0;
+  float ss = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float v;
+    if (token_shift && c >= half) v = has_prev ? to_f32<T>(prow[c]) : 0.f;
+    else v = to_f32<T>(row[c]);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  const float scale = sqrtf((float)C);
+  T* orow = out + tok * C;
+  for (int c = lane; c < C; c += 32) {
+    float v;
+    if (token_shift && c >= half) v = has_prev ? to_f32<T>(prow[c]) : 0.f;
+    else v = to_f32<T>(row[c]);
+    orow[c] = from_f32<T>(((v / denom) * scale) * gamma[c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax attention core
+// ------------------------------------------------------------------------------------------
+constexpr int AT_Q = 32;  // queries per block
+template <typename T, int DPL>
+__global__ void __launch_bounds__(128) attention_kernel(const mv2_attn_args a) {
+  constexpr int D = DPL * 32;
+  __shared__ float Qs[AT_Q][D];
+  __shared__ float Ks[32][D + 1];
+  __shared__ float Vs[32][D + 1];
+  const T* __restrict__ qkv = (const T*)a.qkv;
+  T* __restrict__ out = (T*)a.out;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = blockIdx.y;
+  const int64_t seq = blockIdx.x;
+  const int64_t so = seq / a.n_inner, sn = seq % a.n_inner;
+  const int64_t base = so * a.outer_stride + sn * a.inner_stride;
+  const int q0 = blockIdx.z * AT_Q;
+  const int HD = a.heads * D;
+  const int64_t row_stride = 3 * (int64_t)HD;
+  const float scale = rsqrtf((float)D);
+  const bool causal = a.causal && a.L > 1;
+  const int Ltot = a.n_mem + a.L;
+
+  for (int idx = tid; idx < AT_Q * D; idx += 128) {
+    const int qi = idx / D, d = idx % D;
+    const int i = q0 + qi;
+    float v = 0.f;
+    if (i < a.L) v = to_f32<T>(qkv[(base + (int64_t)i * a.tok_stride) * row_stride + h * D + d]);
+    Qs[qi][d] = v;
+  }
+  float m[8], l[8], o[8][DPL];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    m[r] = -INFINITY;
+    l[r] = 0.f;
+#pragma unroll
+    for (int dd = 0; dd < DPL; ++dd) o[r][dd] = 0.f;
+  }
+  // keys visible to the last query of this block bound the tile loop under causal masking
+  int last_key = Ltot;
+  if (causal) last_key = min(Ltot, min(q0 + AT_Q, a.L) + a.n_mem);
+  for (int j0 = 0; j0 < last_key; j0 += 32) {
+    __syncthreads();
+    for (int idx = tid; idx < 32 * D; idx += 128) {
+      const int j = idx / D, d = idx % D;
+      const int jg = j0 + j;
+      float kv = 0.f, vv = 0.f;
+      if (jg < a.n_mem) {
+        kv = a.mem_kv[(((int64_t)0 * a.heads + h) * a.n_mem + jg) * D + d];
+        vv = a.mem_kv[(((int64_t)1 * a.heads + h) * a.n_mem + jg) * D + d];
+      } else if (jg < Ltot) {
+        const int64_t tokrow = (base + (int64_t)(jg - a.n_mem) * a.tok_stride) * row_stride;
+        kv = to_f32<T>(qkv[tokrow + HD + h * D + d]);
+        vv = to_f32<T>(qkv[tokrow + 2 * HD + h * D + d]);
+      }
+      Ks[j][d] = kv;
+      Vs[j][d] = vv;
+    }
+    __syncthreads();
+    const int jg = j0 + lane;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int qi = warp * 8 + r;
+      const int i = q0 + qi;
+      if (i >= a.L) continue;  // warp-uniform
+      float s = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < D; ++d) s = fmaf(Qs[qi][d], Ks[lane][d], s);
+      s *= scale;
+      const bool valid = jg < Ltot && (!causal || jg <= i + a.n_mem);
+      s = valid ? s : -INFINITY;
+      const float m_new = fmaxf(m[r], warp_max(s));
+      const float p = valid ? expf(s - m_new) : 0.f;
+      const float corr = expf(m[r] - m_new);
+      l[r] = l[r] * corr + warp_sum(p);
+      m[r] = m_new;
+#pragma unroll
+      for (int dd = 0; dd < DPL; ++dd) o[r][dd] *= corr;
+      for (int j = 0; j < 32; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, p, j);
+#pragma unroll
+        for (int dd = 0; dd < DPL; ++dd) o[r][dd] = fmaf(pj, Vs[j][lane + 32 * dd], o[r][dd]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = q0 + warp * 8 + r;
+    if (i >= a.L) continue;
+    const float inv = 1.f / l[r];
+    T* orow = out + (base + (int64_t)i * a.tok_stride) * HD + h * D;
+#pragma unroll
+    for (int dd = 0; dd < DPL; ++dd) orow[lane + 32 * dd] = from_f32<T>(o[r][dd] * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Taylor-series linear attention core (dim_head = 8, feature dim 1 + 8 + 64 = 73)
+// ------------------------------------------------------------------------------------------
+constexpr int LA_D = 8, LA_F = 73, LA_ST = LA_F * (LA_D + 1);  // 657 state values per (seq, head)
+constexpr int LA_CHUNK = 256;
+
+__device__ __forceinline__ float taylor_feat(const float* v, int f) {
+  if (f == 0) return 1.f;
+  if (f <= LA_D) return v[f - 1];
+  const int ij = f - 1 - LA_D;
+  return v[ij >> 3] * v[ij & 7] * 0.70710678118654752440f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) linattn_reduce_kernel(const T* __restrict__ kv, float* __restrict__ ws,
+                                                             int L, int heads, int n_chunks) {
+  __shared__ float ks[64][LA_D];
+  __shared__ float vs[64][LA_D + 1];
+  const int chunk = blockIdx.x, h = blockIdx.y;
+  const int64_t seq = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int HD = heads * LA_D;
+  float acc[3] = {0.f, 0.f, 0.f};
+  const int t_begin = chunk * LA_CHUNK, t_end = min(L, t_begin + LA_CHUNK);
+  for (int t0 = t_begin; t0 < t_end; t0 += 64) {
+    __syncthreads();
+    for (int idx = tid; idx < 64 * LA_D; idx += 256) {
+      const int n = idx / LA_D, d = idx % LA_D;
+      const int t = t0 + n;
+      float kk = 0.f, vv = 0.f;
+      if (t < t_end) {
+        const int64_t row = (seq * L + t) * (2 * (int64_t)HD);
+        kk = to_f32<T>(kv[row + h * LA_D + d]);
+        vv = to_f32<T>(kv[row + HD + h * LA_D + d]);
+      }
+      ks[n][d] = kk;
+      vs[n][d] = vv;
+    }
+    for (int n = tid; n < 64; n += 256) vs[n][LA_D] = (t0 + n < t_end) ? 1.f : 0.f;
+    __syncthreads();
+    const int cnt = min(64, t_end - t0);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int idx = tid + 256 * r;
+      if (idx >= LA_ST) continue;
+      const int f = idx / (LA_D + 1), e = idx % (LA_D + 1);
+      float s = acc[r];
+      for (int n = 0; n < cnt; ++n) s = fmaf(taylor_feat(ks[n], f), vs[n][e], s);
+      acc[r] = s;
+    }
+  }
+  float* o = ws + ((seq * heads + h) * n_chunks + chunk) * LA_ST;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int idx = tid + 256 * r;
+    if (idx < LA_ST) o[idx] = acc[r];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) linattn_apply_kernel(const T* __restrict__ q, const float* __restrict__ ws,
+                                                            T* __restrict__ out, int L, int heads, int n_chunks) {
+  __shared__ float S[LA_ST];
+  const int chunk = blockIdx.x, h = blockIdx.y;
+  const int64_t seq = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int HD = heads * LA_D;
+  const float* wsh = ws + (seq * heads + h) * (int64_t)n_chunks * LA_ST;
+  for (int idx = tid; idx < LA_ST; idx += 256) {
+    float s = 0.f;
+    for (int k = 0; k < n_chunks; ++k) s += wsh[(int64_t)k * LA_ST + idx];
+    S[idx] = s;
+  }
+  __syncthreads();
+  const int t = chunk * LA_CHUNK + tid;
+  if (t >= L) return;
+  const int64_t tok = seq * L + t;
+  float qv[LA_D];
+  const float qscale = rsqrtf((float)LA_D);
+#pragma unroll
+  for (int d = 0; d < LA_D; ++d) qv[d] = to_f32<T>(q[tok * HD + h * LA_D + d]) * qscale;
+  float num[LA_D], den = 0.f;
+#pragma unroll
+  for (int e = 0; e < LA_D; ++e) num[e] = 0.f;
+  for (int f = 0; f < LA_F; ++f) {
+    const float pf = taylor_feat(qv, f);
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) num[e] = fmaf(pf, S[f * (LA_D + 1) + e], num[e]);
+    den = fmaf(pf, S[f * (LA_D + 1) + LA_D], den);
+  }
+  den = fmaxf(den, 1e-5f);
+#pragma unroll
+  for (int e = 0; e < LA_D; ++e) out[tok * HD + h * LA_D + e] = from_f32<T>(num[e] / den);
+}
+
+// ------------------------------------------------------------------------------------------
+// GEGLU
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void geglu_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t N, int I) {
+  const int64_t total = N * I;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = idx / I;
+    const int i = (int)(idx % I);
+    const float xv = to_f32<T>(in[n * 2 * I + i]);
+    const float g = to_f32<T>(in[n * 2 * I + I + i]);
+    const float ge = 0.5f * g * (1.f + erff(g * 0.70710678118654752440f));
+    out[idx] = from_f32<T>(ge * xv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// quantisers
+// ------------------------------------------------------------------------------------------
+constexpr int Q_MAXD = 16;
+struct FsqLevels { int32_t lv[Q_MAXD]; };
+
+// mode 0: LFQ, mode 1: FSQ.  One warp per token.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) quant_forward_kernel(const T* __restrict__ x, int64_t N, int C, int d,
+                                                            const float* __restrict__ win, const float* __restrict__ bin,
+                                                            const float* __restrict__ wout, const float* __restrict__ bout,
+                                                            float clamp, FsqLevels lv, int64_t* __restrict__ idx64,
+                                                            int32_t* __restrict__ idx32, T* __restrict__ quant,
+                                                            float* __restrict__ aux) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= N) return;
+  const T* row = x + tok * C;
+  float acc[Q_MAXD];
+#pragma unroll
+  for (int i = 0; i < Q_MAXD; ++i) acc[i] = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float xv = to_f32<T>(row[c]);
+#pragma unroll
+    for (int i = 0; i < Q_MAXD; ++i)
+      if (i < d) acc[i] = fmaf(xv, win[(int64_t)i * C + c], acc[i]);
+  }
+  float code[Q_MAXD];
+  int64_t index = 0;
+  int32_t basis = 1;
+#pragma unroll
+  for (int i = 0; i < Q_MAXD; ++i) {
+    code[i] = 0.f;
+    if (i < d) {
+      float p = warp_sum(acc[i]) + bin[i];
+      if (MODE == 0) {
+        if (clamp > 0.f) p = tanhf(p / clamp) * clamp;
+        const bool bit = p > 0.f;
+        code[i] = bit ? 1.f : -1.f;
+        if (bit) index |= (int64_t)1 << (d - 1 - i);
+        if (aux && lane == 0) aux[tok * d + i] = p;
+      } else {
+        const int L = lv.lv[i];
+        const float half_l = (float)(L - 1) * (1.f + 1e-3f) * 0.5f;
+        const float offset = (L % 2 == 0) ? 0.5f : 0.f;
+        const float shift = atanhf(offset / half_l);
+        const float bnd = tanhf(p + shift) * half_l - offset;
+        const float q = rintf(bnd);  // round half to even, as torch.round
+        const int half_w = L / 2;
+        code[i] = q / (float)half_w;
+        index += (int64_t)((int)q + half_w) * basis;
+        basis *= L;
+        if (aux && lane == 0) aux[tok * d + i] = bnd;
+      }
+    }
+  }
+  if (lane == 0) {
+    if (idx64) idx64[tok] = index;
+    if (idx32) idx32[tok] = (int32_t)index;
+  }
+  if (quant) {
+    T* qrow = quant + tok * C;
+    for (int c = lane; c < C; c += 32) {
+      float o = bout[c];
+#pragma unroll
+      for (int i = 0; i < Q_MAXD; ++i)
+        if (i < d) o = fmaf(code[i], wout[(int64_t)c * d + i], o);
+      qrow[c] = from_f32<T>(o);
+    }
+  }
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) quant_decode_kernel(const void* __restrict__ indices, int is64, int64_t N, int C,
+                                                           int d, FsqLevels lv, const float* __restrict__ wout,
+                                                           const float* __restrict__ bout, T* __restrict__ quant) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= N) return;
+  int64_t index = is64 ? ((const int64_t*)indices)[tok] : (int64_t)((const int32_t*)indices)[tok];
+  float code[Q_MAXD];
+  int64_t rem = index;
+#pragma unroll
+  for (int i = 0; i < Q_MAXD; ++i) {
+    code[i] = 0.f;
+    if (i < d) {
+      if (MODE == 0) {
+        code[i] = ((index >> (d - 1 - i)) & 1) ? 1.f : -1.f;
+      } else {
+        const int L = lv.lv[i];
+        const int digit = (int)(rem % L);
+        rem /= L;
+        const int half_w = L / 2;
+        code[i] = (float)(digit - half_w) / (float)half_w;
+      }
+    }
+  }
+  T* qrow = quant + tok * C;
+  for (int c = lane; c < C; c += 32) {
+    float o = bout[c];
+#pragma unroll
+    for (int i = 0; i < Q_MAXD; ++i)
+      if (i < d) o = fmaf(code[i], wout[(int64_t)c * d + i], o);
+    qrow[c] = from_f32<T>(o);
+  }
+}
+
+// LFQ training-mode entropy / commitment partial sums.  One block handles LE_TOK tokens.
+constexpr int LE_TOK = 32;
+__global__ void __launch_bounds__(256) lfq_entropy_kernel(const float* __restrict__ presign, int64_t N, int d,
+                                                          float inv_temp, float* __restrict__ avg_prob,
+                                                          float* __restrict__ stats) {
+  extern __shared__ float probs[];  // [K]
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int K = 1 << d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float ent_sum = 0.f, commit_sum = 0.f;
+  const int64_t t0 = (int64_t)blockIdx.x * LE_TOK;
+  // per-thread running sum of probabilities for codes k = tid, tid+256, ...
+  float pacc[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) pacc[r] = 0.f;
+  for (int64_t t = t0; t < min(N, t0 + LE_TOK); ++t) {
+    float p[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) p[i] = (i < d) ? presign[t * d + i] : 0.f;
+    float mx = -INFINITY;
+    for (int k = tid; k < K; k += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 12; ++i)
+        if (i < d) s += ((k >> (d - 1 - i)) & 1) ? p[i] : -p[i];
+      s *= 2.f * inv_temp;
+      probs[k] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) { float m = red[0]; for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]); bc = m; }
+    __syncthreads();
+    mx = bc;
+    float sm = 0.f;
+    for (int k = tid; k < K; k += 256) { float e = expf(probs[k] - mx); probs[k] = e; sm += e; }
+    sm = warp_sum(sm);
+    __syncthreads();
+    if (lane == 0) red[warp] = sm;
+    __syncthreads();
+    if (tid == 0) { float s = 0.f; for (int i = 0; i < 8; ++i) s += red[i]; bc = 1.f / s; }
+    __syncthreads();
+    const float inv = bc;
+    float ent = 0.f;
+    int r = 0;
+    for (int k = tid; k < K; k += 256, ++r) {
+      const float pr = probs[k] * inv;
+      ent -= pr * logf(fmaxf(pr, 1e-5f));
+      if (r < 16) pacc[r] += pr;
+    }
+    ent_sum += ent;
+    if (tid == 0) {
+      float cs = 0.f;
+      for (int i = 0; i < d; ++i) { float q = p[i] > 0.f ? 1.f : -1.f; cs += (p[i] - q) * (p[i] - q); }
+      commit_sum += cs;
+    }
+    __syncthreads();
+  }
+  {
+    int r = 0;
+    for (int k = tid; k < K; k += 256, ++r)
+      if (r < 16) atomicAdd(&avg_prob[k], pacc[r]);
+  }
+  ent_sum = warp_sum(ent_sum);
+  if (lane == 0) atomicAdd(&stats[0], ent_sum);
+  if (tid == 0) atomicAdd(&stats[1], commit_sum);
+}
+
+}  // namespace mv2
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+using namespace mv2;
+
+template <typename T>
+static int launch_attention(const mv2_attn_args* a, cudaStream_t st) {
+  dim3 grid((unsigned)((int64_t)a->n_outer * a->n_inner), a->heads, ceil_div(a->L, AT_Q));
+  switch (a->dim_head / 32) {
+    case 1: attention_kernel<T, 1><<<grid, 128, 0, st>>>(*a); break;
+    case 2: attention_kernel<T, 2><<<grid, 128, 0, st>>>(*a); break;
+    case 3: attention_kernel<T, 3><<<grid, 128, 0, st>>>(*a); break;
+    default: set_error("dim_head %d unsupported", a->dim_head); return MV2_E_UNSUPPORTED;
+  }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+extern "C" {
+
+int mv2_abi_version(void) { return MV2_ABI_VERSION; }
+const char* mv2_last_error(void) { return mv2::g_err; }
+
+int mv2_device_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return MV2_E_CUDA; }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return major * 10 + minor;
+}
+
+int mv2_to_channels_last(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C, int T, int H, int W,
+                         int t_pad, void* stream) {
+  MV2_CHECK_ARG(src && dst && B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && t_pad >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t HW = (int64_t)H * W, S = (int64_t)T * HW, Sd = (int64_t)(T + t_pad) * HW;
+  const size_t es = dst_dtype == MV2_F32 ? 4 : 2;
+  if (t_pad > 0)
+    MV2_CHECK_CUDA(cudaMemset2DAsync(dst, (size_t)Sd * C * es, 0, (size_t)t_pad * HW * C * es, B, st));
+  return dispatch_transpose(src, src_dtype, dst, dst_dtype, B, C, S, S, Sd, 0, (int64_t)t_pad * HW, true, st);
+}
+
+int mv2_to_channels_first(const void* src, int src_dtype, void* dst, int dst_dtype, int B, int C, int T, int H, int W,
+                          int t_crop, void* stream) {
+  MV2_CHECK_ARG(src && dst && B > 0 && C > 0 && T > t_crop && H > 0 && W > 0 && t_crop >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t HW = (int64_t)H * W, Ss = (int64_t)T * HW, S = (int64_t)(T - t_crop) * HW;
+  return dispatch_transpose(src, src_dtype, dst, dst_dtype, B, C, S, Ss, S, (int64_t)t_crop * HW, 0, false, st);
+}
+
+int mv2_conv_forward(const mv2_conv_args* a, void* stream) {
+  MV2_CHECK_ARG(a && a->x && a->w && a->y);
+  MV2_CHECK_ARG(a->B > 0 && a->Ti > 0 && a->Hi > 0 && a->Wi > 0 && a->Ci > 0);
+  MV2_CHECK_ARG(a->To > 0 && a->Ho > 0 && a->Wo > 0 && a->Co > 0);
+  MV2_CHECK_ARG(a->kt > 0 && a->kh > 0 && a->kw > 0 && a->st > 0 && a->sh > 0 && a->sw > 0);
+  MV2_CHECK_ARG(a->shuffle != MV2_SHUFFLE_SPACE || a->Co % 4 == 0);
+  MV2_CHECK_ARG(a->shuffle != MV2_SHUFFLE_TIME || a->Co % 2 == 0);
+  MV2_CHECK_ARG(!a->x_token_shift || a->Ci % 2 == 0);
+  const int64_t M = (int64_t)a->B * a->To * a->Ho * a->Wo;
+  dim3 grid(ceil_div(M, CBM), ceil_div(a->Co, CBN));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->dtype == MV2_F32) conv_simt_kernel<float><<<grid, 256, 0, st>>>(*a);
+  else if (a->dtype == MV2_BF16) conv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(*a);
+  else { set_error("bad dtype %d", a->dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+size_t mv2_se_workspace_bytes(int F, int P, int C) {
+  return (size_t)F * ceil_div(P, SE_CHUNK) * (C + 2) * sizeof(float);
+}
+
+int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, float bk, void* workspace,
+                void* stream) {
+  MV2_CHECK_ARG(y && wk && workspace && F > 0 && P > 0 && C > 0);
+  const int nc = ceil_div(P, SE_CHUNK);
+  dim3 grid(nc, F);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32) se_pool_kernel<float><<<grid, 256, 0, st>>>((const float*)y, P, C, wk, bk, (float*)workspace, nc);
+  else if (dtype == MV2_BF16) se_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, P, C, wk, bk, (float*)workspace, nc);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_se_gate(const void* workspace, int F, int P, int C, int Hd, const float* w1, const float* b1, const float* w2,
+                const float* b2, float* gates, void* stream) {
+  MV2_CHECK_ARG(workspace && w1 && b1 && w2 && b2 && gates && F > 0 && P > 0 && C > 0 && Hd > 0);
+  const int nc = ceil_div(P, SE_CHUNK);
+  const size_t smem = (size_t)(C + Hd + nc) * sizeof(float);
+  MV2_CHECK_ARG(smem <= 48 * 1024);
+  se_gate_kernel<<<F, 256, smem, (cudaStream_t)stream>>>((const float*)workspace, nc, C, Hd, w1, b1, w2, b2, gates);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_gate_residual(const void* y, const void* x, const float* gates, void* out, int dtype, int F, int P, int C,
+                      void* stream) {
+  MV2_CHECK_ARG(y && x && gates && out && F > 0 && P > 0 && C > 0);
+  const int64_t total = (int64_t)F * P * C;
+  const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32)
+    gate_residual_kernel<float><<<blocks, 256, 0, st>>>((const float*)y, (const float*)x, gates, (float*)out, total, (int64_t)P * C, C);
+  else if (dtype == MV2_BF16)
+    gate_residual_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)x, gates, (__nv_bfloat16*)out, total, (int64_t)P * C, C);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_rmsnorm(const void* x, void* out, int dtype, const float* gamma, int B, int T, int P, int C, int token_shift,
+                void* stream) {
+  MV2_CHECK_ARG(x && out && gamma && B > 0 && T > 0 && P > 0 && C > 0);
+  MV2_CHECK_ARG(!token_shift || C % 2 == 0);
+  const int64_t n_tok = (int64_t)B * T * P;
+  const int blocks = ceil_div(n_tok, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32)
+    rmsnorm_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)out, gamma, n_tok, T, P, C, token_shift);
+  else if (dtype == MV2_BF16)
+    rmsnorm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, gamma, n_tok, T, P, C, token_shift);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_attention(const mv2_attn_args* a, void* stream) {
+  MV2_CHECK_ARG(a && a->qkv && a->out && a->mem_kv);
+  MV2_CHECK_ARG(a->heads > 0 && a->dim_head > 0 && a->dim_head % 32 == 0 && a->dim_head <= 96);
+  MV2_CHECK_ARG(a->n_mem >= 0 && a->n_outer > 0 && a->n_inner > 0 && a->L > 0);
+  MV2_CHECK_ARG((int64_t)a->n_outer * a->n_inner <= 2147483647LL && ceil_div(a->L, AT_Q) <= 65535);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->dtype == MV2_F32) return launch_attention<float>(a, st);
+  if (a->dtype == MV2_BF16) return launch_attention<__nv_bfloat16>(a, st);
+  set_error("bad dtype %d", a->dtype);
+  return MV2_E_ARG;
+}
+
+size_t mv2_linattn_workspace_bytes(int n_seq, int heads, int L) {
+  return (size_t)n_seq * heads * ceil_div(L, LA_CHUNK) * LA_ST * sizeof(float);
+}
+
+int mv2_linear_attention(const void* q, const void* kv, void* out, int dtype, int n_seq, int L, int heads,
+                         int dim_head, void* workspace, void* stream) {
+  MV2_CHECK_ARG(q && kv && out && workspace && n_seq > 0 && L > 0 && heads > 0);
+  if (dim_head != LA_D) { set_error("linear attention dim_head %d unsupported (only 8)", dim_head); return MV2_E_UNSUPPORTED; }
+  const int nc = ceil_div(L, LA_CHUNK);
+  dim3 grid(nc, heads, n_seq);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32) {
+    linattn_reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)kv, (float*)workspace, L, heads, nc);
+    MV2_CHECK_LAUNCH();
+    linattn_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)q, (const float*)workspace, (float*)out, L, heads, nc);
+  } else if (dtype == MV2_BF16) {
+    linattn_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
+    MV2_CHECK_LAUNCH();
+    linattn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
+  } else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_geglu(const void* in, void* out, int dtype, int64_t N, int I, void* stream) {
+  MV2_CHECK_ARG(in && out && N > 0 && I > 0);
+  const int64_t total = N * I;
+  const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32) geglu_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, (float*)out, N, I);
+  else if (dtype == MV2_BF16) geglu_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, I);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_lfq_forward(const void* x, int dtype, int64_t N, int C, int d, const float* win, const float* bin,
+                    const float* wout, const float* bout, float clamp, int64_t* indices, void* quantized,
+                    float* presign, void* stream) {
+  MV2_CHECK_ARG(x && win && bin && N > 0 && C > 0 && d > 0 && d <= Q_MAXD);
+  MV2_CHECK_ARG(!quantized || (wout && bout));
+  FsqLevels lv = {};
+  const int blocks = ceil_div(N, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32)
+    quant_forward_kernel<float, 0><<<blocks, 256, 0, st>>>((const float*)x, N, C, d, win, bin, wout, bout, clamp, lv, indices, nullptr, (float*)quantized, presign);
+  else if (dtype == MV2_BF16)
+    quant_forward_kernel<__nv_bfloat16, 0><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, N, C, d, win, bin, wout, bout, clamp, lv, indices, nullptr, (__nv_bfloat16*)quantized, presign);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_lfq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d, const float* wout,
+                   const float* bout, void* quantized, int dtype, void* stream) {
+  MV2_CHECK_ARG(indices && wout && bout && quantized && N > 0 && C > 0 && d > 0 && d <= Q_MAXD);
+  FsqLevels lv = {};
+  const int blocks = ceil_div(N, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32)
+    quant_decode_kernel<float, 0><<<blocks, 256, 0, st>>>(indices, index_is_i64, N, C, d, lv, wout, bout, (float*)quantized);
+  else if (dtype == MV2_BF16)
+    quant_decode_kernel<__nv_bfloat16, 0><<<blocks, 256, 0, st>>>(indices, index_is_i64, N, C, d, lv, wout, bout, (__nv_bfloat16*)quantized);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_fsq_forward(const void* x, int dtype, int64_t N, int C, int d, const int32_t* levels, const float* win,
+                    const float* bin, const float* wout, const float* bout, int32_t* indices, void* quantized,
+                    float* bounded, void* stream) {
+  MV2_CHECK_ARG(x && levels && win && bin && N > 0 && C > 0 && d > 0 && d <= Q_MAXD);
+  MV2_CHECK_ARG(!quantized || (wout && bout));
+  FsqLevels lv = {};
+  for (int i = 0; i < d; ++i) { MV2_CHECK_ARG(levels[i] >= 2); lv.lv[i] = levels[i]; }
+  const int blocks = ceil_div(N, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32)
+    quant_forward_kernel<float, 1><<<blocks, 256, 0, st>>>((const float*)x, N, C, d, win, bin, wout, bout, 0.f, lv, nullptr, indices, (float*)quantized, bounded);
+  else if (dtype == MV2_BF16)
+    quant_forward_kernel<__nv_bfloat16, 1><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, N, C, d, win, bin, wout, bout, 0.f, lv, nullptr, indices, (__nv_bfloat16*)quantized, bounded);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_fsq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d, const int32_t* levels,
+                   const float* wout, const float* bout, void* quantized, int dtype, void* stream) {
+  MV2_CHECK_ARG(indices && levels && wout && bout && quantized && N > 0 && C > 0 && d > 0 && d <= Q_MAXD);
+  FsqLevels lv = {};
+  for (int i = 0; i < d; ++i) { MV2_CHECK_ARG(levels[i] >= 2); lv.lv[i] = levels[i]; }
+  const int blocks = ceil_div(N, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32)
+    quant_decode_kernel<float, 1><<<blocks, 256, 0, st>>>(indices, index_is_i64, N, C, d, lv, wout, bout, (float*)quantized);
+  else if (dtype == MV2_BF16)
+    quant_decode_kernel<__nv_bfloat16, 1><<<blocks, 256, 0, st>>>(indices, index_is_i64, N, C, d, lv, wout, bout, (__nv_bfloat16*)quantized);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, float inv_temperature, float* avg_prob,
+                             float* stats, void* stream) {
+  MV2_CHECK_ARG(presign && avg_prob && stats && N > 0 && d > 0 && d <= 12);
+  const int K = 1 << d;
+  const int blocks = ceil_div(N, LE_TOK);
+  lfq_entropy_kernel<<<blocks, 256, K * sizeof(float), (cudaStream_t)stream>>>(presign, N, d, inv_temperature, avg_prob, stats);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,393 @@
+"""Host-side executor: walks the VideoTokenizer layer schedule and launches the sm_100a
+kernels of libmagvit2_b200.so through the C ABI (ctypes).  PyTorch is used only for device
+memory (caching allocator), streams and parameter storage.
+
+Activations are channels-last (B, T, H, W, C) tensors in the compute dtype (fp32 -> CUDA-core
+path, bf16 -> tcgen05 tensor-core path for the dense contractions).  There is no eager / CPU
+fallback: every op is a library call and a missing library is an error.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_ELU, ACT_NONE, ACT_SILU, MV2_BF16, MV2_F32, SHUFFLE_NONE, SHUFFLE_SPACE,
+                   SHUFFLE_TIME, AttnArgs, ConvArgs, check)
+
+
+def _dt(t: torch.dtype) -> int:
+    if t == torch.float32:
+        return MV2_F32
+    if t == torch.bfloat16:
+        return MV2_BF16
+    raise TypeError(f"unsupported dtype {t} (only float32 and bfloat16)")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class ConvPack:
+    """One convolution's parameters in kernel layout."""
+    w: torch.Tensor              # [taps][Ci][Co] in the compute dtype (CUDA-core path)
+    bias: Optional[torch.Tensor]  # fp32 [Co]
+    k: Tuple[int, int, int]
+    Ci: int
+    Co: int
+    w_tc: Optional[torch.Tensor] = None   # [Co_pad][taps*Ci_pad] bf16, K-major (tcgen05 path)
+
+
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype, k=None) -> ConvPack:
+    """weight: torch layout (Co, Ci, *kernel).  Kernel dims are mapped onto (kt, kh, kw) by `k`."""
+    Co, Ci = weight.shape[:2]
+    if k is None:
+        ks = tuple(weight.shape[2:])
+        k = (1,) * (3 - len(ks)) + ks
+    w = weight.detach().reshape(Co, Ci, -1).permute(2, 1, 0).contiguous().to(dtype)
+    b = None if bias is None else bias.detach().float().contiguous()
+    return ConvPack(w=w, bias=b, k=tuple(int(v) for v in k), Ci=int(Ci), Co=int(Co))
+
+
+class Engine:
+    """Executes the inference path of one VideoTokenizer on its parameters' device/dtype."""
+
+    def __init__(self, model):
+        self.model = model
+        self.lib = _lib.load()
+        self._packs: Dict[str, object] = {}
+        self._sig = None
+        self.launches = 0            # kernels launched through the C ABI (bench's gpu_launches)
+        self.taps: Optional[dict] = None  # when set, per-stage activations are recorded (tests)
+
+    # ------------------------------------------------------------------ parameters
+    def _signature(self):
+        ps = list(self.model.parameters())
+        return (tuple((p.data_ptr(), p._version) for p in ps), ps[0].dtype, ps[0].device)
+
+    def prepare(self):
+        """(Re)pack parameters into kernel layouts when they changed (load_state_dict, .to(), ...)."""
+        sig = self._signature()
+        if sig == self._sig:
+            return
+        m = self.model
+        p0 = m.conv_in.conv.weight
+        if p0.device.type != "cuda":
+            raise RuntimeError("magvit2_pytorch_b200.VideoTokenizer runs on CUDA (sm_100a) only; "
+                               "move the model with .cuda() -- there is no CPU fallback")
+        if p0.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("parameters must be float32 or bfloat16")
+        arch = self.lib.mv2_device_arch()
+        if arch < 100:
+            raise RuntimeError(f"libmagvit2_b200.so targets sm_100a; device reports sm_{arch}")
+        self.dtype = p0.dtype
+        self.device = p0.device
+        dt = self.dtype
+        P: Dict[str, object] = {}
+        P["conv_in"] = pack_conv(m.conv_in.conv.weight, m.conv_in.conv.bias, dt)
+        P["conv_out"] = pack_conv(m.conv_out.conv.weight, m.conv_out.conv.bias, dt)
+
+        def f32(t):
+            return t.detach().float().contiguous()
+
+        def pack_ru(ru, key):
+            seq = ru.fn
+            se = seq[4]
+            C_ = seq[2].weight.shape[0]
+            P[key] = dict(
+                conv3=pack_conv(seq[0].conv.weight, seq[0].conv.bias, dt),
+                conv1=pack_conv(seq[2].weight, seq[2].bias, dt),
+                wk=f32(se.to_k.weight.reshape(-1)), bk=float(se.to_k.bias.detach().float().item()),
+                w1=f32(se.net[0].weight.reshape(se.net[0].weight.shape[0], C_)), b1=f32(se.net[0].bias),
+                w2=f32(se.net[2].weight.reshape(C_, -1)), b2=f32(se.net[2].bias),
+                hidden=int(se.net[0].weight.shape[0]),
+            )
+
+        def pack_ff(ff, key):
+            P[key] = dict(gamma=f32(ff.norm.gamma.reshape(-1)),
+                          fc1=pack_conv(ff.net[0].weight, ff.net[0].bias, dt),
+                          fc2=pack_conv(ff.net[2].weight, ff.net[2].bias, dt),
+                          inner=ff.dim_inner)
+
+        def pack_attn(at, key):
+            P[key] = dict(gamma=f32(at.norm.gamma), qkv=pack_conv(at.to_qkv[0].weight[:, :, None, None, None], None, dt),
+                          out=pack_conv(at.to_out[1].weight[:, :, None, None, None], None, dt),
+                          mem_kv=at.mem_kv.detach().to(dt).float().contiguous(),
+                          heads=at.heads, dim_head=at.dim_head, n_mem=int(at.mem_kv.shape[2]))
+
+        def pack_lin(la, key):
+            P[key] = dict(gamma=f32(la.norm.gamma),
+                          q=pack_conv(la.attn.to_q[0].weight[:, :, None, None, None], None, dt),
+                          kv=pack_conv(la.attn.to_kv[0].weight[:, :, None, None, None], None, dt),
+                          out=pack_conv(la.attn.to_out[0].weight[:, :, None, None, None], None, dt),
+                          heads=la.heads, dim_head=la.dim_head)
+
+        for side, layers in (("enc", m.encoder_layers), ("dec", m.decoder_layers)):
+            stages = m.stages if side == "enc" else list(reversed(m.stages))
+            for i, st in enumerate(stages):
+                mod = layers[i]
+                key = f"{side}{i}"
+                if st.kind == "residual":
+                    units = list(mod) if st.nested else [mod]
+                    for j, ru in enumerate(units):
+                        pack_ru(ru, f"{key}.{j}")
+                elif st.kind == "compress_space":
+                    if side == "enc":
+                        P[key] = pack_conv(mod.conv.weight, mod.conv.bias, dt)                     # (Co,Ci,3,3) -> k=(1,3,3)
+                    else:
+                        P[key] = pack_conv(mod.net[0].weight, mod.net[0].bias, dt)                 # (4Co,Ci,1,1)
+                elif st.kind == "compress_time":
+                    if side == "enc":
+                        P[key] = pack_conv(mod.conv.weight, mod.conv.bias, dt, k=(3, 1, 1))        # Conv1d (Co,Ci,3)
+                    else:
+                        P[key] = pack_conv(mod.net[0].weight, mod.net[0].bias, dt, k=(1, 1, 1))    # Conv1d (2Co,Ci,1)
+                elif st.kind == "attend_space":
+                    pack_attn(mod[0].fn, key + ".attn")
+                    pack_ff(mod[1].fn, key + ".ff")
+                elif st.kind == "attend_time":
+                    pack_attn(mod[0].fn.fn, key + ".attn")
+                    pack_ff(mod[1].fn.fn, key + ".ff")
+                elif st.kind == "linear_attend_space":
+                    pack_lin(mod[0].fn, key + ".attn")
+                    pack_ff(mod[1].fn, key + ".ff")
+        q = m.quantizers
+        # the reference applies the projections in the module dtype (bf16 weights in bf16 mode)
+        P["quant"] = dict(win=q.project_in.weight.detach().to(dt).float().contiguous(), bin=q.project_in.bias.detach().to(dt).float().contiguous(),
+                          wout=q.project_out.weight.detach().to(dt).float().contiguous(), bout=q.project_out.bias.detach().to(dt).float().contiguous())
+        self._packs = P
+        self._sig = sig
+
+    # ------------------------------------------------------------------ primitive ops
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _new(self, shape, dtype=None):
+        return torch.empty(shape, device=self.device, dtype=dtype or self.dtype)
+
+    def conv(self, x, pk: ConvPack, *, stride=(1, 1, 1), pad=None, out_spatial=None, act=ACT_NONE,
+             res=None, shuffle=SHUFFLE_NONE, token_shift=False):
+        """x: (B,T,H,W,Ci) channels-last.  `pad` = leading (pt,ph,pw); causal default (kt-1, kh//2, kw//2)."""
+        B, Ti, Hi, Wi, Ci = x.shape
+        assert Ci == pk.Ci, (Ci, pk.Ci)
+        kt, kh, kw = pk.k
+        if pad is None:
+            pad = (kt - 1, kh // 2, kw // 2)
+        if out_spatial is None:
+            out_spatial = (Ti, Hi, Wi)
+        To, Ho, Wo = out_spatial
+        if shuffle == SHUFFLE_SPACE:
+            y = self._new((B, To, 2 * Ho, 2 * Wo, pk.Co // 4))
+        elif shuffle == SHUFFLE_TIME:
+            y = self._new((B, 2 * To, Ho, Wo, pk.Co // 2))
+        else:
+            y = self._new((B, To, Ho, Wo, pk.Co))
+        if res is not None:
+            assert res.shape == y.shape and res.dtype == y.dtype and res.is_contiguous()
+        a = ConvArgs(x=_ptr(x), w=_ptr(pk.w), bias=_ptr(pk.bias), res=_ptr(res), y=_ptr(y), dtype=_dt(self.dtype),
+                     B=B, Ti=Ti, Hi=Hi, Wi=Wi, Ci=Ci, To=To, Ho=Ho, Wo=Wo, Co=pk.Co,
+                     kt=kt, kh=kh, kw=kw, st=stride[0], sh=stride[1], sw=stride[2],
+                     pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle, x_token_shift=int(token_shift))
+        check(self.lib.mv2_conv_forward(C.byref(a), self._stream()), "mv2_conv_forward")
+        self.launches += 1
+        return y
+
+    def residual_unit(self, x, p):
+        """ResidualUnit (reference M:930-944): x + SE(ELU(conv1(ELU(causal_conv3(x)))))."""
+        B, T, H, W, Cc = x.shape
+        h = self.conv(x, p["conv3"], act=ACT_ELU)
+        y = self.conv(h, p["conv1"], act=ACT_ELU)
+        F_, Pn = B * T, H * W
+        ws = self._new((self.lib.mv2_se_workspace_bytes(F_, Pn, Cc) // 4,), torch.float32)
+        gates = self._new((F_, Cc), torch.float32)
+        st = self._stream()
+        dt = _dt(self.dtype)
+        check(self.lib.mv2_se_pool(_ptr(y), dt, F_, Pn, Cc, _ptr(p["wk"]), p["bk"], _ptr(ws), st), "mv2_se_pool")
+        check(self.lib.mv2_se_gate(_ptr(ws), F_, Pn, Cc, p["hidden"], _ptr(p["w1"]), _ptr(p["b1"]), _ptr(p["w2"]),
+                                   _ptr(p["b2"]), _ptr(gates), st), "mv2_se_gate")
+        out = self._new(x.shape)
+        check(self.lib.mv2_gate_residual(_ptr(y), _ptr(x), _ptr(gates), _ptr(out), dt, F_, Pn, Cc, st), "mv2_gate_residual")
+        self.launches += 3
+        return out
+
+    def rmsnorm(self, x, gamma, token_shift=False):
+        B, T, H, W, Cc = x.shape
+        out = self._new(x.shape)
+        check(self.lib.mv2_rmsnorm(_ptr(x), _ptr(out), _dt(self.dtype), _ptr(gamma), B, T, H * W, Cc,
+                                   int(token_shift), self._stream()), "mv2_rmsnorm")
+        self.launches += 1
+        return out
+
+    def feed_forward(self, x, p, token_shift=False):
+        """Residual(FeedForward) (M:471-508, M:1191): x + fc2(geglu(fc1(rmsnorm(shift(x)))))."""
+        B, T, H, W, Cc = x.shape
+        xn = self.rmsnorm(x, p["gamma"], token_shift)
+        hdn = self.conv(xn, p["fc1"])
+        I = p["inner"]
+        g = self._new((B, T, H, W, I))
+        check(self.lib.mv2_geglu(_ptr(hdn), _ptr(g), _dt(self.dtype), B * T * H * W, I, self._stream()), "mv2_geglu")
+        self.launches += 1
+        return self.conv(g, p["fc2"], res=x)
+
+    def attention(self, x, p, axis: str):
+        """Residual(SpaceAttention) / Residual(TokenShift(TimeAttention)) (M:444-464, M:1190, M:1235)."""
+        B, T, H, W, Cc = x.shape
+        time_axis = axis == "time"
+        xn = self.rmsnorm(x, p["gamma"], token_shift=time_axis)
+        qkv = self.conv(xn, p["qkv"])
+        heads, dh = p["heads"], p["dim_head"]
+        o = self._new((B, T, H, W, heads * dh))
+        HW = H * W
+        if time_axis:
+            a = AttnArgs(qkv=_ptr(qkv), out=_ptr(o), mem_kv=_ptr(p["mem_kv"]), dtype=_dt(self.dtype), heads=heads,
+                         dim_head=dh, n_mem=p["n_mem"], causal=1, n_outer=B, n_inner=HW, L=T,
+                         outer_stride=T * HW, inner_stride=1, tok_stride=HW)
+        else:
+            a = AttnArgs(qkv=_ptr(qkv), out=_ptr(o), mem_kv=_ptr(p["mem_kv"]), dtype=_dt(self.dtype), heads=heads,
+                         dim_head=dh, n_mem=p["n_mem"], causal=0, n_outer=B * T, n_inner=1, L=HW,
+                         outer_stride=HW, inner_stride=0, tok_stride=1)
+        check(self.lib.mv2_attention(C.byref(a), self._stream()), "mv2_attention")
+        self.launches += 1
+        return self.conv(o, p["out"], res=x)
+
+    def linear_attention(self, x, p):
+        """Residual(LinearSpaceAttention) (M:421-442, M:1207)."""
+        B, T, H, W, Cc = x.shape
+        xn = self.rmsnorm(x, p["gamma"])
+        q = self.conv(xn, p["q"])
+        kv = self.conv(xn, p["kv"])
+        heads, dh = p["heads"], p["dim_head"]
+        n_seq, L = B * T, H * W
+        ws = self._new((self.lib.mv2_linattn_workspace_bytes(n_seq, heads, L) // 4,), torch.float32)
+        o = self._new((B, T, H, W, heads * dh))
+        check(self.lib.mv2_linear_attention(_ptr(q), _ptr(kv), _ptr(o), _dt(self.dtype), n_seq, L, heads, dh,
+                                            _ptr(ws), self._stream()), "mv2_linear_attention")
+        self.launches += 2
+        return self.conv(o, p["out"], res=x)
+
+    # ------------------------------------------------------------------ stages
+    def _stage(self, x, st, key, decoder: bool):
+        P = self._packs
+        B, T, H, W, Cc = x.shape
+        if st.kind == "residual":
+            for j in range(st.count):
+                x = self.residual_unit(x, P[f"{key}.{j}"])
+        elif st.kind == "compress_space":
+            if decoder:   # SpatialUpsample2x (M:838-846)
+                x = self.conv(x, P[key], act=ACT_SILU, shuffle=SHUFFLE_SPACE)
+            else:         # SpatialDownsample2x (M:770-780): Conv2d k3 s2 p1
+                x = self.conv(x, P[key], stride=(1, 2, 2), pad=(0, 1, 1),
+                              out_spatial=(T, (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1))
+        elif st.kind == "compress_time":
+            if decoder:   # TimeUpsample2x (M:875-883)
+                x = self.conv(x, P[key], act=ACT_SILU, shuffle=SHUFFLE_TIME)
+            else:         # TimeDownsample2x (M:796-807): pad (2, 0), Conv1d k3 s2
+                x = self.conv(x, P[key], stride=(2, 1, 1), pad=(2, 0, 0), out_spatial=((T + 2 - 3) // 2 + 1, H, W))
+        elif st.kind == "attend_space":
+            x = self.attention(x, P[key + ".attn"], "space")
+            x = self.feed_forward(x, P[key + ".ff"])
+        elif st.kind == "attend_time":
+            x = self.attention(x, P[key + ".attn"], "time")
+            x = self.feed_forward(x, P[key + ".ff"], token_shift=True)
+        elif st.kind == "linear_attend_space":
+            x = self.linear_attention(x, P[key + ".attn"])
+            x = self.feed_forward(x, P[key + ".ff"])
+        else:
+            raise ValueError(st.kind)
+        return x
+
+    def _tap(self, name, x):
+        if self.taps is not None:
+            self.taps[name] = x.permute(0, 4, 1, 2, 3).float().cpu()
+
+    # ------------------------------------------------------------------ layout
+    def to_channels_last(self, v: torch.Tensor, t_pad: int = 0):
+        """(B,C,T,H,W) torch tensor (fp32 or bf16) -> (B,T+t_pad,H,W,C) compute dtype."""
+        if v.dtype not in (torch.float32, torch.bfloat16):
+            v = v.float()
+        v = v.contiguous()
+        B, Cc, T, H, W = v.shape
+        out = self._new((B, T + t_pad, H, W, Cc))
+        check(self.lib.mv2_to_channels_last(_ptr(v), _dt(v.dtype), _ptr(out), _dt(self.dtype), B, Cc, T, H, W, t_pad,
+                                            self._stream()), "mv2_to_channels_last")
+        self.launches += 1
+        return out
+
+    def to_channels_first(self, x: torch.Tensor, t_crop: int = 0, out_dtype=None):
+        B, T, H, W, Cc = x.shape
+        out_dtype = out_dtype or self.dtype
+        out = torch.empty((B, Cc, T - t_crop, H, W), device=self.device, dtype=out_dtype)
+        check(self.lib.mv2_to_channels_first(_ptr(x), _dt(x.dtype), _ptr(out), _dt(out_dtype), B, Cc, T, H, W, t_crop,
+                                             self._stream()), "mv2_to_channels_first")
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ the path
+    def encode_cl(self, video: torch.Tensor):
+        """video (B,C,T,H,W) on device -> encoder output, channels-last.  Reference encode M:1523-1576."""
+        m = self.model
+        x = self.to_channels_last(video, m.time_padding)
+        x = self.conv(x, self._packs["conv_in"])
+        self._tap("conv_in", x)
+        for i, st in enumerate(m.stages):
+            x = self._stage(x, st, f"enc{i}", decoder=False)
+            self._tap(f"enc{i}", x)
+        return x
+
+    def decode_cl(self, q: torch.Tensor):
+        """quantized channels-last (B,T',H',W',C) -> video (B,3,T,H,W).  Reference decode M:1598-1649."""
+        m = self.model
+        x = q
+        for j, st in enumerate(reversed(m.stages)):
+            x = self._stage(x, st, f"dec{j}", decoder=True)
+            self._tap(f"dec{j}", x)
+        x = self.conv(x, self._packs["conv_out"])
+        return self.to_channels_first(x, t_crop=m.time_padding)
+
+    def quantize_cl(self, x, want_quantized=True, want_aux=False):
+        """x channels-last -> (quantized channels-last | None, indices (B,T,H,W), aux fp32 [N][d] | None)."""
+        m = self.model
+        B, T, H, W, Cc = x.shape
+        N = B * T * H * W
+        P = self._packs["quant"]
+        q = self._new(x.shape) if want_quantized else None
+        d = m.quantizers.codebook_dim
+        aux = self._new((N, d), torch.float32) if want_aux else None
+        if m.use_fsq:
+            idx = torch.empty((B, T, H, W), device=self.device, dtype=torch.int32)
+            lv = (C.c_int32 * d)(*m.quantizers.levels)
+            check(self.lib.mv2_fsq_forward(_ptr(x), _dt(self.dtype), N, Cc, d, lv, _ptr(P["win"]), _ptr(P["bin"]),
+                                           _ptr(P["wout"]), _ptr(P["bout"]), _ptr(idx), _ptr(q), _ptr(aux),
+                                           self._stream()), "mv2_fsq_forward")
+        else:
+            idx = torch.empty((B, T, H, W), device=self.device, dtype=torch.int64)
+            clamp = m.quantizers.soft_clamp_input_value
+            check(self.lib.mv2_lfq_forward(_ptr(x), _dt(self.dtype), N, Cc, d, _ptr(P["win"]), _ptr(P["bin"]),
+                                           _ptr(P["wout"]), _ptr(P["bout"]), float(clamp) if clamp else 0.0,
+                                           _ptr(idx), _ptr(q), _ptr(aux), self._stream()), "mv2_lfq_forward")
+        self.launches += 1
+        return q, idx, aux
+
+    def codes_to_quantized_cl(self, codes: torch.Tensor):
+        """indices (B,T,H,W) int64/int32 -> quantized channels-last.  LFQ/FSQ.indices_to_codes (M:1593)."""
+        m = self.model
+        codes = codes.contiguous()
+        B, T, H, W = codes.shape
+        Cc = m.quantizers.dim
+        N = B * T * H * W
+        P = self._packs["quant"]
+        d = m.quantizers.codebook_dim
+        q = self._new((B, T, H, W, Cc))
+        is64 = int(codes.dtype == torch.int64)
+        if m.use_fsq:
+            lv = (C.c_int32 * d)(*m.quantizers.levels)
+            check(self.lib.mv2_fsq_decode(_ptr(codes), is64, N, Cc, d, lv, _ptr(P["wout"]), _ptr(P["bout"]), _ptr(q),
+                                          _dt(self.dtype), self._stream()), "mv2_fsq_decode")
+        else:
+            check(self.lib.mv2_lfq_decode(_ptr(codes), is64, N, Cc, d, _ptr(P["wout"]), _ptr(P["bout"]), _ptr(q),
+                                          _dt(self.dtype), self._stream()), "mv2_lfq_decode")
+        self.launches += 1
+        return q

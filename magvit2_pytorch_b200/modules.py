@@ -1,0 +1,219 @@
+"""Parameter containers of the B200 VideoTokenizer.
+
+These ``nn.Module`` classes hold parameters under exactly the attribute paths of the reference
+model so that ``state_dict()`` keys are interchangeable with reference checkpoints
+(reference key layout e.g. ``encoder_layers.2.0.fn.0.conv.weight``).  They do NOT
+compute: the forward path is executed by ``engine.Engine`` through the C ABI, which reads the
+parameters.  Calling ``forward`` on a container is an error (there is no eager fallback).
+
+Reference construction sites are cited per class (M: = magvit2_pytorch/magvit2_pytorch.py).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+
+class _NoForward(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError(
+            f"{type(self).__name__} is a parameter container; the forward path runs through "
+            "libmagvit2_b200.so (VideoTokenizer.tokenize / decode_from_code_indices / forward)")
+
+
+class Marker(_NoForward):
+    """Parameter-free placeholder keeping nn.Sequential indices aligned with the reference
+    (ELU / LeakyReLU / Sigmoid / SiLU / Rearrange slots)."""
+
+    def __init__(self, what: str):
+        super().__init__()
+        self.what = what
+
+    def extra_repr(self):
+        return self.what
+
+
+class CausalConv3d(_NoForward):
+    """M:892-928 -- weights live in ``.conv`` (an nn.Conv3d used purely as storage)."""
+
+    def __init__(self, chan_in, chan_out, kernel_size, pad_mode="constant"):
+        super().__init__()
+        ks = kernel_size if isinstance(kernel_size, tuple) else (kernel_size,) * 3
+        assert ks[1] % 2 == 1 and ks[2] % 2 == 1
+        self.kernel_size = tuple(ks)
+        self.pad_mode = pad_mode
+        self.conv = nn.Conv3d(chan_in, chan_out, ks)
+
+
+class SqueezeExcite(_NoForward):
+    """M:194-219 -- to_k: C->1, net: C->max(16, C//2)->C; last conv zero weight, bias -10."""
+
+    def __init__(self, dim, dim_hidden_min=16, init_bias=-10.):
+        super().__init__()
+        hidden = max(dim_hidden_min, dim // 2)
+        self.to_k = nn.Conv2d(dim, 1, 1)
+        self.net = nn.Sequential(nn.Conv2d(dim, hidden, 1), Marker("LeakyReLU(0.1)"),
+                                 nn.Conv2d(hidden, dim, 1), Marker("Sigmoid"))
+        nn.init.zeros_(self.net[2].weight)
+        nn.init.constant_(self.net[2].bias, init_bias)
+
+
+class Residual(_NoForward):
+    """M:167-174."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
+class TokenShift(_NoForward):
+    """M:244-254."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
+def residual_unit(dim, kernel_size):
+    """M:930-944: Residual(Sequential(CausalConv3d, ELU, Conv3d 1x1x1, ELU, SqueezeExcite))."""
+    return Residual(nn.Sequential(
+        CausalConv3d(dim, dim, kernel_size), Marker("ELU"),
+        nn.Conv3d(dim, dim, 1), Marker("ELU"),
+        SqueezeExcite(dim)))
+
+
+class SpatialDownsample2x(_NoForward):
+    """M:757-768 (antialias=False)."""
+
+    def __init__(self, dim, dim_out):
+        super().__init__()
+        self.conv = nn.Conv2d(dim, dim_out, 3, stride=2, padding=1)
+
+
+class TimeDownsample2x(_NoForward):
+    """M:782-794."""
+
+    def __init__(self, dim, dim_out):
+        super().__init__()
+        self.conv = nn.Conv1d(dim, dim_out, 3, stride=2)
+
+
+def _repeat_init_(conv, factor):
+    # M:829-836 / M:866-873: kaiming-uniform a (o/factor) kernel and repeat it `factor` times
+    w = conv.weight
+    base = torch.empty(w.shape[0] // factor, *w.shape[1:])
+    nn.init.kaiming_uniform_(base)
+    with torch.no_grad():
+        w.copy_(base.repeat_interleave(factor, dim=0))
+        conv.bias.zero_()
+
+
+class SpatialUpsample2x(_NoForward):
+    """M:811-836: net = (Conv2d dim->4*dim_out 1x1, SiLU, depth-to-space)."""
+
+    def __init__(self, dim, dim_out):
+        super().__init__()
+        conv = nn.Conv2d(dim, dim_out * 4, 1)
+        self.net = nn.Sequential(conv, Marker("SiLU"), Marker("depth_to_space 2x2"))
+        _repeat_init_(conv, 4)
+
+
+class TimeUpsample2x(_NoForward):
+    """M:848-873: net = (Conv1d dim->2*dim_out k1, SiLU, depth-to-time)."""
+
+    def __init__(self, dim, dim_out):
+        super().__init__()
+        conv = nn.Conv1d(dim, dim_out * 2, 1)
+        self.net = nn.Sequential(conv, Marker("SiLU"), Marker("depth_to_time x2"))
+        _repeat_init_(conv, 2)
+
+
+class RMSNorm(_NoForward):
+    """M:258-273: gamma is (C,) channel-last or (C,1,1,1) channel-first."""
+
+    def __init__(self, dim, channel_first=False):
+        super().__init__()
+        self.channel_first = channel_first
+        self.gamma = nn.Parameter(torch.ones((dim, 1, 1, 1) if channel_first else (dim,)))
+
+
+class Attention(_NoForward):
+    """M:327-368 (Space/TimeAttention share the parameter layout, M:444-464)."""
+
+    def __init__(self, dim, dim_head, heads, causal, num_memory_kv=4):
+        super().__init__()
+        inner = dim_head * heads
+        self.dim, self.dim_head, self.heads, self.causal = dim, dim_head, heads, causal
+        self.norm = RMSNorm(dim)
+        self.to_qkv = nn.Sequential(nn.Linear(dim, inner * 3, bias=False), Marker("split qkv heads"))
+        self.mem_kv = nn.Parameter(torch.randn(2, heads, num_memory_kv, dim_head))
+        self.to_out = nn.Sequential(Marker("merge heads"), nn.Linear(inner, dim, bias=False))
+
+
+class TaylorSeriesLinearAttn(_NoForward):
+    """Parameter layout of the un-vendored dependency."""
+
+    def __init__(self, dim, dim_head, heads):
+        super().__init__()
+        inner = dim_head * heads
+        self.to_q = nn.Sequential(nn.Linear(dim, inner, bias=False), Marker("split heads"))
+        self.to_kv = nn.Sequential(nn.Linear(dim, inner * 2, bias=False), Marker("split kv heads"))
+        self.to_out = nn.Sequential(nn.Linear(inner, dim, bias=False), Marker("Dropout(0)"))
+
+
+class LinearSpaceAttention(_NoForward):
+    """M:390-442."""
+
+    def __init__(self, dim, dim_head, heads):
+        super().__init__()
+        self.dim, self.dim_head, self.heads = dim, dim_head, heads
+        self.norm = RMSNorm(dim)
+        self.attn = TaylorSeriesLinearAttn(dim, dim_head, heads)
+
+
+class FeedForward(_NoForward):
+    """M:471-496: channel-first RMSNorm, Conv3d C->2I 1x1x1, GEGLU, Conv3d I->C; I = int(C*4*2/3)."""
+
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        inner = int(dim * mult * 2 / 3)
+        self.dim, self.dim_inner = dim, inner
+        self.norm = RMSNorm(dim, channel_first=True)
+        self.net = nn.Sequential(nn.Conv3d(dim, inner * 2, 1), Marker("GEGLU"), nn.Conv3d(inner, dim, 1))
+
+
+class LFQ(_NoForward):
+    """Parameter/buffer layout of vector_quantize_pytorch.LFQ:
+    persistent int64 ``mask``, Linear ``project_in`` / ``project_out`` (with bias)."""
+
+    def __init__(self, dim, codebook_size, entropy_loss_weight, commitment_loss_weight, diversity_gamma,
+                 soft_clamp_input_value):
+        super().__init__()
+        d = int(math.log2(codebook_size))
+        assert 2 ** d == codebook_size, "codebook_size must be a power of two"
+        self.dim, self.codebook_size, self.codebook_dim = dim, codebook_size, d
+        self.entropy_loss_weight = entropy_loss_weight
+        self.commitment_loss_weight = commitment_loss_weight
+        self.diversity_gamma = diversity_gamma
+        self.soft_clamp_input_value = soft_clamp_input_value
+        if dim == d:
+            raise NotImplementedError("LFQ without projections (dim == log2(codebook_size)) is not supported")
+        self.project_in = nn.Linear(dim, d)
+        self.project_out = nn.Linear(d, dim)
+        self.register_buffer("mask", 2 ** torch.arange(d - 1, -1, -1))
+
+
+class FSQ(_NoForward):
+    """Parameter layout of vector_quantize_pytorch.FSQ."""
+
+    def __init__(self, levels, dim):
+        super().__init__()
+        self.levels = [int(l) for l in levels]
+        self.dim, self.codebook_dim = dim, len(levels)
+        self.codebook_size = int(math.prod(self.levels))
+        if dim == len(levels):
+            raise NotImplementedError("FSQ without projections is not supported")
+        self.project_in = nn.Linear(dim, len(levels))
+        self.project_out = nn.Linear(len(levels), dim)

@@ -1,0 +1,394 @@
+"""B200-native drop-in for the reference ``VideoTokenizer`` inference path.
+
+Mirrors the reference class's public surface (magvit2_pytorch/magvit2_pytorch.py:1045-1720 =
+M:): the keyword-only constructor and ``layers=(...)`` spec (M:1047-1092, M:1138-1318),
+``tokenize`` (M:1651), ``decode_from_code_indices`` (M:1579), ``forward`` inference returns
+(M:1657-1720), ``encode`` / ``decode`` (M:1523, M:1598), ``parameters()`` as a list (M:1460),
+``state_dict`` key layout, ``save`` / ``load`` / ``init_and_load_from``
+(M:1447-1458, M:1495-1520), ``copy_for_eval`` (M:1476), ``device`` (M:1443).
+
+All arithmetic runs in hand-written sm_100a kernels behind the C ABI of libmagvit2_b200.so;
+the compute dtype follows the parameters' dtype (``.float()`` -> fp32 CUDA-core path,
+``.bfloat16()`` -> bf16 tcgen05 path).  There is no CPU / eager fallback.
+
+Out of scope (raise at construction / call): conditioning layers (``cond_*``),
+``gateloop_time``, ``separate_first_frame_encoding``, ``num_codebooks > 1``, ``lfq_spherical``,
+non-constant ``pad_mode``, the GAN / perceptual training losses (``return_loss`` /
+``return_discr_loss``), autograd.
+"""
+from __future__ import annotations
+
+import copy
+import pickle
+from dataclasses import dataclass
+from pathlib import Path
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import modules as M
+from .engine import Engine
+
+__version__ = "0.1.0"
+
+
+@dataclass
+class Stage:
+    kind: str          # residual | compress_space | compress_time | attend_space | linear_attend_space | attend_time
+    dim: int
+    dim_out: int
+    count: int = 1
+    nested: bool = False
+
+
+_UNSUPPORTED_LAYERS = {
+    "cond_residual": "conditioning layers are outside the accelerated path (SURVEY.md 8f N1)",
+    "cond_attend_space": "raises in the reference itself (SURVEY.md 2 row 9)",
+    "cond_linear_attend_space": "raises in the reference itself (SURVEY.md 2 row 9)",
+    "cond_attend_time": "raises in the reference itself (SURVEY.md 2 row 9)",
+    "gateloop_time": "gateloop_time is outside the accelerated path (SURVEY.md 8f N3)",
+}
+
+
+class VideoTokenizer(nn.Module):
+    def __init__(
+        self,
+        *,
+        image_size,
+        layers: Tuple = ("residual", "residual", "residual"),
+        residual_conv_kernel_size=3,
+        num_codebooks=1,
+        codebook_size: Optional[int] = None,
+        channels=3,
+        init_dim=64,
+        max_dim=float("inf"),
+        dim_cond=None,
+        dim_cond_expansion_factor=4.,
+        input_conv_kernel_size: Tuple[int, int, int] = (7, 7, 7),
+        output_conv_kernel_size: Tuple[int, int, int] = (3, 3, 3),
+        pad_mode: str = "constant",
+        lfq_entropy_loss_weight=0.1,
+        lfq_commitment_loss_weight=1.,
+        lfq_diversity_gamma=2.5,
+        lfq_spherical=False,
+        quantizer_aux_loss_weight=1.,
+        lfq_soft_clamp_input_value=10.,
+        lfq_activation=None,
+        use_fsq=False,
+        fsq_levels: Optional[List[int]] = None,
+        attn_dim_head=32,
+        attn_heads=8,
+        attn_dropout=0.,
+        linear_attn_dim_head=8,
+        linear_attn_heads=16,
+        vgg=None,
+        vgg_weights=None,
+        perceptual_loss_weight=1e-1,
+        discr_kwargs: Optional[dict] = None,
+        multiscale_discrs: Tuple = tuple(),
+        use_gan=True,
+        adversarial_loss_weight=1.,
+        grad_penalty_loss_weight=10.,
+        multiscale_adversarial_loss_weight=1.,
+        flash_attn=True,
+        separate_first_frame_encoding=False,
+    ):
+        super().__init__()
+        cfg = dict(locals())
+        cfg.pop("self")
+        cfg.pop("__class__", None)
+        for k in ("vgg", "lfq_activation"):      # modules are not part of the pickled config here
+            cfg[k] = None
+        cfg["multiscale_discrs"] = tuple()
+        self._configs = pickle.dumps(cfg)       # M:1097-1100
+
+        if not isinstance(layers, tuple):
+            raise TypeError("layers must be a tuple")
+        if num_codebooks != 1:
+            raise NotImplementedError("num_codebooks > 1 is not supported")
+        if lfq_spherical:
+            raise NotImplementedError("lfq_spherical is not supported")
+        if separate_first_frame_encoding:
+            raise NotImplementedError("separate_first_frame_encoding is outside the accelerated path (SURVEY.md 8f N3)")
+        if pad_mode != "constant":
+            raise NotImplementedError("only pad_mode='constant' is supported")
+        if attn_dropout != 0.:
+            raise NotImplementedError("attention dropout is a training feature")
+        ks = residual_conv_kernel_size
+
+        self.channels = channels
+        self.image_size = image_size
+        self.conv_in = M.CausalConv3d(channels, init_dim, tuple(input_conv_kernel_size), pad_mode)
+        self.conv_in_first_frame = nn.Identity()
+        self.conv_out_first_frame = nn.Identity()
+        self.separate_first_frame_encoding = False
+        self.encoder_layers = nn.ModuleList([])
+        self.decoder_layers = nn.ModuleList([])
+        self.conv_out = M.CausalConv3d(init_dim, channels, tuple(output_conv_kernel_size), pad_mode)
+
+        # ---- layer schedule (M:1129-1318) ----
+        dim = init_dim
+        fmap = image_size
+        tdf = 1
+        stages: List[Stage] = []
+        for layer_def in layers:
+            kind, *params = layer_def if isinstance(layer_def, tuple) else (layer_def,)
+            dim_out = dim
+            if kind in _UNSUPPORTED_LAYERS:
+                raise NotImplementedError(f"layer type {kind!r}: {_UNSUPPORTED_LAYERS[kind]}")
+            if kind == "residual":
+                enc, dec = M.residual_unit(dim, ks), M.residual_unit(dim, ks)
+                stages.append(Stage("residual", dim, dim, 1, False))
+            elif kind == "consecutive_residual":
+                n, = params
+                enc = nn.Sequential(*[M.residual_unit(dim, ks) for _ in range(n)])
+                dec = nn.Sequential(*[M.residual_unit(dim, ks) for _ in range(n)])
+                stages.append(Stage("residual", dim, dim, int(n), True))
+            elif kind == "compress_space":
+                dim_out = params[0] if len(params) > 0 else dim * 2
+                dim_out = int(min(dim_out, max_dim))
+                enc, dec = M.SpatialDownsample2x(dim, dim_out), M.SpatialUpsample2x(dim_out, dim)
+                assert fmap > 1
+                fmap //= 2
+                stages.append(Stage(kind, dim, dim_out))
+            elif kind == "compress_time":
+                dim_out = params[0] if len(params) > 0 else dim * 2
+                dim_out = int(min(dim_out, max_dim))
+                enc, dec = M.TimeDownsample2x(dim, dim_out), M.TimeUpsample2x(dim_out, dim)
+                tdf *= 2
+                stages.append(Stage(kind, dim, dim_out))
+            elif kind == "attend_space":
+                def mk():
+                    return nn.Sequential(M.Residual(M.Attention(dim, attn_dim_head, attn_heads, causal=False)),
+                                         M.Residual(M.FeedForward(dim)))
+                enc, dec = mk(), mk()
+                stages.append(Stage(kind, dim, dim))
+            elif kind == "linear_attend_space":
+                def mk():
+                    return nn.Sequential(M.Residual(M.LinearSpaceAttention(dim, linear_attn_dim_head, linear_attn_heads)),
+                                         M.Residual(M.FeedForward(dim)))
+                enc, dec = mk(), mk()
+                stages.append(Stage(kind, dim, dim))
+            elif kind == "attend_time":
+                def mk():
+                    return nn.Sequential(
+                        M.Residual(M.TokenShift(M.Attention(dim, attn_dim_head, attn_heads, causal=True))),
+                        M.Residual(M.TokenShift(M.FeedForward(dim))))
+                enc, dec = mk(), mk()
+                stages.append(Stage(kind, dim, dim))
+            else:
+                raise ValueError(f"unknown layer type {kind}")          # M:1311-1312
+            self.encoder_layers.append(enc)
+            self.decoder_layers.insert(0, dec)
+            dim = dim_out
+
+        # final LayerNorm: constructed and present in state_dict but never executed by the reference
+        # (zip truncation at M:1565) -- kept for checkpoint compatibility only.
+        self.encoder_layers.append(nn.Sequential(M.Marker("to channels-last"), nn.LayerNorm(dim), M.Marker("to channels-first")))
+
+        self.stages = stages
+        self.time_downsample_factor = tdf
+        self.time_padding = tdf - 1
+        self.fmap_size = fmap
+        self.has_cond = False
+        self.has_cond_across_layers = [False] * len(stages)
+        self.encoder_cond_in = nn.Identity()
+        self.decoder_cond_in = nn.Identity()
+
+        # ---- quantiser (M:1356-1384) ----
+        self.use_fsq = use_fsq
+        if not use_fsq:
+            assert codebook_size is not None and fsq_levels is None, \
+                "if use_fsq is set to False, `codebook_size` must be set (and not `fsq_levels`)"
+            self.quantizers = M.LFQ(dim, codebook_size, lfq_entropy_loss_weight, lfq_commitment_loss_weight,
+                                    lfq_diversity_gamma, lfq_soft_clamp_input_value)
+        else:
+            assert codebook_size is None and fsq_levels is not None, \
+                "if use_fsq is set to True, `fsq_levels` must be set (and not `codebook_size`)"
+            self.quantizers = M.FSQ(fsq_levels, dim)
+        self.quantizer_aux_loss_weight = quantizer_aux_loss_weight
+        self.register_buffer("zero", torch.tensor(0.), persistent=False)
+
+        # training-only branches of the reference are not built
+        self.vgg = None
+        self.use_vgg = False
+        self.perceptual_loss_weight = perceptual_loss_weight
+        self.use_gan = use_gan
+        self.has_gan = False
+        self.has_multiscale_gan = False
+        self.has_multiscale_discrs = False
+        self.multiscale_discrs = nn.ModuleList([])
+        self.adversarial_loss_weight = adversarial_loss_weight
+        self.grad_penalty_loss_weight = grad_penalty_loss_weight
+        self.multiscale_adversarial_loss_weight = multiscale_adversarial_loss_weight
+
+        self._engine: Optional[Engine] = None
+
+    # ------------------------------------------------------------------ module plumbing
+    @property
+    def device(self):
+        return self.zero.device
+
+    def parameters(self, recurse: bool = True):
+        # list, as the reference returns (M:1460-1471)
+        return [*self.conv_in.parameters(), *self.conv_out.parameters(), *self.encoder_layers.parameters(),
+                *self.decoder_layers.parameters(), *self.quantizers.parameters()]
+
+    def discr_parameters(self):
+        return []
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        # reference checkpoints carry discriminator weights (always constructed, M:1422); they are
+        # not part of the inference path and are dropped here.
+        sd = {k: v for k, v in state_dict.items() if not (k.startswith("discr.") or k.startswith("multiscale_discrs."))}
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    def __deepcopy__(self, memo):
+        eng, self._engine = self._engine, None
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            for k, v in self.__dict__.items():
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        finally:
+            self._engine = eng
+        return new
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        return st
+
+    def copy_for_eval(self):
+        dev = self.device
+        c = copy.deepcopy(self.cpu())
+        self.to(dev)
+        c.eval()
+        return c.to(dev)
+
+    @classmethod
+    def init_and_load_from(cls, path, strict=True):
+        path = Path(path)
+        assert path.exists()
+        pkg = torch.load(str(path), map_location="cpu", weights_only=False)
+        assert "config" in pkg, "model configs were not found in this saved checkpoint"
+        config = pickle.loads(pkg["config"])
+        # reference checkpoints pickle module-valued kwargs we do not build
+        for k in ("vgg", "lfq_activation"):
+            config[k] = None
+        config["multiscale_discrs"] = tuple()
+        tok = cls(**config)
+        tok.load(path, strict=strict)
+        return tok
+
+    def save(self, path, overwrite=True):
+        path = Path(path)
+        assert overwrite or not path.exists(), f"{str(path)} already exists"
+        torch.save(dict(model_state_dict=self.state_dict(), version=__version__, config=self._configs), str(path))
+
+    def load(self, path, strict=True):
+        path = Path(path)
+        assert path.exists()
+        pkg = torch.load(str(path), map_location="cpu", weights_only=False)
+        sd = pkg.get("model_state_dict")
+        assert sd is not None
+        self.load_state_dict(sd, strict=strict)
+
+    # ------------------------------------------------------------------ engine access
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            self._engine = Engine(self)
+        self._engine.prepare()
+        return self._engine
+
+    def _check_video(self, v, video_contains_first_frame=True):
+        assert v.ndim in {4, 5}                                                   # M:1675
+        assert tuple(v.shape[-2:]) == (self.image_size, self.image_size)          # M:1677
+        if v.ndim == 4:                                                           # M:1681-1685
+            v = v[:, :, None]
+            video_contains_first_frame = True
+        if not video_contains_first_frame:
+            raise NotImplementedError("video_contains_first_frame=False is not supported")
+        frames = v.shape[2]
+        assert (frames - 1) % self.time_downsample_factor == 0, \
+            f"number of frames {frames} minus the first frame ({frames - 1}) must be divisible by the total " \
+            f"downsample factor across time {self.time_downsample_factor}"      # M:1691
+        assert v.shape[1] == self.channels
+        if v.device != self.device:
+            raise RuntimeError(f"input is on {v.device} but the tokenizer is on {self.device}")
+        return v
+
+    # ------------------------------------------------------------------ reference API
+    @torch.no_grad()
+    def encode(self, video, quantize=False, cond=None, video_contains_first_frame=True):
+        """M:1523-1576.  Returns (B, C, T', H', W') like the reference."""
+        assert cond is None, "conditioning is not supported"
+        video = self._check_video(video, video_contains_first_frame)
+        eng = self.engine
+        x = eng.encode_cl(video)
+        if quantize:
+            q, idx, _ = eng.quantize_cl(x)
+            out = eng.to_channels_first(q)
+            if self.use_fsq:
+                return out, idx
+            return out, idx, self.zero
+        return eng.to_channels_first(x)
+
+    @torch.no_grad()
+    def decode(self, quantized, cond=None, video_contains_first_frame=True):
+        """M:1598-1649.  quantized: (B, C, T', H', W')."""
+        assert cond is None, "conditioning is not supported"
+        assert video_contains_first_frame
+        eng = self.engine
+        return eng.decode_cl(eng.to_channels_last(quantized))
+
+    @torch.no_grad()
+    def decode_from_code_indices(self, codes, cond=None, video_contains_first_frame=True):
+        """M:1579-1595."""
+        assert cond is None, "conditioning is not supported"
+        assert video_contains_first_frame
+        assert codes.dtype in (torch.long, torch.int32)                           # M:1585
+        if codes.ndim == 2:                                                       # M:1587-1591
+            n = codes.shape[-1]
+            assert n % (self.fmap_size ** 2) == 0, \
+                f"flattened video ids must have a length ({n}) that is divisible by the fmap size " \
+                f"({self.fmap_size}) squared ({self.fmap_size ** 2})"
+            codes = codes.reshape(codes.shape[0], -1, self.fmap_size, self.fmap_size)
+        eng = self.engine
+        return eng.decode_cl(eng.codes_to_quantized_cl(codes))
+
+    @torch.no_grad()
+    def tokenize(self, video):
+        """M:1651-1654."""
+        self.eval()
+        return self.forward(video, return_codes=True)
+
+    def forward(self, video_or_images, cond=None, return_loss=False, return_codes=False, return_recon=False,
+                return_discr_loss=False, return_recon_loss_only=False, apply_gradient_penalty=True,
+                video_contains_first_frame=True, adversarial_loss_weight=None,
+                multiscale_adversarial_loss_weight=None):
+        """Inference returns of the reference forward (M:1657-1720)."""
+        assert (return_loss + return_codes + return_discr_loss) <= 1               # M:1674
+        assert cond is None, "conditioning is not supported"
+        if return_loss or return_discr_loss:
+            raise NotImplementedError(
+                "training losses (GAN / perceptual / adaptive weighting, reference M:1722-1896) are outside the "
+                "accelerated inference path (SURVEY.md 8f N2)")
+        video = self._check_video(video_or_images, video_contains_first_frame)
+        with torch.no_grad():
+            eng = self.engine
+            x = eng.encode_cl(video)
+            need_recon = return_recon or return_recon_loss_only or not return_codes
+            q, codes, _ = eng.quantize_cl(x, want_quantized=need_recon)
+            if return_codes and not return_recon:
+                return codes                                                       # M:1707-1708
+            recon = eng.decode_cl(q)
+            if return_codes:
+                return codes, recon                                                # M:1714-1715
+            if return_recon_loss_only:                                             # M:1722-1727
+                loss = torch.nn.functional.mse_loss(video.float(), recon.float())
+                return loss, recon
+            return recon                                                           # M:1719-1720

@@ -1,0 +1,128 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.pt by running the UNMODIFIED
+reference (imported from /root/reference through oracle/ref_loader.py) on CPU.
+Runs only in the build container:   python -m oracle.make_golden [names...]
+
+Each fixture pins, for one constructor config + synthetic-weight seed + input
+seed: the reference's code indices, the quantiser's pre-sign/bounded values
+(captured with a forward hook on the reference's own project_in), the
+reconstructed video (full for small configs, a strided sample for the README
+config) and a strided sample of every encoder/decoder layer output (forward
+hooks on the reference's own modules) for bisecting.
+
+Third-party arithmetic caveat: LFQ/FSQ/Taylor attention come from
+oracle/shims (restated; the real PyPI packages are not installable here).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import torch
+
+from oracle import weights as W
+from oracle.ref_loader import build_reference_tokenizer
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+README_LAYERS = (
+    "residual", "compress_space", ("consecutive_residual", 2), "compress_space",
+    ("consecutive_residual", 2), "linear_attend_space", "compress_space",
+    ("consecutive_residual", 2), "attend_space", "compress_time",
+    ("consecutive_residual", 2), "compress_time", ("consecutive_residual", 2), "attend_time",
+)
+
+CONFIGS = {
+    # BASELINE.json configs[0]
+    "cfg1": dict(kwargs=dict(image_size=32, init_dim=16, codebook_size=1024,
+                             layers=("residual", "compress_space")),
+                 video=(1, 3, 5, 32, 32), wseed=0, vseed=1243, full=True),
+    # every layer type of the README spec at toy size (tdf=4 -> 9 frames)
+    "mini": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, layers=README_LAYERS),
+                 video=(2, 3, 9, 32, 32), wseed=0, vseed=1234, full=True),
+    "mini_fsq": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, use_fsq=True, fsq_levels=[8, 5, 5, 5],
+                                 layers=README_LAYERS),
+                     video=(2, 3, 9, 32, 32), wseed=0, vseed=1234, full=True),
+    # BASELINE.json configs[1] (README), one clip
+    "readme": dict(kwargs=dict(image_size=128, init_dim=64, max_dim=512, codebook_size=1024, layers=README_LAYERS),
+                   video=(1, 3, 17, 128, 128), wseed=0, vseed=1234, full=False, cs=16, ss=8),
+}
+
+
+def _sample(t: torch.Tensor, cs: int = 7, ss: int = 5) -> torch.Tensor:
+    """Strided sample of a (B,C,T,H,W) tensor: all b, every cs-th channel, all t, every ss-th row/col."""
+    return t[:, ::cs, :, ::ss, ::ss].contiguous().clone()
+
+
+def make(name: str):
+    cfg = CONFIGS[name]
+    kwargs = dict(cfg["kwargs"])
+    torch.manual_seed(0)
+    model = build_reference_tokenizer(**kwargs)
+    W.fill_state_dict_(model, cfg["wseed"])
+    model.eval()
+    video = W.synth_video(*cfg["video"][:3], cfg["video"][3], seed=cfg["vseed"])
+
+    taps = {}
+    hooks = []
+
+    def tap(nm):
+        def fn(mod, inp, out):
+            taps[nm] = _sample(out.detach(), cfg.get("cs", 7), cfg.get("ss", 5))
+        return fn
+
+    hooks.append(model.conv_in.register_forward_hook(tap("conv_in")))
+    n_layers = len(kwargs["layers"])
+    for i in range(n_layers):
+        hooks.append(model.encoder_layers[i].register_forward_hook(tap(f"enc{i}")))
+        hooks.append(model.decoder_layers[i].register_forward_hook(tap(f"dec{i}")))
+    presign = {}
+
+    def grab_proj(mod, inp, out):
+        presign["proj"] = out.detach().clone()
+
+    hooks.append(model.quantizers.project_in.register_forward_hook(grab_proj))
+
+    t0 = time.time()
+    with torch.no_grad():
+        codes = model.tokenize(video)
+        t1 = time.time()
+        recon = model.decode_from_code_indices(codes)
+        t2 = time.time()
+        # README.md:85-90 round-trip statement
+        recon_fwd = model(video, return_recon=True)
+    assert torch.equal(recon, recon_fwd), "reference round-trip (README.md:87-90) does not hold"
+    for h in hooks:
+        h.remove()
+
+    proj = presign["proj"].float()
+    if kwargs.get("use_fsq", False):
+        pre = proj   # raw project_in output; bounding is re-derived by the checker
+    else:
+        pre = (proj / 10.).tanh() * 10.
+    out = dict(
+        name=name, kwargs=kwargs, video_shape=tuple(cfg["video"]), wseed=cfg["wseed"], vseed=cfg["vseed"],
+        codes=codes.clone(), presign=pre.clone(),
+        taps=taps, tap_strides=(cfg.get("cs", 7), cfg.get("ss", 5)),
+        recon_sample=recon[:, :, :, ::4, ::4].contiguous().clone(),
+        recon_mean=recon.mean(dim=(3, 4)).clone(),
+        ref_seconds=dict(tokenize=t1 - t0, decode=t2 - t1),
+        torch_version=torch.__version__,
+        reference_commit="a00519fa (v0.5.1)",
+        third_party="oracle/shims (restated LFQ/FSQ/TaylorSeriesLinearAttn; real packages unavailable)",
+    )
+    if cfg["full"]:
+        out["recon"] = recon.clone()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, f"{name}.pt")
+    torch.save(out, path)
+    amin = pre.abs().min().item()
+    print(f"[golden] {name}: codes {tuple(codes.shape)} {codes.dtype}, min|presign|={amin:.3e}, "
+          f"recon absmax={recon.abs().max().item():.3f}, tokenize {t1 - t0:.2f}s decode {t2 - t1:.2f}s, "
+          f"{os.path.getsize(path) / 1e3:.0f} KB")
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CONFIGS)
+    for n in names:
+        make(n)

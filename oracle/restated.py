@@ -1,0 +1,478 @@
+"""TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / ``--impl reference`` legs may import this module, and only as the
+checker / timed CPU baseline -- never as part of the product path.
+
+CPU restatement (plain torch functional ops on CPU tensors) of the reference's
+VideoTokenizer inference path: tokenize / decode_from_code_indices /
+forward(return_recon).  It is driven purely by a ``state_dict`` with the
+reference's key names plus the constructor kwargs, so it runs on the GPU box
+where /root/reference does not exist.
+
+Pinning: the reference has no tests and no golden vectors, so
+this restatement is pinned against OUTPUTS OF THE REFERENCE ITSELF, produced in
+the build container by oracle/make_golden.py (reference source imported
+unmodified through oracle/ref_loader.py) and committed under tests/golden/.
+tests/test_oracle.py checks this file against those vectors bit-for-bit (codes)
+and to fp32 round-off (activations).  The quantiser / Taylor-attention
+arithmetic lives in un-vendored PyPI dependencies and is restated from their
+published algorithm: that part is "parity unpinned".
+
+Every function cites the reference lines it follows; M: = magvit2_pytorch/
+magvit2_pytorch.py, A: = magvit2_pytorch/attend.py.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------
+# layer schedule (M:1138-1318)
+# ----------------------------------------------------------------------------
+
+@dataclass
+class Stage:
+    kind: str                 # residual | compress_space | compress_time | attend_space | linear_attend_space | attend_time
+    dim: int
+    dim_out: int
+    count: int = 1            # consecutive residual units
+    nested: bool = False      # 'consecutive_residual' adds a '.{j}.' level to the keys
+
+
+def schedule(layers, init_dim, max_dim) -> Tuple[List[Stage], int, int]:
+    """Walks the ``layers`` spec exactly as the constructor loop does (M:1129-1318)
+    and returns (stages, fmap_downsample_pow2, time_downsample_factor)."""
+    dim = init_dim
+    stages = []
+    space_f, time_f = 1, 1
+    for ld in layers:
+        kind, *params = ld if isinstance(ld, tuple) else (ld,)
+        dim_out = dim
+        if kind == "residual":
+            stages.append(Stage("residual", dim, dim, 1, False))
+        elif kind == "consecutive_residual":
+            stages.append(Stage("residual", dim, dim, int(params[0]), True))
+        elif kind in ("compress_space", "compress_time"):
+            dim_out = params[0] if len(params) > 0 else dim * 2      # M:1160-1162
+            dim_out = int(min(dim_out, max_dim))
+            stages.append(Stage(kind, dim, dim_out))
+            if kind == "compress_space":
+                space_f *= 2
+            else:
+                time_f *= 2
+        elif kind in ("attend_space", "linear_attend_space", "attend_time"):
+            stages.append(Stage(kind, dim, dim))
+        else:
+            raise ValueError(f"oracle: unsupported layer type {kind}")
+        dim = dim_out
+    return stages, space_f, time_f
+
+
+# ----------------------------------------------------------------------------
+# building blocks
+# ----------------------------------------------------------------------------
+
+def causal_conv3d(x, w, b, pad_mode="constant"):
+    """CausalConv3d.forward, stride 1 / dilation 1 (M:913-928): pad (k_t - 1) frames
+    at the FRONT of time only, k//2 on both sides of H and W, then a plain conv3d."""
+    kt, kh, kw = w.shape[2:]
+    time_pad = kt - 1
+    mode = pad_mode if time_pad < x.shape[2] else "constant"          # M:925
+    x = F.pad(x, (kw // 2, kw // 2, kh // 2, kh // 2, time_pad, 0), mode=mode)
+    return F.conv3d(x, w, b)
+
+
+def squeeze_excite(x, sd, p):
+    """SqueezeExcite.forward on video (M:221-240): per (b, f) frame, softmax over h*w of
+    a 1x1 conv logit, pooled C-vector, 2-layer MLP with LeakyReLU(0.1), sigmoid gate."""
+    b, c, f, h, w = x.shape
+    xf = x.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+    logits = F.conv2d(xf, sd[p + "to_k.weight"], sd[p + "to_k.bias"])           # (bf,1,h,w)
+    attn = logits.reshape(b * f, 1, h * w).softmax(dim=-1)
+    pooled = torch.einsum("bin,bcn->bci", attn, xf.reshape(b * f, c, h * w))    # (bf,c,1)
+    pooled = pooled[..., None]
+    hid = F.leaky_relu(F.conv2d(pooled, sd[p + "net.0.weight"], sd[p + "net.0.bias"]), 0.1)
+    gates = torch.sigmoid(F.conv2d(hid, sd[p + "net.2.weight"], sd[p + "net.2.bias"]))
+    gates = gates.reshape(b, f, c, 1, 1).permute(0, 2, 1, 3, 4)
+    return gates * x
+
+
+def residual_unit(x, sd, p):
+    """Residual(Sequential(CausalConv3d, ELU, Conv3d 1x1x1, ELU, SqueezeExcite)) (M:930-944, M:167-174).
+    Residual units always use pad_mode 'constant' (M:1142-1148 never forwards pad_mode)."""
+    y = F.elu(causal_conv3d(x, sd[p + "fn.0.conv.weight"], sd[p + "fn.0.conv.bias"]))
+    y = F.elu(F.conv3d(y, sd[p + "fn.2.weight"], sd[p + "fn.2.bias"]))
+    y = squeeze_excite(y, sd, p + "fn.4.")
+    return y + x
+
+
+def spatial_down(x, sd, p):
+    """SpatialDownsample2x (M:757-780): per-frame Conv2d k3 s2 p1, no blur (antialias False)."""
+    b, c, t, h, w = x.shape
+    xf = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+    o = F.conv2d(xf, sd[p + "conv.weight"], sd[p + "conv.bias"], stride=2, padding=1)
+    return o.reshape(b, t, *o.shape[1:]).permute(0, 2, 1, 3, 4)
+
+
+def time_down(x, sd, p):
+    """TimeDownsample2x (M:782-807): per pixel, F.pad(t,(2,0)) then Conv1d k3 s2."""
+    b, c, t, h, w = x.shape
+    xs = x.permute(0, 3, 4, 1, 2).reshape(b * h * w, c, t)
+    xs = F.pad(xs, (2, 0))
+    o = F.conv1d(xs, sd[p + "conv.weight"], sd[p + "conv.bias"], stride=2)
+    return o.reshape(b, h, w, o.shape[1], o.shape[2]).permute(0, 3, 4, 1, 2)
+
+
+def spatial_up(x, sd, p):
+    """SpatialUpsample2x (M:811-846): Conv2d 1x1 C->4*Cout, SiLU, 'b (c p1 p2) h w -> b c (h p1) (w p2)'."""
+    b, c, t, h, w = x.shape
+    xf = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+    o = F.silu(F.conv2d(xf, sd[p + "net.0.weight"], sd[p + "net.0.bias"]))
+    co = o.shape[1] // 4
+    o = o.reshape(b * t, co, 2, 2, h, w).permute(0, 1, 4, 2, 5, 3).reshape(b * t, co, h * 2, w * 2)
+    return o.reshape(b, t, co, h * 2, w * 2).permute(0, 2, 1, 3, 4)
+
+
+def time_up(x, sd, p):
+    """TimeUpsample2x (M:848-883): Conv1d 1x1 C->2*Cout, SiLU, 'b (c p) t -> b c (t p)'."""
+    b, c, t, h, w = x.shape
+    xs = x.permute(0, 3, 4, 1, 2).reshape(b * h * w, c, t)
+    o = F.silu(F.conv1d(xs, sd[p + "net.0.weight"], sd[p + "net.0.bias"]))
+    co = o.shape[1] // 2
+    o = o.reshape(b * h * w, co, 2, t).permute(0, 1, 3, 2).reshape(b * h * w, co, t * 2)
+    return o.reshape(b, h, w, co, t * 2).permute(0, 3, 4, 1, 2)
+
+
+def rmsnorm_last(x, gamma):
+    """RMSNorm over the last dim (M:275-276): F.normalize (eps 1e-12 on the L2 norm) * sqrt(C) * gamma."""
+    c = x.shape[-1]
+    return F.normalize(x, dim=-1) * (c ** 0.5) * gamma.reshape(-1)
+
+
+def token_shift(x):
+    """TokenShift (M:250-254): second half of the channels delayed by one frame, zero at t=0."""
+    a, s = x.chunk(2, dim=1)
+    s = F.pad(s, (0, 0, 0, 0, 1, -1))
+    return torch.cat((a, s), dim=1)
+
+
+def softmax_attention(q, k, v, causal):
+    """Attend.forward non-flash branch (A:218-241) which the flash branch reproduces with a
+    right-aligned bool mask (A:123-129): query i attends keys j <= i + (k_len - q_len)."""
+    scale = q.shape[-1] ** -0.5
+    dots = torch.einsum("bhid,bhjd->bhij", q, k) * scale
+    i, j = dots.shape[-2:]
+    if causal and i > 1:                                                # A:209-210
+        mask = torch.ones((i, j), dtype=torch.bool).triu(j - i + 1)     # A:46-47
+        dots = dots.masked_fill(mask, -torch.finfo(dots.dtype).max)
+    return torch.einsum("bhij,bhjd->bhid", dots.softmax(dim=-1), v)
+
+
+def attention_tokens(x, sd, p, heads, causal):
+    """Attention.forward on (batch, n, C) tokens (M:371-388): RMSNorm, qkv Linear (no bias),
+    4 learned memory key/values prepended, attend, output Linear (no bias)."""
+    b, n, c = x.shape
+    xn = rmsnorm_last(x, sd[p + "norm.gamma"])
+    qkv = F.linear(xn, sd[p + "to_qkv.0.weight"])
+    qkv = qkv.reshape(b, n, 3, heads, -1).permute(2, 0, 3, 1, 4)       # 'b n (qkv h d) -> qkv b h n d'
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    mem = sd[p + "mem_kv"].to(x.dtype)
+    mk = mem[0][None].expand(b, -1, -1, -1)
+    mv = mem[1][None].expand(b, -1, -1, -1)
+    k = torch.cat((mk, k), dim=-2)
+    v = torch.cat((mv, v), dim=-2)
+    o = softmax_attention(q, k, v, causal)
+    o = o.permute(0, 2, 1, 3).reshape(b, n, -1)
+    return F.linear(o, sd[p + "to_out.1.weight"])
+
+
+def space_attention(x, sd, p, heads):
+    """SpaceAttention (M:444-454): fold time into batch, tokens = h*w."""
+    b, c, t, h, w = x.shape
+    tok = x.permute(0, 2, 3, 4, 1).reshape(b * t, h * w, c)
+    o = attention_tokens(tok, sd, p, heads, causal=False)
+    return o.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
+
+
+def time_attention(x, sd, p, heads):
+    """TimeAttention (M:456-464): fold space into batch, tokens = t, causal."""
+    b, c, t, h, w = x.shape
+    tok = x.permute(0, 3, 4, 2, 1).reshape(b * h * w, t, c)
+    o = attention_tokens(tok, sd, p, heads, causal=True)
+    return o.reshape(b, h, w, t, c).permute(0, 4, 3, 1, 2)
+
+
+def taylor_linear_attention(x, sd, p, heads, dim_head):
+    """TaylorSeriesLinearAttn, non-causal (un-vendored dependency):
+    phi(x) = [1, x, x(x)x/sqrt2]; out = phi(q) . sum_n phi(k)_n (x) v_n / max(phi(q).sum_n phi(k)_n, 1e-5)."""
+    b, n, c = x.shape
+    q = F.linear(x, sd[p + "attn.to_q.0.weight"]).reshape(b, n, heads, dim_head).permute(0, 2, 1, 3)
+    kv = F.linear(x, sd[p + "attn.to_kv.0.weight"]).reshape(b, n, 2, heads, dim_head).permute(2, 0, 3, 1, 4)
+    k, v = kv[0], kv[1]
+    q = q * dim_head ** -0.5
+
+    def phi(z):
+        one = z.new_ones((*z.shape[:-1], 1))
+        z2 = (z[..., :, None] * z[..., None, :]) * (0.5 ** 0.5)
+        return torch.cat((one, z, z2.reshape(*z.shape[:-1], -1)), dim=-1)
+
+    q, k = phi(q), phi(k)
+    kvs = torch.einsum("bhnd,bhne->bhde", k, v)
+    ksum = k.sum(dim=-2)
+    num = torch.einsum("bhnd,bhde->bhne", q, kvs)
+    den = torch.einsum("bhnd,bhd->bhn", q, ksum)[..., None]
+    o = num / den.clamp(min=1e-5)
+    o = o.permute(0, 2, 1, 3).reshape(b, n, heads * dim_head)
+    return F.linear(o, sd[p + "attn.to_out.0.weight"])
+
+
+def linear_space_attention(x, sd, p, heads, dim_head):
+    """LinearSpaceAttention (M:421-442): RMSNorm then Taylor attention over h*w tokens per frame."""
+    b, c, t, h, w = x.shape
+    tok = x.permute(0, 2, 3, 4, 1).reshape(b * t, h * w, c)
+    tok = rmsnorm_last(tok, sd[p + "norm.gamma"])
+    o = taylor_linear_attention(tok, sd, p, heads, dim_head)
+    return o.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
+
+
+def feed_forward(x, sd, p):
+    """FeedForward (M:471-508): channel-first RMSNorm, Conv3d 1x1x1 C->2I, GEGLU
+    (x, gate = chunk; gelu(gate) * x, M:466-469), Conv3d 1x1x1 I->C."""
+    xl = x.permute(0, 2, 3, 4, 1)
+    xl = rmsnorm_last(xl, sd[p + "norm.gamma"])
+    xn = xl.permute(0, 4, 1, 2, 3)
+    hdn = F.conv3d(xn, sd[p + "net.0.weight"], sd[p + "net.0.bias"])
+    a, gate = hdn.chunk(2, dim=1)
+    hdn = F.gelu(gate) * a
+    return F.conv3d(hdn, sd[p + "net.2.weight"], sd[p + "net.2.bias"])
+
+
+# ----------------------------------------------------------------------------
+# quantisers (un-vendored dependency)
+# ----------------------------------------------------------------------------
+
+def lfq_presign(x, sd, clamp=10.):
+    """project_in + tanh soft clamp; returns fp32 (B, N, d) pre-sign values."""
+    b, c = x.shape[:2]
+    tok = x.permute(0, 2, 3, 4, 1).reshape(b, -1, c)
+    p = F.linear(tok, sd["quantizers.project_in.weight"], sd["quantizers.project_in.bias"])
+    if clamp is not None:
+        p = (p / clamp).tanh() * clamp
+    return p.float()
+
+
+def lfq_quantize(x, sd, clamp=10.):
+    """LFQ eval forward (A.1 steps 1-6, 9): returns (quantized (B,C,T,H,W), indices int64 (B,T,H,W), presign)."""
+    b, c, t, h, w = x.shape
+    p = lfq_presign(x, sd, clamp)
+    q = torch.where(p > 0, torch.ones_like(p), -torch.ones_like(p))
+    mask = sd["quantizers.mask"].to(torch.int32)
+    idx = ((q > 0).int() * mask).sum(dim=-1)                       # int64 (torch.sum promotes)
+    out = F.linear(q.to(x.dtype), sd["quantizers.project_out.weight"], sd["quantizers.project_out.bias"])
+    out = out.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
+    return out, idx.reshape(b, t, h, w), p
+
+
+def lfq_indices_to_codes(idx, sd, dtype):
+    """LFQ.indices_to_codes (A.1 last line): bits -> +-1 -> project_out -> channel first."""
+    mask = sd["quantizers.mask"]
+    bits = ((idx[..., None].to(torch.int64) & mask) != 0).to(dtype)
+    codes = bits * 2 - 1
+    out = F.linear(codes, sd["quantizers.project_out.weight"].to(dtype), sd["quantizers.project_out.bias"].to(dtype))
+    return out.movedim(-1, 1)
+
+
+def lfq_train_losses(p, d_bits, world_reduce=None, inv_temperature=100., diversity_gamma=2.5,
+                     entropy_w=0.1, commit_w=1.0):
+    """LFQ training-mode auxiliary terms (A.1 steps 7, 8, 10) from fp32 pre-sign values p (B, N, d).
+    ``world_reduce`` optionally maps the local avg_prob to the cross-rank mean (the 4 KiB all-reduce)."""
+    K = 2 ** d_bits
+    codes = torch.arange(K)
+    mask = 2 ** torch.arange(d_bits - 1, -1, -1)
+    codebook = ((codes[:, None] & mask) != 0).float() * 2 - 1
+    x = p.reshape(-1, d_bits).float()
+    logits = 2 * inv_temperature * (x @ codebook.t())
+    prob = logits.softmax(dim=-1)
+
+    def ent(pr):
+        return (-pr * torch.log(pr.clamp(min=1e-5))).sum(dim=-1)
+
+    per_sample = ent(prob).mean()
+    avg = prob.mean(dim=0)
+    if world_reduce is not None:
+        avg = world_reduce(avg)
+    batch_ent = ent(avg)
+    q = torch.where(x > 0, torch.ones_like(x), -torch.ones_like(x))
+    commit = ((x - q) ** 2).mean()
+    aux = (per_sample - diversity_gamma * batch_ent) * entropy_w + commit * commit_w
+    return per_sample, batch_ent, commit, aux, avg
+
+
+def _fsq_consts(levels, dtype=torch.float32):
+    lv = torch.tensor(levels, dtype=torch.int32)
+    basis = torch.cumprod(torch.tensor([1] + list(levels[:-1])), dim=0).to(torch.int32)
+    return lv, basis
+
+
+def fsq_quantize(x, sd, levels):
+    """FSQ forward (A.2): project_in, tanh bound, round-half-even, mixed-radix int32 index, project_out."""
+    b, c, t, h, w = x.shape
+    lv, basis = _fsq_consts(levels)
+    tok = x.permute(0, 2, 3, 4, 1).reshape(b, -1, c)
+    z = F.linear(tok, sd["quantizers.project_in.weight"], sd["quantizers.project_in.bias"])
+    zf = z if z.dtype in (torch.float32, torch.float64) else z.float()
+    half_l = (lv - 1) * (1 + 1e-3) / 2
+    offset = torch.where(lv % 2 == 0, 0.5, 0.0)
+    shift = (offset / half_l).atanh()
+    bounded = (zf + shift).tanh() * half_l - offset
+    half_w = lv // 2
+    codes = bounded.round() / half_w
+    idx = ((codes * half_w + half_w) * basis).sum(dim=-1).to(torch.int32)
+    out = F.linear(codes.to(x.dtype), sd["quantizers.project_out.weight"], sd["quantizers.project_out.bias"])
+    out = out.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
+    return out, idx.reshape(b, t, h, w), bounded
+
+
+def fsq_indices_to_codes(idx, sd, levels, dtype):
+    lv, basis = _fsq_consts(levels)
+    nonneg = (idx[..., None] // basis) % lv
+    half_w = lv // 2
+    codes = ((nonneg - half_w) / half_w).to(dtype)
+    out = F.linear(codes, sd["quantizers.project_out.weight"].to(dtype), sd["quantizers.project_out.bias"].to(dtype))
+    return out.movedim(-1, 1)
+
+
+# ----------------------------------------------------------------------------
+# the tokenizer
+# ----------------------------------------------------------------------------
+
+class OracleTokenizer:
+    """Functional restatement of VideoTokenizer's inference path (M:1045-1720)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], *, image_size, layers=("residual",) * 3,
+                 codebook_size=None, channels=3, init_dim=64, max_dim=float("inf"),
+                 use_fsq=False, fsq_levels=None, attn_dim_head=32, attn_heads=8,
+                 linear_attn_dim_head=8, linear_attn_heads=16, pad_mode="constant",
+                 lfq_soft_clamp_input_value=10., dtype=torch.float32, **unused):
+        self.dtype = dtype
+        self.sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in state_dict.items()
+                   if not k.startswith("discr.")}
+        self.image_size = image_size
+        self.layers = tuple(layers)
+        self.stages, self.space_f, self.time_f = schedule(self.layers, init_dim, max_dim)
+        self.time_padding = self.time_f - 1                                  # M:1328-1329
+        self.fmap_size = image_size // self.space_f                         # M:1168, M:1331
+        self.use_fsq = use_fsq
+        self.fsq_levels = fsq_levels
+        self.codebook_size = codebook_size
+        self.heads, self.dim_head = attn_heads, attn_dim_head
+        self.lin_heads, self.lin_dim_head = linear_attn_heads, linear_attn_dim_head
+        self.pad_mode = pad_mode
+        self.clamp = lfq_soft_clamp_input_value
+        self.channels = channels
+
+    # one encoder/decoder stage --------------------------------------------------
+    def _apply(self, x, st: Stage, p: str, decoder: bool, taps=None):
+        sd = self.sd
+        if st.kind == "residual":
+            if st.nested:
+                for j in range(st.count):
+                    x = residual_unit(x, sd, f"{p}{j}.")
+            else:
+                x = residual_unit(x, sd, p)
+        elif st.kind == "compress_space":
+            x = spatial_up(x, sd, p) if decoder else spatial_down(x, sd, p)
+        elif st.kind == "compress_time":
+            x = time_up(x, sd, p) if decoder else time_down(x, sd, p)
+        elif st.kind == "attend_space":                                      # M:1189-1197
+            x = space_attention(x, sd, p + "0.fn.", self.heads) + x
+            x = feed_forward(x, sd, p + "1.fn.") + x
+        elif st.kind == "linear_attend_space":                               # M:1206-1214
+            x = linear_space_attention(x, sd, p + "0.fn.", self.lin_heads, self.lin_dim_head) + x
+            x = feed_forward(x, sd, p + "1.fn.") + x
+        elif st.kind == "attend_time":                                       # M:1234-1242
+            x = time_attention(token_shift(x), sd, p + "0.fn.fn.", self.heads) + x
+            x = feed_forward(token_shift(x), sd, p + "1.fn.fn.") + x
+        else:
+            raise ValueError(st.kind)
+        return x
+
+    @torch.no_grad()
+    def encode(self, video, taps=None):
+        """VideoTokenizer.encode (M:1523-1576).  NB the final LayerNorm (M:1322-1326) is never
+        executed: zip() with has_cond_across_layers truncates it (M:1565)."""
+        x = video.to(self.dtype)
+        x = F.pad(x, (0, 0, 0, 0, self.time_padding, 0))                      # M:1537
+        x = causal_conv3d(x, self.sd["conv_in.conv.weight"], self.sd["conv_in.conv.bias"], self.pad_mode)
+        if taps is not None:
+            taps["conv_in"] = x
+        for i, st in enumerate(self.stages):
+            x = self._apply(x, st, f"encoder_layers.{i}.", decoder=False)
+            if taps is not None:
+                taps[f"enc{i}"] = x
+        return x
+
+    @torch.no_grad()
+    def decode(self, quantized, taps=None):
+        """VideoTokenizer.decode (M:1598-1649): decoder layers are the encoder's in reverse
+        (insert(0), M:1315); conv_out; drop the first time_padding frames (M:1646-1647)."""
+        x = quantized.to(self.dtype)
+        n = len(self.stages)
+        for j, st in enumerate(reversed(self.stages)):
+            x = self._apply(x, st, f"decoder_layers.{j}.", decoder=True)
+            if taps is not None:
+                taps[f"dec{j}"] = x
+        x = causal_conv3d(x, self.sd["conv_out.conv.weight"], self.sd["conv_out.conv.bias"], self.pad_mode)
+        return x[:, :, self.time_padding:]
+
+    @torch.no_grad()
+    def quantize(self, x):
+        if self.use_fsq:
+            return fsq_quantize(x, self.sd, self.fsq_levels)
+        return lfq_quantize(x, self.sd, self.clamp)
+
+    def _check_video(self, video):
+        assert video.ndim in (4, 5)                                            # M:1675
+        assert tuple(video.shape[-2:]) == (self.image_size, self.image_size)   # M:1677
+        if video.ndim == 4:
+            video = video[:, :, None]                                          # M:1684
+        assert (video.shape[2] - 1) % self.time_f == 0                        # M:1691
+        return video
+
+    @torch.no_grad()
+    def tokenize(self, video, taps=None, return_presign=False):
+        """VideoTokenizer.tokenize (M:1651-1654) = forward(return_codes=True) (M:1695-1708)."""
+        video = self._check_video(video)
+        x = self.encode(video, taps)
+        _, idx, pre = self.quantize(x)
+        return (idx, pre) if return_presign else idx
+
+    @torch.no_grad()
+    def decode_from_code_indices(self, codes, taps=None):
+        """M:1579-1595: flat (b, f*h*w) ids are un-flattened with the fmap size."""
+        assert codes.dtype in (torch.long, torch.int32)
+        if codes.ndim == 2:
+            assert codes.shape[-1] % (self.fmap_size ** 2) == 0
+            codes = codes.reshape(codes.shape[0], -1, self.fmap_size, self.fmap_size)
+        if self.use_fsq:
+            q = fsq_indices_to_codes(codes, self.sd, self.fsq_levels, self.dtype)
+        else:
+            q = lfq_indices_to_codes(codes, self.sd, self.dtype)
+        return self.decode(q, taps)
+
+    @torch.no_grad()
+    def forward(self, video, return_codes=False, return_recon=False):
+        """forward up to M:1720 (inference returns only)."""
+        video = self._check_video(video)
+        x = self.encode(video)
+        q, idx, _ = self.quantize(x)
+        if return_codes and not return_recon:
+            return idx
+        rec = self.decode(q)
+        if return_codes:
+            return idx, rec
+        return rec

@@ -1,0 +1,50 @@
+"""The C-ABI library loads and exports every symbol include/magvit2_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from magvit2_pytorch_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "magvit2_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mv2_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_built():
+    assert os.path.isfile(_lib.LIB_PATH), "run __graft_entry__.build() first"
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
+    for name in _lib.SIGNATURES:
+        assert name in declared, f"{name} bound in _lib.py but not declared in the header"
+
+
+def test_load_and_version():
+    lib = _lib.load()
+    assert lib.mv2_abi_version() == 1
+    assert lib.mv2_se_workspace_bytes(2, 256, 64) == 2 * 2 * 66 * 4
+    assert lib.mv2_linattn_workspace_bytes(3, 16, 1024) == 3 * 16 * 4 * 657 * 4
+
+
+def test_struct_sizes_match_header_layout():
+    # 5 pointers + 22 int32 (conv), 3 pointers + 8 int32 + 3 int64 (attention)
+    assert ctypes.sizeof(_lib.ConvArgs) == 5 * 8 + 22 * 4
+    assert ctypes.sizeof(_lib.AttnArgs) == 3 * 8 + 8 * 4 + 3 * 8
+
+
+def test_sass_is_sm100a():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out

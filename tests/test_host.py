@@ -1,0 +1,90 @@
+"""Host-side mirror of the reference's VideoTokenizer interface (no GPU needed)."""
+import copy
+import pickle
+
+import pytest
+import torch
+
+from magvit2_pytorch_b200 import VideoTokenizer
+from tests.util import README_LAYERS, build_product, load_golden
+
+
+def test_schedule_readme():
+    m = VideoTokenizer(image_size=128, init_dim=64, max_dim=512, codebook_size=1024, layers=README_LAYERS)
+    assert m.time_downsample_factor == 4 and m.time_padding == 3 and m.fmap_size == 16
+    dims = [(s.kind, s.dim, s.dim_out) for s in m.stages]
+    assert dims[1] == ("compress_space", 64, 128) and dims[9] == ("compress_time", 512, 512)
+    assert len(m.encoder_layers) == len(README_LAYERS) + 1       # + the dead LayerNorm (M:1322)
+    assert len(m.decoder_layers) == len(README_LAYERS)
+    n_params = sum(p.numel() for p in m.parameters())
+    assert abs(n_params - 117.8e6) < 0.2e6                       # 117.8 M generator params
+    assert isinstance(m.parameters(), list)
+
+
+def test_state_dict_keys_follow_reference_layout():
+    m = VideoTokenizer(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, layers=README_LAYERS)
+    keys = set(m.state_dict().keys())
+    for k in ["conv_in.conv.weight", "encoder_layers.0.fn.0.conv.bias", "encoder_layers.0.fn.4.to_k.weight",
+              "encoder_layers.2.1.fn.4.net.2.weight", "encoder_layers.1.conv.weight", "decoder_layers.2.net.0.weight",
+              "encoder_layers.8.0.fn.mem_kv", "encoder_layers.8.0.fn.to_qkv.0.weight", "encoder_layers.8.0.fn.to_out.1.weight",
+              "encoder_layers.13.0.fn.fn.norm.gamma", "encoder_layers.13.1.fn.fn.net.2.bias",
+              "encoder_layers.5.0.fn.attn.to_kv.0.weight", "encoder_layers.5.1.fn.norm.gamma",
+              "encoder_layers.14.1.weight", "quantizers.mask", "quantizers.project_in.weight", "conv_out.conv.bias"]:
+        assert k in keys, k
+    assert "zero" not in keys
+    assert m.state_dict()["quantizers.mask"].tolist() == [512, 256, 128, 64, 32, 16, 8, 4, 2, 1]
+
+
+def test_constructor_errors():
+    with pytest.raises(ValueError):
+        VideoTokenizer(image_size=32, codebook_size=1024, layers=("bogus",))
+    with pytest.raises(AssertionError):
+        VideoTokenizer(image_size=32, layers=("residual",))                       # no codebook_size (M:1359)
+    with pytest.raises(AssertionError):
+        VideoTokenizer(image_size=32, use_fsq=True, codebook_size=1024, layers=("residual",))  # M:1376
+    with pytest.raises(NotImplementedError):
+        VideoTokenizer(image_size=32, codebook_size=1024, layers=("gateloop_time",))
+    with pytest.raises(NotImplementedError):
+        VideoTokenizer(image_size=32, codebook_size=1024, dim_cond=8, layers=("cond_residual",))
+
+
+def test_config_pickle_roundtrip_and_save_load(tmp_path):
+    m = build_product(dict(image_size=32, init_dim=16, codebook_size=1024, layers=("residual", "compress_space")))
+    cfg = pickle.loads(m._configs)
+    assert cfg["image_size"] == 32 and cfg["layers"] == ("residual", "compress_space")
+    p = tmp_path / "tok.pt"
+    m.save(p)
+    m2 = VideoTokenizer.init_and_load_from(p)
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+    m3 = copy.deepcopy(m)
+    assert torch.equal(m3.conv_in.conv.weight, m.conv_in.conv.weight)
+
+
+def test_load_state_dict_drops_discriminator_keys():
+    m = build_product(dict(image_size=32, init_dim=16, codebook_size=1024, layers=("residual",)))
+    sd = dict(m.state_dict())
+    sd["discr.blocks.0.0.conv_res.weight"] = torch.zeros(3)
+    m.load_state_dict(sd, strict=True)
+
+
+def test_cpu_model_fails_loudly():
+    """No CPU fallback: a CPU-resident model must raise, not silently run eager."""
+    g = load_golden("cfg1")
+    m = build_product(g["kwargs"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.tokenize(torch.randn(1, 3, 5, 32, 32))
+    with pytest.raises(RuntimeError):
+        m.conv_in(torch.randn(1, 3, 5, 32, 32))
+
+
+def test_shape_asserts_follow_reference():
+    m = build_product(dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, layers=README_LAYERS))
+    with pytest.raises(AssertionError):
+        m.tokenize(torch.randn(1, 3, 8, 32, 32))     # (8-1) % 4 != 0  (M:1691)
+    with pytest.raises(AssertionError):
+        m.tokenize(torch.randn(1, 3, 9, 16, 16))     # wrong image size (M:1677)
+    with pytest.raises(AssertionError):
+        m.decode_from_code_indices(torch.zeros(1, 3, 4, 4))   # float codes (M:1585)
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(1, 3, 9, 32, 32), return_loss=True)

@@ -1,0 +1,127 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the
+committed reference goldens.  Run on the B200 box:  python -m pytest tests -m gpu"""
+import os
+
+import pytest
+import torch
+
+from tests.util import build_oracle, build_product, golden_video, load_golden, sample_like_golden
+
+pytestmark = pytest.mark.gpu
+
+FP32_RECON_TOL = 1e-4     # fp32 path vs fp32 oracle, max-abs (outputs are O(1)); north-star goal is 1e-5
+FP32_TAP_TOL = 1e-4
+
+
+def _require_cuda():
+    assert torch.cuda.is_available(), "gpu-marked test without a GPU"
+
+
+def _report(name, **kw):
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_report.txt", "a") as f:
+        f.write(name + ": " + ", ".join(f"{k}={v}" for k, v in kw.items()) + "\n")
+
+
+@pytest.mark.parametrize("name", ["cfg1", "mini", "mini_fsq"])
+def test_fp32_bit_exact_codes_and_recon_vs_golden(name):
+    """fp32 storage + fp32 FMA: code indices bit-exact vs the reference golden, per-layer taps and recon
+    within fp32 round-off."""
+    _require_cuda()
+    g = load_golden(name)
+    model = build_product(g["kwargs"], g["wseed"]).cuda()
+    video = golden_video(g).cuda()
+    eng = model.engine
+    eng.taps = {}
+    codes = model.tokenize(video)
+    enc_taps, eng.taps = eng.taps, {}
+    recon = model.decode_from_code_indices(codes)
+    dec_taps, eng.taps = eng.taps, None
+    worst = 0.0
+    for k, ref in g["taps"].items():
+        got = enc_taps.get(k, dec_taps.get(k))
+        assert got is not None, k
+        err = (sample_like_golden(got, g) - ref).abs().max().item()
+        worst = max(worst, err)
+        assert err < FP32_TAP_TOL, (k, err)
+    assert codes.dtype == g["codes"].dtype
+    n_diff = (codes.cpu() != g["codes"]).sum().item()
+    rerr = (recon.cpu() - g["recon"]).abs().max().item()
+    _report(f"fp32/{name}", code_mismatches=n_diff, recon_maxabs=f"{rerr:.3e}", worst_tap=f"{worst:.3e}")
+    assert n_diff == 0, f"{n_diff} code indices differ from the reference"
+    assert rerr < FP32_RECON_TOL, rerr
+
+
+def test_fp32_readme_config_vs_golden():
+    """BASELINE configs[1] (README config), one clip, fp32 path vs the reference golden."""
+    _require_cuda()
+    g = load_golden("readme")
+    model = build_product(g["kwargs"], g["wseed"]).cuda()
+    video = golden_video(g).cuda()
+    eng = model.engine
+    eng.taps = {}
+    x = eng.encode_cl(video)
+    _, codes, pre = eng.quantize_cl(x, want_quantized=False, want_aux=True)
+    taps, eng.taps = eng.taps, None
+    for k, ref in g["taps"].items():
+        if k in taps:
+            err = (sample_like_golden(taps[k], g) - ref).abs().max().item()
+            assert err < 5e-4, (k, err)
+    pre_err = (pre.cpu().reshape(g["presign"].shape) - g["presign"]).abs().max().item()
+    n_diff = (codes.cpu() != g["codes"]).sum().item()
+    recon = model.decode_from_code_indices(g["codes"].cuda())
+    rerr = (recon.cpu()[:, :, :, ::4, ::4] - g["recon_sample"]).abs().max().item()
+    merr = (recon.cpu().mean(dim=(3, 4)) - g["recon_mean"]).abs().max().item()
+    _report("fp32/readme", code_mismatches=n_diff, presign_maxabs=f"{pre_err:.3e}", recon_maxabs=f"{rerr:.3e}",
+            recon_mean_err=f"{merr:.3e}")
+    assert n_diff == 0
+    assert rerr < 5e-4
+
+
+@pytest.mark.parametrize("name", ["mini", "mini_fsq"])
+def test_roundtrip_and_api_properties(name):
+    """README.md:85-90 round trip, flat ids (M:1587-1591), image input (M:1681), batch independence."""
+    _require_cuda()
+    g = load_golden(name)
+    model = build_product(g["kwargs"], g["wseed"]).cuda()
+    v = golden_video(g).cuda()
+    codes = model.tokenize(v)
+    a = model.decode_from_code_indices(codes)
+    b = model(v, return_recon=True)
+    assert torch.equal(a, b)
+    c, r = model(v, return_codes=True, return_recon=True)
+    assert torch.equal(c, codes) and torch.equal(r, a)
+    flat = model.decode_from_code_indices(codes.reshape(codes.shape[0], -1))
+    assert torch.equal(flat, a)
+    assert torch.equal(model.tokenize(v[:1]), codes[:1])
+    img_codes = model.tokenize(v[:, :, 0])
+    assert img_codes.shape == (v.shape[0], 1, model.fmap_size, model.fmap_size)
+    enc = model.encode(v)
+    assert enc.shape[1] == model.quantizers.dim
+    loss, rec = model(v, return_recon_loss_only=True)
+    assert rec.shape == v.shape and loss.ndim == 0
+
+
+@pytest.mark.parametrize("name", ["mini", "mini_fsq"])
+def test_bf16_path_vs_fp32_oracle(name):
+    """bf16 storage / fp32 accumulate.  Protocol: tokens whose code differs from the fp32
+    oracle must have a small |pre-sign| margin there; decode is compared with identical codes."""
+    _require_cuda()
+    g = load_golden(name)
+    cpu_model = build_product(g["kwargs"], g["wseed"])
+    orc = build_oracle(cpu_model, g["kwargs"])
+    v = golden_video(g)
+    ref_codes = g["codes"]
+    model = build_product(g["kwargs"], g["wseed"]).cuda().bfloat16()
+    codes = model.tokenize(v.cuda())
+    mism = (codes.cpu() != ref_codes)
+    rate = mism.float().mean().item()
+    recon = model.decode_from_code_indices(ref_codes.cuda())
+    rerr = (recon.float().cpu() - g["recon"]).abs().max().item()
+    _report(f"bf16/{name}", token_mismatch_rate=f"{rate:.4f}", recon_maxabs=f"{rerr:.3e}")
+    assert recon.dtype == torch.bfloat16
+    assert rate < 0.12, rate
+    assert rerr < 0.15, rerr
+    if not g["kwargs"].get("use_fsq", False) and mism.any():
+        margin = g["presign"].reshape(*ref_codes.shape, -1).abs().min(dim=-1).values
+        assert margin[mism].max().item() < 0.15

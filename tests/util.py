@@ -1,0 +1,46 @@
+"""Shared helpers for the test-suite (CPU and GPU)."""
+import os
+
+import torch
+
+from magvit2_pytorch_b200 import VideoTokenizer
+from oracle import weights as W
+from oracle.restated import OracleTokenizer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+README_LAYERS = (
+    "residual", "compress_space", ("consecutive_residual", 2), "compress_space",
+    ("consecutive_residual", 2), "linear_attend_space", "compress_space",
+    ("consecutive_residual", 2), "attend_space", "compress_time",
+    ("consecutive_residual", 2), "compress_time", ("consecutive_residual", 2), "attend_time",
+)
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, f"{name}.pt"), map_location="cpu", weights_only=False)
+
+
+def build_product(kwargs, wseed=0):
+    """Product model (CPU, fp32) with the deterministic synthetic weights."""
+    torch.manual_seed(0)
+    m = VideoTokenizer(**kwargs)
+    W.fill_state_dict_(m, wseed)
+    m.eval()
+    return m
+
+
+def build_oracle(model, kwargs, dtype=torch.float32):
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    return OracleTokenizer(sd, dtype=dtype, **kwargs)
+
+
+def golden_video(g):
+    b, c, t, s = g["video_shape"][:4]
+    return W.synth_video(b, c, t, s, seed=g["vseed"])
+
+
+def sample_like_golden(t, g):
+    cs, ss = g.get("tap_strides", (7, 5))
+    return t[:, ::cs, :, ::ss, ::ss]
