@@ -1,0 +1,315 @@
+"""bench.py -- headline metric of BASELINE.json: video frames/s through tokenize + decode_from_code_indices,
+17x128x128 clips, bf16, README config (BASELINE.json configs[1]), data-parallel over N GPUs of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch of 4 synthetic clips per GPU (weak scaling: the batch
+is sharded by clip, no data-path collective in eval -- SURVEY.md 8e).  Prints ONE JSON line (rank 0).
+
+--impl reference times the reference's own CPU implementation of the path: the reference is pure Python and
+cannot travel to the GPU box, so this arm runs the restated oracle (oracle/restated.py, pinned bit-for-bit to
+the reference's goldens) -- the same torch-eager CPU ops the reference dispatches -- on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+README_LAYERS = (
+    "residual", "compress_space", ("consecutive_residual", 2), "compress_space",
+    ("consecutive_residual", 2), "linear_attend_space", "compress_space",
+    ("consecutive_residual", 2), "attend_space", "compress_time",
+    ("consecutive_residual", 2), "compress_time", ("consecutive_residual", 2), "attend_time",
+)
+README_KW = dict(image_size=128, init_dim=64, max_dim=512, codebook_size=1024, layers=README_LAYERS)
+CLIPS_PER_GPU = 4
+FRAMES = 17
+# SURVEY.md 8d / BASELINE.md 3 (forward hooks on the reference's own modules, 2 FLOP per MAC)
+FLOP_PER_CLIP_CONV_PATH = 1.2787e12       # causal Conv3d path only (k>1 Conv3d)
+FLOP_PER_CLIP_ALL = 1.512e12              # conv + linear + attention einsums
+METRIC = "video-frames/sec tokenize+decode, 17x128x128 bf16"
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference_arm(args):
+    """CPU baseline: the reference's torch-eager CPU path (restated oracle), all host threads, bounded sample."""
+    import torch
+    from oracle import weights as Wt
+    from oracle.restated import OracleTokenizer
+    from magvit2_pytorch_b200 import VideoTokenizer
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = VideoTokenizer(**README_KW)
+    Wt.fill_state_dict_(model, 0)
+    orc = OracleTokenizer({k: v for k, v in model.state_dict().items()}, dtype=torch.bfloat16, **README_KW)
+    del model
+    sample_clips = 1
+    video = Wt.synth_video(sample_clips, 3, FRAMES, 128, seed=1).to(torch.bfloat16)
+
+    def step():
+        codes = orc.tokenize(video)
+        return orc.decode_from_code_indices(codes)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = sample_clips * FRAMES * args.steps / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "README VideoTokenizer (BASELINE configs[1]), tokenize+decode, CPU torch eager",
+                   "clips_per_step": sample_clips},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_clips} clip (17x128x128) per step, bf16, oracle/restated.py "
+                                   "(torch CPU eager, same ATen ops the reference dispatches)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_sample():
+    """Bounded CPU sample for the product arm's cpu_baseline object (rank 0, N=1 only)."""
+    import torch
+    from oracle import weights as Wt
+    from oracle.restated import OracleTokenizer
+    from magvit2_pytorch_b200 import VideoTokenizer
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = VideoTokenizer(**README_KW)
+    Wt.fill_state_dict_(model, 0)
+    orc = OracleTokenizer({k: v for k, v in model.state_dict().items()}, dtype=torch.bfloat16, **README_KW)
+    video = Wt.synth_video(1, 3, FRAMES, 128, seed=1).to(torch.bfloat16)
+    orc.decode_from_code_indices(orc.tokenize(video))     # warm-up
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        orc.decode_from_code_indices(orc.tokenize(video))
+        ts.append(time.perf_counter() - t0)
+    best = min(ts)
+    return {"value": FRAMES / best, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": "1 clip 17x128x128, bf16, tokenize+decode, best of 3 after 1 warm-up (oracle/restated.py, "
+                      "torch CPU eager)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 20 and args.warmup == 5:
+            args.steps, args.warmup = 3, 1
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from oracle import weights as Wt
+    from magvit2_pytorch_b200 import VideoTokenizer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+
+    torch.manual_seed(0)
+    model = VideoTokenizer(**README_KW)
+    Wt.fill_state_dict_(model, 0)
+    model = model.to(dev).bfloat16().eval()
+    eng = model.engine
+
+    # inputs: NB distinct batches per rank so consecutive steps never re-read the same input from L2
+    NB = 12
+    host_batches = [Wt.synth_video(CLIPS_PER_GPU, 3, FRAMES, 128, seed=1000 + rank * NB + i).pin_memory() for i in range(NB)]
+    dev_batches = [hb.to(dev, non_blocking=True) for hb in host_batches]
+    torch.cuda.synchronize()
+
+    def step(v):
+        codes = model.tokenize(v)
+        return codes, model.decode_from_code_indices(codes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(dev_batches[i % NB])
+    # ---------------- timed region: inputs resident in HBM ----------------
+    clk = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clk.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(dev_batches[i % NB])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launches - l0
+    clocks = clk.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = t.item()
+    frames_total = world * CLIPS_PER_GPU * FRAMES * args.steps
+    value = frames_total / (ms_max / 1e3)
+
+    # ---------------- e2e: host (pinned) buffers in, host buffers out, copies inside the timed region ----
+    out_codes = torch.empty((CLIPS_PER_GPU, 5, 16, 16), dtype=torch.int64).pin_memory()
+    out_video = torch.empty((CLIPS_PER_GPU, 3, FRAMES, 128, 128), dtype=torch.bfloat16).pin_memory()
+
+    def step_e2e(hv):
+        v = hv.to(dev, non_blocking=True)
+        codes, rec = step(v)
+        out_codes.copy_(codes, non_blocking=True)
+        out_video.copy_(rec, non_blocking=True)
+
+    for i in range(3):
+        step_e2e(host_batches[i % NB])
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(host_batches[i % NB])
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = frames_total / (t.item() / 1e3)
+    h2d = host_batches[0].numel() * host_batches[0].element_size()
+    d2h = out_codes.numel() * 8 + out_video.numel() * 2
+
+    # ---------------- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), timed live ----------
+    # instrumented pass: CUDA events around every conv launch of one step, on the launching stream
+    conv_ms, conv_launches = None, None
+    if hasattr(eng, "profile_convs"):
+        conv_ms, conv_launches, conv_flops = eng.profile_convs(lambda: step(dev_batches[0]), steps=3)
+    peaks, peaks_src = _peaks()
+    roofline = None
+    if conv_ms:
+        ach = conv_flops / (conv_ms / 1e3) / 1e12
+        roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "kernel": "tc_conv_kernel (tcgen05 implicit-GEMM conv, all dense contractions)",
+                    "launches_per_step": conv_launches, "kernel_ms_per_step": conv_ms,
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks_src})",
+                    "whole_step_frac": (FLOP_PER_CLIP_ALL * CLIPS_PER_GPU * world * args.steps / (ms_max / 1e3) / 1e12)
+                                       / (peaks["bf16_tflops_sustained"] * world)}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "README VideoTokenizer (BASELINE configs[1]): tokenize + decode_from_code_indices, "
+                                   "4 clips of 3x17x128x128 per GPU, batch sharded by clip",
+                       "global_batch": CLIPS_PER_GPU * world, "parallelism": f"dp{world}",
+                       "l2": f"inputs rotate over {NB} distinct batches per rank ({NB * h2d / 1e6:.0f} MB > 126 MB L2); "
+                             "per-step activation working set ~2 GB"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -167,6 +167,31 @@ int mv2_fsq_decode(const void* indices, int index_is_i64, int64_t N, int C, int 
 int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, float inv_temperature,
                              float* avg_prob, float* stats, void* stream);
 
+/* ---- tcgen05 / TMA implicit-GEMM convolution (bf16 in, fp32 accumulate in TMEM) ------------
+ * Same operator family and epilogue as mv2_conv_forward, for bf16 activations, executed on the
+ * 5th-generation tensor cores: TMA box loads with out-of-bounds zero fill implement the causal /
+ * spatial halo (no padded copy, reference M:924-928), strided convs read through stride-phase
+ * tensor maps, accumulators live in TMEM.  Weights are packed K-major: w[co][tap][ci] (bf16);
+ * for depth-to-space / depth-to-time stores the host permutes the Co rows to co' = q*Cy + c
+ * (q = p1*2+p2 or p) so that the shuffled stores are channel-contiguous; bias is permuted alike.
+ * Requirements (mv2_tc_conv_supported): Ci % 16 == 0, strides in {1,2}, <= 64 taps.            */
+typedef struct mv2_tc_conv_args {
+  const void* x;       /* bf16 (B, Ti, Hi, Wi, Ci) */
+  const void* w;       /* bf16 [Co][kt*kh*kw*Ci] */
+  const float* bias;   /* fp32 [Co] or NULL */
+  const void* res;     /* bf16, same shape as y, or NULL */
+  void* y;             /* bf16 */
+  int32_t B, Ti, Hi, Wi, Ci;
+  int32_t To, Ho, Wo, Co;
+  int32_t kt, kh, kw;
+  int32_t st, sh, sw;
+  int32_t pt, ph, pw;
+  int32_t act;
+  int32_t shuffle;
+} mv2_tc_conv_args;
+int mv2_tc_conv_supported(const mv2_tc_conv_args* a);
+int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,8 +53,7 @@ class TcConvArgs(C.Structure):
         ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
         ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
         ("pt", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
-        ("act", C.c_int32), ("shuffle", C.c_int32), ("Co_store", C.c_int32), ("variant", C.c_int32),
-        ("se_wk", C.c_void_p), ("se_bk", C.c_float), ("se_ws", C.c_void_p),
+        ("act", C.c_int32), ("shuffle", C.c_int32),
     ]
 
 
@@ -81,6 +80,8 @@ SIGNATURES = {
     "mv2_fsq_forward": (_I, [_VP, _I, _I64, _I, _I, C.POINTER(C.c_int32), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mv2_fsq_decode": (_I, [_VP, _I, _I64, _I, _I, C.POINTER(C.c_int32), _VP, _VP, _VP, _I, _VP]),
     "mv2_lfq_entropy_partials": (_I, [_VP, _I64, _I, _F, _VP, _VP, _VP]),
+    "mv2_tc_conv_supported": (_I, [C.POINTER(TcConvArgs)]),
+    "mv2_tc_conv_forward": (_I, [C.POINTER(TcConvArgs), _VP]),
 }
 
 _lib = None

@@ -1,0 +1,443 @@
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a (bf16 in, fp32 accumulate in TMEM).
+//
+// One kernel covers the whole dense-contraction family of the VideoTokenizer forward path:
+// causal 3x3x3 convs, 1x1x1 convs / Linear layers, the strided compress_space / compress_time
+// convs and the 1x1 up-samplers with their depth-to-space / depth-to-time stores.
+//
+// GEMM view:  D[m][n] = sum_{tap, c} X[pos(m) + off(tap)][c] * W[n][tap][c]
+//   M = 128 output positions per CTA, laid out as a (bt, bh, bw) box of the output volume
+//   N = up to 256 output channels per CTA
+//   K = taps x Ci, walked in BK-channel slices of one tap at a time
+// Operand staging: one TMA box load per (tap, slice) for A -- the box {BK, bw, bh, bt, 1} of the
+// channels-last activation tensor shifted by the tap offset; out-of-bounds elements (the causal
+// time halo, the spatial halo, ragged tile edges) are zero-filled by the TMA unit, so no padded
+// copy of the activations is ever materialised (the reference does F.pad + conv, M:924-928).
+// Strided convs read through "parity view" tensor maps (one per stride phase).  Both operands are
+// K-major in shared memory with the hardware 128B/64B/32B swizzle (BK = 64/32/16 channels).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+// tcgen05.mma issuer, warps 2-5 = epilogue (tcgen05.ld -> bias/activation/residual -> global).
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <algorithm>
+#include <string.h>
+
+namespace mv2 {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]   (kind::f16: bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major operand with hardware swizzle.
+//   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (ignored for swizzled K-major)
+//   bits [32,46) stride byte offset >> 4   (8 rows x row bytes)     bits [46,48) version = 1 (sm_100)
+//   bits [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
+  const uint32_t sbo = 8 * row_bytes;
+  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+constexpr int TC_MAX_TAPS = 64;
+constexpr int TC_MAX_MAPS = 8;
+constexpr int TC_BM = 128;
+
+struct alignas(64) TcParams {
+  CUtensorMap amap[TC_MAX_MAPS];
+  CUtensorMap wmap;
+  int8_t tap_map[TC_MAX_TAPS], tap_dt[TC_MAX_TAPS], tap_dh[TC_MAX_TAPS], tap_dw[TC_MAX_TAPS];
+  int ntaps, kchunks, ci_pad, bk;
+  int B, To, Ho, Wo, Co;
+  int bt, bh, bw, tt, th, tw;
+  int bn, stages, tmem_cols;
+  int act, shuffle;
+  const float* bias;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bk = p.bk;
+  const uint32_t row_bytes = bk * 2;
+  const uint32_t a_bytes = TC_BM * row_bytes;
+  const uint32_t b_bytes = p.bn * row_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;   // both multiples of 1024 when bn % 16 == 0 and bk >= 32; see host
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  // barriers: full[s] at +8s, empty[s] at +8(S+s), tmem_full at +16S, tmem slot at +16S+8
+  const uint32_t full0 = bar_base, empty0 = bar_base + 8 * p.stages, tfull = bar_base + 16 * p.stages;
+  const uint32_t tslot = tfull + 8;
+
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int iw = tile % p.tw; tile /= p.tw;
+  const int ih = tile % p.th; tile /= p.th;
+  const int it = tile % p.tt; tile /= p.tt;
+  const int b = tile;
+  const int w0 = iw * p.bw, h0 = ih * p.bh, t0 = it * p.bt;
+  const int n0 = blockIdx.y * p.bn;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.wmap);
+    tma_prefetch_desc(&p.amap[0]);
+  }
+  if (warp == 1) tmem_alloc(tslot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+
+  const int n_iters = p.ntaps * p.kchunks;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < n_iters; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        mbar_expect_tx(full0 + 8 * s, stage_bytes);
+        const int tap = i / p.kchunks, kc = i - tap * p.kchunks;
+        const uint32_t sa = smem_base + s * stage_bytes;
+        tma_load_5d(sa, &p.amap[p.tap_map[tap]], full0 + 8 * s, kc * bk, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
+                    t0 + p.tap_dt[tap], b);
+        tma_load_2d(sa + a_bytes, &p.wmap, full0 + 8 * s, tap * p.ci_pad + kc * bk, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int i = 0; i < n_iters; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * stage_bytes;
+        const uint64_t ad = make_kmajor_desc(sa, row_bytes);
+        const uint64_t bd = make_kmajor_desc(sa + a_bytes, row_bytes);
+        for (int k = 0; k < bk / 16; ++k) {
+          // advancing 16 bf16 along K = +32 bytes = +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);   // frees the smem slot once these MMAs retire
+      }
+      umma_commit(tfull);              // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue warps 2..5 : TMEM lanes 32*(warp%4) .. +31 ----------------
+    const int sub = warp & 3;
+    const int row = sub * 32 + lane;
+    const int lw = row % p.bw, lh = (row / p.bw) % p.bh, lt = row / (p.bw * p.bh);
+    const int wo = w0 + lw, ho = h0 + lh, to = t0 + lt;
+    const bool row_ok = wo < p.Wo && ho < p.Ho && to < p.To;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const uint32_t tlane = tmem_base + ((uint32_t)(sub * 32) << 16);
+    const int64_t pos = (((int64_t)b * p.To + to) * p.Ho + ho) * p.Wo + wo;
+    const int cy = p.shuffle == MV2_SHUFFLE_SPACE ? (p.Co >> 2) : (p.shuffle == MV2_SHUFFLE_TIME ? (p.Co >> 1) : p.Co);
+    const bool vec_ok = (cy % 8) == 0;
+    for (int c0 = 0; c0 < p.bn; c0 += 32) {
+      uint32_t r[32];
+      if (p.bn - c0 >= 32) tmem_ld_32x32b_x32(tlane + c0, r);
+      else tmem_ld_32x32b_x16(tlane + c0, r);
+      tmem_ld_wait();
+      const int ncols = min(32, p.bn - c0);
+      if (!row_ok) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g * 8 >= ncols) break;
+        const int n = n0 + c0 + g * 8;   // first (packed) output column of this group of 8
+        if (n >= p.Co) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float x = __uint_as_float(r[g * 8 + j]);
+          if (p.bias && n + j < p.Co) x += p.bias[n + j];
+          v[j] = apply_act(x, p.act);
+        }
+        // destination of packed column n: the host permutes weight rows so that shuffled stores are channel-contiguous
+        int64_t off;
+        if (p.shuffle == MV2_SHUFFLE_SPACE) {
+          const int q = n / cy, c = n - q * cy, p1 = q >> 1, p2 = q & 1;
+          off = ((((int64_t)b * p.To + to) * (2 * p.Ho) + (2 * ho + p1)) * (2 * p.Wo) + (2 * wo + p2)) * cy + c;
+        } else if (p.shuffle == MV2_SHUFFLE_TIME) {
+          const int q = n / cy, c = n - q * cy;
+          off = ((((int64_t)b * (2 * p.To) + (2 * to + q)) * p.Ho + ho) * p.Wo + wo) * cy + c;
+        } else {
+          off = pos * p.Co + n;
+        }
+        if (vec_ok && n + 8 <= p.Co) {
+          if (p.res) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(p.res + off);
+            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(rb[j]);
+              v[2 * j] += f.x;
+              v[2 * j + 1] += f.y;
+            }
+          }
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(p.y + off) = o;
+        } else {
+          for (int j = 0; j < 8 && n + j < p.Co; ++j) {
+            // scalar tail (Co not a multiple of 8, e.g. conv_out's 3 channels); no shuffle support needed here
+            float x = v[j];
+            if (p.res) x += __bfloat162float(p.res[off + j]);
+            p.y[off + j] = __float2bfloat16_rn(x);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+static int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+static int floor_div(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
+
+}  // namespace mv2
+
+using namespace mv2;
+
+extern "C" {
+
+int mv2_tc_conv_supported(const mv2_tc_conv_args* a) {
+  if (!a) return 0;
+  if (a->Ci % 16 != 0) return 0;                    // TMA inner box = 32/64/128 B, global strides multiple of 16 B
+  if (a->kt * a->kh * a->kw > TC_MAX_TAPS) return 0;
+  if (a->st < 1 || a->st > 2 || a->sh < 1 || a->sh > 2 || a->sw < 1 || a->sw > 2) return 0;
+  if (a->shuffle != MV2_SHUFFLE_NONE && ((a->shuffle == MV2_SHUFFLE_SPACE ? a->Co / 4 : a->Co / 2) % 8 != 0)) return 0;
+  if (a->res && a->Co % 8 != 0) return 0;
+  return 1;
+}
+
+int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream) {
+  MV2_CHECK_ARG(a && a->x && a->w && a->y);
+  if (!mv2_tc_conv_supported(a)) { set_error("mv2_tc_conv_forward: unsupported shape (Ci=%d Co=%d)", a->Ci, a->Co); return MV2_E_UNSUPPORTED; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MV2_E_CUDA; }
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const int bk = (a->Ci % 64 == 0) ? 64 : ((a->Ci % 32 == 0) ? 32 : 16);
+  const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  p.bk = bk;
+  p.ci_pad = a->Ci;
+  p.kchunks = a->Ci / bk;
+  p.B = a->B; p.To = a->To; p.Ho = a->Ho; p.Wo = a->Wo; p.Co = a->Co;
+  // output tile box: bw * bh * bt = 128
+  p.bw = std::min(128, pow2_ceil(a->Wo));
+  p.bh = std::min(128 / p.bw, pow2_ceil(a->Ho));
+  p.bt = 128 / (p.bw * p.bh);
+  p.tw = ceil_div(a->Wo, p.bw); p.th = ceil_div(a->Ho, p.bh); p.tt = ceil_div(a->To, p.bt);
+  // N tile: multiple of 16 (UMMA M=128 constraint), rows of B must keep 1024 B stage alignment
+  int bn = std::min(256, (a->Co + 15) / 16 * 16);
+  const int row_bytes = bk * 2;
+  while ((bn * row_bytes) % 1024 != 0) bn += 16;      // bk=16 -> bn % 32 == 0, bk >= 32: already fine
+  MV2_CHECK_ARG(bn <= 256);
+  p.bn = bn;
+  p.tmem_cols = std::max(32, pow2_ceil(bn));
+  const int stage_bytes = TC_BM * row_bytes + bn * row_bytes;
+  MV2_CHECK_ARG((TC_BM * row_bytes) % 1024 == 0);
+  // ring depth: no deeper than the K loop (short-K layers then fit several CTAs per SM, overlapping one CTA's
+  // epilogue with another's loads)
+  int stages = (200 * 1024) / stage_bytes;
+  stages = std::max(2, std::min(stages, 8));
+  stages = std::max(1, std::min(stages, a->kt * a->kh * a->kw * (a->Ci / bk)));
+  p.stages = stages;
+  p.act = a->act; p.shuffle = a->shuffle;
+  p.bias = a->bias; p.res = (const __nv_bfloat16*)a->res; p.y = (__nv_bfloat16*)a->y;
+
+  // ---- activation tensor maps: one per stride-parity phase ----
+  const int st = a->st, sh = a->sh, sw = a->sw;
+  const int nmaps = st * sh * sw;
+  MV2_CHECK_ARG(nmaps <= TC_MAX_MAPS);
+  const int64_t C = a->Ci, W = a->Wi, H = a->Hi, T = a->Ti;
+  for (int pt = 0; pt < st; ++pt)
+    for (int ph = 0; ph < sh; ++ph)
+      for (int pw = 0; pw < sw; ++pw) {
+        const int id = (pt * sh + ph) * sw + pw;
+        const int64_t nW = (W - pw + sw - 1) / sw, nH = (H - ph + sh - 1) / sh, nT = (T - pt + st - 1) / st;
+        if (nW <= 0 || nH <= 0 || nT <= 0) { set_error("empty stride phase (dimension smaller than stride)"); return MV2_E_UNSUPPORTED; }
+        cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)nW, (cuuint64_t)nH, (cuuint64_t)nT, (cuuint64_t)a->B};
+        cuuint64_t strides[4] = {(cuuint64_t)(sw * C * 2), (cuuint64_t)(sh * W * C * 2), (cuuint64_t)(st * H * W * C * 2),
+                                 (cuuint64_t)(T * H * W * C * 2)};
+        cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bt, 1};
+        cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        char* base = (char*)a->x + ((int64_t)pt * H * W + (int64_t)ph * W + pw) * C * 2;
+        CUresult r = enc(&p.amap[id], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations, phase %d) failed: %d", id, (int)r); return MV2_E_CUDA; }
+      }
+  // ---- taps ----
+  p.ntaps = a->kt * a->kh * a->kw;
+  for (int dt = 0; dt < a->kt; ++dt)
+    for (int dh = 0; dh < a->kh; ++dh)
+      for (int dw = 0; dw < a->kw; ++dw) {
+        const int tap = (dt * a->kh + dh) * a->kw + dw;
+        const int ot = dt - a->pt, oh = dh - a->ph, ow = dw - a->pw;
+        const int pt = ((ot % st) + st) % st, ph = ((oh % sh) + sh) % sh, pw = ((ow % sw) + sw) % sw;
+        p.tap_map[tap] = (int8_t)((pt * sh + ph) * sw + pw);
+        p.tap_dt[tap] = (int8_t)floor_div(ot, st);
+        p.tap_dh[tap] = (int8_t)floor_div(oh, sh);
+        p.tap_dw[tap] = (int8_t)floor_div(ow, sw);
+      }
+  // ---- weights map: [Co][taps * Ci] K-major ----
+  {
+    const int64_t K = (int64_t)p.ntaps * a->Ci;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)a->Co};
+    cuuint64_t strides[1] = {(cuuint64_t)(K * 2)};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a->w, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return MV2_E_CUDA; }
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 16 + 1024;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
+  MV2_CHECK_ARG(smem <= 227 * 1024);
+  dim3 grid((unsigned)((int64_t)a->B * p.tt * p.th * p.tw), (unsigned)ceil_div(a->Co, bn));
+  tc_conv_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(p);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+}  // extern "C"

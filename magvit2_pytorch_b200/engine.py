@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_ELU, ACT_NONE, ACT_SILU, MV2_BF16, MV2_F32, SHUFFLE_NONE, SHUFFLE_SPACE,
-                   SHUFFLE_TIME, AttnArgs, ConvArgs, check)
+                   SHUFFLE_TIME, AttnArgs, ConvArgs, TcConvArgs, check)
 
 
 def _dt(t: torch.dtype) -> int:
@@ -39,18 +39,32 @@ class ConvPack:
     k: Tuple[int, int, int]
     Ci: int
     Co: int
-    w_tc: Optional[torch.Tensor] = None   # [Co_pad][taps*Ci_pad] bf16, K-major (tcgen05 path)
+    w_tc: Optional[torch.Tensor] = None      # [Co][taps*Ci] bf16, K-major (tcgen05 path); rows permuted for shuffles
+    bias_tc: Optional[torch.Tensor] = None   # bias in w_tc's row order
 
 
-def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype, k=None) -> ConvPack:
-    """weight: torch layout (Co, Ci, *kernel).  Kernel dims are mapped onto (kt, kh, kw) by `k`."""
+def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype, k=None, shuffle_q: int = 1) -> ConvPack:
+    """weight: torch layout (Co, Ci, *kernel).  Kernel dims are mapped onto (kt, kh, kw) by `k`.
+    shuffle_q = 4 / 2 for the depth-to-space / depth-to-time up-samplers: the tcgen05 kernel wants output
+    rows ordered (q, c) instead of the reference's (c, q) so shuffled stores are channel-contiguous."""
     Co, Ci = weight.shape[:2]
     if k is None:
         ks = tuple(weight.shape[2:])
         k = (1,) * (3 - len(ks)) + ks
-    w = weight.detach().reshape(Co, Ci, -1).permute(2, 1, 0).contiguous().to(dtype)
+    w3 = weight.detach().reshape(Co, Ci, -1)
+    w = w3.permute(2, 1, 0).contiguous().to(dtype)
     b = None if bias is None else bias.detach().float().contiguous()
-    return ConvPack(w=w, bias=b, k=tuple(int(v) for v in k), Ci=int(Ci), Co=int(Co))
+    pk = ConvPack(w=w, bias=b, k=tuple(int(v) for v in k), Ci=int(Ci), Co=int(Co))
+    if dtype == torch.bfloat16:
+        wt = w3.permute(0, 2, 1).reshape(Co, -1)                      # [Co][tap*Ci + ci]
+        bt = b
+        if shuffle_q > 1:
+            cy = Co // shuffle_q
+            wt = wt.reshape(cy, shuffle_q, -1).permute(1, 0, 2).reshape(Co, -1)
+            bt = None if b is None else b.reshape(cy, shuffle_q).t().reshape(Co).contiguous()
+        pk.w_tc = wt.contiguous().to(torch.bfloat16)
+        pk.bias_tc = bt
+    return pk
 
 
 class Engine:
@@ -62,7 +76,11 @@ class Engine:
         self._packs: Dict[str, object] = {}
         self._sig = None
         self.launches = 0            # kernels launched through the C ABI (bench's gpu_launches)
+        self.use_tc = True           # bf16: dense contractions on tcgen05 (False -> CUDA-core cross-check path)
+        self.tc_calls = 0
+        self.simt_conv_calls = 0
         self.taps: Optional[dict] = None  # when set, per-stage activations are recorded (tests)
+        self._prof: Optional[list] = None  # when set, (event0, event1, flops) per tcgen05 conv launch
 
     # ------------------------------------------------------------------ parameters
     def _signature(self):
@@ -139,12 +157,12 @@ class Engine:
                     if side == "enc":
                         P[key] = pack_conv(mod.conv.weight, mod.conv.bias, dt)                     # (Co,Ci,3,3) -> k=(1,3,3)
                     else:
-                        P[key] = pack_conv(mod.net[0].weight, mod.net[0].bias, dt)                 # (4Co,Ci,1,1)
+                        P[key] = pack_conv(mod.net[0].weight, mod.net[0].bias, dt, shuffle_q=4)    # (4Co,Ci,1,1)
                 elif st.kind == "compress_time":
                     if side == "enc":
                         P[key] = pack_conv(mod.conv.weight, mod.conv.bias, dt, k=(3, 1, 1))        # Conv1d (Co,Ci,3)
                     else:
-                        P[key] = pack_conv(mod.net[0].weight, mod.net[0].bias, dt, k=(1, 1, 1))    # Conv1d (2Co,Ci,1)
+                        P[key] = pack_conv(mod.net[0].weight, mod.net[0].bias, dt, k=(1, 1, 1), shuffle_q=2)  # Conv1d (2Co,Ci,1)
                 elif st.kind == "attend_space":
                     pack_attn(mod[0].fn, key + ".attn")
                     pack_ff(mod[1].fn, key + ".ff")
@@ -187,6 +205,23 @@ class Engine:
             y = self._new((B, To, Ho, Wo, pk.Co))
         if res is not None:
             assert res.shape == y.shape and res.dtype == y.dtype and res.is_contiguous()
+        if self.dtype == torch.bfloat16 and self.use_tc and pk.w_tc is not None and not token_shift:
+            ta = TcConvArgs(x=_ptr(x), w=_ptr(pk.w_tc), bias=_ptr(pk.bias_tc), res=_ptr(res), y=_ptr(y),
+                            B=B, Ti=Ti, Hi=Hi, Wi=Wi, Ci=Ci, To=To, Ho=Ho, Wo=Wo, Co=pk.Co,
+                            kt=kt, kh=kh, kw=kw, st=stride[0], sh=stride[1], sw=stride[2],
+                            pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle)
+            if self.lib.mv2_tc_conv_supported(C.byref(ta)):
+                if self._prof is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                check(self.lib.mv2_tc_conv_forward(C.byref(ta), self._stream()), "mv2_tc_conv_forward")
+                if self._prof is not None:
+                    e1.record()
+                    self._prof.append((e0, e1, 2.0 * B * To * Ho * Wo * pk.Co * Ci * kt * kh * kw))
+                self.launches += 1
+                self.tc_calls += 1
+                return y
+        self.simt_conv_calls += 1
         a = ConvArgs(x=_ptr(x), w=_ptr(pk.w), bias=_ptr(pk.bias), res=_ptr(res), y=_ptr(y), dtype=_dt(self.dtype),
                      B=B, Ti=Ti, Hi=Hi, Wi=Wi, Ci=Ci, To=To, Ho=Ho, Wo=Wo, Co=pk.Co,
                      kt=kt, kh=kh, kw=kw, st=stride[0], sh=stride[1], sw=stride[2],
@@ -267,6 +302,25 @@ class Engine:
                                             _ptr(ws), self._stream()), "mv2_linear_attention")
         self.launches += 2
         return self.conv(o, p["out"], res=x)
+
+    def profile_convs(self, fn, steps: int = 3):
+        """Runs fn() `steps` times with CUDA events around every tcgen05 conv launch (on the launching
+        stream).  Returns (kernel ms per step, launches per step, algorithmic FLOPs per step)."""
+        fn()
+        torch.cuda.synchronize(self.device)
+        self._prof = []
+        try:
+            for _ in range(steps):
+                fn()
+            torch.cuda.synchronize(self.device)
+            ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self._prof)
+            fl = sum(f for _, _, f in self._prof)
+            n = len(self._prof)
+        finally:
+            self._prof = None
+        if n == 0:
+            return None, 0, 0.0
+        return ms / steps, n // steps, fl / steps
 
     # ------------------------------------------------------------------ stages
     def _stage(self, x, st, key, decoder: bool):
