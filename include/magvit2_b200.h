@@ -59,6 +59,12 @@ int mv2_to_channels_last(const void* src, int src_dtype, void* dst, int dst_dtyp
                          int B, int C, int T, int H, int W, int t_pad, void* stream);
 int mv2_to_channels_first(const void* src, int src_dtype, void* dst, int dst_dtype,
                           int B, int C, int T, int H, int W, int t_crop, void* stream);
+/* mv2_ingest_kwpack: ingest for the tensor-core conv_in (M:1109, 7x7x7 with C_in = 3): besides the layout change and
+ *   the time_padding zero frames it packs the k_w taps into the channel axis,
+ *   dst[b][t+t_pad][h][w][dw*C + c] = src[b][c][t][h][w + dw - pw]  (bf16, cpack channels, zero padded),
+ *   so conv_in becomes a (k_t x k_h x 1)-tap implicit GEMM over cpack = 32 channels.                            */
+int mv2_ingest_kwpack(const void* src, int src_dtype, void* dst, int B, int C, int T, int H, int W,
+                      int t_pad, int kw, int pw, int cpack, void* stream);
 
 /* ---- convolution family (CUDA-core fp32-accumulate path; any shape) -----------
  * One generic strided N-d convolution over channels-last activations with a fused
@@ -188,9 +194,17 @@ typedef struct mv2_tc_conv_args {
   int32_t pt, ph, pw;
   int32_t act;
   int32_t shuffle;
+  int32_t epi_mode;    /* 0 plain; 1 fused GEGLU (M:466-469): packed columns come in groups of 16 = 8 x-columns then
+                          their 8 gate-columns, output has Co/2 channels: y = gelu_erf(gate) * x */
 } mv2_tc_conv_args;
 int mv2_tc_conv_supported(const mv2_tc_conv_args* a);
 int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream);
+/* "Slab" variant for stride-1 convs with an in-plane kernel (the causal 3x3x3 residual convs): persistent
+ * CTAs, one haloed activation slab per (frame, 64-channel slice) staged in shared memory once and reused by
+ * all k_h*k_w in-plane taps, two 128-position M-tiles sharing each weight tile, double-buffered TMEM
+ * accumulators.  Requirements (mv2_tc_slab_supported): stride 1, Ci % 64 == 0, Co % 32 == 0, no shuffle.   */
+int mv2_tc_slab_supported(const mv2_tc_conv_args* a);
+int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream);
 
 #ifdef __cplusplus
 }

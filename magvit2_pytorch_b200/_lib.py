@@ -53,7 +53,7 @@ class TcConvArgs(C.Structure):
         ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
         ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
         ("pt", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
-        ("act", C.c_int32), ("shuffle", C.c_int32),
+        ("act", C.c_int32), ("shuffle", C.c_int32), ("epi_mode", C.c_int32),
     ]
 
 
@@ -65,6 +65,7 @@ SIGNATURES = {
     "mv2_device_arch": (_I, []),
     "mv2_to_channels_last": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mv2_to_channels_first": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mv2_ingest_kwpack": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mv2_conv_forward": (_I, [C.POINTER(ConvArgs), _VP]),
     "mv2_se_workspace_bytes": (_SZ, [_I, _I, _I]),
     "mv2_se_pool": (_I, [_VP, _I, _I, _I, _I, _VP, _F, _VP, _VP]),
@@ -82,6 +83,8 @@ SIGNATURES = {
     "mv2_lfq_entropy_partials": (_I, [_VP, _I64, _I, _F, _VP, _VP, _VP]),
     "mv2_tc_conv_supported": (_I, [C.POINTER(TcConvArgs)]),
     "mv2_tc_conv_forward": (_I, [C.POINTER(TcConvArgs), _VP]),
+    "mv2_tc_slab_supported": (_I, [C.POINTER(TcConvArgs)]),
+    "mv2_tc_slab_forward": (_I, [C.POINTER(TcConvArgs), _VP]),
 }
 
 _lib = None

@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=../libmagvit2_b200.so
 SRCS="simt_ops.cu"
-[ -f tc_conv.cu ] && SRCS="$SRCS tc_conv.cu"
+SRCS="$SRCS tc_conv.cu tc_slab.cu"
 $NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
   -Xcompiler -fPIC -shared -Xptxas -v \
   -o $OUT $SRCS 2> build.log || { grep -E "error|fatal" -A3 build.log | head -40; exit 1; }

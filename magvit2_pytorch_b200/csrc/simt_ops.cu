@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <mutex>
+#include <algorithm>
 
 namespace mv2 {
 
@@ -96,6 +97,45 @@ static int dispatch_transpose(const void* src, int sd, void* dst, int dd, int B,
     return launch_transpose<__nv_bfloat16, __nv_bfloat16>(src, dst, B, R, S, src_S_total, dst_S_total, s_off_src, s_off_dst, src_is_rs, st);
   set_error("unsupported dtype pair %d -> %d", sd, dd);
   return MV2_E_ARG;
+}
+
+
+// Video ingest for the tcgen05 conv_in: packs the k_w taps of the (tiny-channel) input into the channel axis so the
+// 7x7x7, C_in = 3 conv becomes a (7x7x1)-tap conv over 32 "channels":
+//   dst[b][t + t_pad][h][w][dw * C + c] = src[b][c][t][h][w + dw - pw]   (0 outside the image / for padded channels)
+// One thread writes 8 channels (16 B).
+template <typename TS>
+__global__ void __launch_bounds__(256) ingest_kwpack_kernel(const TS* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                            int B, int C, int T, int H, int W, int t_pad, int kw, int pw,
+                                                            int cpack) {
+  const int groups = cpack >> 3;
+  const int64_t total = (int64_t)B * (T + t_pad) * H * W * groups;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    int64_t r = idx / groups;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int t = (int)(r % (T + t_pad)); r /= (T + t_pad);
+    const int b = (int)r;
+    const int ts = t - t_pad;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = g * 8 + q;
+      const int dw = j / C, c = j - dw * C;
+      const int ws = w + dw - pw;
+      float x = 0.f;
+      if (ts >= 0 && dw < kw && ws >= 0 && ws < W)
+        x = to_f32<TS>(src[((((int64_t)b * C + c) * T + ts) * H + h) * W + ws]);
+      v[q] = x;
+    }
+    uint4 o;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(dst + idx * 8) = o;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -808,6 +848,22 @@ int mv2_to_channels_first(const void* src, int src_dtype, void* dst, int dst_dty
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t HW = (int64_t)H * W, Ss = (int64_t)T * HW, S = (int64_t)(T - t_crop) * HW;
   return dispatch_transpose(src, src_dtype, dst, dst_dtype, B, C, S, Ss, S, (int64_t)t_crop * HW, 0, false, st);
+}
+
+int mv2_ingest_kwpack(const void* src, int src_dtype, void* dst, int B, int C, int T, int H, int W, int t_pad, int kw,
+                      int pw, int cpack, void* stream) {
+  MV2_CHECK_ARG(src && dst && B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && t_pad >= 0 && kw > 0);
+  MV2_CHECK_ARG(cpack % 8 == 0 && kw * C <= cpack);
+  const int64_t total = (int64_t)B * (T + t_pad) * H * W * (cpack / 8);
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_dtype == MV2_F32)
+    ingest_kwpack_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
+  else if (src_dtype == MV2_BF16)
+    ingest_kwpack_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
+  else { set_error("bad dtype %d", src_dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
 }
 
 int mv2_conv_forward(const mv2_conv_args* a, void* stream) {

@@ -1,0 +1,238 @@
+// Shared device-side PTX wrappers (mbarrier / TMA / tcgen05 / TMEM) and host-side tensor-map helpers for the
+// tcgen05 kernels (tc_conv.cu, tc_slab.cu).  sm_100a only.
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace mv2 {
+
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]   (kind::f16: bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major operand with hardware swizzle.
+//   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (ignored for swizzled K-major)
+//   bits [32,46) stride byte offset >> 4   (8 rows x row bytes)     bits [46,48) version = 1 (sm_100)
+//   bits [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
+  const uint32_t sbo = 8 * row_bytes;
+  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+
+// same, with an explicit stride-byte-offset (distance between consecutive 8-row core groups), SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t saddr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+
+
+// ------------------------------------------------------------------------------------------
+// shared epilogue: fp32 accumulator chunk -> bias -> activation -> (GEGLU | shuffle) -> residual -> bf16 store
+// ------------------------------------------------------------------------------------------
+struct TcEpi {
+  const float* bias;             // global, packed column order (only used to decide has-bias; values come from smem)
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+  int act, shuffle, mode;        // mode 0 plain; 1 GEGLU: packed cols [16g, 16g+8) = x, [16g+8, 16g+16) = gate (M:466-469)
+  int Co;                        // packed GEMM output columns
+  int To, Ho, Wo;                // output volume before any depth-to-space/time shuffle
+};
+
+// bf16 outputs carry 8 mantissa bits, so the fast exp intrinsic (2 ulp fp32) is exact enough here.
+__device__ __forceinline__ float fast_act(float x, int act) {
+  if (act == MV2_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
+  if (act == MV2_ACT_SILU) return __fdividef(x, 1.f + __expf(-x));
+  return x;
+}
+
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)[8]) {
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+
+// r: 32 raw accumulator columns of ONE output row (position b,to,ho,wo); n = first packed column; sb = smem bias of
+// these columns (always valid memory; zeros when there is no bias).
+__device__ __forceinline__ void epi_chunk32(const TcEpi& e, const uint32_t (&r)[32], int ncols, int n, const float* sb,
+                                            int b, int to, int ho, int wo) {
+  if (e.mode == 1) {
+    const int I = e.Co >> 1;
+    const int64_t pos = (((int64_t)b * e.To + to) * e.Ho + ho) * e.Wo + wo;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      if (g * 16 >= ncols || n + g * 16 >= e.Co) break;
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float xv = __uint_as_float(r[g * 16 + q]) + sb[g * 16 + q];
+        const float gt = __uint_as_float(r[g * 16 + 8 + q]) + sb[g * 16 + 8 + q];
+        v[q] = 0.5f * gt * (1.f + erff(gt * 0.70710678118654752440f)) * xv;
+      }
+      store8_bf16(e.y + pos * I + ((n + g * 16) >> 1), v);
+    }
+    return;
+  }
+  const int cy = e.shuffle == MV2_SHUFFLE_SPACE ? (e.Co >> 2) : (e.shuffle == MV2_SHUFFLE_TIME ? (e.Co >> 1) : e.Co);
+  const bool vec_ok = (cy & 7) == 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int ng = n + g * 8;
+    if (g * 8 >= ncols || ng >= e.Co) break;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = fast_act(__uint_as_float(r[g * 8 + q]) + sb[g * 8 + q], e.act);
+    int64_t off;
+    if (e.shuffle == MV2_SHUFFLE_SPACE) {
+      const int qd = ng / cy, c = ng - qd * cy, p1 = qd >> 1, p2 = qd & 1;
+      off = ((((int64_t)b * e.To + to) * (2 * e.Ho) + (2 * ho + p1)) * (2 * e.Wo) + (2 * wo + p2)) * cy + c;
+    } else if (e.shuffle == MV2_SHUFFLE_TIME) {
+      const int qd = ng / cy, c = ng - qd * cy;
+      off = ((((int64_t)b * (2 * e.To) + (2 * to + qd)) * e.Ho + ho) * e.Wo + wo) * cy + c;
+    } else {
+      off = ((((int64_t)b * e.To + to) * e.Ho + ho) * e.Wo + wo) * e.Co + ng;
+    }
+    if (vec_ok && ng + 8 <= e.Co) {
+      if (e.res) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(e.res + off);
+        const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __bfloat1622float2(rb[q]);
+          v[2 * q] += f.x;
+          v[2 * q + 1] += f.y;
+        }
+      }
+      store8_bf16(e.y + off, v);
+    } else {
+      for (int q = 0; q < 8 && ng + q < e.Co; ++q) {   // scalar tail (Co % 8 != 0, e.g. conv_out's 3 channels)
+        float x = v[q];
+        if (e.res) x += __bfloat162float(e.res[off + q]);
+        e.y[off + q] = __float2bfloat16_rn(x);
+      }
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+static inline int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+static inline int floor_div(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
+
+
+}  // namespace mv2

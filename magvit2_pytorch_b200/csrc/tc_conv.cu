@@ -17,111 +17,13 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
 // tcgen05.mma issuer, warps 2-5 = epilogue (tcgen05.ld -> bias/activation/residual -> global).
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <cuda.h>
 #include <mutex>
 #include <algorithm>
 #include <string.h>
 
 namespace mv2 {
-
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]   (kind::f16: bf16 inputs, fp32 accumulate)
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory matrix descriptor, K-major operand with hardware swizzle.
-//   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (ignored for swizzled K-major)
-//   bits [32,46) stride byte offset >> 4   (8 rows x row bytes)     bits [46,48) version = 1 (sm_100)
-//   bits [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t row_bytes) {
-  const uint32_t sbo = 8 * row_bytes;
-  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(sbo >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= layout << 61;
-  return d;
-}
 
 // ------------------------------------------------------------------------------------------
 // kernel
@@ -138,18 +40,10 @@ struct alignas(64) TcParams {
   int B, To, Ho, Wo, Co;
   int bt, bh, bw, tt, th, tw;
   int bn, stages, tmem_cols;
-  int act, shuffle;
-  const float* bias;
-  const __nv_bfloat16* res;
-  __nv_bfloat16* y;
+  TcEpi epi;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-__global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,6 +56,7 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
   // barriers: full[s] at +8s, empty[s] at +8(S+s), tmem_full at +16S, tmem slot at +16S+8
   const uint32_t full0 = bar_base, empty0 = bar_base + 8 * p.stages, tfull = bar_base + 16 * p.stages;
   const uint32_t tslot = tfull + 8;
+  float* sbias = reinterpret_cast<float*>(smem_raw + (tslot + 8 - smem_u32(smem_raw)));   // bn floats
 
   // tile coordinates
   int tile = blockIdx.x;
@@ -185,6 +80,8 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
     tma_prefetch_desc(&p.amap[0]);
   }
   if (warp == 1) tmem_alloc(tslot, p.tmem_cols);
+  if (warp >= 2)
+    for (int i = threadIdx.x - 64; i < p.bn; i += 128) sbias[i] = (p.epi.bias && n0 + i < p.Co) ? p.epi.bias[n0 + i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -236,63 +133,12 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
     mbar_wait(tfull, 0);
     tc_fence_after();
     const uint32_t tlane = tmem_base + ((uint32_t)(sub * 32) << 16);
-    const int64_t pos = (((int64_t)b * p.To + to) * p.Ho + ho) * p.Wo + wo;
-    const int cy = p.shuffle == MV2_SHUFFLE_SPACE ? (p.Co >> 2) : (p.shuffle == MV2_SHUFFLE_TIME ? (p.Co >> 1) : p.Co);
-    const bool vec_ok = (cy % 8) == 0;
     for (int c0 = 0; c0 < p.bn; c0 += 32) {
       uint32_t r[32];
       if (p.bn - c0 >= 32) tmem_ld_32x32b_x32(tlane + c0, r);
       else tmem_ld_32x32b_x16(tlane + c0, r);
       tmem_ld_wait();
-      const int ncols = min(32, p.bn - c0);
-      if (!row_ok) continue;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (g * 8 >= ncols) break;
-        const int n = n0 + c0 + g * 8;   // first (packed) output column of this group of 8
-        if (n >= p.Co) break;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float x = __uint_as_float(r[g * 8 + j]);
-          if (p.bias && n + j < p.Co) x += p.bias[n + j];
-          v[j] = apply_act(x, p.act);
-        }
-        // destination of packed column n: the host permutes weight rows so that shuffled stores are channel-contiguous
-        int64_t off;
-        if (p.shuffle == MV2_SHUFFLE_SPACE) {
-          const int q = n / cy, c = n - q * cy, p1 = q >> 1, p2 = q & 1;
-          off = ((((int64_t)b * p.To + to) * (2 * p.Ho) + (2 * ho + p1)) * (2 * p.Wo) + (2 * wo + p2)) * cy + c;
-        } else if (p.shuffle == MV2_SHUFFLE_TIME) {
-          const int q = n / cy, c = n - q * cy;
-          off = ((((int64_t)b * (2 * p.To) + (2 * to + q)) * p.Ho + ho) * p.Wo + wo) * cy + c;
-        } else {
-          off = pos * p.Co + n;
-        }
-        if (vec_ok && n + 8 <= p.Co) {
-          if (p.res) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(p.res + off);
-            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(rb[j]);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
-            }
-          }
-          uint4 o;
-          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(p.y + off) = o;
-        } else {
-          for (int j = 0; j < 8 && n + j < p.Co; ++j) {
-            // scalar tail (Co not a multiple of 8, e.g. conv_out's 3 channels); no shuffle support needed here
-            float x = v[j];
-            if (p.res) x += __bfloat162float(p.res[off + j]);
-            p.y[off + j] = __float2bfloat16_rn(x);
-          }
-        }
-      }
+      if (row_ok) epi_chunk32(p.epi, r, min(32, p.bn - c0), n0 + c0, sbias + c0, b, to, ho, wo);
     }
   }
   tc_fence_before();
@@ -306,26 +152,6 @@ __global__ void __launch_bounds__(192) tc_conv_kernel(const __grid_constant__ Tc
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)f;
-  });
-  return fn;
-}
-
-static int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
-static int floor_div(int a, int b) { int q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
-
 }  // namespace mv2
 
 using namespace mv2;
@@ -339,6 +165,8 @@ int mv2_tc_conv_supported(const mv2_tc_conv_args* a) {
   if (a->st < 1 || a->st > 2 || a->sh < 1 || a->sh > 2 || a->sw < 1 || a->sw > 2) return 0;
   if (a->shuffle != MV2_SHUFFLE_NONE && ((a->shuffle == MV2_SHUFFLE_SPACE ? a->Co / 4 : a->Co / 2) % 8 != 0)) return 0;
   if (a->res && a->Co % 8 != 0) return 0;
+  if (a->epi_mode == 1 && (a->Co % 32 != 0 || a->shuffle != MV2_SHUFFLE_NONE || a->res)) return 0;   // GEGLU pairs
+  if (a->epi_mode != 0 && a->epi_mode != 1) return 0;
   return 1;
 }
 
@@ -376,8 +204,9 @@ int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream) {
   stages = std::max(2, std::min(stages, 8));
   stages = std::max(1, std::min(stages, a->kt * a->kh * a->kw * (a->Ci / bk)));
   p.stages = stages;
-  p.act = a->act; p.shuffle = a->shuffle;
-  p.bias = a->bias; p.res = (const __nv_bfloat16*)a->res; p.y = (__nv_bfloat16*)a->y;
+  p.epi.bias = a->bias; p.epi.res = (const __nv_bfloat16*)a->res; p.epi.y = (__nv_bfloat16*)a->y;
+  p.epi.act = a->act; p.epi.shuffle = a->shuffle; p.epi.mode = a->epi_mode; p.epi.Co = a->Co;
+  p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo;
 
   // ---- activation tensor maps: one per stride-parity phase ----
   const int st = a->st, sh = a->sh, sw = a->sw;
@@ -426,7 +255,7 @@ int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return MV2_E_CUDA; }
   }
-  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 16 + (size_t)bn * 4 + 1024;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {

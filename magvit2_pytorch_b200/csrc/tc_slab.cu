@@ -1,0 +1,303 @@
+// tcgen05 "slab" implicit-GEMM kernel for stride-1 k_t x k_h x k_w convolutions (the causal 3x3x3 residual
+// convs = 82 % of the path's FLOPs), bf16 in / fp32 accumulate in TMEM, persistent CTAs.
+//
+// Why a second kernel: tc_conv.cu reloads the activation tile from L2 once per tap (27x) and the weight tile
+// once per 128 output positions; on B200 that makes the C=64/128 levels L2-bandwidth bound (measured 171 / 343
+// TFLOP/s).  Here
+//   * one TMA box load brings a haloed activation slab  {64 ch, 8*mw+2, 16+2} (one frame, one 64-channel
+//     slice) into shared memory ONCE and all k_h*k_w in-plane taps are fed from it: the UMMA A-descriptor is
+//     simply started (dh*pitch + dw) rows further into the slab (128-byte rows, hardware SWIZZLE_128B is a
+//     function of the absolute smem address, so row-shifted starts stay consistent with what TMA wrote;
+//     8-row core groups are 8 consecutive w positions, group stride (SBO) = slab row pitch);
+//   * a macro tile is mw (1|2) M-tiles of 16(h) x 8(w) positions side by side; both M-tiles consume the same
+//     weight tile from smem (two accumulators in TMEM), halving weight traffic;
+//   * CTAs are persistent (static round-robin over macro tiles), accumulators are double-buffered in TMEM
+//     when they fit (2 * mw * BN <= 512 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * causal frames in front of the clip (t + dt - pt < 0) are all-zero and are skipped outright.
+// Warp roles (256 threads): w0 slab TMA producer, w1 MMA issuer (+TMEM alloc), w2 weight TMA producer,
+// w4-7 epilogue (TMEM lanes 32*(w%4)..+31).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cuda.h>
+#include <algorithm>
+#include <mutex>
+#include <string.h>
+
+namespace mv2 {
+
+struct alignas(64) SlabParams {
+  CUtensorMap amap;
+  CUtensorMap wmap;
+  int kt, kh, kw, pt, ph, pw;
+  int Ci, kchunks;
+  int B, T, H, W, Co;
+  int mw, pitch, slab_h, slab_bytes, slab_stride;
+  int bn, n_tiles_n, tiles_w, tiles_h, total_tiles;
+  int slab_stages, w_stages, nbuf;
+  TcEpi epi;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct TileCoord { int b, t, h0, w0, n0; };
+__device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) {
+  TileCoord c;
+  const int nt = tile % p.n_tiles_n; tile /= p.n_tiles_n;
+  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+  const int th = tile % p.tiles_h; tile /= p.tiles_h;
+  c.t = tile % p.T;
+  c.b = tile / p.T;
+  c.h0 = th * 16;
+  c.w0 = tw * 8 * p.mw;
+  c.n0 = nt * p.bn;
+  return c;
+}
+
+__global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__ SlabParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_bytes = p.bn * 128;
+  const uint32_t slab0 = smem_base;
+  const uint32_t wst0 = smem_base + p.slab_stages * p.slab_stride;
+  const uint32_t bar0 = wst0 + p.w_stages * w_bytes;
+  // barrier table (8 bytes each)
+  const uint32_t slab_full = bar0, slab_empty = slab_full + 8 * p.slab_stages;
+  const uint32_t w_full = slab_empty + 8 * p.slab_stages, w_empty = w_full + 8 * p.w_stages;
+  const uint32_t t_full = w_empty + 8 * p.w_stages, t_empty = t_full + 8 * 2;
+  const uint32_t tslot = t_empty + 8 * 2;
+  float* sbias = reinterpret_cast<float*>(smem_raw + (tslot + 8 - smem_u32(smem_raw)));   // Co floats
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.slab_stages; ++s) { mbar_init(slab_full + 8 * s, 1); mbar_init(slab_empty + 8 * s, 1); }
+    for (int s = 0; s < p.w_stages; ++s) { mbar_init(w_full + 8 * s, 1); mbar_init(w_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(t_full + 8 * s, 1); mbar_init(t_empty + 8 * s, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.amap);
+  if (warp == 2 && lane == 0) tma_prefetch_desc(&p.wmap);
+  if (warp == 1) tmem_alloc(tslot, 512);
+  if (warp >= 4)
+    for (int i = threadIdx.x - 128; i < p.Co; i += 128) sbias[i] = p.epi.bias ? p.epi.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+
+  const int taps2d = p.kh * p.kw;
+  const int acc_cols = p.mw * p.bn;   // TMEM columns of one accumulator buffer
+
+  if (warp == 0) {
+    // ------------------------------ slab producer ------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile(p, tile);
+        const int dt0 = max(0, p.pt - c.t);
+        for (int dt = dt0; dt < p.kt; ++dt)
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            const uint32_t s = it % p.slab_stages, ph = (it / p.slab_stages) & 1;
+            mbar_wait(slab_empty + 8 * s, ph ^ 1);
+            mbar_expect_tx(slab_full + 8 * s, p.slab_bytes);
+            tma_load_5d(slab0 + s * p.slab_stride, &p.amap, slab_full + 8 * s, kc * 64, c.w0 - p.pw, c.h0 - p.ph,
+                        c.t + dt - p.pt, c.b);
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------ weight producer ------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile(p, tile);
+        const int dt0 = max(0, p.pt - c.t);
+        for (int dt = dt0; dt < p.kt; ++dt)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            for (int tp = 0; tp < taps2d; ++tp, ++it) {
+              const uint32_t s = it % p.w_stages, ph = (it / p.w_stages) & 1;
+              mbar_wait(w_empty + 8 * s, ph ^ 1);
+              mbar_expect_tx(w_full + 8 * s, w_bytes);
+              tma_load_2d(wst0 + s * w_bytes, &p.wmap, w_full + 8 * s, (dt * taps2d + tp) * p.Ci + kc * 64, c.n0);
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t sbo = (uint32_t)p.pitch * 128;
+      uint32_t sit = 0, wit = 0, tit = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tit) {
+        const TileCoord c = decode_tile(p, tile);
+        const int dt0 = max(0, p.pt - c.t);
+        const uint32_t buf = tit % p.nbuf;
+        mbar_wait(t_empty + 8 * buf, ((tit / p.nbuf) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * acc_cols;
+        bool first = true;
+        for (int dt = dt0; dt < p.kt; ++dt)
+          for (int kc = 0; kc < p.kchunks; ++kc, ++sit) {
+            const uint32_t s = sit % p.slab_stages;
+            mbar_wait(slab_full + 8 * s, (sit / p.slab_stages) & 1);
+            tc_fence_after();
+            const uint32_t slab = slab0 + s * p.slab_stride;
+            for (int tp = 0; tp < taps2d; ++tp, ++wit) {
+              const uint32_t ws = wit % p.w_stages;
+              mbar_wait(w_full + 8 * ws, (wit / p.w_stages) & 1);
+              tc_fence_after();
+              const int dh = tp / p.kw, dw = tp - dh * p.kw;
+              const uint64_t bd = make_kmajor_desc_sbo(wst0 + ws * w_bytes, 1024);
+              for (int j = 0; j < p.mw; ++j) {
+                const uint64_t ad = make_kmajor_desc_sbo(slab + (uint32_t)(dh * p.pitch + 8 * j + dw) * 128, sbo);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(acc + j * p.bn, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+              }
+              first = false;
+              umma_commit(w_empty + 8 * ws);
+            }
+            umma_commit(slab_empty + 8 * s);
+          }
+        umma_commit(t_full + 8 * buf);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int sub = warp & 3;
+    const int row = sub * 32 + lane;
+    const int lh = row >> 3, lw = row & 7;
+    uint32_t tit = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tit) {
+      const TileCoord c = decode_tile(p, tile);
+      const uint32_t buf = tit % p.nbuf;
+      mbar_wait(t_full + 8 * buf, (tit / p.nbuf) & 1);
+      tc_fence_after();
+      const int h = c.h0 + lh;
+      for (int j = 0; j < p.mw; ++j) {
+        const int w = c.w0 + 8 * j + lw;
+        const bool row_ok = h < p.H && w < p.W;
+        const uint32_t tl = tmem_base + buf * acc_cols + j * p.bn + ((uint32_t)(sub * 32) << 16);
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tl + c0, r);
+          tmem_ld_wait();
+          if (row_ok) epi_chunk32(p.epi, r, 32, c.n0 + c0, sbias + c.n0 + c0, c.b, c.t, h, w);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace mv2
+
+using namespace mv2;
+
+extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
+  if (!a) return 0;
+  if (a->st != 1 || a->sh != 1 || a->sw != 1) return 0;
+  if (a->Ci % 64 != 0 || a->Co % 32 != 0 || a->Co > 2048 || a->epi_mode != 0) return 0;
+  if (a->shuffle != MV2_SHUFFLE_NONE) return 0;
+  if (a->kh * a->kw < 2) return 0;                       // nothing to reuse for 1x1 in-plane kernels
+  if (a->kh > 3 || a->kw > 3 || a->kt > 8) return 0;
+  if (a->To != a->Ti || a->Ho != a->Hi || a->Wo != a->Wi) return 0;
+  return 1;
+}
+
+extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
+  MV2_CHECK_ARG(a && a->x && a->w && a->y);
+  if (!mv2_tc_slab_supported(a)) { set_error("mv2_tc_slab_forward: unsupported shape"); return MV2_E_UNSUPPORTED; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MV2_E_CUDA; }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+
+  SlabParams p;
+  memset(&p, 0, sizeof(p));
+  p.kt = a->kt; p.kh = a->kh; p.kw = a->kw; p.pt = a->pt; p.ph = a->ph; p.pw = a->pw;
+  p.Ci = a->Ci; p.kchunks = a->Ci / 64;
+  p.B = a->B; p.T = a->To; p.H = a->Ho; p.W = a->Wo; p.Co = a->Co;
+  p.epi.bias = a->bias; p.epi.res = (const __nv_bfloat16*)a->res; p.epi.y = (__nv_bfloat16*)a->y;
+  p.epi.act = a->act; p.epi.shuffle = MV2_SHUFFLE_NONE; p.epi.mode = 0; p.epi.Co = a->Co;
+  p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo;
+
+  // ---- tiling heuristic: maximise (wave efficiency) x (tensor-pipe efficiency) / (L2 traffic) ----
+  const int tiles_h = ceil_div(a->Ho, 16);
+  int best_mw = 1, best_bn = 32;
+  double best_score = -1.0;
+  for (int mw = 1; mw <= 2; ++mw) {
+    if (mw == 2 && a->Wo <= 8) continue;
+    for (int bn = 256; bn >= 32; bn >>= 1) {
+      if (bn > a->Co || a->Co % bn != 0) continue;
+      const int64_t units = (int64_t)a->B * a->To * tiles_h * ceil_div(a->Wo, 8 * mw) * (a->Co / bn);
+      const int64_t rounds = (units + n_sm - 1) / n_sm;
+      const double wave_eff = (double)units / (double)(rounds * n_sm);
+      const double n_eff = bn >= 128 ? 1.0 : (bn == 64 ? 0.85 : 0.6);   // small N: A re-read from smem per MMA
+      const double traffic = 1.0 / (128.0 * mw) + 1.3 / (9.0 * bn);      // L2 bytes per MAC (weights + slab)
+      const double score = wave_eff * n_eff / (1.0 + 40.0 * traffic);
+      if (score > best_score) { best_score = score; best_mw = mw; best_bn = bn; }
+    }
+  }
+  p.mw = best_mw; p.bn = best_bn;
+  p.n_tiles_n = a->Co / p.bn;
+  p.tiles_h = tiles_h;
+  p.tiles_w = ceil_div(a->Wo, 8 * p.mw);
+  p.total_tiles = (int)((int64_t)a->B * a->To * p.tiles_h * p.tiles_w * p.n_tiles_n);
+  p.pitch = 8 * p.mw + a->kw - 1;
+  p.slab_h = 16 + a->kh - 1;
+  p.slab_bytes = p.pitch * p.slab_h * 128;
+  p.slab_stride = (p.slab_bytes + 1023) / 1024 * 1024;
+  p.nbuf = (2 * p.mw * p.bn <= 512) ? 2 : 1;
+  const int w_bytes = p.bn * 128;
+  const int budget = 220 * 1024 - a->Co * 4;
+  p.slab_stages = p.slab_stride * 3 + w_bytes * 4 <= budget ? 3 : 2;
+  p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
+  MV2_CHECK_ARG(p.w_stages >= 2);
+
+  {
+    const int64_t C = a->Ci, W = a->Wi, H = a->Hi, T = a->Ti;
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)a->B};
+    cuuint64_t strides[4] = {(cuuint64_t)(C * 2), (cuuint64_t)(W * C * 2), (cuuint64_t)(H * W * C * 2), (cuuint64_t)(T * H * W * C * 2)};
+    cuuint32_t box[5] = {64, (cuuint32_t)p.pitch, (cuuint32_t)p.slab_h, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&p.amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)a->x, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(slab) failed: %d", (int)r); return MV2_E_CUDA; }
+  }
+  {
+    const int64_t K = (int64_t)a->kt * a->kh * a->kw * a->Ci;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)a->Co};
+    cuuint64_t strides[1] = {(cuuint64_t)(K * 2)};
+    cuuint32_t box[2] = {64, (cuuint32_t)p.bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a->w, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return MV2_E_CUDA; }
+  }
+  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 16 + (size_t)a->Co * 4 + 1024;
+  MV2_CHECK_ARG(smem <= 227 * 1024);
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
+  const int grid = std::min(p.total_tiles, n_sm);
+  tc_slab_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}

@@ -41,6 +41,10 @@ class ConvPack:
     Co: int
     w_tc: Optional[torch.Tensor] = None      # [Co][taps*Ci] bf16, K-major (tcgen05 path); rows permuted for shuffles
     bias_tc: Optional[torch.Tensor] = None   # bias in w_tc's row order
+    Ci_tc: int = 0                           # GEMM dims of the tcgen05 call (may be padded / re-paired)
+    Co_tc: int = 0
+    epi_mode: int = 0                        # 1: fused GEGLU (output has Co_tc // 2 channels)
+    k_tc: Optional[Tuple[int, int, int]] = None
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype, k=None, shuffle_q: int = 1) -> ConvPack:
@@ -64,6 +68,57 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype, k=None,
             bt = None if b is None else b.reshape(cy, shuffle_q).t().reshape(Co).contiguous()
         pk.w_tc = wt.contiguous().to(torch.bfloat16)
         pk.bias_tc = bt
+        pk.Ci_tc, pk.Co_tc, pk.k_tc = pk.Ci, pk.Co, pk.k
+    return pk
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def pack_ff(fc1_w, fc1_b, fc2_w, fc2_b, dtype):
+    """FeedForward weights (reference M:492-496).  tcgen05 layout: the hidden width I is padded to a multiple of 64,
+    fc1's rows are re-paired as [8 x-rows, their 8 gate-rows] per group of 16 so GEGLU (M:466-469) fuses into fc1's
+    epilogue, and fc2's K is zero-padded to match."""
+    fc1 = pack_conv(fc1_w, fc1_b, dtype)
+    fc2 = pack_conv(fc2_w, fc2_b, dtype)
+    if dtype == torch.bfloat16:
+        two_i, C_ = fc1_w.shape[:2]
+        I = two_i // 2
+        Ip = _round_up(I, 64)
+        w1 = fc1_w.detach().reshape(two_i, C_).float()
+        b1 = fc1_b.detach().float()
+        wx = torch.zeros((Ip, C_), device=w1.device)
+        wg = torch.zeros((Ip, C_), device=w1.device)
+        bx = torch.zeros((Ip,), device=w1.device)
+        bg = torch.zeros((Ip,), device=w1.device)
+        wx[:I], wg[:I], bx[:I], bg[:I] = w1[:I], w1[I:], b1[:I], b1[I:]
+        wp = torch.stack((wx.reshape(Ip // 8, 8, C_), wg.reshape(Ip // 8, 8, C_)), dim=1).reshape(2 * Ip, C_)
+        bp = torch.stack((bx.reshape(Ip // 8, 8), bg.reshape(Ip // 8, 8)), dim=1).reshape(2 * Ip)
+        fc1.w_tc, fc1.bias_tc = wp.contiguous().to(torch.bfloat16), bp.contiguous()
+        fc1.Ci_tc, fc1.Co_tc, fc1.epi_mode = int(C_), 2 * Ip, 1
+        w2 = fc2_w.detach().reshape(fc2_w.shape[0], I).float()
+        w2p = torch.zeros((w2.shape[0], Ip), device=w2.device)
+        w2p[:, :I] = w2
+        fc2.w_tc = w2p.contiguous().to(torch.bfloat16)
+        fc2.Ci_tc, fc2.Co_tc = Ip, int(w2.shape[0])
+    return fc1, fc2
+
+
+def pack_conv_in_kwpack(weight, bias, cpack=32):
+    """conv_in (M:1109) for the tcgen05 path: (Co, Cin, kt, kh, kw) -> [Co][(dt, dh)][dw * Cin + c], zero padded to
+    `cpack` channels -- pairs with mv2_ingest_kwpack."""
+    Co, Cin, kt, kh, kw = weight.shape
+    if Cin * kw > cpack:
+        return None
+    w = weight.detach().float().permute(0, 2, 3, 4, 1).reshape(Co, kt * kh, kw * Cin)
+    wp = torch.zeros((Co, kt * kh, cpack), device=w.device)
+    wp[:, :, :kw * Cin] = w
+    pk = ConvPack(w=None, bias=None, k=(kt, kh, 1), Ci=cpack, Co=int(Co))
+    pk.w_tc = wp.reshape(Co, kt * kh * cpack).contiguous().to(torch.bfloat16)
+    pk.bias_tc = None if bias is None else bias.detach().float().contiguous()
+    pk.Ci_tc, pk.Co_tc, pk.k_tc = cpack, int(Co), (kt, kh, 1)
+    pk.kw_orig, pk.cin_orig = int(kw), int(Cin)
     return pk
 
 
@@ -77,7 +132,9 @@ class Engine:
         self._sig = None
         self.launches = 0            # kernels launched through the C ABI (bench's gpu_launches)
         self.use_tc = True           # bf16: dense contractions on tcgen05 (False -> CUDA-core cross-check path)
+        self.tc_variant = "auto"     # "auto" | "tap" (tc_conv.cu only) | "slab" (prefer tc_slab.cu)
         self.tc_calls = 0
+        self.slab_calls = 0
         self.simt_conv_calls = 0
         self.taps: Optional[dict] = None  # when set, per-stage activations are recorded (tests)
         self._prof: Optional[list] = None  # when set, (event0, event1, flops) per tcgen05 conv launch
@@ -107,6 +164,7 @@ class Engine:
         dt = self.dtype
         P: Dict[str, object] = {}
         P["conv_in"] = pack_conv(m.conv_in.conv.weight, m.conv_in.conv.bias, dt)
+        P["conv_in_tc"] = pack_conv_in_kwpack(m.conv_in.conv.weight, m.conv_in.conv.bias) if dt == torch.bfloat16 else None
         P["conv_out"] = pack_conv(m.conv_out.conv.weight, m.conv_out.conv.bias, dt)
 
         def f32(t):
@@ -125,11 +183,9 @@ class Engine:
                 hidden=int(se.net[0].weight.shape[0]),
             )
 
-        def pack_ff(ff, key):
-            P[key] = dict(gamma=f32(ff.norm.gamma.reshape(-1)),
-                          fc1=pack_conv(ff.net[0].weight, ff.net[0].bias, dt),
-                          fc2=pack_conv(ff.net[2].weight, ff.net[2].bias, dt),
-                          inner=ff.dim_inner)
+        def pack_ffn(ff, key):
+            fc1, fc2 = pack_ff(ff.net[0].weight, ff.net[0].bias, ff.net[2].weight, ff.net[2].bias, dt)
+            P[key] = dict(gamma=f32(ff.norm.gamma.reshape(-1)), fc1=fc1, fc2=fc2, inner=ff.dim_inner)
 
         def pack_attn(at, key):
             P[key] = dict(gamma=f32(at.norm.gamma), qkv=pack_conv(at.to_qkv[0].weight[:, :, None, None, None], None, dt),
@@ -165,13 +221,13 @@ class Engine:
                         P[key] = pack_conv(mod.net[0].weight, mod.net[0].bias, dt, k=(1, 1, 1), shuffle_q=2)  # Conv1d (2Co,Ci,1)
                 elif st.kind == "attend_space":
                     pack_attn(mod[0].fn, key + ".attn")
-                    pack_ff(mod[1].fn, key + ".ff")
+                    pack_ffn(mod[1].fn, key + ".ff")
                 elif st.kind == "attend_time":
                     pack_attn(mod[0].fn.fn, key + ".attn")
-                    pack_ff(mod[1].fn.fn, key + ".ff")
+                    pack_ffn(mod[1].fn.fn, key + ".ff")
                 elif st.kind == "linear_attend_space":
                     pack_lin(mod[0].fn, key + ".attn")
-                    pack_ff(mod[1].fn, key + ".ff")
+                    pack_ffn(mod[1].fn, key + ".ff")
         q = m.quantizers
         # the reference applies the projections in the module dtype (bf16 weights in bf16 mode)
         P["quant"] = dict(win=q.project_in.weight.detach().to(dt).float().contiguous(), bin=q.project_in.bias.detach().to(dt).float().contiguous(),
@@ -190,13 +246,49 @@ class Engine:
              res=None, shuffle=SHUFFLE_NONE, token_shift=False):
         """x: (B,T,H,W,Ci) channels-last.  `pad` = leading (pt,ph,pw); causal default (kt-1, kh//2, kw//2)."""
         B, Ti, Hi, Wi, Ci = x.shape
-        assert Ci == pk.Ci, (Ci, pk.Ci)
-        kt, kh, kw = pk.k
+        tc_ok = (self.dtype == torch.bfloat16 and self.use_tc and pk.w_tc is not None and not token_shift
+                 and Ci == pk.Ci_tc)
+        kt, kh, kw = pk.k_tc if (tc_ok and pk.k_tc) else pk.k
         if pad is None:
             pad = (kt - 1, kh // 2, kw // 2)
         if out_spatial is None:
             out_spatial = (Ti, Hi, Wi)
         To, Ho, Wo = out_spatial
+        if tc_ok:
+            co_gemm = pk.Co_tc
+            co_out = co_gemm // 2 if pk.epi_mode == 1 else co_gemm
+            if shuffle == SHUFFLE_SPACE:
+                y = self._new((B, To, 2 * Ho, 2 * Wo, co_out // 4))
+            elif shuffle == SHUFFLE_TIME:
+                y = self._new((B, 2 * To, Ho, Wo, co_out // 2))
+            else:
+                y = self._new((B, To, Ho, Wo, co_out))
+            if res is not None:
+                assert res.shape == y.shape and res.dtype == y.dtype and res.is_contiguous()
+            ta = TcConvArgs(x=_ptr(x), w=_ptr(pk.w_tc), bias=_ptr(pk.bias_tc), res=_ptr(res), y=_ptr(y),
+                            B=B, Ti=Ti, Hi=Hi, Wi=Wi, Ci=Ci, To=To, Ho=Ho, Wo=Wo, Co=co_gemm,
+                            kt=kt, kh=kh, kw=kw, st=stride[0], sh=stride[1], sw=stride[2],
+                            pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle, epi_mode=pk.epi_mode)
+            use_slab = self.tc_variant != "tap" and bool(self.lib.mv2_tc_slab_supported(C.byref(ta)))
+            if use_slab or self.lib.mv2_tc_conv_supported(C.byref(ta)):
+                if self._prof is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                if use_slab:
+                    check(self.lib.mv2_tc_slab_forward(C.byref(ta), self._stream()), "mv2_tc_slab_forward")
+                    self.slab_calls += 1
+                else:
+                    check(self.lib.mv2_tc_conv_forward(C.byref(ta), self._stream()), "mv2_tc_conv_forward")
+                if self._prof is not None:
+                    e1.record()
+                    self._prof.append((e0, e1, 2.0 * B * To * Ho * Wo * pk.Co * pk.Ci * pk.k[0] * pk.k[1] * pk.k[2]))
+                self.launches += 1
+                self.tc_calls += 1
+                return y
+            assert pk.w is not None and pk.epi_mode == 0 and Ci == pk.Ci, "tcgen05-only weight pack has no CUDA-core fallback"
+            kt, kh, kw = pk.k
+        assert Ci == pk.Ci, (Ci, pk.Ci)
+        assert pk.w is not None
         if shuffle == SHUFFLE_SPACE:
             y = self._new((B, To, 2 * Ho, 2 * Wo, pk.Co // 4))
         elif shuffle == SHUFFLE_TIME:
@@ -205,22 +297,6 @@ class Engine:
             y = self._new((B, To, Ho, Wo, pk.Co))
         if res is not None:
             assert res.shape == y.shape and res.dtype == y.dtype and res.is_contiguous()
-        if self.dtype == torch.bfloat16 and self.use_tc and pk.w_tc is not None and not token_shift:
-            ta = TcConvArgs(x=_ptr(x), w=_ptr(pk.w_tc), bias=_ptr(pk.bias_tc), res=_ptr(res), y=_ptr(y),
-                            B=B, Ti=Ti, Hi=Hi, Wi=Wi, Ci=Ci, To=To, Ho=Ho, Wo=Wo, Co=pk.Co,
-                            kt=kt, kh=kh, kw=kw, st=stride[0], sh=stride[1], sw=stride[2],
-                            pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle)
-            if self.lib.mv2_tc_conv_supported(C.byref(ta)):
-                if self._prof is not None:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                check(self.lib.mv2_tc_conv_forward(C.byref(ta), self._stream()), "mv2_tc_conv_forward")
-                if self._prof is not None:
-                    e1.record()
-                    self._prof.append((e0, e1, 2.0 * B * To * Ho * Wo * pk.Co * Ci * kt * kh * kw))
-                self.launches += 1
-                self.tc_calls += 1
-                return y
         self.simt_conv_calls += 1
         a = ConvArgs(x=_ptr(x), w=_ptr(pk.w), bias=_ptr(pk.bias), res=_ptr(res), y=_ptr(y), dtype=_dt(self.dtype),
                      B=B, Ti=Ti, Hi=Hi, Wi=Wi, Ci=Ci, To=To, Ho=Ho, Wo=Wo, Co=pk.Co,
@@ -260,12 +336,23 @@ class Engine:
         """Residual(FeedForward) (M:471-508, M:1191): x + fc2(geglu(fc1(rmsnorm(shift(x)))))."""
         B, T, H, W, Cc = x.shape
         xn = self.rmsnorm(x, p["gamma"], token_shift)
-        hdn = self.conv(xn, p["fc1"])
+        if self.dtype == torch.bfloat16 and self.use_tc and p["fc1"].epi_mode == 1:
+            g = self.conv(xn, p["fc1"])                       # fc1 + bias + GEGLU fused, hidden width padded to 64
+            return self.conv(g, p["fc2"], res=x)
+        fc1 = p["fc1"]
+        hdn = self._conv_simt_only(xn, fc1)
         I = p["inner"]
         g = self._new((B, T, H, W, I))
         check(self.lib.mv2_geglu(_ptr(hdn), _ptr(g), _dt(self.dtype), B * T * H * W, I, self._stream()), "mv2_geglu")
         self.launches += 1
-        return self.conv(g, p["fc2"], res=x)
+        return self._conv_simt_only(g, p["fc2"], res=x)
+
+    def _conv_simt_only(self, x, pk, **kw):
+        use, self.use_tc = self.use_tc, False
+        try:
+            return self.conv(x, pk, **kw)
+        finally:
+            self.use_tc = use
 
     def attention(self, x, p, axis: str):
         """Residual(SpaceAttention) / Residual(TokenShift(TimeAttention)) (M:444-464, M:1190, M:1235)."""
@@ -370,6 +457,18 @@ class Engine:
         self.launches += 1
         return out
 
+    def ingest_kwpack(self, v: torch.Tensor, t_pad: int, pin):
+        """(B,C,T,H,W) -> (B,T+t_pad,H,W,32) bf16 with the k_w taps packed into channels (mv2_ingest_kwpack)."""
+        if v.dtype not in (torch.float32, torch.bfloat16):
+            v = v.float()
+        v = v.contiguous()
+        B, Cc, T, H, W = v.shape
+        out = self._new((B, T + t_pad, H, W, pin.Ci_tc), torch.bfloat16)
+        check(self.lib.mv2_ingest_kwpack(_ptr(v), _dt(v.dtype), _ptr(out), B, Cc, T, H, W, t_pad, pin.kw_orig,
+                                         pin.kw_orig // 2, pin.Ci_tc, self._stream()), "mv2_ingest_kwpack")
+        self.launches += 1
+        return out
+
     def to_channels_first(self, x: torch.Tensor, t_crop: int = 0, out_dtype=None):
         B, T, H, W, Cc = x.shape
         out_dtype = out_dtype or self.dtype
@@ -383,8 +482,13 @@ class Engine:
     def encode_cl(self, video: torch.Tensor):
         """video (B,C,T,H,W) on device -> encoder output, channels-last.  Reference encode M:1523-1576."""
         m = self.model
-        x = self.to_channels_last(video, m.time_padding)
-        x = self.conv(x, self._packs["conv_in"])
+        pin = self._packs.get("conv_in_tc")
+        if self.dtype == torch.bfloat16 and self.use_tc and pin is not None:
+            x = self.ingest_kwpack(video, m.time_padding, pin)
+            x = self.conv(x, pin, pad=(pin.k_tc[0] - 1, pin.k_tc[1] // 2, 0))
+        else:
+            x = self.to_channels_last(video, m.time_padding)
+            x = self.conv(x, self._packs["conv_in"])
         self._tap("conv_in", x)
         for i, st in enumerate(m.stages):
             x = self._stage(x, st, f"enc{i}", decoder=False)

@@ -71,6 +71,7 @@ def test_tc_matches_cuda_core(case):
         return eng.conv(x, pk, res=res, **kw)
 
     eng.tc_calls = 0
+    eng.tc_variant = "tap"
     y_tc = run(True)
     assert eng.tc_calls == 1, "tcgen05 path was not taken"
     y_ref = run(False)
@@ -82,3 +83,99 @@ def test_tc_matches_cuda_core(case):
     err = (a - b).abs().max().item()
     assert err <= tol, f"{name}: max-abs diff {err} > {tol}"
     assert (a - b).abs().mean().item() < 0.002 * b.abs().mean().item() + 1e-4
+
+
+SLAB_CASES = [
+    ("slab_c64_32x32", (64, 64, 3, 3, 3), (1, 3, 32, 32), dict(act=ACT_ELU)),
+    ("slab_c64_w128", (64, 64, 3, 3, 3), (1, 2, 16, 128), dict(act=ACT_ELU)),
+    ("slab_c128_64x64_b2", (128, 128, 3, 3, 3), (2, 3, 64, 64), dict(act=ACT_ELU)),
+    ("slab_c256_32x32", (256, 256, 3, 3, 3), (1, 4, 32, 32), dict()),
+    ("slab_c512_16x16", (512, 512, 3, 3, 3), (2, 5, 16, 16), dict(act=ACT_ELU)),
+    ("slab_c512_16x16_T10", (512, 512, 3, 3, 3), (1, 10, 16, 16), dict(act=ACT_ELU)),
+    ("slab_ragged_24x20", (64, 64, 3, 3, 3), (1, 3, 24, 20), dict(act=ACT_ELU)),
+    ("slab_small_8x8", (128, 64, 3, 3, 3), (2, 3, 8, 8), dict()),
+    ("slab_res", (64, 64, 3, 3, 3), (1, 2, 32, 32), dict(res=True)),
+    ("slab_k133", (64, 64, 1, 3, 3), (1, 3, 32, 32), dict()),
+]
+
+
+@pytest.mark.parametrize("case", SLAB_CASES, ids=[c[0] for c in SLAB_CASES])
+def test_slab_matches_cuda_core(case):
+    assert torch.cuda.is_available()
+    name, wshape, xshape, kw = case
+    kw = dict(kw)
+    g = torch.Generator(device="cpu").manual_seed(sum(map(ord, name)))
+    fan_in = 1
+    for v in wshape[1:]:
+        fan_in *= v
+    w = (torch.randn(wshape, generator=g) * fan_in ** -0.5).cuda()
+    bias = (torch.randn(wshape[0], generator=g) * 0.1).cuda()
+    B, T, H, W = xshape
+    x = torch.randn((B, T, H, W, wshape[1]), generator=g).cuda().to(torch.bfloat16)
+    eng = _engine()
+    pk = pack_conv(w, bias, torch.bfloat16)
+    want_res = kw.pop("res", False)
+    res = torch.randn((B, T, H, W, wshape[0]), generator=g).cuda().to(torch.bfloat16) if want_res else None
+    eng.use_tc, eng.tc_variant, eng.slab_calls = True, "slab", 0
+    y_slab = eng.conv(x, pk, res=res, **kw)
+    assert eng.slab_calls == 1, "slab kernel was not taken"
+    eng.tc_variant = "tap"
+    y_tap = eng.conv(x, pk, res=res, **kw)
+    eng.use_tc = False
+    y_ref = eng.conv(x, pk, res=res, **kw)
+    torch.cuda.synchronize()
+    a, b, c = y_slab.float(), y_ref.float(), y_tap.float()
+    assert torch.isfinite(a).all()
+    tol = 0.008 * b.abs().max().item() + 1e-3
+    err = (a - b).abs().max().item()
+    assert err <= tol, f"{name}: slab vs cuda-core max-abs diff {err} > {tol}"
+    assert (a - c).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("C_,tshift", [(256, False), (512, True), (64, False)])
+def test_fused_geglu_feed_forward_matches_cuda_core(C_, tshift):
+    """fc1 + GEGLU fused in the tcgen05 epilogue (hidden width padded to 64) + fc2 vs the unfused CUDA-core path."""
+    from magvit2_pytorch_b200.engine import pack_ff
+    assert torch.cuda.is_available()
+    g = torch.Generator(device="cpu").manual_seed(C_)
+    I = int(C_ * 4 * 2 / 3)
+    w1 = (torch.randn((2 * I, C_, 1, 1, 1), generator=g) * C_ ** -0.5).cuda()
+    b1 = (torch.randn(2 * I, generator=g) * 0.1).cuda()
+    w2 = (torch.randn((C_, I, 1, 1, 1), generator=g) * I ** -0.5).cuda()
+    b2 = (torch.randn(C_, generator=g) * 0.1).cuda()
+    fc1, fc2 = pack_ff(w1, b1, w2, b2, torch.bfloat16)
+    p = dict(gamma=torch.ones(C_, device="cuda"), fc1=fc1, fc2=fc2, inner=I)
+    x = torch.randn((2, 3, 8, 8, C_), generator=g).cuda().to(torch.bfloat16)
+    eng = _engine()
+    eng.use_tc, eng.tc_calls = True, 0
+    y_tc = eng.feed_forward(x, p, token_shift=tshift)
+    assert eng.tc_calls == 2
+    eng.use_tc = False
+    y_ref = eng.feed_forward(x, p, token_shift=tshift)
+    torch.cuda.synchronize()
+    a, b = y_tc.float(), y_ref.float()
+    assert torch.isfinite(a).all()
+    # the unfused path rounds the hidden activations to bf16 twice (fc1 output, GEGLU output); the fused one once
+    assert (a - b).abs().max().item() <= 0.02 * b.abs().max().item() + 2e-3
+    assert (a - b).abs().mean().item() <= 0.004 * b.abs().mean().item() + 1e-4
+
+
+def test_conv_in_kwpack_matches_cuda_core():
+    """conv_in (7x7x7, C_in=3) through mv2_ingest_kwpack + tcgen05 (49 taps x 32 packed channels) vs the CUDA-core conv."""
+    assert torch.cuda.is_available()
+    m = VideoTokenizer(image_size=32, init_dim=64, codebook_size=1024, layers=("residual",)).cuda().bfloat16()
+    eng = m.engine
+    g = torch.Generator(device="cpu").manual_seed(3)
+    v = torch.randn((2, 3, 5, 32, 32), generator=g).cuda()
+    pin = eng._packs["conv_in_tc"]
+    assert pin is not None
+    eng.use_tc, eng.tc_calls = True, 0
+    x = eng.ingest_kwpack(v, 2, pin)
+    y_tc = eng.conv(x, pin, pad=(6, 3, 0))
+    assert eng.tc_calls == 1
+    eng.use_tc = False
+    y_ref = eng.conv(eng.to_channels_last(v, 2), eng._packs["conv_in"])
+    torch.cuda.synchronize()
+    a, b = y_tc.float(), y_ref.float()
+    assert a.shape == b.shape
+    assert (a - b).abs().max().item() <= 0.008 * b.abs().max().item() + 1e-3

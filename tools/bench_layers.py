@@ -48,9 +48,10 @@ for name, wshape, k3, (T, H, W), kw in LAYERS:
         taps *= v
     flops = 2.0 * B * To * Ho * Wo * wshape[0] * wshape[1] * taps
     res = {}
-    for mode in ("tc", "simt"):
-        eng.use_tc = mode == "tc"
-        if mode == "simt" and flops > 3e11:
+    for mode in ("tc", "slab"):
+        eng.use_tc = True
+        eng.tc_variant = "tap" if mode == "tc" else "slab"
+        if mode == "slab" and not (len(wshape) == 5 and wshape[2] * wshape[3] * wshape[4] > 1 and wshape[0] > 3):
             continue
         for _ in range(3):
             eng.conv(x, pk, **kw)
@@ -64,10 +65,11 @@ for name, wshape, k3, (T, H, W), kw in LAYERS:
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         res[mode] = min(ts)
-    row = dict(layer=name, B=B, gflop=flops / 1e9, tc_ms=res.get("tc"), simt_ms=res.get("simt"),
-               tc_tflops=flops / res["tc"] / 1e9 if "tc" in res else None)
+    row = dict(layer=name, B=B, gflop=flops / 1e9, tc_ms=res.get("tc"), slab_ms=res.get("slab"),
+               tc_tflops=flops / res["tc"] / 1e9 if "tc" in res else None,
+               slab_tflops=flops / res["slab"] / 1e9 if "slab" in res else None)
     rows.append(row)
-    print(f"{name:28s} {flops/1e9:9.1f} GF  tc {res.get('tc', float('nan')):8.3f} ms = {row['tc_tflops']:7.1f} TF/s"
-          f"   simt {res.get('simt', float('nan')):8.3f} ms", flush=True)
+    print(f"{name:28s} {flops/1e9:9.1f} GF  tap {res.get('tc', float('nan')):8.3f} ms = {row['tc_tflops']:7.1f} TF/s"
+          f"   slab {res.get('slab', float('nan')):8.3f} ms = {(row['slab_tflops'] or float('nan')):7.1f} TF/s", flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/layers.json", "w"), indent=1)
