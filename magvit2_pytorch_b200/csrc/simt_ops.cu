@@ -319,14 +319,13 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const T* __restrict__ y, i
   }
 }
 
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ ws, int n_chunks, int C, int Hd,
-                                                      const float* __restrict__ w1, const float* __restrict__ b1,
-                                                      const float* __restrict__ w2, const float* __restrict__ b2,
-                                                      float* __restrict__ gates) {
+__global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict__ ws, int n_chunks, int C, int Hd,
+                                                        const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        float* __restrict__ hidden_out) {
+  // grid (F, ceil(Hd / 32)): combine the chunk partials into pooled[C] (redundantly per block: cheap), then 32 hidden units.
   extern __shared__ float sm[];
   float* pooled = sm;          // [C]
-  float* hidden = sm + C;      // [Hd]
-  float* coef = hidden + Hd;   // [n_chunks]
+  float* coef = sm + C;        // [n_chunks]
   __shared__ float s_inv;
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* wf = ws + (int64_t)f * n_chunks * (C + 2);
@@ -350,21 +349,46 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
     pooled[c] = acc * s_inv;
   }
   __syncthreads();
-  for (int j = warp; j < Hd; j += 8) {
-    float acc = 0.f;
-    for (int c = lane; c < C; c += 32) acc = fmaf(w1[(int64_t)j * C + c], pooled[c], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float h = acc + b1[j];
-      hidden[j] = h > 0.f ? h : 0.1f * h;
+  const int j0 = blockIdx.y * 32 + warp * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = lane; c < C; c += 32) {
+    const float pv = pooled[c];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (j0 + u < Hd) acc[u] = fmaf(w1[(int64_t)(j0 + u) * C + c], pv, acc[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float a = warp_sum(acc[u]);
+    if (lane == 0 && j0 + u < Hd) {
+      const float h = a + b1[j0 + u];
+      hidden_out[(int64_t)f * Hd + j0 + u] = h > 0.f ? h : 0.1f * h;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) se_out_kernel(const float* __restrict__ hidden, int C, int Hd,
+                                                     const float* __restrict__ w2, const float* __restrict__ b2,
+                                                     float* __restrict__ gates) {
+  // grid (F, ceil(C / 64)): 8 warps x 8 output channels each
+  extern __shared__ float sm[];   // hidden[Hd]
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int j = tid; j < Hd; j += 256) sm[j] = hidden[(int64_t)f * Hd + j];
   __syncthreads();
-  for (int c = warp; c < C; c += 8) {
-    float acc = 0.f;
-    for (int j = lane; j < Hd; j += 32) acc = fmaf(w2[(int64_t)c * Hd + j], hidden[j], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) gates[(int64_t)f * C + c] = 1.f / (1.f + expf(-(acc + b2[c])));
+  const int c0 = blockIdx.y * 64 + warp * 8;
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  for (int j = lane; j < Hd; j += 32) {
+    const float hv = sm[j];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (c0 + u < C) acc[u] = fmaf(w2[(int64_t)(c0 + u) * Hd + j], hv, acc[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float a = warp_sum(acc[u]);
+    if (lane == 0 && c0 + u < C) gates[(int64_t)f * C + c0 + u] = 1.f / (1.f + expf(-(a + b2[c0 + u])));
   }
 }
 
@@ -376,6 +400,31 @@ __global__ void gate_residual_kernel(const T* __restrict__ y, const T* __restric
     const int64_t f = i / PC;
     const int c = (int)(i % C);
     out[i] = from_f32<T>(fmaf(gates[f * C + c], to_f32<T>(y[i]), to_f32<T>(x[i])));
+  }
+}
+
+// 8 bf16 per thread (16-byte accesses); requires C % 8 == 0
+__global__ void gate_residual_bf16x8_kernel(const uint4* __restrict__ y, const uint4* __restrict__ x,
+                                            const float* __restrict__ gates, uint4* __restrict__ out,
+                                            int64_t total8, int64_t PC8, int C8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / PC8;
+    const int c = (int)(i % C8) * 8;
+    const uint4 yv = y[i], xv = x[i];
+    const float4 g0 = *reinterpret_cast<const float4*>(gates + f * (C8 * 8) + c);
+    const float4 g1 = *reinterpret_cast<const float4*>(gates + f * (C8 * 8) + c + 4);
+    const __nv_bfloat162* yb = reinterpret_cast<const __nv_bfloat162*>(&yv);
+    const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xv);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    uint4 o;
+    uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 yf = __bfloat1622float2(yb[q]), xf = __bfloat1622float2(xb[q]);
+      __nv_bfloat162 r = __floats2bfloat162_rn(fmaf(gg[2 * q], yf.x, xf.x), fmaf(gg[2 * q + 1], yf.y, xf.y));
+      ob[q] = *reinterpret_cast<uint32_t*>(&r);
+    }
+    out[i] = o;
   }
 }
 
@@ -885,7 +934,8 @@ int mv2_conv_forward(const mv2_conv_args* a, void* stream) {
 }
 
 size_t mv2_se_workspace_bytes(int F, int P, int C) {
-  return (size_t)F * ceil_div(P, SE_CHUNK) * (C + 2) * sizeof(float);
+  // chunk partials + room for the SE hidden layer (at most max(16, C/2) <= C + 16 units per frame)
+  return ((size_t)F * ceil_div(P, SE_CHUNK) * (C + 2) + (size_t)F * (C + 16)) * sizeof(float);
 }
 
 int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, float bk, void* workspace,
@@ -905,9 +955,14 @@ int mv2_se_gate(const void* workspace, int F, int P, int C, int Hd, const float*
                 const float* b2, float* gates, void* stream) {
   MV2_CHECK_ARG(workspace && w1 && b1 && w2 && b2 && gates && F > 0 && P > 0 && C > 0 && Hd > 0);
   const int nc = ceil_div(P, SE_CHUNK);
-  const size_t smem = (size_t)(C + Hd + nc) * sizeof(float);
-  MV2_CHECK_ARG(smem <= 48 * 1024);
-  se_gate_kernel<<<F, 256, smem, (cudaStream_t)stream>>>((const float*)workspace, nc, C, Hd, w1, b1, w2, b2, gates);
+  const size_t smem1 = (size_t)(C + nc) * sizeof(float), smem2 = (size_t)Hd * sizeof(float);
+  MV2_CHECK_ARG(smem1 <= 48 * 1024 && smem2 <= 48 * 1024);
+  // hidden activations live behind the chunk partials (mv2_se_workspace_bytes reserves F*Hd_max floats)
+  float* hidden = (float*)workspace + (size_t)F * nc * (C + 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  se_hidden_kernel<<<dim3(F, ceil_div(Hd, 32)), 256, smem1, st>>>((const float*)workspace, nc, C, Hd, w1, b1, hidden);
+  MV2_CHECK_LAUNCH();
+  se_out_kernel<<<dim3(F, ceil_div(C, 64)), 256, smem2, st>>>(hidden, C, Hd, w2, b2, gates);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }
@@ -920,7 +975,11 @@ int mv2_gate_residual(const void* y, const void* x, const float* gates, void* ou
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
     gate_residual_kernel<float><<<blocks, 256, 0, st>>>((const float*)y, (const float*)x, gates, (float*)out, total, (int64_t)P * C, C);
-  else if (dtype == MV2_BF16)
+  else if (dtype == MV2_BF16 && C % 8 == 0) {
+    const int64_t total8 = total / 8;
+    const int b8 = (int)std::min<int64_t>((total8 + 255) / 256, 148 * 16);
+    gate_residual_bf16x8_kernel<<<b8, 256, 0, st>>>((const uint4*)y, (const uint4*)x, gates, (uint4*)out, total8, (int64_t)P * C / 8, C / 8);
+  } else if (dtype == MV2_BF16)
     gate_residual_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)x, gates, (__nv_bfloat16*)out, total, (int64_t)P * C, C);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();

@@ -108,6 +108,18 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t ro
 }
 
 
+// general: explicit SBO and row width (128 B rows -> SWIZZLE_128B, 64 B -> SWIZZLE_64B, 32 B -> SWIZZLE_32B)
+__device__ __forceinline__ uint64_t make_kmajor_desc_rb(uint32_t saddr, uint32_t sbo, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
 // same, with an explicit stride-byte-offset (distance between consecutive 8-row core groups), SWIZZLE_128B
 __device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t saddr, uint32_t sbo) {
   uint64_t d = 0;

@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace mv2 {
 
@@ -29,7 +30,7 @@ struct alignas(64) SlabParams {
   CUtensorMap amap;
   CUtensorMap wmap;
   int kt, kh, kw, pt, ph, pw;
-  int Ci, kchunks;
+  int Ci, kchunks, row_bytes;
   int B, T, H, W, Co;
   int mw, pitch, slab_h, slab_bytes, slab_stride;
   int bn, n_tiles_n, tiles_w, tiles_h, total_tiles;
@@ -59,7 +60,9 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t w_bytes = p.bn * 128;
+  const uint32_t row_bytes = p.row_bytes;          // 128 (64 channels, SWIZZLE_128B) or 64 (32 channels, SWIZZLE_64B)
+  const uint32_t bk = row_bytes >> 1;
+  const uint32_t w_bytes = p.bn * row_bytes;
   const uint32_t slab0 = smem_base;
   const uint32_t wst0 = smem_base + p.slab_stages * p.slab_stride;
   const uint32_t bar0 = wst0 + p.w_stages * w_bytes;
@@ -79,8 +82,10 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
   if (warp == 0 && lane == 0) tma_prefetch_desc(&p.amap);
   if (warp == 2 && lane == 0) tma_prefetch_desc(&p.wmap);
   if (warp == 1) tmem_alloc(tslot, 512);
-  if (warp >= 4)
-    for (int i = threadIdx.x - 128; i < p.Co; i += 128) sbias[i] = p.epi.bias ? p.epi.bias[i] : 0.f;
+  if (warp >= 4) {
+    const int nb = p.n_tiles_n * p.bn;   // >= Co; padded columns read zeros
+    for (int i = threadIdx.x - 128; i < nb; i += 128) sbias[i] = (p.epi.bias && i < p.Co) ? p.epi.bias[i] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
             const uint32_t s = it % p.slab_stages, ph = (it / p.slab_stages) & 1;
             mbar_wait(slab_empty + 8 * s, ph ^ 1);
             mbar_expect_tx(slab_full + 8 * s, p.slab_bytes);
-            tma_load_5d(slab0 + s * p.slab_stride, &p.amap, slab_full + 8 * s, kc * 64, c.w0 - p.pw, c.h0 - p.ph,
+            tma_load_5d(slab0 + s * p.slab_stride, &p.amap, slab_full + 8 * s, kc * bk, c.w0 - p.pw, c.h0 - p.ph,
                         c.t + dt - p.pt, c.b);
           }
       }
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
               const uint32_t s = it % p.w_stages, ph = (it / p.w_stages) & 1;
               mbar_wait(w_empty + 8 * s, ph ^ 1);
               mbar_expect_tx(w_full + 8 * s, w_bytes);
-              tma_load_2d(wst0 + s * w_bytes, &p.wmap, w_full + 8 * s, (dt * taps2d + tp) * p.Ci + kc * 64, c.n0);
+              tma_load_2d(wst0 + s * w_bytes, &p.wmap, w_full + 8 * s, (dt * taps2d + tp) * p.Ci + kc * bk, c.n0);
             }
       }
     }
@@ -128,7 +133,8 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t sbo = (uint32_t)p.pitch * 128;
+      const uint32_t sbo = (uint32_t)p.pitch * row_bytes;
+      const int ksteps = bk >> 4;
       uint32_t sit = 0, wit = 0, tit = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tit) {
         const TileCoord c = decode_tile(p, tile);
@@ -149,11 +155,10 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
               mbar_wait(w_full + 8 * ws, (wit / p.w_stages) & 1);
               tc_fence_after();
               const int dh = tp / p.kw, dw = tp - dh * p.kw;
-              const uint64_t bd = make_kmajor_desc_sbo(wst0 + ws * w_bytes, 1024);
+              const uint64_t bd = make_kmajor_desc_rb(wst0 + ws * w_bytes, 8 * row_bytes, row_bytes);
               for (int j = 0; j < p.mw; ++j) {
-                const uint64_t ad = make_kmajor_desc_sbo(slab + (uint32_t)(dh * p.pitch + 8 * j + dw) * 128, sbo);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
+                const uint64_t ad = make_kmajor_desc_rb(slab + (uint32_t)(dh * p.pitch + 8 * j + dw) * row_bytes, sbo, row_bytes);
+                for (int k = 0; k < ksteps; ++k)
                   umma_bf16(acc + j * p.bn, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
               }
               first = false;
@@ -207,10 +212,12 @@ using namespace mv2;
 extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
   if (!a) return 0;
   if (a->st != 1 || a->sh != 1 || a->sw != 1) return 0;
-  if (a->Ci % 64 != 0 || a->Co % 32 != 0 || a->Co > 2048 || a->epi_mode != 0) return 0;
+  if (a->Ci % 32 != 0 || a->Co > 2048 || a->epi_mode != 0) return 0;
+  if (a->Co % 32 != 0 && a->Co > 32) return 0;           // ragged N only as a single (zero padded) 32-column tile
+  if (a->Ci % 64 != 0 && a->kw != 1) return 0;           // 64-byte rows (32 channels): only h-shifted taps (1024 B multiples)
+  if (a->res && a->Co % 8 != 0) return 0;
   if (a->shuffle != MV2_SHUFFLE_NONE) return 0;
-  if (a->kh * a->kw < 2) return 0;                       // nothing to reuse for 1x1 in-plane kernels
-  if (a->kh > 3 || a->kw > 3 || a->kt > 8) return 0;
+  if (a->kh > 7 || a->kw > 3 || a->kt > 8) return 0;
   if (a->To != a->Ti || a->Ho != a->Hi || a->Wo != a->Wi) return 0;
   return 1;
 }
@@ -227,53 +234,66 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   SlabParams p;
   memset(&p, 0, sizeof(p));
   p.kt = a->kt; p.kh = a->kh; p.kw = a->kw; p.pt = a->pt; p.ph = a->ph; p.pw = a->pw;
-  p.Ci = a->Ci; p.kchunks = a->Ci / 64;
+  p.row_bytes = (a->Ci % 64 == 0) ? 128 : 64;
+  const int bk = p.row_bytes / 2;
+  p.Ci = a->Ci; p.kchunks = a->Ci / bk;
   p.B = a->B; p.T = a->To; p.H = a->Ho; p.W = a->Wo; p.Co = a->Co;
   p.epi.bias = a->bias; p.epi.res = (const __nv_bfloat16*)a->res; p.epi.y = (__nv_bfloat16*)a->y;
   p.epi.act = a->act; p.epi.shuffle = MV2_SHUFFLE_NONE; p.epi.mode = 0; p.epi.Co = a->Co;
   p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo;
 
-  // ---- tiling heuristic: maximise (wave efficiency) x (tensor-pipe efficiency) / (L2 traffic) ----
+  // ---- tiling: minimise a simple time model  rounds x max(MMA issue, L2 stream) ----
   const int tiles_h = ceil_div(a->Ho, 16);
+  const int co_pad = (a->Co + 31) / 32 * 32;
   int best_mw = 1, best_bn = 32;
-  double best_score = -1.0;
+  double best_t = 1e30;
   for (int mw = 1; mw <= 2; ++mw) {
     if (mw == 2 && a->Wo <= 8) continue;
     for (int bn = 256; bn >= 32; bn >>= 1) {
-      if (bn > a->Co || a->Co % bn != 0) continue;
-      const int64_t units = (int64_t)a->B * a->To * tiles_h * ceil_div(a->Wo, 8 * mw) * (a->Co / bn);
+      if (bn > co_pad || co_pad % bn != 0) continue;
+      const int pitch = 8 * mw + a->kw - 1, slab_h = 16 + a->kh - 1;
+      const double slab_b = (double)pitch * slab_h * p.row_bytes;
+      const int64_t units = (int64_t)a->B * a->To * tiles_h * ceil_div(a->Wo, 8 * mw) * (co_pad / bn);
       const int64_t rounds = (units + n_sm - 1) / n_sm;
-      const double wave_eff = (double)units / (double)(rounds * n_sm);
-      const double n_eff = bn >= 128 ? 1.0 : (bn == 64 ? 0.85 : 0.6);   // small N: A re-read from smem per MMA
-      const double traffic = 1.0 / (128.0 * mw) + 1.3 / (9.0 * bn);      // L2 bytes per MAC (weights + slab)
-      const double score = wave_eff * n_eff / (1.0 + 40.0 * traffic);
-      if (score > best_score) { best_score = score; best_mw = mw; best_bn = bn; }
+      const double taps = (double)a->kt * p.kchunks * a->kh * a->kw;
+      const double mma = mw * (bk / 16) * std::max(bn / 2.0, 32.0);          // cycles per tap
+      const double issue = std::max(mma, 220.0);                            // barrier wait + descriptor + commit latency
+      const double l2 = ((double)bn * p.row_bytes + slab_b / (a->kh * a->kw)) / 35.0;   // ~10 TB/s over 148 SMs
+      const double epi = (2 * mw * bn <= 512) ? 0.0 : mw * (bn / 32) * 300.0;
+      const double t = rounds * (taps * std::max(issue, l2) + epi + 1500.0);
+      if (t < best_t) { best_t = t; best_mw = mw; best_bn = bn; }
     }
   }
+  if (const char* env = getenv("MV2_SLAB_CFG")) {   // debug / tuning override: "mw,bn"
+    int emw = 0, ebn = 0;
+    if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2) && ebn >= 32 && ebn <= 256 && co_pad % ebn == 0 &&
+        !(emw == 2 && a->Wo <= 8)) { best_mw = emw; best_bn = ebn; }
+  }
   p.mw = best_mw; p.bn = best_bn;
-  p.n_tiles_n = a->Co / p.bn;
+  p.n_tiles_n = co_pad / p.bn;
   p.tiles_h = tiles_h;
   p.tiles_w = ceil_div(a->Wo, 8 * p.mw);
   p.total_tiles = (int)((int64_t)a->B * a->To * p.tiles_h * p.tiles_w * p.n_tiles_n);
   p.pitch = 8 * p.mw + a->kw - 1;
   p.slab_h = 16 + a->kh - 1;
-  p.slab_bytes = p.pitch * p.slab_h * 128;
+  p.slab_bytes = p.pitch * p.slab_h * p.row_bytes;
   p.slab_stride = (p.slab_bytes + 1023) / 1024 * 1024;
   p.nbuf = (2 * p.mw * p.bn <= 512) ? 2 : 1;
-  const int w_bytes = p.bn * 128;
-  const int budget = 220 * 1024 - a->Co * 4;
+  const int w_bytes = p.bn * p.row_bytes;
+  const int budget = 220 * 1024 - co_pad * 4;
   p.slab_stages = p.slab_stride * 3 + w_bytes * 4 <= budget ? 3 : 2;
   p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
   MV2_CHECK_ARG(p.w_stages >= 2);
 
+  const CUtensorMapSwizzle swz = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
     const int64_t C = a->Ci, W = a->Wi, H = a->Hi, T = a->Ti;
     cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)a->B};
     cuuint64_t strides[4] = {(cuuint64_t)(C * 2), (cuuint64_t)(W * C * 2), (cuuint64_t)(H * W * C * 2), (cuuint64_t)(T * H * W * C * 2)};
-    cuuint32_t box[5] = {64, (cuuint32_t)p.pitch, (cuuint32_t)p.slab_h, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)p.pitch, (cuuint32_t)p.slab_h, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(&p.amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)a->x, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(slab) failed: %d", (int)r); return MV2_E_CUDA; }
   }
@@ -281,14 +301,14 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
     const int64_t K = (int64_t)a->kt * a->kh * a->kw * a->Ci;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)a->Co};
     cuuint64_t strides[1] = {(cuuint64_t)(K * 2)};
-    cuuint32_t box[2] = {64, (cuuint32_t)p.bn};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.bn};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a->w, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return MV2_E_CUDA; }
   }
-  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 16 + (size_t)a->Co * 4 + 1024;
+  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 16 + (size_t)co_pad * 4 + 1024;
   MV2_CHECK_ARG(smem <= 227 * 1024);
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;

@@ -34,13 +34,14 @@ def test_every_declared_symbol_is_exported_and_bound():
 def test_load_and_version():
     lib = _lib.load()
     assert lib.mv2_abi_version() == 1
-    assert lib.mv2_se_workspace_bytes(2, 256, 64) == 2 * 2 * 66 * 4
+    assert lib.mv2_se_workspace_bytes(2, 256, 64) == (2 * 2 * 66 + 2 * 80) * 4
     assert lib.mv2_linattn_workspace_bytes(3, 16, 1024) == 3 * 16 * 4 * 657 * 4
 
 
 def test_struct_sizes_match_header_layout():
     # 5 pointers + 22 int32 (conv), 3 pointers + 8 int32 + 3 int64 (attention)
     assert ctypes.sizeof(_lib.ConvArgs) == 5 * 8 + 22 * 4
+    assert ctypes.sizeof(_lib.TcConvArgs) == 5 * 8 + 22 * 4
     assert ctypes.sizeof(_lib.AttnArgs) == 3 * 8 + 8 * 4 + 3 * 8
 
 

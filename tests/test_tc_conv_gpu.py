@@ -96,6 +96,11 @@ SLAB_CASES = [
     ("slab_small_8x8", (128, 64, 3, 3, 3), (2, 3, 8, 8), dict()),
     ("slab_res", (64, 64, 3, 3, 3), (1, 2, 32, 32), dict(res=True)),
     ("slab_k133", (64, 64, 1, 3, 3), (1, 3, 32, 32), dict()),
+    ("slab_pointwise_c64", (64, 64, 1, 1, 1), (2, 3, 32, 32), dict(act=ACT_ELU)),
+    ("slab_pointwise_c512_res", (512, 512, 1, 1, 1), (1, 4, 16, 16), dict(res=True)),
+    ("slab_linear_512_768", (768, 512, 1, 1, 1), (1, 2, 16, 16), dict()),
+    ("slab_conv_out_co3", (3, 64, 3, 3, 3), (1, 3, 16, 32), dict()),
+    ("slab_co16", (16, 64, 3, 3, 3), (1, 2, 16, 16), dict(act=ACT_ELU)),
 ]
 
 
@@ -160,7 +165,8 @@ def test_fused_geglu_feed_forward_matches_cuda_core(C_, tshift):
     assert (a - b).abs().mean().item() <= 0.004 * b.abs().mean().item() + 1e-4
 
 
-def test_conv_in_kwpack_matches_cuda_core():
+@pytest.mark.parametrize("variant", ["tap", "slab"])
+def test_conv_in_kwpack_matches_cuda_core(variant):
     """conv_in (7x7x7, C_in=3) through mv2_ingest_kwpack + tcgen05 (49 taps x 32 packed channels) vs the CUDA-core conv."""
     assert torch.cuda.is_available()
     m = VideoTokenizer(image_size=32, init_dim=64, codebook_size=1024, layers=("residual",)).cuda().bfloat16()
@@ -169,10 +175,10 @@ def test_conv_in_kwpack_matches_cuda_core():
     v = torch.randn((2, 3, 5, 32, 32), generator=g).cuda()
     pin = eng._packs["conv_in_tc"]
     assert pin is not None
-    eng.use_tc, eng.tc_calls = True, 0
+    eng.use_tc, eng.tc_calls, eng.slab_calls, eng.tc_variant = True, 0, 0, variant
     x = eng.ingest_kwpack(v, 2, pin)
     y_tc = eng.conv(x, pin, pad=(6, 3, 0))
-    assert eng.tc_calls == 1
+    assert eng.tc_calls == 1 and eng.slab_calls == (1 if variant == "slab" else 0)
     eng.use_tc = False
     y_ref = eng.conv(eng.to_channels_last(v, 2), eng._packs["conv_in"])
     torch.cuda.synchronize()
