@@ -319,6 +319,104 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const T* __restrict__ y, i
   }
 }
 
+// bf16 / C % 8 == 0 variant of se_pool_kernel: 16-byte loads, one 8-channel group per thread.
+//   G = C / 8 groups per position; 256 / G positions are processed per pass (G <= 256 required).
+__global__ void __launch_bounds__(256) se_pool_bf16x8_kernel(const __nv_bfloat16* __restrict__ y, int P, int C,
+                                                             const float* __restrict__ wk, float bk,
+                                                             float* __restrict__ ws, int n_chunks) {
+  __shared__ float e[SE_CHUNK];
+  __shared__ float red[8];
+  __shared__ float bcast;
+  extern __shared__ float dyn[];         // pooled partial sums [256 / G][C] for the cross-row reduction
+  const int f = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = C >> 3;
+  const int rows_per_pass = 256 / G;
+  const int g = tid % G, rsub = tid / G;
+  const int p0 = chunk * SE_CHUNK;
+  const int cnt = min(SE_CHUNK, P - p0);
+  const uint4* yf = reinterpret_cast<const uint4*>(y + ((int64_t)f * P + p0) * C);
+  float wv[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) wv[q] = wk[g * 8 + q];
+  if (tid < SE_CHUNK) e[tid] = 0.f;
+  __syncthreads();
+  // phase 1: logits (partial dot per thread, reduced across the G threads that share a row).  The loop is
+  // warp-uniform (every lane runs every pass) so the full-mask shuffles are safe for ragged chunk sizes.
+  for (int nb = 0; nb < cnt; nb += rows_per_pass) {
+    const int n = nb + rsub;
+    const bool ok = n < cnt;
+    float s = 0.f;
+    if (ok) {
+      const uint4 v = yf[(int64_t)n * G + g];
+      const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 fv = __bfloat1622float2(vb[q]);
+        s = fmaf(fv.x, wv[2 * q], s);
+        s = fmaf(fv.y, wv[2 * q + 1], s);
+      }
+    }
+    if (G <= 32) {   // G is a power of two here (256 % G == 0): rows occupy aligned lane groups
+      for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (g == 0 && ok) e[n] = s;
+    } else if (ok) {
+      atomicAdd(&e[n], s);
+    }
+  }
+  __syncthreads();
+  float v = (tid < cnt) ? e[tid] + bk : -INFINITY;
+  float mx = warp_max(v);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  const float m = bcast;
+  const float ev = (tid < cnt) ? expf(v - m) : 0.f;
+  __syncthreads();
+  if (tid < SE_CHUNK) e[tid] = ev;
+  float sm = warp_sum(ev);
+  if (lane == 0) red[warp] = sm;
+  __syncthreads();
+  float* out = ws + ((int64_t)f * n_chunks + chunk) * (C + 2);
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    out[0] = m;
+    out[1] = s;
+  }
+  // phase 3: pooled partials: each thread accumulates its 8 channels over its rows, then reduce across row groups
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+  if (rsub < rows_per_pass)
+    for (int n = rsub; n < cnt; n += rows_per_pass) {
+      const uint4 vv = yf[(int64_t)n * G + g];
+      const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&vv);
+      const float en = e[n];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 fv = __bfloat1622float2(vb[q]);
+        acc[2 * q] = fmaf(en, fv.x, acc[2 * q]);
+        acc[2 * q + 1] = fmaf(en, fv.y, acc[2 * q + 1]);
+      }
+    }
+  if (rsub < rows_per_pass) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dyn[rsub * C + g * 8 + q] = acc[q];
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    float t = 0.f;
+    for (int r = 0; r < rows_per_pass; ++r) t += dyn[r * C + c];
+    out[2 + c] = t;
+  }
+}
+
 __global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict__ ws, int n_chunks, int C, int Hd,
                                                         const float* __restrict__ w1, const float* __restrict__ b1,
                                                         float* __restrict__ hidden_out) {
@@ -559,6 +657,168 @@ __global__ void __launch_bounds__(128) attention_kernel(const mv2_attn_args a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// softmax attention core on tensor cores (warp-level mma.sync m16n8k16, bf16 in / fp32 accumulate):
+// flash-style, non-causal, memory key/values prepended, sequences addressed through strides.
+// 4 warps x 16 queries per block; keys/values staged per 64-key tile (V transposed) in shared memory;
+// online softmax with quad shuffles.  Used for bf16 sequences with L >= 64 (space attention).
+// ------------------------------------------------------------------------------------------
+constexpr int FA_Q = 64, FA_KT = 64;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) attention_mma_kernel(const mv2_attn_args a) {
+  constexpr int DK = D / 16, DN = D / 8;
+  __shared__ __align__(16) __nv_bfloat16 Ks[FA_KT][D + 8];
+  __shared__ __align__(16) __nv_bfloat16 Vt[D][FA_KT + 8];
+  const __nv_bfloat16* __restrict__ qkv = (const __nv_bfloat16*)a.qkv;
+  __nv_bfloat16* __restrict__ out = (__nv_bfloat16*)a.out;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.y;
+  const int64_t seq = blockIdx.x;
+  const int64_t so = seq / a.n_inner, sn = seq % a.n_inner;
+  const int64_t base = so * a.outer_stride + sn * a.inner_stride;
+  const int q0 = blockIdx.z * FA_Q + warp * 16;
+  const int HD = a.heads * D;
+  const int64_t row_stride = 3 * (int64_t)HD;
+  const float sc = rsqrtf((float)D) * 1.4426950408889634f;   // softmax scale folded with log2(e)
+  const int Ltot = a.n_mem + a.L;
+
+  // Q fragments for rows q0+g and q0+g+8
+  uint32_t qa[DK][4];
+  {
+    const int r0 = q0 + g, r1 = q0 + g + 8;
+    const __nv_bfloat16* p0 = qkv + (base + (int64_t)min(r0, a.L - 1) * a.tok_stride) * row_stride + h * D;
+    const __nv_bfloat16* p1 = qkv + (base + (int64_t)min(r1, a.L - 1) * a.tok_stride) * row_stride + h * D;
+#pragma unroll
+    for (int k = 0; k < DK; ++k) {
+      qa[k][0] = *reinterpret_cast<const uint32_t*>(p0 + k * 16 + t * 2);
+      qa[k][1] = *reinterpret_cast<const uint32_t*>(p1 + k * 16 + t * 2);
+      qa[k][2] = *reinterpret_cast<const uint32_t*>(p0 + k * 16 + 8 + t * 2);
+      qa[k][3] = *reinterpret_cast<const uint32_t*>(p1 + k * 16 + 8 + t * 2);
+    }
+  }
+  float o[DN][4];
+#pragma unroll
+  for (int i = 0; i < DN; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int j0 = 0; j0 < Ltot; j0 += FA_KT) {
+    __syncthreads();
+    // ---- stage K (row major) and V (transposed) for keys j0 .. j0+63 ----
+    for (int idx = tid; idx < FA_KT * (D / 8); idx += 128) {
+      const int j = idx / (D / 8), c = (idx % (D / 8)) * 8;
+      const int jg = j0 + j;
+      uint4 kv4 = make_uint4(0, 0, 0, 0), vv4 = make_uint4(0, 0, 0, 0);
+      if (jg < a.n_mem) {
+        const float* mk = a.mem_kv + (((int64_t)0 * a.heads + h) * a.n_mem + jg) * D + c;
+        const float* mv = a.mem_kv + (((int64_t)1 * a.heads + h) * a.n_mem + jg) * D + c;
+        kv4.x = pack2_bf16(mk[0], mk[1]); kv4.y = pack2_bf16(mk[2], mk[3]);
+        kv4.z = pack2_bf16(mk[4], mk[5]); kv4.w = pack2_bf16(mk[6], mk[7]);
+        vv4.x = pack2_bf16(mv[0], mv[1]); vv4.y = pack2_bf16(mv[2], mv[3]);
+        vv4.z = pack2_bf16(mv[4], mv[5]); vv4.w = pack2_bf16(mv[6], mv[7]);
+      } else if (jg < Ltot) {
+        const __nv_bfloat16* row = qkv + (base + (int64_t)(jg - a.n_mem) * a.tok_stride) * row_stride;
+        kv4 = *reinterpret_cast<const uint4*>(row + HD + h * D + c);
+        vv4 = *reinterpret_cast<const uint4*>(row + 2 * HD + h * D + c);
+      }
+      *reinterpret_cast<uint4*>(&Ks[j][c]) = kv4;
+      const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(&vv4);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) Vt[c + q][j] = vb[q];
+    }
+    __syncthreads();
+    // ---- S = Q K^T (16 x 64 per warp) ----
+    float sfr[FA_KT / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < FA_KT / 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sfr[nt][j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < DK; ++k) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][k * 16 + t * 2]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][k * 16 + 8 + t * 2]);
+        mma_bf16_16816(sfr[nt], qa[k], b0, b1);
+      }
+    }
+    // ---- online softmax ----
+    float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < FA_KT / 8; ++nt) {
+      const int kcol = j0 + nt * 8 + t * 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool valid = (kcol + (j & 1)) < Ltot;
+        sfr[nt][j] = valid ? sfr[nt][j] * sc : -INFINITY;
+      }
+      tm0 = fmaxf(tm0, fmaxf(sfr[nt][0], sfr[nt][1]));
+      tm1 = fmaxf(tm1, fmaxf(sfr[nt][2], sfr[nt][3]));
+    }
+    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
+    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
+    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+    const float mn0 = fmaxf(m0, tm0), mn1 = fmaxf(m1, tm1);   // finite: every tile holds >= 1 valid key
+    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int i = 0; i < DN; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+#pragma unroll
+    for (int nt = 0; nt < FA_KT / 8; ++nt) {
+      sfr[nt][0] = exp2f(sfr[nt][0] - mn0); sfr[nt][1] = exp2f(sfr[nt][1] - mn0);
+      sfr[nt][2] = exp2f(sfr[nt][2] - mn1); sfr[nt][3] = exp2f(sfr[nt][3] - mn1);
+      l0 += sfr[nt][0] + sfr[nt][1];
+      l1 += sfr[nt][2] + sfr[nt][3];
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int kk = 0; kk < FA_KT / 16; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack2_bf16(sfr[2 * kk][0], sfr[2 * kk][1]);
+      pa[1] = pack2_bf16(sfr[2 * kk][2], sfr[2 * kk][3]);
+      pa[2] = pack2_bf16(sfr[2 * kk + 1][0], sfr[2 * kk + 1][1]);
+      pa[3] = pack2_bf16(sfr[2 * kk + 1][2], sfr[2 * kk + 1][3]);
+#pragma unroll
+      for (int dn = 0; dn < DN; ++dn) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Vt[dn * 8 + g][kk * 16 + t * 2]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Vt[dn * 8 + g][kk * 16 + 8 + t * 2]);
+        mma_bf16_16816(o[dn], pa, b0, b1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int r0 = q0 + g, r1 = q0 + g + 8;
+  if (r0 < a.L) {
+    __nv_bfloat16* orow = out + (base + (int64_t)r0 * a.tok_stride) * HD + h * D;
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) *reinterpret_cast<uint32_t*>(orow + dn * 8 + t * 2) = pack2_bf16(o[dn][0] * i0, o[dn][1] * i0);
+  }
+  if (r1 < a.L) {
+    __nv_bfloat16* orow = out + (base + (int64_t)r1 * a.tok_stride) * HD + h * D;
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) *reinterpret_cast<uint32_t*>(orow + dn * 8 + t * 2) = pack2_bf16(o[dn][2] * i1, o[dn][3] * i1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Taylor-series linear attention core (dim_head = 8, feature dim 1 + 8 + 64 = 73)
 // ------------------------------------------------------------------------------------------
@@ -575,17 +835,28 @@ __device__ __forceinline__ float taylor_feat(const float* v, int f) {
 template <typename T>
 __global__ void __launch_bounds__(256) linattn_reduce_kernel(const T* __restrict__ kv, float* __restrict__ ws,
                                                              int L, int heads, int n_chunks) {
-  __shared__ float ks[64][LA_D];
-  __shared__ float vs[64][LA_D + 1];
+  // S[f][e] = sum_n phi(k_n)[f] * [v_n, 1][e]; phi is evaluated once per token into shared memory, then each thread
+  // accumulates its (f, e) outputs with two smem reads + one FMA per token.
+  constexpr int TB = 64;
+  __shared__ float phi[TB][LA_F + 1];
+  __shared__ float vs[TB][LA_D + 1];
+  __shared__ float ks[TB][LA_D];
   const int chunk = blockIdx.x, h = blockIdx.y;
   const int64_t seq = blockIdx.z;
   const int tid = threadIdx.x;
   const int HD = heads * LA_D;
   float acc[3] = {0.f, 0.f, 0.f};
+  int fo[3], eo[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int idx = tid + 256 * r;
+    fo[r] = idx / (LA_D + 1);
+    eo[r] = idx % (LA_D + 1);
+  }
   const int t_begin = chunk * LA_CHUNK, t_end = min(L, t_begin + LA_CHUNK);
-  for (int t0 = t_begin; t0 < t_end; t0 += 64) {
+  for (int t0 = t_begin; t0 < t_end; t0 += TB) {
     __syncthreads();
-    for (int idx = tid; idx < 64 * LA_D; idx += 256) {
+    for (int idx = tid; idx < TB * LA_D; idx += 256) {
       const int n = idx / LA_D, d = idx % LA_D;
       const int t = t0 + n;
       float kk = 0.f, vv = 0.f;
@@ -597,17 +868,21 @@ __global__ void __launch_bounds__(256) linattn_reduce_kernel(const T* __restrict
       ks[n][d] = kk;
       vs[n][d] = vv;
     }
-    for (int n = tid; n < 64; n += 256) vs[n][LA_D] = (t0 + n < t_end) ? 1.f : 0.f;
+    for (int n = tid; n < TB; n += 256) vs[n][LA_D] = (t0 + n < t_end) ? 1.f : 0.f;
     __syncthreads();
-    const int cnt = min(64, t_end - t0);
+    for (int idx = tid; idx < TB * LA_F; idx += 256) {
+      const int n = idx / LA_F, f = idx % LA_F;
+      phi[n][f] = (t0 + n < t_end) ? taylor_feat(ks[n], f) : 0.f;
+    }
+    __syncthreads();
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const int idx = tid + 256 * r;
-      if (idx >= LA_ST) continue;
-      const int f = idx / (LA_D + 1), e = idx % (LA_D + 1);
-      float s = acc[r];
-      for (int n = 0; n < cnt; ++n) s = fmaf(taylor_feat(ks[n], f), vs[n][e], s);
-      acc[r] = s;
+      if (tid + 256 * r >= LA_ST) continue;
+      float sacc = acc[r];
+      const int f = fo[r], e = eo[r];
+#pragma unroll 8
+      for (int n = 0; n < TB; ++n) sacc = fmaf(phi[n][f], vs[n][e], sacc);
+      acc[r] = sacc;
     }
   }
   float* o = ws + ((seq * heads + h) * n_chunks + chunk) * LA_ST;
@@ -945,7 +1220,10 @@ int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, 
   dim3 grid(nc, F);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32) se_pool_kernel<float><<<grid, 256, 0, st>>>((const float*)y, P, C, wk, bk, (float*)workspace, nc);
-  else if (dtype == MV2_BF16) se_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, P, C, wk, bk, (float*)workspace, nc);
+  else if (dtype == MV2_BF16 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0) {
+    const size_t dsm = (size_t)(256 / (C / 8)) * C * sizeof(float);
+    se_pool_bf16x8_kernel<<<grid, 256, dsm, st>>>((const __nv_bfloat16*)y, P, C, wk, bk, (float*)workspace, nc);
+  } else if (dtype == MV2_BF16) se_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, P, C, wk, bk, (float*)workspace, nc);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1009,6 +1287,13 @@ int mv2_attention(const mv2_attn_args* a, void* stream) {
   MV2_CHECK_ARG((int64_t)a->n_outer * a->n_inner <= 2147483647LL && ceil_div(a->L, AT_Q) <= 65535);
   cudaStream_t st = (cudaStream_t)stream;
   if (a->dtype == MV2_F32) return launch_attention<float>(a, st);
+  if (a->dtype == MV2_BF16 && !a->causal && a->L >= 64 && (a->dim_head == 32 || a->dim_head == 64) && a->heads * a->dim_head % 8 == 0) {
+    dim3 grid((unsigned)((int64_t)a->n_outer * a->n_inner), a->heads, ceil_div(a->L, FA_Q));
+    if (a->dim_head == 32) attention_mma_kernel<32><<<grid, 128, 0, st>>>(*a);
+    else attention_mma_kernel<64><<<grid, 128, 0, st>>>(*a);
+    MV2_CHECK_LAUNCH();
+    return MV2_OK;
+  }
   if (a->dtype == MV2_BF16) return launch_attention<__nv_bfloat16>(a, st);
   set_error("bad dtype %d", a->dtype);
   return MV2_E_ARG;

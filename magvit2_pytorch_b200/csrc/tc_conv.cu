@@ -104,25 +104,31 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int i = 0; i < n_iters; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (i / p.stages) & 1;
-        mbar_wait(full0 + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t sa = smem_base + s * stage_bytes;
-        const uint64_t ad = make_kmajor_desc(sa, row_bytes);
-        const uint64_t bd = make_kmajor_desc(sa + a_bytes, row_bytes);
-        for (int k = 0; k < bk / 16; ++k) {
-          // advancing 16 bf16 along K = +32 bytes = +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+    // whole warp runs the loop (uniform operands); one elected lane issues the tcgen05 instructions
+    // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t leader = elect_one();
+    const int ksteps = bk >> 4;
+    for (int i = 0; i < n_iters; ++i) {
+      const int s = i % p.stages;
+      const uint32_t ph = (i / p.stages) & 1;
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      const uint32_t sa = smem_base + s * stage_bytes;
+      const uint64_t ad = make_kmajor_desc(sa, row_bytes);
+      const uint64_t bd = make_kmajor_desc(sa + a_bytes, row_bytes);
+      if (leader) {
+        // advancing 16 bf16 along K = +32 bytes = +2 in the (addr >> 4) field
+        umma_bf16(tmem_base, ad, bd, idesc, i > 0 ? 1u : 0u);
+        if (ksteps > 1) umma_bf16(tmem_base, ad + 2, bd + 2, idesc, 1u);
+        if (ksteps > 2) {
+          umma_bf16(tmem_base, ad + 4, bd + 4, idesc, 1u);
+          umma_bf16(tmem_base, ad + 6, bd + 6, idesc, 1u);
         }
         umma_commit(empty0 + 8 * s);   // frees the smem slot once these MMAs retire
       }
-      umma_commit(tfull);              // accumulator complete
     }
+    if (leader) umma_commit(tfull);    // accumulator complete
   } else {
     // ---------------- epilogue warps 2..5 : TMEM lanes 32*(warp%4) .. +31 ----------------
     const int sub = warp & 3;

@@ -131,42 +131,55 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow and operands, so descriptors live in uniform
+    // registers); only the tcgen05 instructions themselves are issued by one elected lane.
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t sbo = (uint32_t)p.pitch * row_bytes;
-      const int ksteps = bk >> 4;
+      const uint64_t lay = (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;
+      const uint64_t a_hi = ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 16) | lay;
+      const uint64_t b_hi = ((uint64_t)((8 * row_bytes) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 16) | lay;
+      const bool k4 = bk == 64;
+      const uint32_t leader = elect_one();
       uint32_t sit = 0, wit = 0, tit = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tit) {
-        const TileCoord c = decode_tile(p, tile);
-        const int dt0 = max(0, p.pt - c.t);
+        const int t_of_tile = (tile / (p.n_tiles_n * p.tiles_w * p.tiles_h)) % p.T;
+        const int dt0 = max(0, p.pt - t_of_tile);
         const uint32_t buf = tit % p.nbuf;
         mbar_wait(t_empty + 8 * buf, ((tit / p.nbuf) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * acc_cols;
-        bool first = true;
+        uint32_t accum = 0;
         for (int dt = dt0; dt < p.kt; ++dt)
           for (int kc = 0; kc < p.kchunks; ++kc, ++sit) {
             const uint32_t s = sit % p.slab_stages;
             mbar_wait(slab_full + 8 * s, (sit / p.slab_stages) & 1);
-            tc_fence_after();
             const uint32_t slab = slab0 + s * p.slab_stride;
-            for (int tp = 0; tp < taps2d; ++tp, ++wit) {
-              const uint32_t ws = wit % p.w_stages;
-              mbar_wait(w_full + 8 * ws, (wit / p.w_stages) & 1);
-              tc_fence_after();
-              const int dh = tp / p.kw, dw = tp - dh * p.kw;
-              const uint64_t bd = make_kmajor_desc_rb(wst0 + ws * w_bytes, 8 * row_bytes, row_bytes);
-              for (int j = 0; j < p.mw; ++j) {
-                const uint64_t ad = make_kmajor_desc_rb(slab + (uint32_t)(dh * p.pitch + 8 * j + dw) * row_bytes, sbo, row_bytes);
-                for (int k = 0; k < ksteps; ++k)
-                  umma_bf16(acc + j * p.bn, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+            for (int dh = 0; dh < p.kh; ++dh)
+              for (int dw = 0; dw < p.kw; ++dw, ++wit) {
+                const uint32_t ws = wit % p.w_stages;
+                mbar_wait(w_full + 8 * ws, (wit / p.w_stages) & 1);
+                tc_fence_after();
+                const uint64_t bd = b_hi | (uint64_t)(((wst0 + ws * w_bytes) & 0x3FFFF) >> 4);
+                const uint32_t a0 = slab + (uint32_t)(dh * p.pitch + dw) * row_bytes;
+                if (leader) {
+                  for (int j = 0; j < p.mw; ++j) {
+                    const uint64_t ad = a_hi | (uint64_t)(((a0 + (uint32_t)j * 8 * row_bytes) & 0x3FFFF) >> 4);
+                    const uint32_t d = acc + j * p.bn;
+                    umma_bf16(d, ad, bd, idesc, accum);
+                    umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                    if (k4) {
+                      umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                      umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                    }
+                  }
+                  umma_commit(w_empty + 8 * ws);
+                }
+                accum = 1;
               }
-              first = false;
-              umma_commit(w_empty + 8 * ws);
-            }
-            umma_commit(slab_empty + 8 * s);
+            if (leader) umma_commit(slab_empty + 8 * s);
           }
-        umma_commit(t_full + 8 * buf);
+        if (leader) umma_commit(t_full + 8 * buf);
       }
     }
   } else if (warp >= 4) {
@@ -242,28 +255,14 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   p.epi.act = a->act; p.epi.shuffle = MV2_SHUFFLE_NONE; p.epi.mode = 0; p.epi.Co = a->Co;
   p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo;
 
-  // ---- tiling: minimise a simple time model  rounds x max(MMA issue, L2 stream) ----
+  // ---- tiling (profiles/r01_sweep_slab_v2.json): widest N tile; two M-tiles per weight tile whenever both
+  //      accumulator sets still double-buffer in TMEM (2 * mw * bn <= 512), which also halves weight traffic ----
   const int tiles_h = ceil_div(a->Ho, 16);
   const int co_pad = (a->Co + 31) / 32 * 32;
-  int best_mw = 1, best_bn = 32;
-  double best_t = 1e30;
-  for (int mw = 1; mw <= 2; ++mw) {
-    if (mw == 2 && a->Wo <= 8) continue;
-    for (int bn = 256; bn >= 32; bn >>= 1) {
-      if (bn > co_pad || co_pad % bn != 0) continue;
-      const int pitch = 8 * mw + a->kw - 1, slab_h = 16 + a->kh - 1;
-      const double slab_b = (double)pitch * slab_h * p.row_bytes;
-      const int64_t units = (int64_t)a->B * a->To * tiles_h * ceil_div(a->Wo, 8 * mw) * (co_pad / bn);
-      const int64_t rounds = (units + n_sm - 1) / n_sm;
-      const double taps = (double)a->kt * p.kchunks * a->kh * a->kw;
-      const double mma = mw * (bk / 16) * std::max(bn / 2.0, 32.0);          // cycles per tap
-      const double issue = std::max(mma, 220.0);                            // barrier wait + descriptor + commit latency
-      const double l2 = ((double)bn * p.row_bytes + slab_b / (a->kh * a->kw)) / 35.0;   // ~10 TB/s over 148 SMs
-      const double epi = (2 * mw * bn <= 512) ? 0.0 : mw * (bn / 32) * 300.0;
-      const double t = rounds * (taps * std::max(issue, l2) + epi + 1500.0);
-      if (t < best_t) { best_t = t; best_mw = mw; best_bn = bn; }
-    }
-  }
+  int best_bn = 32;
+  for (int bn = 256; bn >= 32; bn >>= 1)
+    if (bn <= co_pad && co_pad % bn == 0) { best_bn = bn; break; }
+  int best_mw = (best_bn <= 128 && a->Wo > 8) ? 2 : 1;
   if (const char* env = getenv("MV2_SLAB_CFG")) {   // debug / tuning override: "mw,bn"
     int emw = 0, ebn = 0;
     if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2) && ebn >= 32 && ebn <= 256 && co_pad % ebn == 0 &&

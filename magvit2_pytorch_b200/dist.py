@@ -1,0 +1,93 @@
+"""Multi-GPU plumbing for the VideoTokenizer path: one process per GPU, torch.distributed (NCCL on
+GPUs, gloo in the CPU tests) for the plumbing.
+
+The eval forward is batch independent, so clips are simply sharded across ranks with NO data-path collective.
+The only collective on the path is LFQ's training-mode batch-entropy term (reached
+from reference M:1705): every rank's mean code-probability vector ``avg_prob`` (num_codebooks x codebook_size fp32
+= 4 KiB at the README config) is summed over ranks and divided by the world size.  It is latency bound, so it is
+issued on a side stream and overlaps whatever the caller runs next (the decoder).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of n clips owned by `rank` (first n % world ranks get one extra)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_clips(batch: torch.Tensor, rank: Optional[int] = None, world: Optional[int] = None) -> torch.Tensor:
+    if rank is None or world is None:
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+        else:
+            rank, world = 0, 1
+    lo, hi = shard_range(batch.shape[0], rank, world)
+    return batch[lo:hi]
+
+
+def allreduce_mean_(t: torch.Tensor, group=None, async_op: bool = False):
+    """In-place cross-rank mean (SUM all-reduce then / world), as vector-quantize-pytorch's maybe_distributed_mean.
+    No-op when torch.distributed is not initialised or world == 1.  Returns the work handle when async_op."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    world = dist.get_world_size(group)
+    if world == 1:
+        return None
+    work = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    if async_op:
+        return work, world
+    t.div_(world)
+    return None
+
+
+def entropy_from_avg_prob(avg_prob: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """codebook (batch) entropy  sum_k -p_k log(clamp(p_k, eps))  (A.1 step 7)."""
+    return (-avg_prob * torch.log(avg_prob.clamp(min=eps))).sum(dim=-1)
+
+
+class LfqBatchEntropy:
+    """LFQ training-mode auxiliary terms on the GPU: per-rank partials by mv2_lfq_entropy_partials, then the 4 KiB
+    all-reduce on a side stream.  start() launches; finish() returns
+    (per_sample_entropy, batch_entropy, commitment, aux_loss) as 0-d tensors."""
+
+    def __init__(self, engine, inv_temperature: float = 100.0):
+        self.eng = engine
+        self.inv_temperature = inv_temperature
+        self.side = torch.cuda.Stream(device=engine.device)
+        self._pending = None
+
+    def start(self, presign: torch.Tensor, group=None):
+        from ._lib import check
+        eng = self.eng
+        N, d = presign.shape
+        K = 1 << d
+        avg = torch.zeros(K, device=presign.device, dtype=torch.float32)
+        stats = torch.zeros(2, device=presign.device, dtype=torch.float32)
+        self.side.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(self.side):
+            check(eng.lib.mv2_lfq_entropy_partials(presign.data_ptr(), N, d, float(self.inv_temperature), avg.data_ptr(),
+                                                   stats.data_ptr(), C.c_void_p(self.side.cuda_stream)),
+                  "mv2_lfq_entropy_partials")
+            eng.launches += 1
+            avg.div_(N)                       # local mean code probability
+            allreduce_mean_(avg, group)       # the one collective of the path (NCCL, 4 KiB)
+        presign.record_stream(self.side)
+        self._pending = (avg, stats, N, d)
+
+    def finish(self, diversity_gamma=2.5, entropy_w=0.1, commit_w=1.0):
+        avg, stats, N, d = self._pending
+        torch.cuda.current_stream(self.eng.device).wait_stream(self.side)
+        per_sample = stats[0] / N
+        commitment = stats[1] / (N * d)
+        batch_entropy = entropy_from_avg_prob(avg)
+        aux = (per_sample - diversity_gamma * batch_entropy) * entropy_w + commitment * commit_w
+        self._pending = None
+        return per_sample, batch_entropy, commitment, aux

@@ -361,6 +361,24 @@ class VideoTokenizer(nn.Module):
         return eng.decode_cl(eng.codes_to_quantized_cl(codes))
 
     @torch.no_grad()
+    def lfq_loss_breakdown(self, video, group=None):
+        """Training-mode LFQ auxiliary terms the reference computes at M:1705 (``quantizer_loss_breakdown``):
+        returns ``(codes, (per_sample_entropy, batch_entropy, commitment), aux_loss)``.  ``batch_entropy`` uses the
+        cross-rank mean code probability -- the single 4 KiB all-reduce of the path (dist.LfqBatchEntropy), issued
+        on a side stream.  (The losses' backward and the GAN/perceptual terms are out of scope)"""
+        from .dist import LfqBatchEntropy
+        assert not self.use_fsq, "FSQ has no auxiliary loss (reference M:1702)"
+        video = self._check_video(video)
+        eng = self.engine
+        x = eng.encode_cl(video)
+        _, codes, pre = eng.quantize_cl(x, want_quantized=False, want_aux=True)
+        q = self.quantizers
+        be = LfqBatchEntropy(eng)
+        be.start(pre, group)
+        ps, bent, commit, aux = be.finish(q.diversity_gamma, q.entropy_loss_weight, q.commitment_loss_weight)
+        return codes, (ps, bent, commit), aux
+
+    @torch.no_grad()
     def tokenize(self, video):
         """M:1651-1654."""
         self.eval()

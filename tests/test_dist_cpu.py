@@ -1,0 +1,75 @@
+"""world_size-2 gloo tests (CPU) for the host-side multi-GPU logic: clip sharding and the LFQ batch-entropy
+all-reduce (the only collective on the path)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from magvit2_pytorch_b200.dist import allreduce_mean_, entropy_from_avg_prob, shard_clips, shard_range
+
+
+def test_shard_range_partitions_exactly():
+    for n in (1, 4, 7, 32, 33):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.restated import lfq_train_losses
+    g = torch.Generator().manual_seed(0)
+    presign = torch.randn(8, 40, 10, generator=g) * 0.7          # (clips, tokens, bits) -- the full batch
+    local = shard_clips(presign)                                  # this rank's clips
+    assert local.shape[0] == 4
+
+    def reduce(avg):
+        avg = avg.clone()
+        allreduce_mean_(avg)
+        return avg
+
+    ps, be, cm, aux, avg = lfq_train_losses(local, 10, world_reduce=reduce)
+    q.put((rank, ps.item(), be.item(), cm.item(), aux.item(), avg))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_lfq_batch_entropy_allreduce_world2_gloo():
+    from oracle.restated import lfq_train_losses
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(0)
+    presign = torch.randn(8, 40, 10, generator=g) * 0.7
+    ps_all, be_all, cm_all, _, avg_all = lfq_train_losses(presign, 10)
+    # batch entropy comes from the GLOBAL mean code probability -> identical on both ranks and equal to the
+    # single-process value on the whole batch; per-sample entropy / commitment are per-rank means
+    for rank, ps, be, cm, aux, avg in res:
+        assert abs(be - be_all.item()) < 1e-5
+        assert torch.allclose(avg, avg_all, atol=1e-6)
+        assert abs(be - entropy_from_avg_prob(avg).item()) < 1e-6
+    assert abs((res[0][1] + res[1][1]) / 2 - ps_all.item()) < 1e-5
+    assert abs((res[0][3] + res[1][3]) / 2 - cm_all.item()) < 1e-5

@@ -125,3 +125,17 @@ def test_bf16_path_vs_fp32_oracle(name):
     if not g["kwargs"].get("use_fsq", False) and mism.any():
         margin = g["presign"].reshape(*ref_codes.shape, -1).abs().min(dim=-1).values
         assert margin[mism].max().item() < 0.15
+
+
+def test_lfq_training_aux_terms_vs_oracle():
+    """LFQ entropy / commitment terms from the CUDA partial-sum kernel (+ the
+    all-reduce path at world size 1) against the oracle, fp32."""
+    _require_cuda()
+    from oracle.restated import lfq_train_losses
+    g = load_golden("mini")
+    model = build_product(g["kwargs"], g["wseed"]).cuda()
+    codes, (ps, be, cm), aux = model.lfq_loss_breakdown(golden_video(g).cuda())
+    assert torch.equal(codes.cpu(), g["codes"])
+    rps, rbe, rcm, raux, _ = lfq_train_losses(g["presign"], 10)
+    for got, ref in ((ps, rps), (be, rbe), (cm, rcm), (aux, raux)):
+        assert abs(got.item() - ref.item()) <= 2e-4 * max(1.0, abs(ref.item())), (got.item(), ref.item())

@@ -185,3 +185,30 @@ def test_conv_in_kwpack_matches_cuda_core(variant):
     a, b = y_tc.float(), y_ref.float()
     assert a.shape == b.shape
     assert (a - b).abs().max().item() <= 0.008 * b.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("L,D,heads,nseq", [(256, 32, 8, 6), (100, 32, 4, 3), (1024, 32, 2, 2), (128, 64, 4, 2)])
+def test_attention_tensor_core_kernel_matches_fp32_cuda_core(L, D, heads, nseq):
+    """bf16 mma.sync flash-attention kernel (space attention) vs the fp32 CUDA-core attention kernel on the same
+    (bf16-representable) inputs."""
+    import ctypes as C
+    from magvit2_pytorch_b200 import _lib
+    from magvit2_pytorch_b200._lib import AttnArgs, check
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(L + D)
+    HD = heads * D
+    qkv = (torch.randn((nseq * L, 3 * HD), generator=g) * 1.5).to(torch.bfloat16).cuda()
+    mem = torch.randn((2, heads, 4, D), generator=g).to(torch.bfloat16).float().cuda()
+    outs = {}
+    for dt, code in ((torch.bfloat16, 1), (torch.float32, 0)):
+        x = qkv.to(dt).contiguous()
+        o = torch.empty((nseq * L, HD), device="cuda", dtype=dt)
+        a = AttnArgs(qkv=x.data_ptr(), out=o.data_ptr(), mem_kv=mem.data_ptr(), dtype=code, heads=heads, dim_head=D,
+                     n_mem=4, causal=0, n_outer=nseq, n_inner=1, L=L, outer_stride=L, inner_stride=0, tok_stride=1)
+        check(lib.mv2_attention(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mv2_attention")
+        outs[dt] = o.float()
+    torch.cuda.synchronize()
+    a_, b_ = outs[torch.bfloat16], outs[torch.float32]
+    assert torch.isfinite(a_).all()
+    assert (a_ - b_).abs().max().item() < 0.03 * b_.abs().max().item() + 5e-3
+    assert (a_ - b_).abs().mean().item() < 0.006 * b_.abs().mean().item() + 1e-3
