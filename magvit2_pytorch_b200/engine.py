@@ -130,6 +130,7 @@ class Engine:
         self.lib = _lib.load()
         self._packs: Dict[str, object] = {}
         self._sig = None
+        self._sig_id = 0             # bumped whenever parameters are re-packed (invalidates cached CUDA graphs)
         self.launches = 0            # kernels launched through the C ABI (bench's gpu_launches)
         self.use_tc = True           # bf16: dense contractions on tcgen05 (False -> CUDA-core cross-check path)
         self.tc_variant = "auto"     # "auto" | "tap" (tc_conv.cu only) | "slab" (prefer tc_slab.cu)
@@ -234,6 +235,7 @@ class Engine:
                           wout=q.project_out.weight.detach().to(dt).float().contiguous(), bout=q.project_out.bias.detach().to(dt).float().contiguous())
         self._packs = P
         self._sig = sig
+        self._sig_id += 1
 
     # ------------------------------------------------------------------ primitive ops
     def _stream(self):
@@ -288,7 +290,8 @@ class Engine:
                     check(self.lib.mv2_tc_conv_forward(C.byref(ta), self._stream()), "mv2_tc_conv_forward")
                 if self._prof is not None:
                     e1.record()
-                    self._prof.append((e0, e1, 2.0 * B * To * Ho * Wo * pk.Co * pk.Ci * pk.k[0] * pk.k[1] * pk.k[2]))
+                    self._prof.append((e0, e1, 2.0 * B * To * Ho * Wo * pk.Co * pk.Ci * pk.k[0] * pk.k[1] * pk.k[2],
+                                       "slab" if use_slab else "tap", pk.k[1] * pk.k[2] * pk.k[0]))
                 self.launches += 1
                 self.tc_calls += 1
                 return y
@@ -398,23 +401,27 @@ class Engine:
         return self.conv(o, p["out"], res=x)
 
     def profile_convs(self, fn, steps: int = 3):
-        """Runs fn() `steps` times with CUDA events around every tcgen05 conv launch (on the launching
-        stream).  Returns (kernel ms per step, launches per step, algorithmic FLOPs per step)."""
+        """Runs fn() `steps` times with CUDA events around every tcgen05 conv launch (on the launching stream).
+        A long spin kernel is queued first so the host runs ahead of the GPU and the event pairs bracket pure
+        kernel time, not host launch gaps.  Returns {class: (kernel ms per step, launches per step, FLOPs per step)}
+        for class in 'conv3d' (taps > 1 convs in tc_slab_kernel: the causal Conv3d path) and 'all' (every tcgen05 launch)."""
         fn()
         torch.cuda.synchronize(self.device)
         self._prof = []
         try:
             for _ in range(steps):
+                torch.cuda._sleep(int(40e6))          # ~20 ms of GPU busy-wait: lets the host enqueue the whole step
                 fn()
             torch.cuda.synchronize(self.device)
-            ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self._prof)
-            fl = sum(f for _, _, f in self._prof)
-            n = len(self._prof)
+            recs = [(e0.elapsed_time(e1), f, kind, taps) for e0, e1, f, kind, taps in self._prof]
         finally:
             self._prof = None
-        if n == 0:
-            return None, 0, 0.0
-        return ms / steps, n // steps, fl / steps
+        out = {}
+        for name, sel in (("conv3d", lambda r: r[2] == "slab" and r[3] > 1), ("all", lambda r: True)):
+            rs = [r for r in recs if sel(r)]
+            if rs:
+                out[name] = (sum(r[0] for r in rs) / steps, len(rs) // steps, sum(r[1] for r in rs) / steps)
+        return out
 
     # ------------------------------------------------------------------ stages
     def _stage(self, x, st, key, decoder: bool):

@@ -139,3 +139,24 @@ def test_lfq_training_aux_terms_vs_oracle():
     rps, rbe, rcm, raux, _ = lfq_train_losses(g["presign"], 10)
     for got, ref in ((ps, rps), (be, rbe), (cm, rcm), (aux, raux)):
         assert abs(got.item() - ref.item()) <= 2e-4 * max(1.0, abs(ref.item())), (got.item(), ref.item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cuda_graph_replay_equals_eager(dtype):
+    """Opt-in CUDA-graph replay of the static launch plan returns exactly what the eager launches return."""
+    _require_cuda()
+    g = load_golden("mini")
+    model = build_product(g["kwargs"], g["wseed"]).cuda().to(dtype)
+    vids = [golden_video(g).cuda() + 0.1 * i for i in range(4)]
+    eager = [(model.tokenize(v), model(v, return_recon=True)) for v in vids]
+    dec_eager = [model.decode_from_code_indices(c) for c, _ in eager]
+    model.cuda_graphs = True
+    for rep in range(2):
+        for i, v in enumerate(vids):                # call 0 warms up, call 1 captures, later calls replay
+            c = model.tokenize(v)
+            r = model(v, return_recon=True)
+            d = model.decode_from_code_indices(c)
+            assert torch.equal(c, eager[i][0])
+            assert torch.equal(r, eager[i][1])
+            assert torch.equal(d, dec_eager[i])
+    assert any(isinstance(e, tuple) for e in model._graphs.values()), "no graph was captured"
