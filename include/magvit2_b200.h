@@ -106,7 +106,7 @@ int mv2_conv_forward(const mv2_conv_args* a, void* stream);
 size_t mv2_se_workspace_bytes(int F, int P, int C);
 int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, float bk,
                 void* workspace, void* stream);
-int mv2_se_gate(const void* workspace, int F, int P, int C, int Hd,
+int mv2_se_gate(const void* workspace, int dtype /* of the y passed to mv2_se_pool */, int F, int P, int C, int Hd,
                 const float* w1, const float* b1, const float* w2, const float* b2,
                 float* gates, void* stream);
 int mv2_gate_residual(const void* y, const void* x, const float* gates, void* out, int dtype,

@@ -69,7 +69,7 @@ SIGNATURES = {
     "mv2_conv_forward": (_I, [C.POINTER(ConvArgs), _VP]),
     "mv2_se_workspace_bytes": (_SZ, [_I, _I, _I]),
     "mv2_se_pool": (_I, [_VP, _I, _I, _I, _I, _VP, _F, _VP, _VP]),
-    "mv2_se_gate": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "mv2_se_gate": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mv2_gate_residual": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "mv2_rmsnorm": (_I, [_VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP]),
     "mv2_attention": (_I, [C.POINTER(AttnArgs), _VP]),

@@ -319,100 +319,85 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const T* __restrict__ y, i
   }
 }
 
-// bf16 / C % 8 == 0 variant of se_pool_kernel: 16-byte loads, one 8-channel group per thread.
-//   G = C / 8 groups per position; 256 / G positions are processed per pass (G <= 256 required).
-__global__ void __launch_bounds__(256) se_pool_bf16x8_kernel(const __nv_bfloat16* __restrict__ y, int P, int C,
+// bf16 single-pass variant of se_pool_kernel (online softmax): a row's C channels are spread over G = C / VEC lanes
+// (VEC = 8, 16 or 32 bf16 per lane, G <= 32 a power of two), 256 / G row groups per block walk the chunk's rows once:
+//   logit (lane-group shuffle reduce) -> running max / rescale -> acc[c] += exp(l - m) * y[c].
+// The row groups' partial (m, s, acc) are merged through shared memory and one (m, s, pooled[C]) record per chunk is
+// written, same workspace format as se_pool_kernel.
+template <int VEC>
+__global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16* __restrict__ y, int P, int C,
                                                              const float* __restrict__ wk, float bk,
-                                                             float* __restrict__ ws, int n_chunks) {
-  __shared__ float e[SE_CHUNK];
-  __shared__ float red[8];
-  __shared__ float bcast;
-  extern __shared__ float dyn[];         // pooled partial sums [256 / G][C] for the cross-row reduction
+                                                             float* __restrict__ ws, int n_chunks, int chunk_rows) {
+  extern __shared__ float dyn[];           // [R][C + 2]
   const int f = blockIdx.y, chunk = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int G = C >> 3;
-  const int rows_per_pass = 256 / G;
+  const int tid = threadIdx.x;
+  const int G = C / VEC, R = 256 / G;
   const int g = tid % G, rsub = tid / G;
-  const int p0 = chunk * SE_CHUNK;
-  const int cnt = min(SE_CHUNK, P - p0);
-  const uint4* yf = reinterpret_cast<const uint4*>(y + ((int64_t)f * P + p0) * C);
-  float wv[8];
+  const int p0 = chunk * chunk_rows;
+  const int cnt = min(chunk_rows, P - p0);
+  const __nv_bfloat16* yf = y + ((int64_t)f * P + p0) * C + g * VEC;
+  float wv[VEC], acc[VEC];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) wv[q] = wk[g * 8 + q];
-  if (tid < SE_CHUNK) e[tid] = 0.f;
-  __syncthreads();
-  // phase 1: logits (partial dot per thread, reduced across the G threads that share a row).  The loop is
-  // warp-uniform (every lane runs every pass) so the full-mask shuffles are safe for ragged chunk sizes.
-  for (int nb = 0; nb < cnt; nb += rows_per_pass) {
+  for (int q = 0; q < VEC; ++q) { wv[q] = wk[g * VEC + q]; acc[q] = 0.f; }
+  float m = -INFINITY, ssum = 0.f;
+  for (int nb = 0; nb < cnt; nb += R) {     // warp-uniform trip count
     const int n = nb + rsub;
     const bool ok = n < cnt;
-    float s = 0.f;
+    float v[VEC];
+    float dot = 0.f;
     if (ok) {
-      const uint4 v = yf[(int64_t)n * G + g];
-      const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const uint4* src = reinterpret_cast<const uint4*>(yf + (int64_t)n * C);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 fv = __bfloat1622float2(vb[q]);
-        s = fmaf(fv.x, wv[2 * q], s);
-        s = fmaf(fv.y, wv[2 * q + 1], s);
+      for (int u = 0; u < VEC / 8; ++u) {
+        const uint4 raw = src[u];
+        const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 fv = __bfloat1622float2(vb[q]);
+          v[u * 8 + 2 * q] = fv.x;
+          v[u * 8 + 2 * q + 1] = fv.y;
+        }
       }
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) dot = fmaf(v[q], wv[q], dot);
+    } else {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) v[q] = 0.f;
     }
-    if (G <= 32) {   // G is a power of two here (256 % G == 0): rows occupy aligned lane groups
-      for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (g == 0 && ok) e[n] = s;
-    } else if (ok) {
-      atomicAdd(&e[n], s);
+    for (int o = G >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (ok) {
+      const float l = dot + bk;
+      const float mn = fmaxf(m, l);
+      const float sc = __expf(m - mn), e = __expf(l - mn);
+      ssum = ssum * sc + e;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc[q] = fmaf(e, v[q], acc[q] * sc);
+      m = mn;
     }
   }
+  float* mine = dyn + (size_t)rsub * (C + 2);
+  if (g == 0) { mine[0] = m; mine[1] = ssum; }
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) mine[2 + g * VEC + q] = acc[q];
   __syncthreads();
-  float v = (tid < cnt) ? e[tid] + bk : -INFINITY;
-  float mx = warp_max(v);
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  if (tid == 0) {
-    float m = red[0];
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
-    bcast = m;
-  }
-  __syncthreads();
-  const float m = bcast;
-  const float ev = (tid < cnt) ? expf(v - m) : 0.f;
-  __syncthreads();
-  if (tid < SE_CHUNK) e[tid] = ev;
-  float sm = warp_sum(ev);
-  if (lane == 0) red[warp] = sm;
-  __syncthreads();
+  float M = -INFINITY;
+  for (int r = 0; r < R; ++r) M = fmaxf(M, dyn[(size_t)r * (C + 2)]);
   float* out = ws + ((int64_t)f * n_chunks + chunk) * (C + 2);
   if (tid == 0) {
-    float s = 0.f;
-    for (int i = 0; i < 8; ++i) s += red[i];
-    out[0] = m;
-    out[1] = s;
-  }
-  // phase 3: pooled partials: each thread accumulates its 8 channels over its rows, then reduce across row groups
-  float acc[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-  if (rsub < rows_per_pass)
-    for (int n = rsub; n < cnt; n += rows_per_pass) {
-      const uint4 vv = yf[(int64_t)n * G + g];
-      const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&vv);
-      const float en = e[n];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 fv = __bfloat1622float2(vb[q]);
-        acc[2 * q] = fmaf(en, fv.x, acc[2 * q]);
-        acc[2 * q + 1] = fmaf(en, fv.y, acc[2 * q + 1]);
-      }
+    float S = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const float mr = dyn[(size_t)r * (C + 2)];
+      if (mr > -INFINITY) S += dyn[(size_t)r * (C + 2) + 1] * __expf(mr - M);
     }
-  if (rsub < rows_per_pass) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) dyn[rsub * C + g * 8 + q] = acc[q];
+    out[0] = M;
+    out[1] = S;
   }
-  __syncthreads();
   for (int c = tid; c < C; c += 256) {
     float t = 0.f;
-    for (int r = 0; r < rows_per_pass; ++r) t += dyn[r * C + c];
+    for (int r = 0; r < R; ++r) {
+      const float mr = dyn[(size_t)r * (C + 2)];
+      if (mr > -INFINITY) t = fmaf(dyn[(size_t)r * (C + 2) + 2 + c], __expf(mr - M), t);
+    }
     out[2 + c] = t;
   }
 }
@@ -557,6 +542,62 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, T
     if (token_shift && c >= half) v = has_prev ? to_f32<T>(prow[c]) : 0.f;
     else v = to_f32<T>(row[c]);
     orow[c] = from_f32<T>(((v / denom) * scale) * gamma[c]);
+  }
+}
+
+
+// bf16, C % 8 == 0: one warp per token, 16-byte accesses, the row is held in registers between the two phases
+// (C <= 1024: at most 4 uint4 per lane).
+__global__ void __launch_bounds__(256) rmsnorm_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                             const float* __restrict__ gamma, int64_t n_tok, int T_,
+                                                             int P, int C, int token_shift) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= n_tok) return;
+  const int t = (int)((tok / P) % T_);
+  const int half = C >> 1;
+  const __nv_bfloat16* row = x + tok * C;
+  const __nv_bfloat16* prow = row - (int64_t)P * C;
+  const bool has_prev = t > 0;
+  uint4 v[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = (u * 32 + lane) * 8;
+    v[u] = make_uint4(0, 0, 0, 0);
+    if (c < C) {
+      if (token_shift && c >= half) { if (has_prev) v[u] = *reinterpret_cast<const uint4*>(prow + c); }
+      else v[u] = *reinterpret_cast<const uint4*>(row + c);
+      const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(vb[q]);
+        ss = fmaf(f.x, f.x, ss);
+        ss = fmaf(f.y, f.y, ss);
+      }
+    }
+  }
+  ss = warp_sum(ss);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  const float scale = sqrtf((float)C);
+  __nv_bfloat16* orow = out + tok * C;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = (u * 32 + lane) * 8;
+    if (c < C) {
+      const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      uint4 o;
+      uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(vb[q]);
+        __nv_bfloat162 r = __floats2bfloat162_rn(((f.x / denom) * scale) * gg[2 * q], ((f.y / denom) * scale) * gg[2 * q + 1]);
+        ob[q] = *reinterpret_cast<uint32_t*>(&r);
+      }
+      *reinterpret_cast<uint4*>(orow + c) = o;
+    }
   }
 }
 
@@ -894,39 +935,84 @@ __global__ void __launch_bounds__(256) linattn_reduce_kernel(const T* __restrict
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) linattn_apply_kernel(const T* __restrict__ q, const float* __restrict__ ws,
-                                                            T* __restrict__ out, int L, int heads, int n_chunks) {
+__global__ void __launch_bounds__(64) linattn_apply_kernel(const T* __restrict__ q, const float* __restrict__ ws,
+                                                           T* __restrict__ out, int L, int heads, int n_chunks) {
+  // block = 64 threads x 4 tokens = one LA_CHUNK of tokens; every state value read from smem feeds 4 tokens
   __shared__ float S[LA_ST];
   const int chunk = blockIdx.x, h = blockIdx.y;
   const int64_t seq = blockIdx.z;
   const int tid = threadIdx.x;
   const int HD = heads * LA_D;
   const float* wsh = ws + (seq * heads + h) * (int64_t)n_chunks * LA_ST;
-  for (int idx = tid; idx < LA_ST; idx += 256) {
+  for (int idx = tid; idx < LA_ST; idx += 64) {
     float s = 0.f;
     for (int k = 0; k < n_chunks; ++k) s += wsh[(int64_t)k * LA_ST + idx];
     S[idx] = s;
   }
   __syncthreads();
-  const int t = chunk * LA_CHUNK + tid;
-  if (t >= L) return;
-  const int64_t tok = seq * L + t;
-  float qv[LA_D];
+  constexpr int TPT = LA_CHUNK / 64;   // 4 tokens per thread, strided by 64 for coalescing
+  float qv[TPT][LA_D], num[TPT][LA_D], den[TPT];
   const float qscale = rsqrtf((float)LA_D);
+  bool ok[TPT];
 #pragma unroll
-  for (int d = 0; d < LA_D; ++d) qv[d] = to_f32<T>(q[tok * HD + h * LA_D + d]) * qscale;
-  float num[LA_D], den = 0.f;
+  for (int u = 0; u < TPT; ++u) {
+    const int t = chunk * LA_CHUNK + u * 64 + tid;
+    ok[u] = t < L;
+    const int64_t tok = seq * L + (ok[u] ? t : 0);
 #pragma unroll
-  for (int e = 0; e < LA_D; ++e) num[e] = 0.f;
-  for (int f = 0; f < LA_F; ++f) {
-    const float pf = taylor_feat(qv, f);
-#pragma unroll
-    for (int e = 0; e < LA_D; ++e) num[e] = fmaf(pf, S[f * (LA_D + 1) + e], num[e]);
-    den = fmaf(pf, S[f * (LA_D + 1) + LA_D], den);
+    for (int d = 0; d < LA_D; ++d) {
+      qv[u][d] = ok[u] ? to_f32<T>(q[tok * HD + h * LA_D + d]) * qscale : 0.f;
+      num[u][d] = 0.f;
+    }
+    den[u] = 0.f;
   }
-  den = fmaxf(den, 1e-5f);
+  // f = 0 (constant feature)
 #pragma unroll
-  for (int e = 0; e < LA_D; ++e) out[tok * HD + h * LA_D + e] = from_f32<T>(num[e] / den);
+  for (int u = 0; u < TPT; ++u) {
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) num[u][e] = S[e];
+    den[u] = S[LA_D];
+  }
+  // linear features
+#pragma unroll
+  for (int i = 0; i < LA_D; ++i) {
+    const float* Sr = S + (1 + i) * (LA_D + 1);
+    float sv[LA_D + 1];
+#pragma unroll
+    for (int e = 0; e <= LA_D; ++e) sv[e] = Sr[e];
+#pragma unroll
+    for (int u = 0; u < TPT; ++u) {
+      const float pf = qv[u][i];
+#pragma unroll
+      for (int e = 0; e < LA_D; ++e) num[u][e] = fmaf(pf, sv[e], num[u][e]);
+      den[u] = fmaf(pf, sv[LA_D], den[u]);
+    }
+  }
+  // quadratic features
+#pragma unroll
+  for (int i = 0; i < LA_D; ++i)
+#pragma unroll
+    for (int j = 0; j < LA_D; ++j) {
+      const float* Sr = S + (1 + LA_D + i * LA_D + j) * (LA_D + 1);
+      float sv[LA_D + 1];
+#pragma unroll
+      for (int e = 0; e <= LA_D; ++e) sv[e] = Sr[e];
+#pragma unroll
+      for (int u = 0; u < TPT; ++u) {
+        const float pf = qv[u][i] * qv[u][j] * 0.70710678118654752440f;
+#pragma unroll
+        for (int e = 0; e < LA_D; ++e) num[u][e] = fmaf(pf, sv[e], num[u][e]);
+        den[u] = fmaf(pf, sv[LA_D], den[u]);
+      }
+    }
+#pragma unroll
+  for (int u = 0; u < TPT; ++u) {
+    if (!ok[u]) continue;
+    const int64_t tok = seq * L + chunk * LA_CHUNK + u * 64 + tid;
+    const float dn = fmaxf(den[u], 1e-5f);
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) out[tok * HD + h * LA_D + e] = from_f32<T>(num[u][e] / dn);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1213,30 +1299,51 @@ size_t mv2_se_workspace_bytes(int F, int P, int C) {
   return ((size_t)F * ceil_div(P, SE_CHUNK) * (C + 2) + (size_t)F * (C + 16)) * sizeof(float);
 }
 
+// the single-pass bf16 kernel processes SE_CHUNK * se_chunk_mult(P) rows per block but keeps the workspace stride of
+// ceil(P / SE_CHUNK) records per frame (only the first ceil(P / rows) records are written; unused ones are skipped by
+// passing the matching chunk count to se_hidden_kernel)
+static int se_online_vec(int C) {
+  for (int vec = 8; vec <= 32; vec <<= 1) {
+    const int G = C / vec;
+    if (C % vec == 0 && G >= 1 && G <= 32 && (G & (G - 1)) == 0) return vec;
+  }
+  return 0;
+}
+static int se_rows_per_block(int dtype, int P, int C) {
+  if (dtype == MV2_BF16 && se_online_vec(C) != 0) return P >= 4096 ? 512 : (P >= 1024 ? 256 : SE_CHUNK);
+  return SE_CHUNK;
+}
+
 int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, float bk, void* workspace,
                 void* stream) {
   MV2_CHECK_ARG(y && wk && workspace && F > 0 && P > 0 && C > 0);
-  const int nc = ceil_div(P, SE_CHUNK);
+  const int rows = se_rows_per_block(dtype, P, C);
+  const int nc = ceil_div(P, rows);
   dim3 grid(nc, F);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32) se_pool_kernel<float><<<grid, 256, 0, st>>>((const float*)y, P, C, wk, bk, (float*)workspace, nc);
-  else if (dtype == MV2_BF16 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0) {
-    const size_t dsm = (size_t)(256 / (C / 8)) * C * sizeof(float);
-    se_pool_bf16x8_kernel<<<grid, 256, dsm, st>>>((const __nv_bfloat16*)y, P, C, wk, bk, (float*)workspace, nc);
+  else if (dtype == MV2_BF16 && se_online_vec(C) != 0) {
+    const int vec = se_online_vec(C);
+    const size_t dsm = (size_t)(256 / (C / vec)) * (C + 2) * sizeof(float);
+    MV2_CHECK_ARG(dsm <= 48 * 1024);
+    const __nv_bfloat16* yb = (const __nv_bfloat16*)y;
+    if (vec == 8) se_pool_online_kernel<8><<<grid, 256, dsm, st>>>(yb, P, C, wk, bk, (float*)workspace, nc, rows);
+    else if (vec == 16) se_pool_online_kernel<16><<<grid, 256, dsm, st>>>(yb, P, C, wk, bk, (float*)workspace, nc, rows);
+    else se_pool_online_kernel<32><<<grid, 256, dsm, st>>>(yb, P, C, wk, bk, (float*)workspace, nc, rows);
   } else if (dtype == MV2_BF16) se_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, P, C, wk, bk, (float*)workspace, nc);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }
 
-int mv2_se_gate(const void* workspace, int F, int P, int C, int Hd, const float* w1, const float* b1, const float* w2,
-                const float* b2, float* gates, void* stream) {
+int mv2_se_gate(const void* workspace, int dtype, int F, int P, int C, int Hd, const float* w1, const float* b1,
+                const float* w2, const float* b2, float* gates, void* stream) {
   MV2_CHECK_ARG(workspace && w1 && b1 && w2 && b2 && gates && F > 0 && P > 0 && C > 0 && Hd > 0);
-  const int nc = ceil_div(P, SE_CHUNK);
+  const int nc = ceil_div(P, se_rows_per_block(dtype, P, C));      // chunk records se_pool wrote per frame
   const size_t smem1 = (size_t)(C + nc) * sizeof(float), smem2 = (size_t)Hd * sizeof(float);
   MV2_CHECK_ARG(smem1 <= 48 * 1024 && smem2 <= 48 * 1024);
   // hidden activations live behind the chunk partials (mv2_se_workspace_bytes reserves F*Hd_max floats)
-  float* hidden = (float*)workspace + (size_t)F * nc * (C + 2);
+  float* hidden = (float*)workspace + (size_t)F * ceil_div(P, SE_CHUNK) * (C + 2);
   cudaStream_t st = (cudaStream_t)stream;
   se_hidden_kernel<<<dim3(F, ceil_div(Hd, 32)), 256, smem1, st>>>((const float*)workspace, nc, C, Hd, w1, b1, hidden);
   MV2_CHECK_LAUNCH();
@@ -1273,6 +1380,8 @@ int mv2_rmsnorm(const void* x, void* out, int dtype, const float* gamma, int B, 
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
     rmsnorm_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)out, gamma, n_tok, T, P, C, token_shift);
+  else if (dtype == MV2_BF16 && C % 8 == 0 && C <= 1024 && (!token_shift || (C / 2) % 8 == 0))
+    rmsnorm_bf16x8_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, gamma, n_tok, T, P, C, token_shift);
   else if (dtype == MV2_BF16)
     rmsnorm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, gamma, n_tok, T, P, C, token_shift);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
@@ -1313,11 +1422,11 @@ int mv2_linear_attention(const void* q, const void* kv, void* out, int dtype, in
   if (dtype == MV2_F32) {
     linattn_reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();
-    linattn_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)q, (const float*)workspace, (float*)out, L, heads, nc);
+    linattn_apply_kernel<float><<<grid, 64, 0, st>>>((const float*)q, (const float*)workspace, (float*)out, L, heads, nc);
   } else if (dtype == MV2_BF16) {
     linattn_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();
-    linattn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
+    linattn_apply_kernel<__nv_bfloat16><<<grid, 64, 0, st>>>((const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
   } else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;

@@ -177,8 +177,9 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)
 
 // r: 32 raw accumulator columns of ONE output row (position b,to,ho,wo); n = first packed column; sb = smem bias of
 // these columns (always valid memory; zeros when there is no bias).
+// row_base = linear position index * Co (plain mode), computed once per row by the caller.
 __device__ __forceinline__ void epi_chunk32(const TcEpi& e, const uint32_t (&r)[32], int ncols, int n, const float* sb,
-                                            int b, int to, int ho, int wo) {
+                                            int b, int to, int ho, int wo, int64_t row_base) {
   if (e.mode == 1) {
     const int I = e.Co >> 1;
     const int64_t pos = (((int64_t)b * e.To + to) * e.Ho + ho) * e.Wo + wo;
@@ -213,7 +214,7 @@ __device__ __forceinline__ void epi_chunk32(const TcEpi& e, const uint32_t (&r)[
       const int qd = ng / cy, c = ng - qd * cy;
       off = ((((int64_t)b * (2 * e.To) + (2 * to + qd)) * e.Ho + ho) * e.Wo + wo) * cy + c;
     } else {
-      off = ((((int64_t)b * e.To + to) * e.Ho + ho) * e.Wo + wo) * e.Co + ng;
+      off = row_base + ng;
     }
     if (vec_ok && ng + 8 <= e.Co) {
       if (e.res) {

@@ -139,12 +139,13 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
     mbar_wait(tfull, 0);
     tc_fence_after();
     const uint32_t tlane = tmem_base + ((uint32_t)(sub * 32) << 16);
+    const int64_t row_base = ((((int64_t)b * p.To + to) * p.Ho + ho) * p.Wo + wo) * p.Co;
     for (int c0 = 0; c0 < p.bn; c0 += 32) {
       uint32_t r[32];
       if (p.bn - c0 >= 32) tmem_ld_32x32b_x32(tlane + c0, r);
       else tmem_ld_32x32b_x16(tlane + c0, r);
       tmem_ld_wait();
-      if (row_ok) epi_chunk32(p.epi, r, min(32, p.bn - c0), n0 + c0, sbias + c0, b, to, ho, wo);
+      if (row_ok) epi_chunk32(p.epi, r, min(32, p.bn - c0), n0 + c0, sbias + c0, b, to, ho, wo, row_base);
     }
   }
   tc_fence_before();

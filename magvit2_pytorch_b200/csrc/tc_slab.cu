@@ -15,7 +15,7 @@
 //     when they fit (2 * mw * BN <= 512 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
 //   * causal frames in front of the clip (t + dt - pt < 0) are all-zero and are skipped outright.
 // Warp roles (256 threads): w0 slab TMA producer, w1 MMA issuer (+TMEM alloc), w2 weight TMA producer,
-// w4-7 epilogue (TMEM lanes 32*(w%4)..+31).
+// w4-11 epilogue (TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the column chunks).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <cuda.h>
@@ -56,7 +56,7 @@ __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) 
   return c;
 }
 
-__global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__ SlabParams p) {
+__global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__ SlabParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.slab_stages; ++s) { mbar_init(slab_full + 8 * s, 1); mbar_init(slab_empty + 8 * s, 1); }
     for (int s = 0; s < p.w_stages; ++s) { mbar_init(w_full + 8 * s, 1); mbar_init(w_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(t_full + 8 * s, 1); mbar_init(t_empty + 8 * s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(t_full + 8 * s, 1); mbar_init(t_empty + 8 * s, 8); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&p.amap);
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
   if (warp == 1) tmem_alloc(tslot, 512);
   if (warp >= 4) {
     const int nb = p.n_tiles_n * p.bn;   // >= Co; padded columns read zeros
-    for (int i = threadIdx.x - 128; i < nb; i += 128) sbias[i] = (p.epi.bias && i < p.Co) ? p.epi.bias[i] : 0.f;
+    for (int i = threadIdx.x - 128; i < nb; i += 256) sbias[i] = (p.epi.bias && i < p.Co) ? p.epi.bias[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
-    const int sub = warp & 3;
+    // 8 epilogue warps: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 4) / 4
+    const int sub = warp & 3, half = (warp - 4) >> 2;
     const int row = sub * 32 + lane;
     const int lh = row >> 3, lw = row & 7;
     uint32_t tit = 0;
@@ -198,11 +199,13 @@ __global__ void __launch_bounds__(256, 1) tc_slab_kernel(const __grid_constant__
         const int w = c.w0 + 8 * j + lw;
         const bool row_ok = h < p.H && w < p.W;
         const uint32_t tl = tmem_base + buf * acc_cols + j * p.bn + ((uint32_t)(sub * 32) << 16);
-        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+        const int64_t row_base = ((((int64_t)c.b * p.T + c.t) * p.H + h) * p.W + w) * p.Co;
+        // column chunks are dealt round-robin to the two warps that share this lane quarter
+        for (int c0 = ((j + half) & 1) * 32; c0 < p.bn; c0 += 64) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tl + c0, r);
           tmem_ld_wait();
-          if (row_ok) epi_chunk32(p.epi, r, 32, c.n0 + c0, sbias + c.n0 + c0, c.b, c.t, h, w);
+          if (row_ok) epi_chunk32(p.epi, r, 32, c.n0 + c0, sbias + c.n0 + c0, c.b, c.t, h, w, row_base);
         }
       }
       tc_fence_before();
@@ -316,7 +319,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
   const int grid = std::min(p.total_tiles, n_sm);
-  tc_slab_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  tc_slab_kernel<<<grid, 384, smem, (cudaStream_t)stream>>>(p);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

@@ -327,7 +327,7 @@ class Engine:
         st = self._stream()
         dt = _dt(self.dtype)
         check(self.lib.mv2_se_pool(_ptr(y), dt, F_, Pn, Cc, _ptr(p["wk"]), p["bk"], _ptr(ws), st), "mv2_se_pool")
-        check(self.lib.mv2_se_gate(_ptr(ws), F_, Pn, Cc, p["hidden"], _ptr(p["w1"]), _ptr(p["b1"]), _ptr(p["w2"]),
+        check(self.lib.mv2_se_gate(_ptr(ws), dt, F_, Pn, Cc, p["hidden"], _ptr(p["w1"]), _ptr(p["b1"]), _ptr(p["w2"]),
                                    _ptr(p["b2"]), _ptr(gates), st), "mv2_se_gate")
         out = self._new(x.shape)
         check(self.lib.mv2_gate_residual(_ptr(y), _ptr(x), _ptr(gates), _ptr(out), dt, F_, Pn, Cc, st), "mv2_gate_residual")
