@@ -228,11 +228,13 @@ using namespace mv2;
 extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
   if (!a) return 0;
   if (a->st != 1 || a->sh != 1 || a->sw != 1) return 0;
-  if (a->Ci % 32 != 0 || a->Co > 2048 || a->epi_mode != 0) return 0;
+  if (a->Ci % 32 != 0 || a->Co > 4096) return 0;
+  if (a->epi_mode == 1 && (a->Co % 32 != 0 || a->shuffle != MV2_SHUFFLE_NONE || a->res)) return 0;   // fused GEGLU
+  if (a->epi_mode != 0 && a->epi_mode != 1) return 0;
   if (a->Co % 32 != 0 && a->Co > 32) return 0;           // ragged N only as a single (zero padded) 32-column tile
   if (a->Ci % 64 != 0 && a->kw != 1) return 0;           // 64-byte rows (32 channels): only h-shifted taps (1024 B multiples)
   if (a->res && a->Co % 8 != 0) return 0;
-  if (a->shuffle != MV2_SHUFFLE_NONE) return 0;
+  if (a->shuffle != MV2_SHUFFLE_NONE && ((a->shuffle == MV2_SHUFFLE_SPACE ? a->Co / 4 : a->Co / 2) % 8 != 0 || a->Co % 32 != 0)) return 0;
   if (a->kh > 7 || a->kw > 3 || a->kt > 8) return 0;
   if (a->To != a->Ti || a->Ho != a->Hi || a->Wo != a->Wi) return 0;
   return 1;
@@ -255,7 +257,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   p.Ci = a->Ci; p.kchunks = a->Ci / bk;
   p.B = a->B; p.T = a->To; p.H = a->Ho; p.W = a->Wo; p.Co = a->Co;
   p.epi.bias = a->bias; p.epi.res = (const __nv_bfloat16*)a->res; p.epi.y = (__nv_bfloat16*)a->y;
-  p.epi.act = a->act; p.epi.shuffle = MV2_SHUFFLE_NONE; p.epi.mode = 0; p.epi.Co = a->Co;
+  p.epi.act = a->act; p.epi.shuffle = a->shuffle; p.epi.mode = a->epi_mode; p.epi.Co = a->Co;
   p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo;
 
   // ---- tiling (profiles/r01_sweep_slab_v2.json): widest N tile; two M-tiles per weight tile whenever both

@@ -101,6 +101,8 @@ SLAB_CASES = [
     ("slab_linear_512_768", (768, 512, 1, 1, 1), (1, 2, 16, 16), dict()),
     ("slab_conv_out_co3", (3, 64, 3, 3, 3), (1, 3, 16, 32), dict()),
     ("slab_co16", (16, 64, 3, 3, 3), (1, 2, 16, 16), dict(act=ACT_ELU)),
+    ("slab_up_space", (256, 128, 1, 1), (1, 3, 16, 16), dict(act=ACT_SILU, shuffle=SHUFFLE_SPACE, q=4)),
+    ("slab_up_time", (1024, 512, 1), (1, 3, 8, 8), dict(act=ACT_SILU, shuffle=SHUFFLE_TIME, q=2, k3=(1, 1, 1))),
 ]
 
 
@@ -118,7 +120,7 @@ def test_slab_matches_cuda_core(case):
     B, T, H, W = xshape
     x = torch.randn((B, T, H, W, wshape[1]), generator=g).cuda().to(torch.bfloat16)
     eng = _engine()
-    pk = pack_conv(w, bias, torch.bfloat16)
+    pk = pack_conv(w, bias, torch.bfloat16, k=kw.pop("k3", None), shuffle_q=kw.pop("q", 1))
     want_res = kw.pop("res", False)
     res = torch.randn((B, T, H, W, wshape[0]), generator=g).cuda().to(torch.bfloat16) if want_res else None
     eng.use_tc, eng.tc_variant, eng.slab_calls = True, "slab", 0

@@ -24,6 +24,8 @@ LAYERS = [
     ("pw c512 T5 16", (512, 512, 1, 1, 1), (5, 16, 16)),
     ("qkv 512->768 T20 16", (768, 512, 1, 1, 1), (20, 16, 16)),
     ("conv_out 64->3", (3, 64, 3, 3, 3), (20, 128, 128)),
+    ("up 128->64x4 T20 64", (256, 128, 1, 1), (20, 64, 64)),
+    ("up 512->256x4 T20 16", (1024, 512, 1, 1), (20, 16, 16)),
     ("conv_in kwpack", None, (20, 128, 128)),
 ]
 CFGS = ["tap"] + [f"{mw},{bn}" for mw in (1, 2) for bn in (256, 128, 64, 32)]
@@ -53,10 +55,13 @@ for name, wshape, (T, H, W) in LAYERS:
         co = 64
     else:
         w = torch.randn(wshape, device="cuda") * 0.02
-        pk = pack_conv(w, torch.zeros(wshape[0], device="cuda"), torch.bfloat16)
+        is_up = name.startswith("up ")
+        pk = pack_conv(w, torch.zeros(wshape[0], device="cuda"), torch.bfloat16, shuffle_q=4 if is_up else 1)
         x = torch.randn((B, T, H, W, wshape[1]), device="cuda").to(torch.bfloat16)
-        kw = dict(act=ACT_ELU)
-        taps = wshape[2] * wshape[3] * wshape[4]
+        kw = dict(act=ACT_ELU, shuffle=1) if is_up else dict(act=ACT_ELU)
+        taps = 1
+        for v_ in wshape[2:]:
+            taps *= v_
         flops = 2.0 * B * T * H * W * wshape[0] * wshape[1] * taps
         co = wshape[0]
     res = {}
