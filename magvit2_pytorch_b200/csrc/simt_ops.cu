@@ -876,24 +876,23 @@ __device__ __forceinline__ float taylor_feat(const float* v, int f) {
 template <typename T>
 __global__ void __launch_bounds__(256) linattn_reduce_kernel(const T* __restrict__ kv, float* __restrict__ ws,
                                                              int L, int heads, int n_chunks) {
-  // S[f][e] = sum_n phi(k_n)[f] * [v_n, 1][e]; phi is evaluated once per token into shared memory, then each thread
-  // accumulates its (f, e) outputs with two smem reads + one FMA per token.
-  constexpr int TB = 64;
+  // S[f][e] = sum_n phi(k_n)[f] * [v_n, 1][e].  phi is evaluated once per token into shared memory; thread (slice, f)
+  // owns the 9 outputs of feature f for every third token: per token it reads phi[n][f] (conflict free) and the 9
+  // values [v_n, 1] (warp broadcast) for 9 FMAs.  The three slices are summed through shared memory at the end.
+  constexpr int TB = 64, NS = 3;
   __shared__ float phi[TB][LA_F + 1];
-  __shared__ float vs[TB][LA_D + 1];
+  __shared__ __align__(16) float vs[TB][12];
   __shared__ float ks[TB][LA_D];
+  __shared__ float part[NS][LA_ST];
   const int chunk = blockIdx.x, h = blockIdx.y;
   const int64_t seq = blockIdx.z;
   const int tid = threadIdx.x;
   const int HD = heads * LA_D;
-  float acc[3] = {0.f, 0.f, 0.f};
-  int fo[3], eo[3];
+  const bool worker = tid < NS * LA_F;
+  const int slice = tid / LA_F, f = tid % LA_F;
+  float acc[LA_D + 1];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int idx = tid + 256 * r;
-    fo[r] = idx / (LA_D + 1);
-    eo[r] = idx % (LA_D + 1);
-  }
+  for (int e = 0; e <= LA_D; ++e) acc[e] = 0.f;
   const int t_begin = chunk * LA_CHUNK, t_end = min(L, t_begin + LA_CHUNK);
   for (int t0 = t_begin; t0 < t_end; t0 += TB) {
     __syncthreads();
@@ -912,26 +911,32 @@ __global__ void __launch_bounds__(256) linattn_reduce_kernel(const T* __restrict
     for (int n = tid; n < TB; n += 256) vs[n][LA_D] = (t0 + n < t_end) ? 1.f : 0.f;
     __syncthreads();
     for (int idx = tid; idx < TB * LA_F; idx += 256) {
-      const int n = idx / LA_F, f = idx % LA_F;
-      phi[n][f] = (t0 + n < t_end) ? taylor_feat(ks[n], f) : 0.f;
+      const int n = idx / LA_F, ff = idx % LA_F;
+      phi[n][ff] = (t0 + n < t_end) ? taylor_feat(ks[n], ff) : 0.f;
     }
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      if (tid + 256 * r >= LA_ST) continue;
-      float sacc = acc[r];
-      const int f = fo[r], e = eo[r];
-#pragma unroll 8
-      for (int n = 0; n < TB; ++n) sacc = fmaf(phi[n][f], vs[n][e], sacc);
-      acc[r] = sacc;
+    if (worker) {
+#pragma unroll 4
+      for (int n = slice; n < TB; n += NS) {
+        const float pf = phi[n][f];
+        const float4 v0 = *reinterpret_cast<const float4*>(&vs[n][0]);
+        const float4 v1 = *reinterpret_cast<const float4*>(&vs[n][4]);
+        const float v8 = vs[n][8];
+        acc[0] = fmaf(pf, v0.x, acc[0]); acc[1] = fmaf(pf, v0.y, acc[1]);
+        acc[2] = fmaf(pf, v0.z, acc[2]); acc[3] = fmaf(pf, v0.w, acc[3]);
+        acc[4] = fmaf(pf, v1.x, acc[4]); acc[5] = fmaf(pf, v1.y, acc[5]);
+        acc[6] = fmaf(pf, v1.z, acc[6]); acc[7] = fmaf(pf, v1.w, acc[7]);
+        acc[8] = fmaf(pf, v8, acc[8]);
+      }
     }
   }
-  float* o = ws + ((seq * heads + h) * n_chunks + chunk) * LA_ST;
+  if (worker) {
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int idx = tid + 256 * r;
-    if (idx < LA_ST) o[idx] = acc[r];
+    for (int e = 0; e <= LA_D; ++e) part[slice][f * (LA_D + 1) + e] = acc[e];
   }
+  __syncthreads();
+  float* o = ws + ((seq * heads + h) * n_chunks + chunk) * LA_ST;
+  for (int idx = tid; idx < LA_ST; idx += 256) o[idx] = part[0][idx] + part[1][idx] + part[2][idx];
 }
 
 template <typename T>
