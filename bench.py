@@ -34,6 +34,19 @@ README_LAYERS = (
     ("consecutive_residual", 2), "compress_time", ("consecutive_residual", 2), "attend_time",
 )
 README_KW = dict(image_size=128, init_dim=64, max_dim=512, codebook_size=1024, layers=README_LAYERS)
+# the other BASELINE.json configs (not the headline; `--workload cfg4|fsq` for the record)
+WORKLOADS = {
+    "readme": dict(kw=README_KW, clips=4, size=128, flop_clip=1.512e12,
+                   name="README VideoTokenizer (BASELINE configs[1]): tokenize + decode_from_code_indices, "
+                        "4 clips of 3x17x128x128 per GPU, batch sharded by clip"),
+    "cfg4": dict(kw=dict(image_size=256, init_dim=64, max_dim=1024, codebook_size=1024, layers=README_LAYERS), clips=3,
+                 size=256, flop_clip=8.944e12,
+                 name="BASELINE configs[3]: image_size=256 max_dim=1024, tokenize + decode, 3 clips of 3x17x256x256 per GPU"),
+    "fsq": dict(kw=dict(image_size=128, init_dim=64, max_dim=512, use_fsq=True, fsq_levels=[8, 5, 5, 5], layers=README_LAYERS),
+                clips=4, size=128, flop_clip=1.512e12,
+                name="BASELINE configs[4]: FSQ [8,5,5,5] variant, tokenize + decode_from_code_indices round trip, "
+                     "4 clips of 3x17x128x128 per GPU"),
+}
 CLIPS_PER_GPU = 4
 FRAMES = 17
 # SURVEY.md 8d / BASELINE.md 3 (forward hooks on the reference's own modules, 2 FLOP per MAC)
@@ -210,6 +223,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="readme", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 20 and args.warmup == 5:
@@ -231,8 +245,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     args.warmup = max(args.warmup, 3)
 
+    wl = WORKLOADS[args.workload]
+    global CLIPS_PER_GPU, FLOP_PER_CLIP_ALL
+    CLIPS_PER_GPU, FLOP_PER_CLIP_ALL = wl["clips"], wl["flop_clip"]
     torch.manual_seed(0)
-    model = VideoTokenizer(**README_KW)
+    model = VideoTokenizer(**wl["kw"])
     Wt.fill_state_dict_(model, 0)
     model = model.to(dev).bfloat16().eval()
     model.cuda_graphs = True            # public opt-in: replay the static launch plan as one CUDA graph per entry point
@@ -240,7 +257,9 @@ def main():
 
     # inputs: NB distinct batches per rank so consecutive steps never re-read the same input from L2
     NB = 12
-    host_batches = [Wt.synth_video(CLIPS_PER_GPU, 3, FRAMES, 128, seed=1000 + rank * NB + i).pin_memory() for i in range(NB)]
+    if args.workload == "cfg4":
+        NB = 4
+    host_batches = [Wt.synth_video(CLIPS_PER_GPU, 3, FRAMES, wl["size"], seed=1000 + rank * NB + i).pin_memory() for i in range(NB)]
     dev_batches = [hb.to(dev, non_blocking=True) for hb in host_batches]
     torch.cuda.synchronize()
 
@@ -278,8 +297,9 @@ def main():
     value = frames_total / (ms_max / 1e3)
 
     # ---------------- e2e: host (pinned) buffers in, host buffers out, copies inside the timed region ----
-    out_codes = torch.empty((CLIPS_PER_GPU, 5, 16, 16), dtype=torch.int64).pin_memory()
-    out_video = torch.empty((CLIPS_PER_GPU, 3, FRAMES, 128, 128), dtype=torch.bfloat16).pin_memory()
+    fm = wl["size"] // 8
+    out_codes = torch.empty((CLIPS_PER_GPU, 5, fm, fm), dtype=torch.int32 if wl["kw"].get("use_fsq") else torch.int64).pin_memory()
+    out_video = torch.empty((CLIPS_PER_GPU, 3, FRAMES, wl["size"], wl["size"]), dtype=torch.bfloat16).pin_memory()
 
     def step_e2e(hv):
         v = hv.to(dev, non_blocking=True)
@@ -300,7 +320,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = frames_total / (t.item() / 1e3)
     h2d = host_batches[0].numel() * host_batches[0].element_size()
-    d2h = out_codes.numel() * 8 + out_video.numel() * 2
+    d2h = out_codes.numel() * out_codes.element_size() + out_video.numel() * 2
 
     # ---------------- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), timed live ----------
     # instrumented pass: CUDA events around every conv launch of one step, on the launching stream
@@ -330,8 +350,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "README VideoTokenizer (BASELINE configs[1]): tokenize + decode_from_code_indices, "
-                                   "4 clips of 3x17x128x128 per GPU, batch sharded by clip",
+            "config": {"workload": wl["name"],
                        "global_batch": CLIPS_PER_GPU * world, "parallelism": f"dp{world}",
                        "l2": f"inputs rotate over {NB} distinct batches per rank ({NB * h2d / 1e6:.0f} MB > 126 MB L2); "
                              "per-step activation working set ~2 GB"},
@@ -340,7 +359,7 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "readme":
             out["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(out), flush=True)
     if world > 1:
