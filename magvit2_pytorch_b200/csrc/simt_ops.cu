@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const mv2_conv_args a) {
 // ------------------------------------------------------------------------------------------
 // SqueezeExcite
 // ------------------------------------------------------------------------------------------
-constexpr int SE_CHUNK = 128;
+constexpr int SE_CHUNK = 128;     // rows per block of the generic kernel
+constexpr int SE_MIN_ROWS = 32;   // smallest chunk the single-pass bf16 kernel may use (sizes the workspace)
 
 template <typename T>
 __global__ void __launch_bounds__(256) se_pool_kernel(const T* __restrict__ y, int P, int C,
@@ -1020,6 +1021,196 @@ __global__ void __launch_bounds__(64) linattn_apply_kernel(const T* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Taylor linear attention on tensor cores (bf16 path): both contractions are small GEMMs
+//   reduce:  S[f][e]   = sum_n phi_f(k_n) * [v_n, 1][e]        (M = 80 padded features, N = 16, K = tokens)
+//   apply :  out[n][e] = sum_f phi_f(q_n) * S[f][e]             (M = tokens, N = 16, K = 80)
+// evaluated with warp-level mma.sync m16n8k16 (bf16 operands, fp32 accumulate); the feature map phi is evaluated once
+// per token into shared memory by the thread that owns the token (compile-time feature index -> registers only).
+// ------------------------------------------------------------------------------------------
+constexpr int LAM_F = 80;      // 73 features padded to 5 x 16
+constexpr int LAM_TB = 128;    // tokens per staging batch
+
+template <int F_IDX>
+__device__ __forceinline__ float taylor_feat_ct(const float (&k)[LA_D]) {
+  if (F_IDX == 0) return 1.f;
+  if (F_IDX <= LA_D) return k[(F_IDX - 1) & 7];
+  if (F_IDX < LA_F) return k[((F_IDX - 1 - LA_D) >> 3) & 7] * k[(F_IDX - 1 - LA_D) & 7] * 0.70710678118654752440f;
+  return 0.f;
+}
+template <int F0, typename Fn>
+__device__ __forceinline__ void for_each_feature_pair(const float (&k)[LA_D], Fn&& fn) {
+  if constexpr (F0 < LAM_F) {
+    fn(F0, taylor_feat_ct<F0>(k), taylor_feat_ct<F0 + 1>(k));
+    for_each_feature_pair<F0 + 2>(k, fn);
+  }
+}
+
+__global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bfloat16* __restrict__ kv, float* __restrict__ ws,
+                                                                 int L, int heads, int n_chunks) {
+  __shared__ __align__(16) __nv_bfloat16 phi_t[LAM_F][LAM_TB + 8];   // [feature][token]
+  __shared__ __align__(16) __nv_bfloat16 vt[16][LAM_TB + 8];         // [e][token]; e = 8 is the all-ones column
+  const int chunk = blockIdx.x, h = blockIdx.y;
+  const int64_t seq = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int HD = heads * LA_D;
+  float acc[5][2][4];
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  const int t_begin = chunk * LA_CHUNK, t_end = min(L, t_begin + LA_CHUNK);
+  for (int t0 = t_begin; t0 < t_end; t0 += LAM_TB) {
+    __syncthreads();
+    {   // stage: thread = token
+      const int tok = t0 + tid;
+      const bool ok = tok < t_end;
+      float kk[LA_D], vv[LA_D];
+      if (ok) {
+        const __nv_bfloat16* row = kv + (seq * L + tok) * (2 * (int64_t)HD);
+        const uint4 kr = *reinterpret_cast<const uint4*>(row + h * LA_D);
+        const uint4 vr = *reinterpret_cast<const uint4*>(row + HD + h * LA_D);
+        const __nv_bfloat162* kb = reinterpret_cast<const __nv_bfloat162*>(&kr);
+        const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&vr);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a = __bfloat1622float2(kb[q]), b = __bfloat1622float2(vb[q]);
+          kk[2 * q] = a.x; kk[2 * q + 1] = a.y; vv[2 * q] = b.x; vv[2 * q + 1] = b.y;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < LA_D; ++q) { kk[q] = 0.f; vv[q] = 0.f; }
+      }
+      for_each_feature_pair<0>(kk, [&](int f, float a, float b) {
+        phi_t[f][tid] = __float2bfloat16_rn(ok ? a : 0.f);
+        phi_t[f + 1][tid] = __float2bfloat16_rn(ok ? b : 0.f);
+      });
+#pragma unroll
+      for (int e = 0; e < LA_D; ++e) vt[e][tid] = __float2bfloat16_rn(vv[e]);
+      vt[LA_D][tid] = __float2bfloat16_rn(ok ? 1.f : 0.f);
+#pragma unroll
+      for (int e = LA_D + 1; e < 16; ++e) vt[e][tid] = __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+    // each warp contracts its 32 tokens (2 k-steps of 16)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int n0 = warp * 32 + ks * 16;
+      uint32_t b[2][2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        b[nt][0] = *reinterpret_cast<const uint32_t*>(&vt[nt * 8 + g][n0 + t * 2]);
+        b[nt][1] = *reinterpret_cast<const uint32_t*>(&vt[nt * 8 + g][n0 + 8 + t * 2]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 5; ++mt) {
+        uint32_t a[4];
+        a[0] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g][n0 + t * 2]);
+        a[1] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g + 8][n0 + t * 2]);
+        a[2] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g][n0 + 8 + t * 2]);
+        a[3] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g + 8][n0 + 8 + t * 2]);
+        mma_bf16_16816(acc[mt][0], a, b[0][0], b[0][1]);
+        mma_bf16_16816(acc[mt][1], a, b[1][0], b[1][1]);
+      }
+    }
+  }
+  // cross-warp reduction through shared memory (reuse phi_t storage as fp32 [4][80*16]... too small: do it in 2 halves)
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(&phi_t[0][0]);          // 80 * 136 * 2 B = 21760 B = 5440 floats >= 4 * 80 * 16 = 5120
+#pragma unroll
+  for (int mt = 0; mt < 5; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int f0 = mt * 16 + g, e0 = nt * 8 + t * 2;
+      float* w = red + warp * (LAM_F * 16);
+      w[f0 * 16 + e0] = acc[mt][nt][0];
+      w[f0 * 16 + e0 + 1] = acc[mt][nt][1];
+      w[(f0 + 8) * 16 + e0] = acc[mt][nt][2];
+      w[(f0 + 8) * 16 + e0 + 1] = acc[mt][nt][3];
+    }
+  __syncthreads();
+  float* o = ws + ((seq * heads + h) * n_chunks + chunk) * LA_ST;
+  for (int idx = tid; idx < LA_ST; idx += 128) {
+    const int f = idx / (LA_D + 1), e = idx % (LA_D + 1);
+    const int si = f * 16 + e;
+    o[idx] = red[si] + red[LAM_F * 16 + si] + red[2 * LAM_F * 16 + si] + red[3 * LAM_F * 16 + si];
+  }
+}
+
+__global__ void __launch_bounds__(128) linattn_apply_mma_kernel(const __nv_bfloat16* __restrict__ q, const float* __restrict__ ws,
+                                                                __nv_bfloat16* __restrict__ out, int L, int heads, int n_chunks) {
+  __shared__ __align__(16) __nv_bfloat16 phi_s[LAM_TB][LAM_F + 8];   // [token][feature]
+  __shared__ __align__(16) __nv_bfloat16 st[16][LAM_F + 8];          // [e][feature]  (S transposed; e = 8 is the denominator)
+  const int blk = blockIdx.x, h = blockIdx.y;
+  const int64_t seq = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int HD = heads * LA_D;
+  const float* wsh = ws + (seq * heads + h) * (int64_t)n_chunks * LA_ST;
+  for (int idx = tid; idx < 16 * LAM_F; idx += 128) {
+    const int e = idx / LAM_F, f = idx % LAM_F;
+    float sv = 0.f;
+    if (e <= LA_D && f < LA_F)
+      for (int k = 0; k < n_chunks; ++k) sv += wsh[(int64_t)k * LA_ST + f * (LA_D + 1) + e];
+    st[e][f] = __float2bfloat16_rn(sv);
+  }
+  {
+    const int tok = blk * LAM_TB + tid;
+    const bool ok = tok < L;
+    float qq[LA_D];
+    if (ok) {
+      const uint4 qr = *reinterpret_cast<const uint4*>(q + (seq * L + tok) * HD + h * LA_D);
+      const __nv_bfloat162* qb = reinterpret_cast<const __nv_bfloat162*>(&qr);
+      const float qs = rsqrtf((float)LA_D);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a = __bfloat1622float2(qb[i]);
+        qq[2 * i] = a.x * qs; qq[2 * i + 1] = a.y * qs;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < LA_D; ++i) qq[i] = 0.f;
+    }
+    for_each_feature_pair<0>(qq, [&](int f, float a, float b) {
+      *reinterpret_cast<uint32_t*>(&phi_s[tid][f]) = pack2_bf16(a, b);
+    });
+  }
+  __syncthreads();
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+    const int n0 = warp * 32 + mi * 16;
+    float c[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[nt][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < LAM_F / 16; ++ks) {
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g][ks * 16 + t * 2]);
+      a[1] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g + 8][ks * 16 + t * 2]);
+      a[2] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g][ks * 16 + 8 + t * 2]);
+      a[3] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g + 8][ks * 16 + 8 + t * 2]);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&st[nt * 8 + g][ks * 16 + t * 2]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&st[nt * 8 + g][ks * 16 + 8 + t * 2]);
+        mma_bf16_16816(c[nt], a, b0, b1);
+      }
+    }
+    // denominator = column 8 = c[1][0] (row g) / c[1][2] (row g+8) of the quad's t == 0 lane
+    const float d0 = fmaxf(__shfl_sync(0xffffffffu, c[1][0], lane & ~3), 1e-5f);
+    const float d1 = fmaxf(__shfl_sync(0xffffffffu, c[1][2], lane & ~3), 1e-5f);
+    const int r0 = blk * LAM_TB + n0 + g, r1 = r0 + 8;
+    if (r0 < L) *reinterpret_cast<uint32_t*>(out + (seq * L + r0) * HD + h * LA_D + t * 2) = pack2_bf16(c[0][0] / d0, c[0][1] / d0);
+    if (r1 < L) *reinterpret_cast<uint32_t*>(out + (seq * L + r1) * HD + h * LA_D + t * 2) = pack2_bf16(c[0][2] / d1, c[0][3] / d1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // GEGLU
 // ------------------------------------------------------------------------------------------
@@ -1301,7 +1492,7 @@ int mv2_conv_forward(const mv2_conv_args* a, void* stream) {
 
 size_t mv2_se_workspace_bytes(int F, int P, int C) {
   // chunk partials + room for the SE hidden layer (at most max(16, C/2) <= C + 16 units per frame)
-  return ((size_t)F * ceil_div(P, SE_CHUNK) * (C + 2) + (size_t)F * (C + 16)) * sizeof(float);
+  return ((size_t)F * ceil_div(P, SE_MIN_ROWS) * (C + 2) + (size_t)F * (C + 16)) * sizeof(float);
 }
 
 // the single-pass bf16 kernel processes SE_CHUNK * se_chunk_mult(P) rows per block but keeps the workspace stride of
@@ -1314,15 +1505,19 @@ static int se_online_vec(int C) {
   }
   return 0;
 }
-static int se_rows_per_block(int dtype, int P, int C) {
-  if (dtype == MV2_BF16 && se_online_vec(C) != 0) return P >= 4096 ? 512 : (P >= 1024 ? 256 : SE_CHUNK);
-  return SE_CHUNK;
+static int se_rows_per_block(int dtype, int F, int P, int C) {
+  if (!(dtype == MV2_BF16 && se_online_vec(C) != 0)) return SE_CHUNK;
+  // aim for >= ~8 blocks per SM while every row group still walks >= 4 rows (workspace holds ceil(P / SE_MIN_ROWS) records)
+  const int R = 256 / (C / se_online_vec(C));
+  int rows = 512;
+  while (rows > 4 * R && rows > SE_MIN_ROWS && (int64_t)F * ceil_div(P, rows) < 1184) rows >>= 1;
+  return rows;
 }
 
 int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, float bk, void* workspace,
                 void* stream) {
   MV2_CHECK_ARG(y && wk && workspace && F > 0 && P > 0 && C > 0);
-  const int rows = se_rows_per_block(dtype, P, C);
+  const int rows = se_rows_per_block(dtype, F, P, C);
   const int nc = ceil_div(P, rows);
   dim3 grid(nc, F);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1344,11 +1539,11 @@ int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, 
 int mv2_se_gate(const void* workspace, int dtype, int F, int P, int C, int Hd, const float* w1, const float* b1,
                 const float* w2, const float* b2, float* gates, void* stream) {
   MV2_CHECK_ARG(workspace && w1 && b1 && w2 && b2 && gates && F > 0 && P > 0 && C > 0 && Hd > 0);
-  const int nc = ceil_div(P, se_rows_per_block(dtype, P, C));      // chunk records se_pool wrote per frame
+  const int nc = ceil_div(P, se_rows_per_block(dtype, F, P, C));   // chunk records se_pool wrote per frame
   const size_t smem1 = (size_t)(C + nc) * sizeof(float), smem2 = (size_t)Hd * sizeof(float);
   MV2_CHECK_ARG(smem1 <= 48 * 1024 && smem2 <= 48 * 1024);
   // hidden activations live behind the chunk partials (mv2_se_workspace_bytes reserves F*Hd_max floats)
-  float* hidden = (float*)workspace + (size_t)F * ceil_div(P, SE_CHUNK) * (C + 2);
+  float* hidden = (float*)workspace + (size_t)F * ceil_div(P, SE_MIN_ROWS) * (C + 2);
   cudaStream_t st = (cudaStream_t)stream;
   se_hidden_kernel<<<dim3(F, ceil_div(Hd, 32)), 256, smem1, st>>>((const float*)workspace, nc, C, Hd, w1, b1, hidden);
   MV2_CHECK_LAUNCH();
@@ -1428,6 +1623,11 @@ int mv2_linear_attention(const void* q, const void* kv, void* out, int dtype, in
     linattn_reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();
     linattn_apply_kernel<float><<<grid, 64, 0, st>>>((const float*)q, (const float*)workspace, (float*)out, L, heads, nc);
+  } else if (dtype == MV2_BF16 && (heads * LA_D) % 8 == 0) {
+    linattn_reduce_mma_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
+    MV2_CHECK_LAUNCH();
+    dim3 grid2(ceil_div(L, LAM_TB), heads, n_seq);
+    linattn_apply_mma_kernel<<<grid2, 128, 0, st>>>((const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
   } else if (dtype == MV2_BF16) {
     linattn_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();

@@ -214,3 +214,30 @@ def test_attention_tensor_core_kernel_matches_fp32_cuda_core(L, D, heads, nseq):
     assert torch.isfinite(a_).all()
     assert (a_ - b_).abs().max().item() < 0.03 * b_.abs().max().item() + 5e-3
     assert (a_ - b_).abs().mean().item() < 0.006 * b_.abs().mean().item() + 1e-3
+
+
+@pytest.mark.parametrize("L,heads,nseq", [(1024, 16, 3), (200, 4, 2), (4096, 2, 1)])
+def test_linear_attention_tensor_core_kernels_match_fp32_cuda_core(L, heads, nseq):
+    """bf16 mma.sync Taylor-linear-attention kernels vs the fp32 CUDA-core kernels on the same bf16-representable inputs."""
+    import ctypes as C
+    from magvit2_pytorch_b200 import _lib
+    from magvit2_pytorch_b200._lib import check
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(L + heads)
+    HD = heads * 8
+    q = (torch.randn((nseq * L, HD), generator=g)).to(torch.bfloat16).cuda()
+    kv = (torch.randn((nseq * L, 2 * HD), generator=g)).to(torch.bfloat16).cuda()
+    outs = {}
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for dt, code in ((torch.bfloat16, 1), (torch.float32, 0)):
+        ws = torch.empty(lib.mv2_linattn_workspace_bytes(nseq, heads, L) // 4, device="cuda", dtype=torch.float32)
+        qq, kk = q.to(dt).contiguous(), kv.to(dt).contiguous()
+        o = torch.empty((nseq * L, HD), device="cuda", dtype=dt)
+        check(lib.mv2_linear_attention(qq.data_ptr(), kk.data_ptr(), o.data_ptr(), code, nseq, L, heads, 8, ws.data_ptr(), st),
+              "mv2_linear_attention")
+        outs[dt] = o.float()
+    torch.cuda.synchronize()
+    a_, b_ = outs[torch.bfloat16], outs[torch.float32]
+    assert torch.isfinite(a_).all()
+    assert (a_ - b_).abs().max().item() < 0.04 * b_.abs().max().item() + 5e-3
+    assert (a_ - b_).abs().mean().item() < 0.01 * b_.abs().mean().item() + 1e-3
