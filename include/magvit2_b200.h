@@ -48,6 +48,11 @@ int mv2_abi_version(void);
 const char* mv2_last_error(void);
 /* Compute capability of the current device as major*10+minor (100 on B200), <0 on error. */
 int mv2_device_arch(void);
+/* Programmatic dependent launch: when on, every kernel is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization so its prologue (barrier init, TMEM allocation, bias staging,
+ * block scheduling) overlaps the tail of the previous kernel of the stream; all kernels execute griddepcontrol.wait
+ * before touching activations.  Returns the previous setting.  Off by default. */
+int mv2_set_pdl(int on);
 
 /* ---- layout: torch (B,C,T,H,W) <-> channels-last activations ------------------
  * mv2_to_channels_last : video ingest.  Replaces pad_at_dim (M:86-89, use M:1537) +

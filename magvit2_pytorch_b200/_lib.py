@@ -63,6 +63,7 @@ SIGNATURES = {
     "mv2_abi_version": (_I, []),
     "mv2_last_error": (C.c_char_p, []),
     "mv2_device_arch": (_I, []),
+    "mv2_set_pdl": (_I, [_I]),
     "mv2_to_channels_last": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mv2_to_channels_first": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mv2_ingest_kwpack": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),

@@ -68,4 +68,28 @@ __device__ __forceinline__ float warp_max(float v) {
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// Every kernel of the library starts with pdl_wait() (everything before it -- barrier init, TMEM allocation, bias
+// staging -- may overlap the tail of the previous kernel in the stream) and signals pdl_launch_dependents() right
+// after, so the next kernel's CTAs move in as this kernel's CTAs retire.  Without the launch attribute both
+// instructions are no-ops.  mv2_set_pdl(1) turns the attribute on for all launches.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through MV2_CHECK_LAUNCH
+}
+
 }  // namespace mv2

@@ -14,6 +14,7 @@
 
 namespace mv2 {
 
+int g_pdl = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -31,6 +32,8 @@ template <typename TS, typename TD>
 __global__ void transpose_rs_kernel(const TS* __restrict__ src, TD* __restrict__ dst, int R, int64_t S,
                                     int64_t src_S_total, int64_t dst_S_total, int64_t s_off_src,
                                     int64_t s_off_dst, bool src_is_rs) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int64_t s0 = (int64_t)blockIdx.x * 32;
@@ -78,7 +81,7 @@ static int launch_transpose(const void* src, void* dst, int B, int R, int64_t S,
                             int64_t dst_S_total, int64_t s_off_src, int64_t s_off_dst, bool src_is_rs,
                             cudaStream_t st) {
   dim3 grid(ceil_div(S, 32), ceil_div(R, 32), B), block(32, 8);
-  transpose_rs_kernel<TS, TD><<<grid, block, 0, st>>>((const TS*)src, (TD*)dst, R, S, src_S_total, dst_S_total,
+  launch_k(transpose_rs_kernel<TS, TD>, dim3(grid), dim3(block), 0, st, (const TS*)src, (TD*)dst, R, S, src_S_total, dst_S_total,
                                                       s_off_src, s_off_dst, src_is_rs);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -108,6 +111,8 @@ template <typename TS>
 __global__ void __launch_bounds__(256) ingest_kwpack_kernel(const TS* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                             int B, int C, int T, int H, int W, int t_pad, int kw, int pw,
                                                             int cpack) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int groups = cpack >> 3;
   const int64_t total = (int64_t)B * (T + t_pad) * H * W * groups;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -145,6 +150,8 @@ constexpr int CBM = 64, CBN = 64, CBK = 16;
 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const mv2_conv_args a) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float As[CBK][CBM + 4];
   __shared__ float Bs[CBK][CBN + 4];
   const T* __restrict__ x = (const T*)a.x;
@@ -270,6 +277,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) se_pool_kernel(const T* __restrict__ y, int P, int C,
                                                       const float* __restrict__ wk, float bk,
                                                       float* __restrict__ ws, int n_chunks) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float e[SE_CHUNK];
   __shared__ float red[8];
   __shared__ float bcast[2];
@@ -329,6 +338,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16* __restrict__ y, int P, int C,
                                                              const float* __restrict__ wk, float bk,
                                                              float* __restrict__ ws, int n_chunks, int chunk_rows) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float dyn[];           // [R][C + 2]
   const int f = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x;
@@ -406,6 +417,8 @@ __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16
 __global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict__ ws, int n_chunks, int C, int Hd,
                                                         const float* __restrict__ w1, const float* __restrict__ b1,
                                                         float* __restrict__ hidden_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   // grid (F, ceil(Hd / 32)): combine the chunk partials into pooled[C] (redundantly per block: cheap), then 32 hidden units.
   extern __shared__ float sm[];
   float* pooled = sm;          // [C]
@@ -454,6 +467,8 @@ __global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) se_out_kernel(const float* __restrict__ hidden, int C, int Hd,
                                                      const float* __restrict__ w2, const float* __restrict__ b2,
                                                      float* __restrict__ gates) {
+  pdl_wait();
+  pdl_launch_dependents();
   // grid (F, ceil(C / 64)): 8 warps x 8 output channels each
   extern __shared__ float sm[];   // hidden[Hd]
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -480,6 +495,8 @@ template <typename T>
 __global__ void gate_residual_kernel(const T* __restrict__ y, const T* __restrict__ x,
                                      const float* __restrict__ gates, T* __restrict__ out,
                                      int64_t total, int64_t PC, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t f = i / PC;
     const int c = (int)(i % C);
@@ -491,6 +508,8 @@ __global__ void gate_residual_kernel(const T* __restrict__ y, const T* __restric
 __global__ void gate_residual_bf16x8_kernel(const uint4* __restrict__ y, const uint4* __restrict__ x,
                                             const float* __restrict__ gates, uint4* __restrict__ out,
                                             int64_t total8, int64_t PC8, int C8) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t f = i / PC8;
     const int c = (int)(i % C8) * 8;
@@ -519,6 +538,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, T* __restrict__ out,
                                                       const float* __restrict__ gamma, int64_t n_tok, int T_,
                                                       int P, int C, int token_shift) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (tok >= n_tok) return;
@@ -552,6 +573,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, T
 __global__ void __launch_bounds__(256) rmsnorm_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                              const float* __restrict__ gamma, int64_t n_tok, int T_,
                                                              int P, int C, int token_shift) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (tok >= n_tok) return;
@@ -608,6 +631,8 @@ __global__ void __launch_bounds__(256) rmsnorm_bf16x8_kernel(const __nv_bfloat16
 constexpr int AT_Q = 32;  // queries per block
 template <typename T, int DPL>
 __global__ void __launch_bounds__(128) attention_kernel(const mv2_attn_args a) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int D = DPL * 32;
   __shared__ float Qs[AT_Q][D];
   __shared__ float Ks[32][D + 1];
@@ -721,6 +746,8 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
 
 template <int D>
 __global__ void __launch_bounds__(128) attention_mma_kernel(const mv2_attn_args a) {
+  pdl_wait();
+  pdl_launch_dependents();
   constexpr int DK = D / 16, DN = D / 8;
   __shared__ __align__(16) __nv_bfloat16 Ks[FA_KT][D + 8];
   __shared__ __align__(16) __nv_bfloat16 Vt[D][FA_KT + 8];
@@ -877,6 +904,8 @@ __device__ __forceinline__ float taylor_feat(const float* v, int f) {
 template <typename T>
 __global__ void __launch_bounds__(256) linattn_reduce_kernel(const T* __restrict__ kv, float* __restrict__ ws,
                                                              int L, int heads, int n_chunks) {
+  pdl_wait();
+  pdl_launch_dependents();
   // S[f][e] = sum_n phi(k_n)[f] * [v_n, 1][e].  phi is evaluated once per token into shared memory; thread (slice, f)
   // owns the 9 outputs of feature f for every third token: per token it reads phi[n][f] (conflict free) and the 9
   // values [v_n, 1] (warp broadcast) for 9 FMAs.  The three slices are summed through shared memory at the end.
@@ -943,6 +972,8 @@ __global__ void __launch_bounds__(256) linattn_reduce_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(64) linattn_apply_kernel(const T* __restrict__ q, const float* __restrict__ ws,
                                                            T* __restrict__ out, int L, int heads, int n_chunks) {
+  pdl_wait();
+  pdl_launch_dependents();
   // block = 64 threads x 4 tokens = one LA_CHUNK of tokens; every state value read from smem feeds 4 tokens
   __shared__ float S[LA_ST];
   const int chunk = blockIdx.x, h = blockIdx.y;
@@ -1049,6 +1080,8 @@ __device__ __forceinline__ void for_each_feature_pair(const float (&k)[LA_D], Fn
 
 __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bfloat16* __restrict__ kv, float* __restrict__ ws,
                                                                  int L, int heads, int n_chunks) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __align__(16) __nv_bfloat16 phi_t[LAM_F][LAM_TB + 8];   // [feature][token]
   __shared__ __align__(16) __nv_bfloat16 vt[16][LAM_TB + 8];         // [e][token]; e = 8 is the all-ones column
   const int chunk = blockIdx.x, h = blockIdx.y;
@@ -1143,6 +1176,8 @@ __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bflo
 
 __global__ void __launch_bounds__(128) linattn_apply_mma_kernel(const __nv_bfloat16* __restrict__ q, const float* __restrict__ ws,
                                                                 __nv_bfloat16* __restrict__ out, int L, int heads, int n_chunks) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __align__(16) __nv_bfloat16 phi_s[LAM_TB][LAM_F + 8];   // [token][feature]
   __shared__ __align__(16) __nv_bfloat16 st[16][LAM_F + 8];          // [e][feature]  (S transposed; e = 8 is the denominator)
   const int blk = blockIdx.x, h = blockIdx.y;
@@ -1216,6 +1251,8 @@ __global__ void __launch_bounds__(128) linattn_apply_mma_kernel(const __nv_bfloa
 // ------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void geglu_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t N, int I) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t total = N * I;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t n = idx / I;
@@ -1241,6 +1278,8 @@ __global__ void __launch_bounds__(256) quant_forward_kernel(const T* __restrict_
                                                             float clamp, FsqLevels lv, int64_t* __restrict__ idx64,
                                                             int32_t* __restrict__ idx32, T* __restrict__ quant,
                                                             float* __restrict__ aux) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (tok >= N) return;
@@ -1303,6 +1342,8 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256) quant_decode_kernel(const void* __restrict__ indices, int is64, int64_t N, int C,
                                                            int d, FsqLevels lv, const float* __restrict__ wout,
                                                            const float* __restrict__ bout, T* __restrict__ quant) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (tok >= N) return;
@@ -1339,6 +1380,8 @@ constexpr int LE_TOK = 32;
 __global__ void __launch_bounds__(256) lfq_entropy_kernel(const float* __restrict__ presign, int64_t N, int d,
                                                           float inv_temp, float* __restrict__ avg_prob,
                                                           float* __restrict__ stats) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float probs[];  // [K]
   __shared__ float red[8];
   __shared__ float bc;
@@ -1415,9 +1458,9 @@ template <typename T>
 static int launch_attention(const mv2_attn_args* a, cudaStream_t st) {
   dim3 grid((unsigned)((int64_t)a->n_outer * a->n_inner), a->heads, ceil_div(a->L, AT_Q));
   switch (a->dim_head / 32) {
-    case 1: attention_kernel<T, 1><<<grid, 128, 0, st>>>(*a); break;
-    case 2: attention_kernel<T, 2><<<grid, 128, 0, st>>>(*a); break;
-    case 3: attention_kernel<T, 3><<<grid, 128, 0, st>>>(*a); break;
+    case 1: launch_k(attention_kernel<T, 1>, dim3(grid), dim3(128), 0, st, *a); break;
+    case 2: launch_k(attention_kernel<T, 2>, dim3(grid), dim3(128), 0, st, *a); break;
+    case 3: launch_k(attention_kernel<T, 3>, dim3(grid), dim3(128), 0, st, *a); break;
     default: set_error("dim_head %d unsupported", a->dim_head); return MV2_E_UNSUPPORTED;
   }
   MV2_CHECK_LAUNCH();
@@ -1428,6 +1471,12 @@ extern "C" {
 
 int mv2_abi_version(void) { return MV2_ABI_VERSION; }
 const char* mv2_last_error(void) { return mv2::g_err; }
+
+int mv2_set_pdl(int on) {
+  const int prev = mv2::g_pdl;
+  mv2::g_pdl = on ? 1 : 0;
+  return prev;
+}
 
 int mv2_device_arch(void) {
   int dev = 0, major = 0, minor = 0;
@@ -1464,9 +1513,9 @@ int mv2_ingest_kwpack(const void* src, int src_dtype, void* dst, int B, int C, i
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
   cudaStream_t st = (cudaStream_t)stream;
   if (src_dtype == MV2_F32)
-    ingest_kwpack_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
+    launch_k(ingest_kwpack_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
   else if (src_dtype == MV2_BF16)
-    ingest_kwpack_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
+    launch_k(ingest_kwpack_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
   else { set_error("bad dtype %d", src_dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1483,8 +1532,8 @@ int mv2_conv_forward(const mv2_conv_args* a, void* stream) {
   const int64_t M = (int64_t)a->B * a->To * a->Ho * a->Wo;
   dim3 grid(ceil_div(M, CBM), ceil_div(a->Co, CBN));
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->dtype == MV2_F32) conv_simt_kernel<float><<<grid, 256, 0, st>>>(*a);
-  else if (a->dtype == MV2_BF16) conv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(*a);
+  if (a->dtype == MV2_F32) launch_k(conv_simt_kernel<float>, dim3(grid), dim3(256), 0, st, *a);
+  else if (a->dtype == MV2_BF16) launch_k(conv_simt_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, *a);
   else { set_error("bad dtype %d", a->dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1521,16 +1570,16 @@ int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, 
   const int nc = ceil_div(P, rows);
   dim3 grid(nc, F);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == MV2_F32) se_pool_kernel<float><<<grid, 256, 0, st>>>((const float*)y, P, C, wk, bk, (float*)workspace, nc);
+  if (dtype == MV2_F32) launch_k(se_pool_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)y, P, C, wk, bk, (float*)workspace, nc);
   else if (dtype == MV2_BF16 && se_online_vec(C) != 0) {
     const int vec = se_online_vec(C);
     const size_t dsm = (size_t)(256 / (C / vec)) * (C + 2) * sizeof(float);
     MV2_CHECK_ARG(dsm <= 48 * 1024);
     const __nv_bfloat16* yb = (const __nv_bfloat16*)y;
-    if (vec == 8) se_pool_online_kernel<8><<<grid, 256, dsm, st>>>(yb, P, C, wk, bk, (float*)workspace, nc, rows);
-    else if (vec == 16) se_pool_online_kernel<16><<<grid, 256, dsm, st>>>(yb, P, C, wk, bk, (float*)workspace, nc, rows);
-    else se_pool_online_kernel<32><<<grid, 256, dsm, st>>>(yb, P, C, wk, bk, (float*)workspace, nc, rows);
-  } else if (dtype == MV2_BF16) se_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, P, C, wk, bk, (float*)workspace, nc);
+    if (vec == 8) launch_k(se_pool_online_kernel<8>, dim3(grid), dim3(256), dsm, st, yb, P, C, wk, bk, (float*)workspace, nc, rows);
+    else if (vec == 16) launch_k(se_pool_online_kernel<16>, dim3(grid), dim3(256), dsm, st, yb, P, C, wk, bk, (float*)workspace, nc, rows);
+    else launch_k(se_pool_online_kernel<32>, dim3(grid), dim3(256), dsm, st, yb, P, C, wk, bk, (float*)workspace, nc, rows);
+  } else if (dtype == MV2_BF16) launch_k(se_pool_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)y, P, C, wk, bk, (float*)workspace, nc);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1545,9 +1594,9 @@ int mv2_se_gate(const void* workspace, int dtype, int F, int P, int C, int Hd, c
   // hidden activations live behind the chunk partials (mv2_se_workspace_bytes reserves F*Hd_max floats)
   float* hidden = (float*)workspace + (size_t)F * ceil_div(P, SE_MIN_ROWS) * (C + 2);
   cudaStream_t st = (cudaStream_t)stream;
-  se_hidden_kernel<<<dim3(F, ceil_div(Hd, 32)), 256, smem1, st>>>((const float*)workspace, nc, C, Hd, w1, b1, hidden);
+  launch_k(se_hidden_kernel, dim3(dim3(F, ceil_div(Hd, 32))), dim3(256), smem1, st, (const float*)workspace, nc, C, Hd, w1, b1, hidden);
   MV2_CHECK_LAUNCH();
-  se_out_kernel<<<dim3(F, ceil_div(C, 64)), 256, smem2, st>>>(hidden, C, Hd, w2, b2, gates);
+  launch_k(se_out_kernel, dim3(dim3(F, ceil_div(C, 64))), dim3(256), smem2, st, hidden, C, Hd, w2, b2, gates);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }
@@ -1559,13 +1608,13 @@ int mv2_gate_residual(const void* y, const void* x, const float* gates, void* ou
   const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
-    gate_residual_kernel<float><<<blocks, 256, 0, st>>>((const float*)y, (const float*)x, gates, (float*)out, total, (int64_t)P * C, C);
+    launch_k(gate_residual_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)y, (const float*)x, gates, (float*)out, total, (int64_t)P * C, C);
   else if (dtype == MV2_BF16 && C % 8 == 0) {
     const int64_t total8 = total / 8;
     const int b8 = (int)std::min<int64_t>((total8 + 255) / 256, 148 * 16);
-    gate_residual_bf16x8_kernel<<<b8, 256, 0, st>>>((const uint4*)y, (const uint4*)x, gates, (uint4*)out, total8, (int64_t)P * C / 8, C / 8);
+    launch_k(gate_residual_bf16x8_kernel, dim3(b8), dim3(256), 0, st, (const uint4*)y, (const uint4*)x, gates, (uint4*)out, total8, (int64_t)P * C / 8, C / 8);
   } else if (dtype == MV2_BF16)
-    gate_residual_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)x, gates, (__nv_bfloat16*)out, total, (int64_t)P * C, C);
+    launch_k(gate_residual_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)y, (const __nv_bfloat16*)x, gates, (__nv_bfloat16*)out, total, (int64_t)P * C, C);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1579,11 +1628,11 @@ int mv2_rmsnorm(const void* x, void* out, int dtype, const float* gamma, int B, 
   const int blocks = ceil_div(n_tok, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
-    rmsnorm_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)out, gamma, n_tok, T, P, C, token_shift);
+    launch_k(rmsnorm_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)x, (float*)out, gamma, n_tok, T, P, C, token_shift);
   else if (dtype == MV2_BF16 && C % 8 == 0 && C <= 1024 && (!token_shift || (C / 2) % 8 == 0))
-    rmsnorm_bf16x8_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, gamma, n_tok, T, P, C, token_shift);
+    launch_k(rmsnorm_bf16x8_kernel, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, gamma, n_tok, T, P, C, token_shift);
   else if (dtype == MV2_BF16)
-    rmsnorm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, gamma, n_tok, T, P, C, token_shift);
+    launch_k(rmsnorm_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, gamma, n_tok, T, P, C, token_shift);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1598,8 +1647,8 @@ int mv2_attention(const mv2_attn_args* a, void* stream) {
   if (a->dtype == MV2_F32) return launch_attention<float>(a, st);
   if (a->dtype == MV2_BF16 && !a->causal && a->L >= 64 && (a->dim_head == 32 || a->dim_head == 64) && a->heads * a->dim_head % 8 == 0) {
     dim3 grid((unsigned)((int64_t)a->n_outer * a->n_inner), a->heads, ceil_div(a->L, FA_Q));
-    if (a->dim_head == 32) attention_mma_kernel<32><<<grid, 128, 0, st>>>(*a);
-    else attention_mma_kernel<64><<<grid, 128, 0, st>>>(*a);
+    if (a->dim_head == 32) launch_k(attention_mma_kernel<32>, dim3(grid), dim3(128), 0, st, *a);
+    else launch_k(attention_mma_kernel<64>, dim3(grid), dim3(128), 0, st, *a);
     MV2_CHECK_LAUNCH();
     return MV2_OK;
   }
@@ -1620,18 +1669,18 @@ int mv2_linear_attention(const void* q, const void* kv, void* out, int dtype, in
   dim3 grid(nc, heads, n_seq);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32) {
-    linattn_reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)kv, (float*)workspace, L, heads, nc);
+    launch_k(linattn_reduce_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();
-    linattn_apply_kernel<float><<<grid, 64, 0, st>>>((const float*)q, (const float*)workspace, (float*)out, L, heads, nc);
+    launch_k(linattn_apply_kernel<float>, dim3(grid), dim3(64), 0, st, (const float*)q, (const float*)workspace, (float*)out, L, heads, nc);
   } else if (dtype == MV2_BF16 && (heads * LA_D) % 8 == 0) {
-    linattn_reduce_mma_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
+    launch_k(linattn_reduce_mma_kernel, dim3(grid), dim3(128), 0, st, (const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();
     dim3 grid2(ceil_div(L, LAM_TB), heads, n_seq);
-    linattn_apply_mma_kernel<<<grid2, 128, 0, st>>>((const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
+    launch_k(linattn_apply_mma_kernel, dim3(grid2), dim3(128), 0, st, (const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
   } else if (dtype == MV2_BF16) {
-    linattn_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
+    launch_k(linattn_reduce_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();
-    linattn_apply_kernel<__nv_bfloat16><<<grid, 64, 0, st>>>((const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
+    launch_k(linattn_apply_kernel<__nv_bfloat16>, dim3(grid), dim3(64), 0, st, (const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
   } else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1642,8 +1691,8 @@ int mv2_geglu(const void* in, void* out, int dtype, int64_t N, int I, void* stre
   const int64_t total = N * I;
   const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == MV2_F32) geglu_kernel<float><<<blocks, 256, 0, st>>>((const float*)in, (float*)out, N, I);
-  else if (dtype == MV2_BF16) geglu_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, I);
+  if (dtype == MV2_F32) launch_k(geglu_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)in, (float*)out, N, I);
+  else if (dtype == MV2_BF16) launch_k(geglu_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, N, I);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1658,9 +1707,9 @@ int mv2_lfq_forward(const void* x, int dtype, int64_t N, int C, int d, const flo
   const int blocks = ceil_div(N, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
-    quant_forward_kernel<float, 0><<<blocks, 256, 0, st>>>((const float*)x, N, C, d, win, bin, wout, bout, clamp, lv, indices, nullptr, (float*)quantized, presign);
+    launch_k(quant_forward_kernel<float, 0>, dim3(blocks), dim3(256), 0, st, (const float*)x, N, C, d, win, bin, wout, bout, clamp, lv, indices, nullptr, (float*)quantized, presign);
   else if (dtype == MV2_BF16)
-    quant_forward_kernel<__nv_bfloat16, 0><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, N, C, d, win, bin, wout, bout, clamp, lv, indices, nullptr, (__nv_bfloat16*)quantized, presign);
+    launch_k(quant_forward_kernel<__nv_bfloat16, 0>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, N, C, d, win, bin, wout, bout, clamp, lv, indices, nullptr, (__nv_bfloat16*)quantized, presign);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1673,9 +1722,9 @@ int mv2_lfq_decode(const void* indices, int index_is_i64, int64_t N, int C, int 
   const int blocks = ceil_div(N, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
-    quant_decode_kernel<float, 0><<<blocks, 256, 0, st>>>(indices, index_is_i64, N, C, d, lv, wout, bout, (float*)quantized);
+    launch_k(quant_decode_kernel<float, 0>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, lv, wout, bout, (float*)quantized);
   else if (dtype == MV2_BF16)
-    quant_decode_kernel<__nv_bfloat16, 0><<<blocks, 256, 0, st>>>(indices, index_is_i64, N, C, d, lv, wout, bout, (__nv_bfloat16*)quantized);
+    launch_k(quant_decode_kernel<__nv_bfloat16, 0>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, lv, wout, bout, (__nv_bfloat16*)quantized);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1691,9 +1740,9 @@ int mv2_fsq_forward(const void* x, int dtype, int64_t N, int C, int d, const int
   const int blocks = ceil_div(N, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
-    quant_forward_kernel<float, 1><<<blocks, 256, 0, st>>>((const float*)x, N, C, d, win, bin, wout, bout, 0.f, lv, nullptr, indices, (float*)quantized, bounded);
+    launch_k(quant_forward_kernel<float, 1>, dim3(blocks), dim3(256), 0, st, (const float*)x, N, C, d, win, bin, wout, bout, 0.f, lv, nullptr, indices, (float*)quantized, bounded);
   else if (dtype == MV2_BF16)
-    quant_forward_kernel<__nv_bfloat16, 1><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, N, C, d, win, bin, wout, bout, 0.f, lv, nullptr, indices, (__nv_bfloat16*)quantized, bounded);
+    launch_k(quant_forward_kernel<__nv_bfloat16, 1>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, N, C, d, win, bin, wout, bout, 0.f, lv, nullptr, indices, (__nv_bfloat16*)quantized, bounded);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1707,9 +1756,9 @@ int mv2_fsq_decode(const void* indices, int index_is_i64, int64_t N, int C, int 
   const int blocks = ceil_div(N, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
-    quant_decode_kernel<float, 1><<<blocks, 256, 0, st>>>(indices, index_is_i64, N, C, d, lv, wout, bout, (float*)quantized);
+    launch_k(quant_decode_kernel<float, 1>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, lv, wout, bout, (float*)quantized);
   else if (dtype == MV2_BF16)
-    quant_decode_kernel<__nv_bfloat16, 1><<<blocks, 256, 0, st>>>(indices, index_is_i64, N, C, d, lv, wout, bout, (__nv_bfloat16*)quantized);
+    launch_k(quant_decode_kernel<__nv_bfloat16, 1>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, lv, wout, bout, (__nv_bfloat16*)quantized);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1720,7 +1769,7 @@ int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, float inv_t
   MV2_CHECK_ARG(presign && avg_prob && stats && N > 0 && d > 0 && d <= 12);
   const int K = 1 << d;
   const int blocks = ceil_div(N, LE_TOK);
-  lfq_entropy_kernel<<<blocks, 256, K * sizeof(float), (cudaStream_t)stream>>>(presign, N, d, inv_temperature, avg_prob, stats);
+  launch_k(lfq_entropy_kernel, dim3(blocks), dim3(256), K * sizeof(float), (cudaStream_t)stream, presign, N, d, inv_temperature, avg_prob, stats);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+  // everything above overlapped the previous kernel's tail (PDL); activations may only be touched from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int n_iters = p.ntaps * p.kchunks;
   if (warp == 0) {
@@ -271,7 +274,7 @@ int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream) {
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
   MV2_CHECK_ARG(smem <= 227 * 1024);
   dim3 grid((unsigned)((int64_t)a->B * p.tt * p.th * p.tw), (unsigned)ceil_div(a->Co, bn));
-  tc_conv_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(p);
+  launch_k(tc_conv_kernel, dim3(grid), dim3(192), smem, (cudaStream_t)stream, p);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

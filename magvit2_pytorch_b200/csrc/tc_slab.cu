@@ -91,6 +91,9 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+  // everything above overlapped the previous kernel's tail (PDL); activations may only be touched from here on
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int taps2d = p.kh * p.kw;
   const int acc_cols = p.mw * p.bn;   // TMEM columns of one accumulator buffer
@@ -321,7 +324,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
   const int grid = std::min(p.total_tiles, n_sm);
-  tc_slab_kernel<<<grid, 384, smem, (cudaStream_t)stream>>>(p);
+  launch_k(tc_slab_kernel, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

@@ -229,6 +229,8 @@ class VideoTokenizer(nn.Module):
         # of the graph's static buffers.
         self.cuda_graphs = False
         self._graphs = {}
+        # opt-in: programmatic dependent launch for every kernel of the path (mv2_set_pdl); process-wide library state
+        self.pdl = False
 
     # ------------------------------------------------------------------ module plumbing
     @property
@@ -307,6 +309,7 @@ class VideoTokenizer(nn.Module):
         if self._engine is None:
             self._engine = Engine(self)
         self._engine.prepare()
+        self._engine.lib.mv2_set_pdl(1 if self.pdl else 0)
         return self._engine
 
     def _graph_call(self, name, fn, *tensors):
