@@ -253,7 +253,7 @@ def main():
     Wt.fill_state_dict_(model, 0)
     model = model.to(dev).bfloat16().eval()
     model.cuda_graphs = True            # public opt-in: replay the static launch plan as one CUDA graph per entry point
-    model.pdl = os.environ.get("MV2_PDL", "1") == "1"   # public opt-in: programmatic dependent launch between kernels
+    model.pdl = os.environ.get("MV2_PDL", "0") == "1"   # public opt-in: programmatic dependent launch between kernels
     eng = model.engine
 
     # inputs: NB distinct batches per rank so consecutive steps never re-read the same input from L2

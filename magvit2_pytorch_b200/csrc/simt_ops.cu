@@ -1082,7 +1082,9 @@ __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bflo
                                                                  int L, int heads, int n_chunks) {
   pdl_wait();
   pdl_launch_dependents();
-  __shared__ __align__(16) __nv_bfloat16 phi_t[LAM_F][LAM_TB + 8];   // [feature][token]
+  // phi is carried as a bf16 hi + lo pair (two MMAs) so the quadratic features keep ~16 mantissa bits; v is bf16 already
+  __shared__ __align__(16) __nv_bfloat16 phi_t[LAM_F][LAM_TB + 8];   // [feature][token] hi
+  __shared__ __align__(16) __nv_bfloat16 phi_l[LAM_F][LAM_TB + 8];   // lo = bf16(phi - hi)
   __shared__ __align__(16) __nv_bfloat16 vt[16][LAM_TB + 8];         // [e][token]; e = 8 is the all-ones column
   const int chunk = blockIdx.x, h = blockIdx.y;
   const int64_t seq = blockIdx.z;
@@ -1119,8 +1121,13 @@ __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bflo
         for (int q = 0; q < LA_D; ++q) { kk[q] = 0.f; vv[q] = 0.f; }
       }
       for_each_feature_pair<0>(kk, [&](int f, float a, float b) {
-        phi_t[f][tid] = __float2bfloat16_rn(ok ? a : 0.f);
-        phi_t[f + 1][tid] = __float2bfloat16_rn(ok ? b : 0.f);
+        a = ok ? a : 0.f;
+        b = ok ? b : 0.f;
+        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+        phi_t[f][tid] = ah;
+        phi_t[f + 1][tid] = bh;
+        phi_l[f][tid] = __float2bfloat16_rn(a - __bfloat162float(ah));
+        phi_l[f + 1][tid] = __float2bfloat16_rn(b - __bfloat162float(bh));
       });
 #pragma unroll
       for (int e = 0; e < LA_D; ++e) vt[e][tid] = __float2bfloat16_rn(vv[e]);
@@ -1146,6 +1153,12 @@ __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bflo
         a[1] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g + 8][n0 + t * 2]);
         a[2] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g][n0 + 8 + t * 2]);
         a[3] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g + 8][n0 + 8 + t * 2]);
+        mma_bf16_16816(acc[mt][0], a, b[0][0], b[0][1]);
+        mma_bf16_16816(acc[mt][1], a, b[1][0], b[1][1]);
+        a[0] = *reinterpret_cast<const uint32_t*>(&phi_l[mt * 16 + g][n0 + t * 2]);
+        a[1] = *reinterpret_cast<const uint32_t*>(&phi_l[mt * 16 + g + 8][n0 + t * 2]);
+        a[2] = *reinterpret_cast<const uint32_t*>(&phi_l[mt * 16 + g][n0 + 8 + t * 2]);
+        a[3] = *reinterpret_cast<const uint32_t*>(&phi_l[mt * 16 + g + 8][n0 + 8 + t * 2]);
         mma_bf16_16816(acc[mt][0], a, b[0][0], b[0][1]);
         mma_bf16_16816(acc[mt][1], a, b[1][0], b[1][1]);
       }
@@ -1174,27 +1187,33 @@ __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bflo
   }
 }
 
-__global__ void __launch_bounds__(128) linattn_apply_mma_kernel(const __nv_bfloat16* __restrict__ q, const float* __restrict__ ws,
-                                                                __nv_bfloat16* __restrict__ out, int L, int heads, int n_chunks) {
+constexpr int LAM_AT = 64;     // tokens per block in the apply kernel (2 warps x 32)
+__global__ void __launch_bounds__(64) linattn_apply_mma_kernel(const __nv_bfloat16* __restrict__ q, const float* __restrict__ ws,
+                                                               __nv_bfloat16* __restrict__ out, int L, int heads, int n_chunks) {
   pdl_wait();
   pdl_launch_dependents();
-  __shared__ __align__(16) __nv_bfloat16 phi_s[LAM_TB][LAM_F + 8];   // [token][feature]
-  __shared__ __align__(16) __nv_bfloat16 st[16][LAM_F + 8];          // [e][feature]  (S transposed; e = 8 is the denominator)
+  // both operands are carried as bf16 hi + lo pairs (3 MMAs: hi*hi + lo*hi + hi*lo) -> ~fp32-level accuracy
+  __shared__ __align__(16) __nv_bfloat16 phi_s[LAM_AT][LAM_F + 8];   // [token][feature] hi
+  __shared__ __align__(16) __nv_bfloat16 phi_l[LAM_AT][LAM_F + 8];   // lo
+  __shared__ __align__(16) __nv_bfloat16 st[16][LAM_F + 8];          // [e][feature] hi  (S transposed; e = 8 is the denominator)
+  __shared__ __align__(16) __nv_bfloat16 sl[16][LAM_F + 8];          // lo
   const int blk = blockIdx.x, h = blockIdx.y;
   const int64_t seq = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int HD = heads * LA_D;
   const float* wsh = ws + (seq * heads + h) * (int64_t)n_chunks * LA_ST;
-  for (int idx = tid; idx < 16 * LAM_F; idx += 128) {
+  for (int idx = tid; idx < 16 * LAM_F; idx += 64) {
     const int e = idx / LAM_F, f = idx % LAM_F;
     float sv = 0.f;
     if (e <= LA_D && f < LA_F)
       for (int k = 0; k < n_chunks; ++k) sv += wsh[(int64_t)k * LA_ST + f * (LA_D + 1) + e];
-    st[e][f] = __float2bfloat16_rn(sv);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(sv);
+    st[e][f] = hi;
+    sl[e][f] = __float2bfloat16_rn(sv - __bfloat162float(hi));
   }
   {
-    const int tok = blk * LAM_TB + tid;
+    const int tok = blk * LAM_AT + tid;
     const bool ok = tok < L;
     float qq[LA_D];
     if (ok) {
@@ -1211,7 +1230,10 @@ __global__ void __launch_bounds__(128) linattn_apply_mma_kernel(const __nv_bfloa
       for (int i = 0; i < LA_D; ++i) qq[i] = 0.f;
     }
     for_each_feature_pair<0>(qq, [&](int f, float a, float b) {
-      *reinterpret_cast<uint32_t*>(&phi_s[tid][f]) = pack2_bf16(a, b);
+      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+      __nv_bfloat162 hi; hi.x = ah; hi.y = bh;
+      *reinterpret_cast<__nv_bfloat162*>(&phi_s[tid][f]) = hi;
+      *reinterpret_cast<uint32_t*>(&phi_l[tid][f]) = pack2_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
     });
   }
   __syncthreads();
@@ -1225,22 +1247,30 @@ __global__ void __launch_bounds__(128) linattn_apply_mma_kernel(const __nv_bfloa
       for (int j = 0; j < 4; ++j) c[nt][j] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < LAM_F / 16; ++ks) {
-      uint32_t a[4];
-      a[0] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g][ks * 16 + t * 2]);
-      a[1] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g + 8][ks * 16 + t * 2]);
-      a[2] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g][ks * 16 + 8 + t * 2]);
-      a[3] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g + 8][ks * 16 + 8 + t * 2]);
+      uint32_t ah[4], al[4];
+      ah[0] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g][ks * 16 + t * 2]);
+      ah[1] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g + 8][ks * 16 + t * 2]);
+      ah[2] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g][ks * 16 + 8 + t * 2]);
+      ah[3] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g + 8][ks * 16 + 8 + t * 2]);
+      al[0] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g][ks * 16 + t * 2]);
+      al[1] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g + 8][ks * 16 + t * 2]);
+      al[2] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g][ks * 16 + 8 + t * 2]);
+      al[3] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g + 8][ks * 16 + 8 + t * 2]);
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&st[nt * 8 + g][ks * 16 + t * 2]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&st[nt * 8 + g][ks * 16 + 8 + t * 2]);
-        mma_bf16_16816(c[nt], a, b0, b1);
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&st[nt * 8 + g][ks * 16 + t * 2]);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&st[nt * 8 + g][ks * 16 + 8 + t * 2]);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&sl[nt * 8 + g][ks * 16 + t * 2]);
+        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&sl[nt * 8 + g][ks * 16 + 8 + t * 2]);
+        mma_bf16_16816(c[nt], ah, bh0, bh1);
+        mma_bf16_16816(c[nt], al, bh0, bh1);
+        mma_bf16_16816(c[nt], ah, bl0, bl1);
       }
     }
     // denominator = column 8 = c[1][0] (row g) / c[1][2] (row g+8) of the quad's t == 0 lane
     const float d0 = fmaxf(__shfl_sync(0xffffffffu, c[1][0], lane & ~3), 1e-5f);
     const float d1 = fmaxf(__shfl_sync(0xffffffffu, c[1][2], lane & ~3), 1e-5f);
-    const int r0 = blk * LAM_TB + n0 + g, r1 = r0 + 8;
+    const int r0 = blk * LAM_AT + n0 + g, r1 = r0 + 8;
     if (r0 < L) *reinterpret_cast<uint32_t*>(out + (seq * L + r0) * HD + h * LA_D + t * 2) = pack2_bf16(c[0][0] / d0, c[0][1] / d0);
     if (r1 < L) *reinterpret_cast<uint32_t*>(out + (seq * L + r1) * HD + h * LA_D + t * 2) = pack2_bf16(c[0][2] / d1, c[0][3] / d1);
   }
@@ -1675,8 +1705,8 @@ int mv2_linear_attention(const void* q, const void* kv, void* out, int dtype, in
   } else if (dtype == MV2_BF16 && (heads * LA_D) % 8 == 0) {
     launch_k(linattn_reduce_mma_kernel, dim3(grid), dim3(128), 0, st, (const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();
-    dim3 grid2(ceil_div(L, LAM_TB), heads, n_seq);
-    launch_k(linattn_apply_mma_kernel, dim3(grid2), dim3(128), 0, st, (const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
+    dim3 grid2(ceil_div(L, LAM_AT), heads, n_seq);
+    launch_k(linattn_apply_mma_kernel, dim3(grid2), dim3(64), 0, st, (const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
   } else if (dtype == MV2_BF16) {
     launch_k(linattn_reduce_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();

@@ -35,6 +35,7 @@ struct alignas(64) SlabParams {
   int mw, pitch, slab_h, slab_bytes, slab_stride;
   int bn, n_tiles_n, tiles_w, tiles_h, total_tiles;
   int slab_stages, w_stages, nbuf;
+  int tpw;               // in-plane taps per weight stage (one 3-D TMA box {bk, bn, tpw})
   TcEpi epi;
 };
 
@@ -62,7 +63,8 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_bytes = p.row_bytes;          // 128 (64 channels, SWIZZLE_128B) or 64 (32 channels, SWIZZLE_64B)
   const uint32_t bk = row_bytes >> 1;
-  const uint32_t w_bytes = p.bn * row_bytes;
+  const uint32_t w_tile = p.bn * row_bytes;          // one tap's weight tile
+  const uint32_t w_bytes = w_tile * p.tpw;           // one ring stage = tpw consecutive in-plane taps
   const uint32_t slab0 = smem_base;
   const uint32_t wst0 = smem_base + p.slab_stages * p.slab_stride;
   const uint32_t bar0 = wst0 + p.w_stages * w_bytes;
@@ -124,11 +126,11 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         const int dt0 = max(0, p.pt - c.t);
         for (int dt = dt0; dt < p.kt; ++dt)
           for (int kc = 0; kc < p.kchunks; ++kc)
-            for (int tp = 0; tp < taps2d; ++tp, ++it) {
+            for (int tp = 0; tp < taps2d; tp += p.tpw, ++it) {
               const uint32_t s = it % p.w_stages, ph = (it / p.w_stages) & 1;
               mbar_wait(w_empty + 8 * s, ph ^ 1);
               mbar_expect_tx(w_full + 8 * s, w_bytes);
-              tma_load_2d(wst0 + s * w_bytes, &p.wmap, w_full + 8 * s, (dt * taps2d + tp) * p.Ci + kc * bk, c.n0);
+              tma_load_3d(wst0 + s * w_bytes, &p.wmap, w_full + 8 * s, kc * bk, c.n0, dt * taps2d + tp);
             }
       }
     }
@@ -158,14 +160,16 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
             const uint32_t s = sit % p.slab_stages;
             mbar_wait(slab_full + 8 * s, (sit / p.slab_stages) & 1);
             const uint32_t slab = slab0 + s * p.slab_stride;
-            for (int dh = 0; dh < p.kh; ++dh)
-              for (int dw = 0; dw < p.kw; ++dw, ++wit) {
-                const uint32_t ws = wit % p.w_stages;
-                mbar_wait(w_full + 8 * ws, (wit / p.w_stages) & 1);
-                tc_fence_after();
-                const uint64_t bd = b_hi | (uint64_t)(((wst0 + ws * w_bytes) & 0x3FFFF) >> 4);
-                const uint32_t a0 = slab + (uint32_t)(dh * p.pitch + dw) * row_bytes;
-                if (leader) {
+            for (int tp0 = 0; tp0 < taps2d; tp0 += p.tpw, ++wit) {
+              const uint32_t ws = wit % p.w_stages;
+              mbar_wait(w_full + 8 * ws, (wit / p.w_stages) & 1);
+              tc_fence_after();
+              if (leader) {
+                for (int u = 0; u < p.tpw; ++u) {
+                  const int tp = tp0 + u;
+                  const int dh = tp / p.kw, dw = tp - dh * p.kw;
+                  const uint64_t bd = b_hi | (uint64_t)(((wst0 + ws * w_bytes + u * w_tile) & 0x3FFFF) >> 4);
+                  const uint32_t a0 = slab + (uint32_t)(dh * p.pitch + dw) * row_bytes;
                   for (int j = 0; j < p.mw; ++j) {
                     const uint64_t ad = a_hi | (uint64_t)(((a0 + (uint32_t)j * 8 * row_bytes) & 0x3FFFF) >> 4);
                     const uint32_t d = acc + j * p.bn;
@@ -176,10 +180,12 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
                       umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
                     }
                   }
-                  umma_commit(w_empty + 8 * ws);
+                  accum = 1;
                 }
-                accum = 1;
+                umma_commit(w_empty + 8 * ws);
               }
+              accum = 1;
+            }
             if (leader) umma_commit(slab_empty + 8 * s);
           }
         if (leader) umma_commit(t_full + 8 * buf);
@@ -271,10 +277,11 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   for (int bn = 256; bn >= 32; bn >>= 1)
     if (bn <= co_pad && co_pad % bn == 0) { best_bn = bn; break; }
   int best_mw = (best_bn <= 128 && a->Wo > 8) ? 2 : 1;
+  if (p.row_bytes == 64 && best_bn <= 64 && a->Wo > 16) best_mw = 4;   // conv_in: tiny K per tap -> more rows per weight tile
   if (const char* env = getenv("MV2_SLAB_CFG")) {   // debug / tuning override: "mw,bn"
     int emw = 0, ebn = 0;
-    if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2) && ebn >= 32 && ebn <= 256 && co_pad % ebn == 0 &&
-        !(emw == 2 && a->Wo <= 8)) { best_mw = emw; best_bn = ebn; }
+    if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2 || emw == 4) && ebn >= 32 && ebn <= 256 &&
+        co_pad % ebn == 0 && emw * ebn <= 512 && !(emw >= 2 && a->Wo <= 8)) { best_mw = emw; best_bn = ebn; }
   }
   p.mw = best_mw; p.bn = best_bn;
   p.n_tiles_n = co_pad / p.bn;
@@ -286,10 +293,17 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   p.slab_bytes = p.pitch * p.slab_h * p.row_bytes;
   p.slab_stride = (p.slab_bytes + 1023) / 1024 * 1024;
   p.nbuf = (2 * p.mw * p.bn <= 512) ? 2 : 1;
-  const int w_bytes = p.bn * p.row_bytes;
+  // weight ring stage = tpw consecutive in-plane taps (fewer barrier round trips for small tiles), <= 32 KB
+  const int taps2d = a->kh * a->kw;
+  p.tpw = 1;
+  for (int d = taps2d; d >= 1; --d)
+    if (taps2d % d == 0 && d * p.bn * p.row_bytes <= 32 * 1024) { p.tpw = d; break; }
+  if (const char* env = getenv("MV2_SLAB_TPW")) { const int v = atoi(env); if (v >= 1 && taps2d % v == 0 && v * p.bn * p.row_bytes <= 64 * 1024) p.tpw = v; }
+  const int w_bytes = p.bn * p.row_bytes * p.tpw;
   const int budget = 220 * 1024 - co_pad * 4;
-  p.slab_stages = p.slab_stride * 3 + w_bytes * 4 <= budget ? 3 : 2;
+  p.slab_stages = p.slab_stride * 3 + w_bytes * 3 <= budget ? 3 : 2;
   p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
+  if (p.w_stages < 2 && p.slab_stages > 2) { p.slab_stages = 2; p.w_stages = std::min(12, (budget - 2 * p.slab_stride) / w_bytes); }
   MV2_CHECK_ARG(p.w_stages >= 2);
 
   const CUtensorMapSwizzle swz = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -305,12 +319,14 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(slab) failed: %d", (int)r); return MV2_E_CUDA; }
   }
   {
-    const int64_t K = (int64_t)a->kt * a->kh * a->kw * a->Ci;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)a->Co};
-    cuuint64_t strides[1] = {(cuuint64_t)(K * 2)};
-    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.bn};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a->w, dims, strides, box, es,
+    // weights [Co][tap][Ci] viewed as {ci, co, tap}: a box {bk, bn, tpw} lands as tpw consecutive K-major tiles
+    const int64_t ntaps = (int64_t)a->kt * a->kh * a->kw;
+    const int64_t K = ntaps * a->Ci;
+    cuuint64_t dims[3] = {(cuuint64_t)a->Ci, (cuuint64_t)a->Co, (cuuint64_t)ntaps};
+    cuuint64_t strides[2] = {(cuuint64_t)(K * 2), (cuuint64_t)(a->Ci * 2)};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.bn, (cuuint32_t)p.tpw};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)a->w, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return MV2_E_CUDA; }

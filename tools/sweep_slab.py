@@ -28,7 +28,7 @@ LAYERS = [
     ("up 512->256x4 T20 16", (1024, 512, 1, 1), (20, 16, 16)),
     ("conv_in kwpack", None, (20, 128, 128)),
 ]
-CFGS = ["tap"] + [f"{mw},{bn}" for mw in (1, 2) for bn in (256, 128, 64, 32)]
+CFGS = ["tap"] + [f"{mw},{bn}" for mw in (1, 2, 4) for bn in (256, 128, 64, 32)]
 
 
 def timeit(fn):
@@ -72,7 +72,7 @@ for name, wshape, (T, H, W) in LAYERS:
         else:
             mw, bn = map(int, cfg.split(","))
             co_pad = (co + 31) // 32 * 32
-            if bn > co_pad or co_pad % bn or (mw == 2 and W <= 8):
+            if bn > co_pad or co_pad % bn or (mw >= 2 and W <= 8) or mw * bn > 512:
                 continue
             eng.tc_variant = "slab"
             os.environ["MV2_SLAB_CFG"] = cfg
