@@ -36,6 +36,7 @@ struct alignas(64) SlabParams {
   int bn, n_tiles_n, tiles_w, tiles_h, total_tiles;
   int slab_stages, w_stages, nbuf;
   int tpw;               // in-plane taps per weight stage (one 3-D TMA box {bk, bn, tpw})
+  int cluster;           // 1, or 2: CTA pairs on neighbouring tiles multicast each other half of every weight tile
   TcEpi epi;
 };
 
@@ -46,9 +47,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 struct TileCoord { int b, t, h0, w0, n0; };
 __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) {
   TileCoord c;
-  const int nt = tile % p.n_tiles_n; tile /= p.n_tiles_n;
-  const int tw = tile % p.tiles_w; tile /= p.tiles_w;
-  const int th = tile % p.tiles_h; tile /= p.tiles_h;
+  int nt, tw, th;
+  if (p.cluster == 1) {      // n-tile fastest: CTAs running side by side share the activation slab through L2
+    nt = tile % p.n_tiles_n; tile /= p.n_tiles_n;
+    tw = tile % p.tiles_w; tile /= p.tiles_w;
+    th = tile % p.tiles_h; tile /= p.tiles_h;
+  } else {                   // w-tile fastest: the two CTAs of a cluster work on neighbouring tiles of the same (b, t, n-tile)
+    tw = tile % p.tiles_w; tile /= p.tiles_w;
+    th = tile % p.tiles_h; tile /= p.tiles_h;
+    nt = tile % p.n_tiles_n; tile /= p.n_tiles_n;
+  }
   c.t = tile % p.T;
   c.b = tile / p.T;
   c.h0 = th * 16;
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.slab_stages; ++s) { mbar_init(slab_full + 8 * s, 1); mbar_init(slab_empty + 8 * s, 1); }
-    for (int s = 0; s < p.w_stages; ++s) { mbar_init(w_full + 8 * s, 1); mbar_init(w_empty + 8 * s, 1); }
+    for (int s = 0; s < p.w_stages; ++s) { mbar_init(w_full + 8 * s, 1); mbar_init(w_empty + 8 * s, p.cluster); }
     for (int s = 0; s < 2; ++s) { mbar_init(t_full + 8 * s, 1); mbar_init(t_empty + 8 * s, 8); }
     fence_barrier_init();
   }
@@ -90,6 +98,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();     // peer barriers must be initialised before any multicast / remote arrive
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
@@ -130,7 +139,14 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
               const uint32_t s = it % p.w_stages, ph = (it / p.w_stages) & 1;
               mbar_wait(w_empty + 8 * s, ph ^ 1);
               mbar_expect_tx(w_full + 8 * s, w_bytes);
-              tma_load_3d(wst0 + s * w_bytes, &p.wmap, w_full + 8 * s, kc * bk, c.n0, dt * taps2d + tp);
+              if (p.cluster == 1) {
+                tma_load_3d(wst0 + s * w_bytes, &p.wmap, w_full + 8 * s, kc * bk, c.n0, dt * taps2d + tp);
+              } else {   // my half of the rows goes to both CTAs; the peer sends the other half (tpw == 1 here)
+                const uint32_t rank = cluster_ctarank();
+                const uint32_t half_rows = p.bn >> 1;
+                tma_load_3d_mcast(wst0 + s * w_bytes + rank * half_rows * row_bytes, &p.wmap, w_full + 8 * s, kc * bk,
+                                  c.n0 + rank * half_rows, dt * taps2d + tp, (uint16_t)0x3);
+              }
             }
       }
     }
@@ -164,12 +180,13 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
               const uint32_t ws = wit % p.w_stages;
               mbar_wait(w_full + 8 * ws, (wit / p.w_stages) & 1);
               tc_fence_after();
-              if (leader) {
-                for (int u = 0; u < p.tpw; ++u) {
-                  const int tp = tp0 + u;
-                  const int dh = tp / p.kw, dw = tp - dh * p.kw;
-                  const uint64_t bd = b_hi | (uint64_t)(((wst0 + ws * w_bytes + u * w_tile) & 0x3FFFF) >> 4);
-                  const uint32_t a0 = slab + (uint32_t)(dh * p.pitch + dw) * row_bytes;
+              // operands are computed warp-uniformly (uniform registers); only the tcgen05 issue is predicated
+              for (int u = 0; u < p.tpw; ++u) {
+                const int tp = tp0 + u;
+                const int dh = tp / p.kw, dw = tp - dh * p.kw;
+                const uint64_t bd = b_hi | (uint64_t)(((wst0 + ws * w_bytes + u * w_tile) & 0x3FFFF) >> 4);
+                const uint32_t a0 = slab + (uint32_t)(dh * p.pitch + dw) * row_bytes;
+                if (leader) {
                   for (int j = 0; j < p.mw; ++j) {
                     const uint64_t ad = a_hi | (uint64_t)(((a0 + (uint32_t)j * 8 * row_bytes) & 0x3FFFF) >> 4);
                     const uint32_t d = acc + j * p.bn;
@@ -180,9 +197,12 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
                       umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
                     }
                   }
-                  accum = 1;
                 }
-                umma_commit(w_empty + 8 * ws);
+                accum = 1;
+              }
+              if (leader) {
+                if (p.cluster == 1) umma_commit(w_empty + 8 * ws);
+                else umma_commit_mcast(w_empty + 8 * ws, (uint16_t)0x3);   // the slot is free once BOTH CTAs consumed it
               }
               accum = 1;
             }
@@ -224,6 +244,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();     // the peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -277,7 +298,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   for (int bn = 256; bn >= 32; bn >>= 1)
     if (bn <= co_pad && co_pad % bn == 0) { best_bn = bn; break; }
   int best_mw = (best_bn <= 128 && a->Wo > 8) ? 2 : 1;
-  if (p.row_bytes == 64 && best_bn <= 64 && a->Wo > 16) best_mw = 4;   // conv_in: tiny K per tap -> more rows per weight tile
+  if (best_bn <= 64 && a->Wo > 16) best_mw = 4;   // narrow N: four M-tiles per weight tile still double-buffer in TMEM
   if (const char* env = getenv("MV2_SLAB_CFG")) {   // debug / tuning override: "mw,bn"
     int emw = 0, ebn = 0;
     if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2 || emw == 4) && ebn >= 32 && ebn <= 256 &&
@@ -285,6 +306,10 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   }
   p.mw = best_mw; p.bn = best_bn;
   p.n_tiles_n = co_pad / p.bn;
+  // weight multicast across CTA pairs: when one M-tile per CTA cannot amortise the weight stream (mw == 1, deep
+  // layers) two CTAs on neighbouring tiles fetch half of every weight tile each and multicast it to both
+  p.cluster = (p.mw == 1 && ceil_div(a->Wo, 8) % 2 == 0 && p.bn >= 64 && a->kt * a->kh * a->kw > 1 && a->Co % p.bn == 0) ? 2 : 1;
+  if (const char* env = getenv("MV2_SLAB_CLUSTER")) p.cluster = (atoi(env) == 2 && p.mw == 1 && ceil_div(a->Wo, 8) % 2 == 0 && p.bn >= 64 && a->Co % p.bn == 0) ? 2 : 1;
   p.tiles_h = tiles_h;
   p.tiles_w = ceil_div(a->Wo, 8 * p.mw);
   p.total_tiles = (int)((int64_t)a->B * a->To * p.tiles_h * p.tiles_w * p.n_tiles_n);
@@ -298,6 +323,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   p.tpw = 1;
   for (int d = taps2d; d >= 1; --d)
     if (taps2d % d == 0 && d * p.bn * p.row_bytes <= 32 * 1024) { p.tpw = d; break; }
+  if (p.cluster > 1) p.tpw = 1;
   if (const char* env = getenv("MV2_SLAB_TPW")) { const int v = atoi(env); if (v >= 1 && taps2d % v == 0 && v * p.bn * p.row_bytes <= 64 * 1024) p.tpw = v; }
   const int w_bytes = p.bn * p.row_bytes * p.tpw;
   const int budget = 220 * 1024 - co_pad * 4;
@@ -324,7 +350,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
     const int64_t K = ntaps * a->Ci;
     cuuint64_t dims[3] = {(cuuint64_t)a->Ci, (cuuint64_t)a->Co, (cuuint64_t)ntaps};
     cuuint64_t strides[2] = {(cuuint64_t)(K * 2), (cuuint64_t)(a->Ci * 2)};
-    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.bn, (cuuint32_t)p.tpw};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(p.bn / p.cluster), (cuuint32_t)p.tpw};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)a->w, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -339,8 +365,9 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
     attr_err = cudaFuncSetAttribute(tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
-  const int grid = std::min(p.total_tiles, n_sm);
-  launch_k(tc_slab_kernel, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p);
+  int grid = std::min(p.total_tiles, n_sm);
+  if (p.cluster > 1) grid &= ~1;
+  launch_kc(tc_slab_kernel, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

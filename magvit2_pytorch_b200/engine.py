@@ -273,10 +273,9 @@ class Engine:
                             pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle, epi_mode=pk.epi_mode)
             use_slab = self.tc_variant != "tap" and bool(self.lib.mv2_tc_slab_supported(C.byref(ta)))
             if use_slab and self.tc_variant == "auto":
-                # measured policy (profiles/r01_sweep_slab_v3.json): the persistent slab kernel wins on every layer it
-                # supports except the 64-byte-row conv_in (tiny N=64, K=32 MMAs are issue bound there)
-                if Ci % 64 != 0:
-                    use_slab = False
+                # measured policy (profiles/r01_sweep_slab_v*.json): the persistent slab kernel wins on every layer it
+                # supports (incl. the 64-byte-row conv_in once it runs 4 M-tiles and 7 taps per weight stage)
+                pass
             if use_slab or self.lib.mv2_tc_conv_supported(C.byref(ta)):
                 if self._prof is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
