@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmagvit2_b200.so")
+LIB_PATH = os.environ.get("MV2_LIB_PATH") or os.path.join(_HERE, "libmagvit2_b200.so")   # env override: A/B builds
 
 MV2_F32, MV2_BF16 = 0, 1
 ACT_NONE, ACT_ELU, ACT_SILU = 0, 1, 2

@@ -28,7 +28,8 @@ namespace mv2 {
 
 struct alignas(64) SlabParams {
   CUtensorMap amap;
-  CUtensorMap wmap;
+  CUtensorMap wmap;      // weights as {ci, co, tap} (3-D boxes of tpw taps)
+  CUtensorMap wmap2;     // weights as {k, co} (2-D boxes, used when tpw == 1)
   int kt, kh, kw, pt, ph, pw;
   int Ci, kchunks, row_bytes;
   int B, T, H, W, Co;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&p.amap);
-  if (warp == 2 && lane == 0) tma_prefetch_desc(&p.wmap);
+  if (warp == 2 && lane == 0) { tma_prefetch_desc(&p.wmap); tma_prefetch_desc(&p.wmap2); }
   if (warp == 1) tmem_alloc(tslot, 512);
   if (warp >= 4) {
     const int nb = p.n_tiles_n * p.bn;   // >= Co; padded columns read zeros
@@ -112,41 +113,42 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
   if (warp == 0) {
     // ------------------------------ slab producer ------------------------------
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord c = decode_tile(p, tile);
         const int dt0 = max(0, p.pt - c.t);
         for (int dt = dt0; dt < p.kt; ++dt)
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-            const uint32_t s = it % p.slab_stages, ph = (it / p.slab_stages) & 1;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(slab_empty + 8 * s, ph ^ 1);
             mbar_expect_tx(slab_full + 8 * s, p.slab_bytes);
             tma_load_5d(slab0 + s * p.slab_stride, &p.amap, slab_full + 8 * s, kc * bk, c.w0 - p.pw, c.h0 - p.ph,
                         c.t + dt - p.pt, c.b);
+            if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1; }
           }
       }
     }
   } else if (warp == 2) {
     // ------------------------------ weight producer ------------------------------
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord c = decode_tile(p, tile);
         const int dt0 = max(0, p.pt - c.t);
         for (int dt = dt0; dt < p.kt; ++dt)
           for (int kc = 0; kc < p.kchunks; ++kc)
-            for (int tp = 0; tp < taps2d; tp += p.tpw, ++it) {
-              const uint32_t s = it % p.w_stages, ph = (it / p.w_stages) & 1;
+            for (int tp = 0; tp < taps2d; tp += p.tpw) {
               mbar_wait(w_empty + 8 * s, ph ^ 1);
               mbar_expect_tx(w_full + 8 * s, w_bytes);
               if (p.cluster == 1) {
-                tma_load_3d(wst0 + s * w_bytes, &p.wmap, w_full + 8 * s, kc * bk, c.n0, dt * taps2d + tp);
+                if (p.tpw == 1) tma_load_2d(wst0 + s * w_bytes, &p.wmap2, w_full + 8 * s, (dt * taps2d + tp) * p.Ci + kc * bk, c.n0);
+                else tma_load_3d(wst0 + s * w_bytes, &p.wmap, w_full + 8 * s, kc * bk, c.n0, dt * taps2d + tp);
               } else {   // my half of the rows goes to both CTAs; the peer sends the other half (tpw == 1 here)
                 const uint32_t rank = cluster_ctarank();
                 const uint32_t half_rows = p.bn >> 1;
-                tma_load_3d_mcast(wst0 + s * w_bytes + rank * half_rows * row_bytes, &p.wmap, w_full + 8 * s, kc * bk,
-                                  c.n0 + rank * half_rows, dt * taps2d + tp, (uint16_t)0x3);
+                tma_load_2d_mcast(wst0 + s * w_bytes + rank * half_rows * row_bytes, &p.wmap2, w_full + 8 * s,
+                                  (dt * taps2d + tp) * p.Ci + kc * bk, c.n0 + rank * half_rows, (uint16_t)0x3);
               }
+              if (++s == (uint32_t)p.w_stages) { s = 0; ph ^= 1; }
             }
       }
     }
@@ -162,54 +164,66 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
       const uint64_t b_hi = ((uint64_t)((8 * row_bytes) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 16) | lay;
       const bool k4 = bk == 64;
       const uint32_t leader = elect_one();
-      uint32_t sit = 0, wit = 0, tit = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tit) {
-        const int t_of_tile = (tile / (p.n_tiles_n * p.tiles_w * p.tiles_h)) % p.T;
+      // All ring bookkeeping is incremental (stage index, parity, descriptor low words): the per-tap issue path holds no
+      // integer division / modulo and only a handful of uniform adds.
+      const uint32_t a_row = row_bytes >> 4;                       // descriptor-address units per slab row
+      const uint32_t a_next_dh = (uint32_t)(p.pitch - p.kw + 1) * a_row;
+      const uint32_t a_mtile = 8 * a_row;                          // next M-tile: 8 positions further along w
+      const uint32_t w_tile16 = w_tile >> 4, w_stage16 = w_bytes >> 4;
+      const uint32_t b_lo0 = (wst0 & 0x3FFFF) >> 4;
+      uint32_t s_idx = 0, s_par = 0;                               // slab ring
+      uint32_t w_idx = 0, w_par = 0, b_lo = b_lo0;                 // weight ring
+      uint32_t t_idx = 0, t_par = 0;                               // TMEM accumulator ring
+      int t_frame = -1, tile_in_frame = 0;
+      const int tiles_per_frame = p.n_tiles_n * p.tiles_w * p.tiles_h;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int t_of_tile = (tile / tiles_per_frame) % p.T;      // once per tile (hundreds of taps)
         const int dt0 = max(0, p.pt - t_of_tile);
-        const uint32_t buf = tit % p.nbuf;
-        mbar_wait(t_empty + 8 * buf, ((tit / p.nbuf) & 1) ^ 1);
+        mbar_wait(t_empty + 8 * t_idx, t_par ^ 1);
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * acc_cols;
+        const uint32_t acc = tmem_base + t_idx * acc_cols;
         uint32_t accum = 0;
         for (int dt = dt0; dt < p.kt; ++dt)
-          for (int kc = 0; kc < p.kchunks; ++kc, ++sit) {
-            const uint32_t s = sit % p.slab_stages;
-            mbar_wait(slab_full + 8 * s, (sit / p.slab_stages) & 1);
-            const uint32_t slab = slab0 + s * p.slab_stride;
-            for (int tp0 = 0; tp0 < taps2d; tp0 += p.tpw, ++wit) {
-              const uint32_t ws = wit % p.w_stages;
-              mbar_wait(w_full + 8 * ws, (wit / p.w_stages) & 1);
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(slab_full + 8 * s_idx, s_par);
+            uint32_t a_lo = ((slab0 + s_idx * p.slab_stride) & 0x3FFFF) >> 4;   // descriptor low word of tap (0, 0)
+            int dw = 0;
+            for (int tp0 = 0; tp0 < taps2d; tp0 += p.tpw) {
+              mbar_wait(w_full + 8 * w_idx, w_par);
               tc_fence_after();
-              // operands are computed warp-uniformly (uniform registers); only the tcgen05 issue is predicated
+              uint32_t b_cur = b_lo;
               for (int u = 0; u < p.tpw; ++u) {
-                const int tp = tp0 + u;
-                const int dh = tp / p.kw, dw = tp - dh * p.kw;
-                const uint64_t bd = b_hi | (uint64_t)(((wst0 + ws * w_bytes + u * w_tile) & 0x3FFFF) >> 4);
-                const uint32_t a0 = slab + (uint32_t)(dh * p.pitch + dw) * row_bytes;
                 if (leader) {
+                  uint32_t a_j = a_lo, d = acc;
                   for (int j = 0; j < p.mw; ++j) {
-                    const uint64_t ad = a_hi | (uint64_t)(((a0 + (uint32_t)j * 8 * row_bytes) & 0x3FFFF) >> 4);
-                    const uint32_t d = acc + j * p.bn;
+                    const uint64_t ad = a_hi | (uint64_t)a_j, bd = b_hi | (uint64_t)b_cur;
                     umma_bf16(d, ad, bd, idesc, accum);
                     umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
                     if (k4) {
                       umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
                       umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
                     }
+                    a_j += a_mtile;
+                    d += p.bn;
                   }
                 }
                 accum = 1;
+                b_cur += w_tile16;
+                if (++dw == p.kw) { dw = 0; a_lo += a_next_dh; } else { a_lo += a_row; }
               }
               if (leader) {
-                if (p.cluster == 1) umma_commit(w_empty + 8 * ws);
-                else umma_commit_mcast(w_empty + 8 * ws, (uint16_t)0x3);   // the slot is free once BOTH CTAs consumed it
+                if (p.cluster == 1) umma_commit(w_empty + 8 * w_idx);
+                else umma_commit_mcast(w_empty + 8 * w_idx, (uint16_t)0x3);   // the slot is free once BOTH CTAs consumed it
               }
-              accum = 1;
+              if (++w_idx == (uint32_t)p.w_stages) { w_idx = 0; w_par ^= 1; b_lo = b_lo0; } else { b_lo += w_stage16; }
             }
-            if (leader) umma_commit(slab_empty + 8 * s);
+            if (leader) umma_commit(slab_empty + 8 * s_idx);
+            if (++s_idx == (uint32_t)p.slab_stages) { s_idx = 0; s_par ^= 1; }
           }
-        if (leader) umma_commit(t_full + 8 * buf);
+        if (leader) umma_commit(t_full + 8 * t_idx);
+        if (++t_idx == (uint32_t)p.nbuf) { t_idx = 0; t_par ^= 1; }
       }
+      (void)t_frame; (void)tile_in_frame;
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
@@ -217,11 +231,10 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
     const int sub = warp & 3, half = (warp - 4) >> 2;
     const int row = sub * 32 + lane;
     const int lh = row >> 3, lw = row & 7;
-    uint32_t tit = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tit) {
+    uint32_t buf = 0, bpar = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord c = decode_tile(p, tile);
-      const uint32_t buf = tit % p.nbuf;
-      mbar_wait(t_full + 8 * buf, (tit / p.nbuf) & 1);
+      mbar_wait(t_full + 8 * buf, bpar);
       tc_fence_after();
       const int h = c.h0 + lh;
       for (int j = 0; j < p.mw; ++j) {
@@ -240,6 +253,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty + 8 * buf);
+      if (++buf == (uint32_t)p.nbuf) { buf = 0; bpar ^= 1; }
     }
   }
   tc_fence_before();
@@ -308,7 +322,9 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   p.n_tiles_n = co_pad / p.bn;
   // weight multicast across CTA pairs: when one M-tile per CTA cannot amortise the weight stream (mw == 1, deep
   // layers) two CTAs on neighbouring tiles fetch half of every weight tile each and multicast it to both
-  p.cluster = (p.mw == 1 && ceil_div(a->Wo, 8) % 2 == 0 && p.bn >= 64 && a->kt * a->kh * a->kw > 1 && a->Co % p.bn == 0) ? 2 : 1;
+  // (measured: no gain on B200 at these shapes -- the deep layers are wave-quantisation bound, not weight-stream bound --
+  //  so it is off unless MV2_SLAB_CLUSTER=2)
+  p.cluster = 1;
   if (const char* env = getenv("MV2_SLAB_CLUSTER")) p.cluster = (atoi(env) == 2 && p.mw == 1 && ceil_div(a->Wo, 8) % 2 == 0 && p.bn >= 64 && a->Co % p.bn == 0) ? 2 : 1;
   p.tiles_h = tiles_h;
   p.tiles_w = ceil_div(a->Wo, 8 * p.mw);
@@ -356,6 +372,13 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return MV2_E_CUDA; }
+    cuuint64_t dims2[2] = {(cuuint64_t)K, (cuuint64_t)a->Co};
+    cuuint64_t strides2[1] = {(cuuint64_t)(K * 2)};
+    cuuint32_t box2[2] = {(cuuint32_t)bk, (cuuint32_t)(p.bn / p.cluster)};
+    cuuint32_t es2[2] = {1, 1};
+    r = enc(&p.wmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a->w, dims2, strides2, box2, es2,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights 2-D) failed: %d", (int)r); return MV2_E_CUDA; }
   }
   const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 16 + (size_t)co_pad * 4 + 1024;
   MV2_CHECK_ARG(smem <= 227 * 1024);
