@@ -94,16 +94,18 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
   const int n_iters = p.ntaps * p.kchunks;
   if (warp == 0) {
     if (lane == 0) {
+      // incremental ring / tap bookkeeping: no division or modulo in the loop
+      uint32_t s = 0, ph = 0;
+      int tap = 0, kc = 0;
       for (int i = 0; i < n_iters; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (i / p.stages) & 1;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         mbar_expect_tx(full0 + 8 * s, stage_bytes);
-        const int tap = i / p.kchunks, kc = i - tap * p.kchunks;
         const uint32_t sa = smem_base + s * stage_bytes;
         tma_load_5d(sa, &p.amap[p.tap_map[tap]], full0 + 8 * s, kc * bk, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap],
                     t0 + p.tap_dt[tap], b);
         tma_load_2d(sa + a_bytes, &p.wmap, full0 + 8 * s, tap * p.ci_pad + kc * bk, n0);
+        if (++kc == p.kchunks) { kc = 0; ++tap; }
+        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -112,14 +114,14 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     const uint32_t leader = elect_one();
     const int ksteps = bk >> 4;
+    const uint64_t d_hi = make_kmajor_desc(0, row_bytes);     // descriptor with a zero start address
+    const uint32_t stage16 = stage_bytes >> 4, a16 = a_bytes >> 4, base16 = (smem_base & 0x3FFFF) >> 4;
+    uint32_t s = 0, ph = 0, lo = base16;
     for (int i = 0; i < n_iters; ++i) {
-      const int s = i % p.stages;
-      const uint32_t ph = (i / p.stages) & 1;
       mbar_wait(full0 + 8 * s, ph);
       tc_fence_after();
-      const uint32_t sa = smem_base + s * stage_bytes;
-      const uint64_t ad = make_kmajor_desc(sa, row_bytes);
-      const uint64_t bd = make_kmajor_desc(sa + a_bytes, row_bytes);
+      const uint64_t ad = d_hi | (uint64_t)lo;
+      const uint64_t bd = d_hi | (uint64_t)(lo + a16);
       if (leader) {
         // advancing 16 bf16 along K = +32 bytes = +2 in the (addr >> 4) field
         umma_bf16(tmem_base, ad, bd, idesc, i > 0 ? 1u : 0u);
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
         }
         umma_commit(empty0 + 8 * s);   // frees the smem slot once these MMAs retire
       }
+      if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; lo = base16; } else { lo += stage16; }
     }
     if (leader) umma_commit(tfull);    // accumulator complete
   } else {
