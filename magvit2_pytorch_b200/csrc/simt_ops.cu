@@ -1188,8 +1188,31 @@ __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bflo
 }
 
 constexpr int LAM_AT = 64;     // tokens per block in the apply kernel (2 warps x 32)
-__global__ void __launch_bounds__(64) linattn_apply_mma_kernel(const __nv_bfloat16* __restrict__ q, const float* __restrict__ ws,
-                                                               __nv_bfloat16* __restrict__ out, int L, int heads, int n_chunks) {
+constexpr int LAM_SW = 16 * (LAM_F + 8);   // bf16 elements of one transposed state operand [e][feature]
+
+// Sums the per-chunk partial states of one (sequence, head) and writes the transposed MMA B operand as a bf16
+// hi + lo pair, once, so the apply blocks only copy 5.6 KB instead of re-reducing the partials.
+__global__ void __launch_bounds__(128) linattn_finalize_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ sw,
+                                                               int heads, int n_chunks) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int h = blockIdx.x;
+  const int64_t seq = blockIdx.y;
+  const float* wsh = ws + (seq * heads + h) * (int64_t)n_chunks * LA_ST;
+  __nv_bfloat16* o = sw + (seq * heads + h) * (int64_t)(2 * LAM_SW);
+  for (int idx = threadIdx.x; idx < LAM_SW; idx += 128) {
+    const int e = idx / (LAM_F + 8), f = idx % (LAM_F + 8);
+    float sv = 0.f;
+    if (e <= LA_D && f < LA_F)
+      for (int k = 0; k < n_chunks; ++k) sv += wsh[(int64_t)k * LA_ST + f * (LA_D + 1) + e];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(sv);
+    o[idx] = hi;
+    o[LAM_SW + idx] = __float2bfloat16_rn(sv - __bfloat162float(hi));
+  }
+}
+
+__global__ void __launch_bounds__(64) linattn_apply_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ sw,
+                                                               __nv_bfloat16* __restrict__ out, int L, int heads) {
   pdl_wait();
   pdl_launch_dependents();
   // both operands are carried as bf16 hi + lo pairs (3 MMAs: hi*hi + lo*hi + hi*lo) -> ~fp32-level accuracy
@@ -1202,15 +1225,12 @@ __global__ void __launch_bounds__(64) linattn_apply_mma_kernel(const __nv_bfloat
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int HD = heads * LA_D;
-  const float* wsh = ws + (seq * heads + h) * (int64_t)n_chunks * LA_ST;
-  for (int idx = tid; idx < 16 * LAM_F; idx += 64) {
-    const int e = idx / LAM_F, f = idx % LAM_F;
-    float sv = 0.f;
-    if (e <= LA_D && f < LA_F)
-      for (int k = 0; k < n_chunks; ++k) sv += wsh[(int64_t)k * LA_ST + f * (LA_D + 1) + e];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(sv);
-    st[e][f] = hi;
-    sl[e][f] = __float2bfloat16_rn(sv - __bfloat162float(hi));
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(sw + (seq * heads + h) * (int64_t)(2 * LAM_SW));
+    uint4* d0 = reinterpret_cast<uint4*>(&st[0][0]);
+    uint4* d1 = reinterpret_cast<uint4*>(&sl[0][0]);
+    constexpr int NV = LAM_SW / 8;
+    for (int i = tid; i < NV; i += 64) { d0[i] = src[i]; d1[i] = src[NV + i]; }
   }
   {
     const int tok = blk * LAM_AT + tid;
@@ -1688,7 +1708,9 @@ int mv2_attention(const mv2_attn_args* a, void* stream) {
 }
 
 size_t mv2_linattn_workspace_bytes(int n_seq, int heads, int L) {
-  return (size_t)n_seq * heads * ceil_div(L, LA_CHUNK) * LA_ST * sizeof(float);
+  // per-chunk fp32 partial states + the finalised bf16 hi/lo MMA operand of every (sequence, head)
+  const size_t part_bytes = ((size_t)n_seq * heads * ceil_div(L, LA_CHUNK) * LA_ST * sizeof(float) + 15) / 16 * 16;
+  return part_bytes + (size_t)n_seq * heads * 2 * LAM_SW * 2;
 }
 
 int mv2_linear_attention(const void* q, const void* kv, void* out, int dtype, int n_seq, int L, int heads,
@@ -1705,8 +1727,13 @@ int mv2_linear_attention(const void* q, const void* kv, void* out, int dtype, in
   } else if (dtype == MV2_BF16 && (heads * LA_D) % 8 == 0) {
     launch_k(linattn_reduce_mma_kernel, dim3(grid), dim3(128), 0, st, (const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();
+    MV2_CHECK_LAUNCH();
+    const size_t part_bytes = ((size_t)n_seq * heads * nc * LA_ST * sizeof(float) + 15) / 16 * 16;
+    __nv_bfloat16* sw = reinterpret_cast<__nv_bfloat16*>((char*)workspace + part_bytes);
+    launch_k(linattn_finalize_kernel, dim3(heads, n_seq), dim3(128), 0, st, (const float*)workspace, sw, heads, nc);
+    MV2_CHECK_LAUNCH();
     dim3 grid2(ceil_div(L, LAM_AT), heads, n_seq);
-    launch_k(linattn_apply_mma_kernel, dim3(grid2), dim3(64), 0, st, (const __nv_bfloat16*)q, (const float*)workspace, (__nv_bfloat16*)out, L, heads, nc);
+    launch_k(linattn_apply_mma_kernel, dim3(grid2), dim3(64), 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)sw, (__nv_bfloat16*)out, L, heads);
   } else if (dtype == MV2_BF16) {
     launch_k(linattn_reduce_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();
