@@ -335,7 +335,13 @@ def main():
         msa, na, fla = prof["all"]
         ach = fl3 / (ms3 / 1e3) / 1e12
         pk = peaks["bf16_tflops_sustained"]
-        roofline = {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": None,
+        traffic = None
+        try:     # dram__bytes_read + write per conv3d launch, from the committed ncu capture of one step (profiles/)
+            if args.workload == "readme":
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_step_metrics_summary.json")))["conv3d"]["avg_dram_bytes"]
+        except Exception:
+            traffic = None
+        roofline = {"bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk, "traffic": traffic,
                     "kernel": "tc_slab_kernel on the causal 3x3x3 Conv3d layers (82% of the step's FLOPs)",
                     "launches_per_step": n3, "kernel_ms_per_step": ms3, "flop_per_launch_avg": fl3 / max(n3, 1),
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks_src})",

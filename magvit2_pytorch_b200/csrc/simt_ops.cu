@@ -352,17 +352,27 @@ __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16
 #pragma unroll
   for (int q = 0; q < VEC; ++q) { wv[q] = wk[g * VEC + q]; acc[q] = 0.f; }
   float m = -INFINITY, ssum = 0.f;
-  for (int nb = 0; nb < cnt; nb += R) {     // warp-uniform trip count
-    const int n = nb + rsub;
-    const bool ok = n < cnt;
-    float v[VEC];
-    float dot = 0.f;
-    if (ok) {
-      const uint4* src = reinterpret_cast<const uint4*>(yf + (int64_t)n * C);
+  // rows are walked U at a time per row group: the U independent 16..64-byte loads are issued before any of them is
+  // consumed (memory-level parallelism), then the online-softmax updates run back to back.  Trip counts are warp uniform.
+  constexpr int U = (VEC == 8) ? 4 : 2;
+  for (int nb = 0; nb < cnt; nb += R * U) {
+    uint4 raw[U][VEC / 8];
+    bool ok[U];
+#pragma unroll
+    for (int uu = 0; uu < U; ++uu) {
+      const int n = nb + uu * R + rsub;
+      ok[uu] = n < cnt;
+      const uint4* src = reinterpret_cast<const uint4*>(yf + (int64_t)(ok[uu] ? n : 0) * C);
+#pragma unroll
+      for (int u = 0; u < VEC / 8; ++u) raw[uu][u] = ok[uu] ? src[u] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int uu = 0; uu < U; ++uu) {
+      float v[VEC];
+      float dot = 0.f;
 #pragma unroll
       for (int u = 0; u < VEC / 8; ++u) {
-        const uint4 raw = src[u];
-        const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&raw[uu][u]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 fv = __bfloat1622float2(vb[q]);
@@ -372,19 +382,16 @@ __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16
       }
 #pragma unroll
       for (int q = 0; q < VEC; ++q) dot = fmaf(v[q], wv[q], dot);
-    } else {
+      for (int o = G >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (ok[uu]) {
+        const float l = dot + bk;
+        const float mn = fmaxf(m, l);
+        const float sc = __expf(m - mn), e = __expf(l - mn);
+        ssum = ssum * sc + e;
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) v[q] = 0.f;
-    }
-    for (int o = G >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (ok) {
-      const float l = dot + bk;
-      const float mn = fmaxf(m, l);
-      const float sc = __expf(m - mn), e = __expf(l - mn);
-      ssum = ssum * sc + e;
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) acc[q] = fmaf(e, v[q], acc[q] * sc);
-      m = mn;
+        for (int q = 0; q < VEC; ++q) acc[q] = fmaf(e, v[q], acc[q] * sc);
+        m = mn;
+      }
     }
   }
   float* mine = dyn + (size_t)rsub * (C + 2);
