@@ -209,12 +209,24 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)
   *reinterpret_cast<uint4*>(dst) = o;
 }
 
+// Epilogue flavours are compile-time so each kernel instance carries only the code it runs (the generic version was
+// ~2300 SASS instructions per 32-column chunk and thrashed the instruction cache of the 8 epilogue warps).
+enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_SHUFFLE = 2 };
+
+template <int ACT>
+__device__ __forceinline__ float act_ct(float x) {
+  if (ACT == MV2_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
+  if (ACT == MV2_ACT_SILU) return __fdividef(x, 1.f + __expf(-x));
+  return x;
+}
+
 // r: 32 raw accumulator columns of ONE output row (position b,to,ho,wo); n = first packed column; sb = smem bias of
 // these columns (always valid memory; zeros when there is no bias).
 // row_base = linear position index * Co (plain mode), computed once per row by the caller.
-__device__ __forceinline__ void epi_chunk32(const TcEpi& e, const uint32_t (&r)[32], int ncols, int n, const float* sb,
-                                            int b, int to, int ho, int wo, int64_t row_base) {
-  if (e.mode == 1) {
+template <int MODE, int ACT>
+__device__ __forceinline__ void epi_chunk32_t(const TcEpi& e, const uint32_t (&r)[32], int ncols, int n, const float* sb,
+                                              int b, int to, int ho, int wo, int64_t row_base) {
+  if (MODE == EPI_GEGLU) {
     const int I = e.Co >> 1;
     const int64_t pos = (((int64_t)b * e.To + to) * e.Ho + ho) * e.Wo + wo;
 #pragma unroll
@@ -231,7 +243,7 @@ __device__ __forceinline__ void epi_chunk32(const TcEpi& e, const uint32_t (&r)[
     }
     return;
   }
-  const int cy = e.shuffle == MV2_SHUFFLE_SPACE ? (e.Co >> 2) : (e.shuffle == MV2_SHUFFLE_TIME ? (e.Co >> 1) : e.Co);
+  const int cy = MODE == EPI_SHUFFLE ? (e.shuffle == MV2_SHUFFLE_SPACE ? (e.Co >> 2) : (e.Co >> 1)) : e.Co;
   const bool vec_ok = (cy & 7) == 0;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -239,14 +251,16 @@ __device__ __forceinline__ void epi_chunk32(const TcEpi& e, const uint32_t (&r)[
     if (g * 8 >= ncols || ng >= e.Co) break;
     float v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = fast_act(__uint_as_float(r[g * 8 + q]) + sb[g * 8 + q], e.act);
+    for (int q = 0; q < 8; ++q) v[q] = act_ct<ACT>(__uint_as_float(r[g * 8 + q]) + sb[g * 8 + q]);
     int64_t off;
-    if (e.shuffle == MV2_SHUFFLE_SPACE) {
-      const int qd = ng / cy, c = ng - qd * cy, p1 = qd >> 1, p2 = qd & 1;
-      off = ((((int64_t)b * e.To + to) * (2 * e.Ho) + (2 * ho + p1)) * (2 * e.Wo) + (2 * wo + p2)) * cy + c;
-    } else if (e.shuffle == MV2_SHUFFLE_TIME) {
+    if (MODE == EPI_SHUFFLE) {
       const int qd = ng / cy, c = ng - qd * cy;
-      off = ((((int64_t)b * (2 * e.To) + (2 * to + qd)) * e.Ho + ho) * e.Wo + wo) * cy + c;
+      if (e.shuffle == MV2_SHUFFLE_SPACE) {
+        const int p1 = qd >> 1, p2 = qd & 1;
+        off = ((((int64_t)b * e.To + to) * (2 * e.Ho) + (2 * ho + p1)) * (2 * e.Wo) + (2 * wo + p2)) * cy + c;
+      } else {
+        off = ((((int64_t)b * (2 * e.To) + (2 * to + qd)) * e.Ho + ho) * e.Wo + wo) * cy + c;
+      }
     } else {
       off = row_base + ng;
     }
@@ -270,6 +284,16 @@ __device__ __forceinline__ void epi_chunk32(const TcEpi& e, const uint32_t (&r)[
       }
     }
   }
+}
+
+// activation is a kernel argument; dispatch once per chunk (warp uniform) into the compile-time variants
+template <int MODE>
+__device__ __forceinline__ void epi_chunk32(const TcEpi& e, const uint32_t (&r)[32], int ncols, int n, const float* sb,
+                                            int b, int to, int ho, int wo, int64_t row_base) {
+  if (MODE == EPI_GEGLU) { epi_chunk32_t<EPI_GEGLU, MV2_ACT_NONE>(e, r, ncols, n, sb, b, to, ho, wo, row_base); return; }
+  if (e.act == MV2_ACT_ELU) epi_chunk32_t<MODE, MV2_ACT_ELU>(e, r, ncols, n, sb, b, to, ho, wo, row_base);
+  else if (e.act == MV2_ACT_SILU) epi_chunk32_t<MODE, MV2_ACT_SILU>(e, r, ncols, n, sb, b, to, ho, wo, row_base);
+  else epi_chunk32_t<MODE, MV2_ACT_NONE>(e, r, ncols, n, sb, b, to, ho, wo, row_base);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -43,6 +43,7 @@ struct alignas(64) TcParams {
   TcEpi epi;
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
       if (p.bn - c0 >= 32) tmem_ld_32x32b_x32(tlane + c0, r);
       else tmem_ld_32x32b_x16(tlane + c0, r);
       tmem_ld_wait();
-      if (row_ok) epi_chunk32(p.epi, r, min(32, p.bn - c0), n0 + c0, sbias + c0, b, to, ho, wo, row_base);
+      if (row_ok) epi_chunk32<MODE>(p.epi, r, min(32, p.bn - c0), n0 + c0, sbias + c0, b, to, ho, wo, row_base);
     }
   }
   tc_fence_before();
@@ -272,12 +273,16 @@ int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(tc_conv_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_conv_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_conv_kernel<EPI_SHUFFLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
   MV2_CHECK_ARG(smem <= 227 * 1024);
   dim3 grid((unsigned)((int64_t)a->B * p.tt * p.th * p.tw), (unsigned)ceil_div(a->Co, bn));
-  launch_k(tc_conv_kernel, dim3(grid), dim3(192), smem, (cudaStream_t)stream, p);
+  if (a->epi_mode == 1) launch_k(tc_conv_kernel<EPI_GEGLU>, dim3(grid), dim3(192), smem, (cudaStream_t)stream, p);
+  else if (a->shuffle != MV2_SHUFFLE_NONE) launch_k(tc_conv_kernel<EPI_SHUFFLE>, dim3(grid), dim3(192), smem, (cudaStream_t)stream, p);
+  else launch_k(tc_conv_kernel<EPI_PLAIN>, dim3(grid), dim3(192), smem, (cudaStream_t)stream, p);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

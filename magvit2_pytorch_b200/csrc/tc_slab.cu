@@ -66,6 +66,7 @@ __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) 
   return c;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__ SlabParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
           uint32_t r[32];
           tmem_ld_32x32b_x32(tl + c0, r);
           tmem_ld_wait();
-          if (row_ok) epi_chunk32(p.epi, r, 32, c.n0 + c0, sbias + c.n0 + c0, c.b, c.t, h, w, row_base);
+          if (row_ok) epi_chunk32<MODE>(p.epi, r, 32, c.n0 + c0, sbias + c.n0 + c0, c.b, c.t, h, w, row_base);
         }
       }
       tc_fence_before();
@@ -385,12 +386,16 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(tc_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_SHUFFLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
   int grid = std::min(p.total_tiles, n_sm);
   if (p.cluster > 1) grid &= ~1;
-  launch_kc(tc_slab_kernel, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
+  if (a->epi_mode == 1) launch_kc(tc_slab_kernel<EPI_GEGLU>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
+  else if (a->shuffle != MV2_SHUFFLE_NONE) launch_kc(tc_slab_kernel<EPI_SHUFFLE>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
+  else launch_kc(tc_slab_kernel<EPI_PLAIN>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

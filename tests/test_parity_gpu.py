@@ -214,3 +214,35 @@ def test_bf16_tensor_core_path_vs_bf16_cuda_core_path():
     for k, v in worst.items():
         assert v < 0.03, (k, v)
     assert (c_tc != c_cc).float().mean().item() < 0.08
+
+
+WIDE_KW = dict(image_size=32, init_dim=128, max_dim=1024, codebook_size=4096,
+               layers=("residual", "compress_space", ("consecutive_residual", 2), "linear_attend_space", "compress_space",
+                       "residual", "attend_space", "compress_time", "residual", "compress_space", "residual", "attend_time"))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_wide_channel_config_vs_oracle(dtype):
+    """Channel widths of BASELINE configs[3] (max_dim 1024: 128 -> 256 -> 512 -> 1024) at toy spatial size, checked live
+    against the CPU oracle: exercises the 4-n-tile slab path, the 32-wide SE / norm vector variants and a 12-bit LFQ."""
+    _require_cuda()
+    cpu_model = build_product(WIDE_KW, 3)
+    orc = build_oracle(cpu_model, WIDE_KW)
+    from oracle import weights as W
+    v = W.synth_video(2, 3, 5, 32, seed=77)
+    ref_codes, pre = orc.tokenize(v, return_presign=True)
+    ref_recon = orc.decode_from_code_indices(ref_codes)
+    model = build_product(WIDE_KW, 3).cuda().to(dtype)
+    codes = model.tokenize(v.cuda())
+    recon = model.decode_from_code_indices(ref_codes.cuda())
+    mism = codes.cpu() != ref_codes
+    rerr = (recon.float().cpu() - ref_recon).abs()
+    _report(f"wide/{str(dtype).split('.')[-1]}", token_mismatch_rate=f"{mism.float().mean().item():.4f}",
+            recon_maxabs=f"{rerr.max().item():.3e}", min_margin=f"{pre.abs().min().item():.2e}")
+    if dtype == torch.float32:
+        margin = pre.reshape(*ref_codes.shape, -1).abs().min(dim=-1).values
+        assert (not mism.any()) or margin[mism].max().item() < 2e-5      # only sign tests on a ~1e-5 margin may flip
+        assert rerr.max().item() < 2e-4
+    else:
+        assert mism.float().mean().item() < 0.15
+        assert rerr.mean().item() < 0.02 and rerr.max().item() < 0.2
