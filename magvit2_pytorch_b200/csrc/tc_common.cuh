@@ -195,13 +195,6 @@ struct TcEpi {
   int To, Ho, Wo;                // output volume before any depth-to-space/time shuffle
 };
 
-// bf16 outputs carry 8 mantissa bits, so the fast exp intrinsic (2 ulp fp32) is exact enough here.
-__device__ __forceinline__ float fast_act(float x, int act) {
-  if (act == MV2_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
-  if (act == MV2_ACT_SILU) return __fdividef(x, 1.f + __expf(-x));
-  return x;
-}
-
 __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)[8]) {
   uint4 o;
   o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
@@ -211,12 +204,29 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)
 
 // Epilogue flavours are compile-time so each kernel instance carries only the code it runs (the generic version was
 // ~2300 SASS instructions per 32-column chunk and thrashed the instruction cache of the 8 epilogue warps).
-enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_SHUFFLE = 2 };
+// EPI_PLAIN (slab kernel only) additionally requires Co % 8 == 0 and stores through a shared-memory transpose;
+// EPI_RAGGED is the direct per-row path with scalar tails (conv_out's 3 channels, and the tap kernel's plain mode).
+enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_SHUFFLE = 2, EPI_RAGGED = 3 };
 
+// Branch-free activations on the bare MUFU approximations (ex2/rcp with flush-to-zero): the results are rounded to
+// bf16 right after, and __expf's denormal range handling costs ~5 extra instructions per element.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <int ACT>
 __device__ __forceinline__ float act_ct(float x) {
-  if (ACT == MV2_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
-  if (ACT == MV2_ACT_SILU) return __fdividef(x, 1.f + __expf(-x));
+  if (ACT == MV2_ACT_ELU) {
+    const float e = ex2_approx(x * 1.4426950408889634f) - 1.f;
+    return x > 0.f ? x : e;
+  }
+  if (ACT == MV2_ACT_SILU) return x * rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x));
   return x;
 }
 
@@ -250,8 +260,12 @@ __device__ __forceinline__ void epi_chunk32_t(const TcEpi& e, const uint32_t (&r
     const int ng = n + g * 8;
     if (g * 8 >= ncols || ng >= e.Co) break;
     float v[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(sb + g * 8), b1 = *reinterpret_cast<const float4*>(sb + g * 8 + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = act_ct<ACT>(__uint_as_float(r[g * 8 + q]) + sb[g * 8 + q]);
+      for (int q = 0; q < 8; ++q) v[q] = act_ct<ACT>(__uint_as_float(r[g * 8 + q]) + bb[q]);
+    }
     int64_t off;
     if (MODE == EPI_SHUFFLE) {
       const int qd = ng / cy, c = ng - qd * cy;
@@ -284,6 +298,22 @@ __device__ __forceinline__ void epi_chunk32_t(const TcEpi& e, const uint32_t (&r
       }
     }
   }
+}
+
+// bias + activation + bf16 packing of one 32-column chunk (row-per-lane), for the staged epilogue
+template <int ACT>
+__device__ __forceinline__ void epi_pack32_t(const uint32_t (&r)[32], const float* sb, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + g * 4);
+    pk[2 * g] = pack_bf16x2(act_ct<ACT>(__uint_as_float(r[4 * g]) + b.x), act_ct<ACT>(__uint_as_float(r[4 * g + 1]) + b.y));
+    pk[2 * g + 1] = pack_bf16x2(act_ct<ACT>(__uint_as_float(r[4 * g + 2]) + b.z), act_ct<ACT>(__uint_as_float(r[4 * g + 3]) + b.w));
+  }
+}
+__device__ __forceinline__ void epi_pack32(int act, const uint32_t (&r)[32], const float* sb, uint32_t (&pk)[16]) {
+  if (act == MV2_ACT_ELU) epi_pack32_t<MV2_ACT_ELU>(r, sb, pk);
+  else if (act == MV2_ACT_SILU) epi_pack32_t<MV2_ACT_SILU>(r, sb, pk);
+  else epi_pack32_t<MV2_ACT_NONE>(r, sb, pk);
 }
 
 // activation is a kernel argument; dispatch once per chunk (warp uniform) into the compile-time variants

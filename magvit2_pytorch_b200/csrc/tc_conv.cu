@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(192, 2) tc_conv_kernel(const __grid_constant__
   // barriers: full[s] at +8s, empty[s] at +8(S+s), tmem_full at +16S, tmem slot at +16S+8
   const uint32_t full0 = bar_base, empty0 = bar_base + 8 * p.stages, tfull = bar_base + 16 * p.stages;
   const uint32_t tslot = tfull + 8;
-  float* sbias = reinterpret_cast<float*>(smem_raw + (tslot + 8 - smem_u32(smem_raw)));   // bn floats
+  float* sbias = reinterpret_cast<float*>(smem_raw + (((tslot + 8 + 15) & ~15u) - smem_u32(smem_raw)));   // bn floats, 16-byte aligned
 
   // tile coordinates
   int tile = blockIdx.x;
@@ -269,11 +269,11 @@ int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return MV2_E_CUDA; }
   }
-  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 16 + (size_t)bn * 4 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 32 + (size_t)bn * 4 + 1024;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(tc_conv_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(tc_conv_kernel<EPI_RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_conv_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_conv_kernel<EPI_SHUFFLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
@@ -282,7 +282,7 @@ int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream) {
   dim3 grid((unsigned)((int64_t)a->B * p.tt * p.th * p.tw), (unsigned)ceil_div(a->Co, bn));
   if (a->epi_mode == 1) launch_k(tc_conv_kernel<EPI_GEGLU>, dim3(grid), dim3(192), smem, (cudaStream_t)stream, p);
   else if (a->shuffle != MV2_SHUFFLE_NONE) launch_k(tc_conv_kernel<EPI_SHUFFLE>, dim3(grid), dim3(192), smem, (cudaStream_t)stream, p);
-  else launch_k(tc_conv_kernel<EPI_PLAIN>, dim3(grid), dim3(192), smem, (cudaStream_t)stream, p);
+  else launch_k(tc_conv_kernel<EPI_RAGGED>, dim3(grid), dim3(192), smem, (cudaStream_t)stream, p);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

@@ -83,7 +83,10 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
   const uint32_t w_full = slab_empty + 8 * p.slab_stages, w_empty = w_full + 8 * p.w_stages;
   const uint32_t t_full = w_empty + 8 * p.w_stages, t_empty = t_full + 8 * 2;
   const uint32_t tslot = t_empty + 8 * 2;
-  float* sbias = reinterpret_cast<float*>(smem_raw + (tslot + 8 - smem_u32(smem_raw)));   // Co floats
+  const uint32_t sbias_u = (tslot + 8 + 15) & ~15u;
+  float* sbias = reinterpret_cast<float*>(smem_raw + (sbias_u - smem_u32(smem_raw)));   // Co floats, 16-byte aligned
+  // EPI_PLAIN: one 2 KB transpose buffer per epilogue warp (32 rows x 64 B, 16-byte pieces XOR-swizzled)
+  const uint32_t stage0 = sbias_u + (uint32_t)(p.n_tiles_n * p.bn) * 4;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.slab_stages; ++s) { mbar_init(slab_full + 8 * s, 1); mbar_init(slab_empty + 8 * s, 1); }
@@ -244,11 +247,54 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         const uint32_t tl = tmem_base + buf * acc_cols + j * p.bn + ((uint32_t)(sub * 32) << 16);
         const int64_t row_base = ((((int64_t)c.b * p.T + c.t) * p.H + h) * p.W + w) * p.Co;
         // column chunks are dealt round-robin to the two warps that share this lane quarter
-        for (int c0 = ((j + half) & 1) * 32; c0 < p.bn; c0 += 64) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tl + c0, r);
-          tmem_ld_wait();
-          if (row_ok) epi_chunk32<MODE>(p.epi, r, 32, c.n0 + c0, sbias + c.n0 + c0, c.b, c.t, h, w, row_base);
+        if (MODE == EPI_PLAIN) {
+          // Row-per-lane results are transposed through shared memory so that every store instruction writes 8 rows
+          // x 64 contiguous bytes (full sectors; the 8 rows are neighbours along w, i.e. one contiguous run when the
+          // tile spans all of Co) instead of 32 scattered 16-byte pieces.  The residual is read with the same mapping.
+          const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 2048;
+          const uint32_t wr = stg + lane * 64, wsw = (lane >> 1) & 3;
+          const int rl = lane >> 2, piece = lane & 3;                 // read side: row within an 8-row group, 16-byte piece
+          const int w2 = c.w0 + 8 * j + rl;
+          const uint32_t rd = stg + rl * 64;
+          for (int c0 = ((j + half) & 1) * 32; c0 < p.bn; c0 += 64) {
+            uint32_t r[32], pk[16];
+            tmem_ld_32x32b_x32(tl + c0, r);
+            tmem_ld_wait();
+            epi_pack32(p.epi.act, r, sbias + c.n0 + c0, pk);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((g ^ wsw) << 4)), "r"(pk[4 * g]),
+                           "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3]) : "memory");
+            __syncwarp();
+            const int ncol = c.n0 + c0 + piece * 8;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int h2 = c.h0 + sub * 4 + k;
+              const uint32_t rrow = 8 * k + rl;
+              uint4 v;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(rd + k * 512 + ((piece ^ ((rrow >> 1) & 3)) << 4)));
+              if (h2 < p.H && w2 < p.W && ncol < p.Co) {
+                const int64_t off = ((((int64_t)c.b * p.T + c.t) * p.H + h2) * p.W + w2) * p.Co + ncol;
+                if (p.epi.res) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(p.epi.res + off);
+                  __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&v);
+                  const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) a2[q] = __hadd2(a2[q], b2[q]);
+                }
+                *reinterpret_cast<uint4*>(p.epi.y + off) = v;
+              }
+            }
+            __syncwarp();
+          }
+        } else {
+          for (int c0 = ((j + half) & 1) * 32; c0 < p.bn; c0 += 64) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tl + c0, r);
+            tmem_ld_wait();
+            if (row_ok) epi_chunk32<MODE>(p.epi, r, 32, c.n0 + c0, sbias + c.n0 + c0, c.b, c.t, h, w, row_base);
+          }
         }
       }
       tc_fence_before();
@@ -343,7 +389,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   if (p.cluster > 1) p.tpw = 1;
   if (const char* env = getenv("MV2_SLAB_TPW")) { const int v = atoi(env); if (v >= 1 && taps2d % v == 0 && v * p.bn * p.row_bytes <= 64 * 1024) p.tpw = v; }
   const int w_bytes = p.bn * p.row_bytes * p.tpw;
-  const int budget = 220 * 1024 - co_pad * 4;
+  const int budget = 204 * 1024 - co_pad * 4;   // 227 KB minus 16 KB epilogue transpose buffers, barriers, alignment slack
   p.slab_stages = p.slab_stride * 3 + w_bytes * 3 <= budget ? 3 : 2;
   p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
   if (p.w_stages < 2 && p.slab_stages > 2) { p.slab_stages = 2; p.w_stages = std::min(12, (budget - 2 * p.slab_stride) / w_bytes); }
@@ -381,7 +427,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights 2-D) failed: %d", (int)r); return MV2_E_CUDA; }
   }
-  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 16 + (size_t)co_pad * 4 + 1024;
+  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 32 + (size_t)co_pad * 4 + 8 * 2048 + 1024;
   MV2_CHECK_ARG(smem <= 227 * 1024);
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
@@ -389,12 +435,14 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
     attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_SHUFFLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
   int grid = std::min(p.total_tiles, n_sm);
   if (p.cluster > 1) grid &= ~1;
   if (a->epi_mode == 1) launch_kc(tc_slab_kernel<EPI_GEGLU>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   else if (a->shuffle != MV2_SHUFFLE_NONE) launch_kc(tc_slab_kernel<EPI_SHUFFLE>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
+  else if (a->Co % 8 != 0) launch_kc(tc_slab_kernel<EPI_RAGGED>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   else launch_kc(tc_slab_kernel<EPI_PLAIN>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   MV2_CHECK_LAUNCH();
   return MV2_OK;

@@ -213,7 +213,12 @@ def test_bf16_tensor_core_path_vs_bf16_cuda_core_path():
     # ~0.4 % per rounding point; the stack is ~30 layers deep
     for k, v in worst.items():
         assert v < 0.03, (k, v)
-    assert (c_tc != c_cc).float().mean().item() < 0.08
+    # mini has 96 tokens x 10 sign bits with many pre-sign values within bf16 noise of zero: bound the flip rate loosely
+    # and require that every flipped token sits on a small fp32 margin (a real defect flips confident tokens too)
+    mism = (c_tc != c_cc).cpu()
+    margin = g["presign"].reshape(*g["codes"].shape, -1).abs().min(dim=-1).values
+    assert mism.float().mean().item() < 0.15
+    assert (margin[mism].max().item() if mism.any() else 0.0) < 0.1
 
 
 WIDE_KW = dict(image_size=32, init_dim=128, max_dim=1024, codebook_size=4096,
