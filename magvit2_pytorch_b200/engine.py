@@ -139,6 +139,7 @@ class Engine:
         self.simt_conv_calls = 0
         self.taps: Optional[dict] = None  # when set, per-stage activations are recorded (tests)
         self._prof: Optional[list] = None  # when set, (event0, event1, flops) per tcgen05 conv launch
+        self.conv_log: Optional[list] = None  # when set, one shape record per tcgen05 conv launch (tools/step_breakdown.py)
 
     # ------------------------------------------------------------------ parameters
     def _signature(self):
@@ -289,6 +290,9 @@ class Engine:
                     e1.record()
                     self._prof.append((e0, e1, 2.0 * B * To * Ho * Wo * pk.Co * pk.Ci * pk.k[0] * pk.k[1] * pk.k[2],
                                        "slab" if use_slab else "tap", pk.k[1] * pk.k[2] * pk.k[0]))
+                if self.conv_log is not None:
+                    self.conv_log.append(dict(kind="slab" if use_slab else "tap", Ci=Ci, Co=co_out, k=tuple(pk.k), out=(B, To, Ho, Wo),
+                                              geglu=pk.epi_mode == 1, shuffle=shuffle, res=res is not None))
                 self.launches += 1
                 self.tc_calls += 1
                 return y
