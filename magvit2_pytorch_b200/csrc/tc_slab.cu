@@ -21,6 +21,8 @@
 #include <cuda.h>
 #include <algorithm>
 #include <mutex>
+#include <map>
+#include <vector>
 #include <string.h>
 #include <stdlib.h>
 
@@ -36,6 +38,7 @@ struct alignas(64) SlabParams {
   int mw, pitch, slab_h, slab_bytes, slab_stride;
   int bn, n_tiles_n, tiles_w, tiles_h, total_tiles;
   int slab_stages, w_stages, nbuf;
+  int acc_stride;        // TMEM columns between the two accumulator buffers (256 when double buffered)
   int tpw;               // in-plane taps per weight stage (one 3-D TMA box {bk, bn, tpw})
   int cluster;           // 1, or 2: CTA pairs on neighbouring tiles multicast each other half of every weight tile
   TcEpi epi;
@@ -112,7 +115,6 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
   pdl_launch_dependents();
 
   const int taps2d = p.kh * p.kw;
-  const int acc_cols = p.mw * p.bn;   // TMEM columns of one accumulator buffer
 
   if (warp == 0) {
     // ------------------------------ slab producer ------------------------------
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         const int dt0 = max(0, p.pt - t_of_tile);
         mbar_wait(t_empty + 8 * t_idx, t_par ^ 1);
         tc_fence_after();
-        const uint32_t acc = tmem_base + t_idx * acc_cols;
+        const uint32_t acc = tmem_base + t_idx * p.acc_stride;
         uint32_t accum = 0;
         for (int dt = dt0; dt < p.kt; ++dt)
           for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
       for (int j = 0; j < p.mw; ++j) {
         const int w = c.w0 + 8 * j + lw;
         const bool row_ok = h < p.H && w < p.W;
-        const uint32_t tl = tmem_base + buf * acc_cols + j * p.bn + ((uint32_t)(sub * 32) << 16);
+        const uint32_t tl = tmem_base + buf * p.acc_stride + j * p.bn + ((uint32_t)(sub * 32) << 16);
         const int64_t row_base = ((((int64_t)c.b * p.T + c.t) * p.H + h) * p.W + w) * p.Co;
         // column chunks are dealt round-robin to the two warps that share this lane quarter
         if (MODE == EPI_PLAIN) {
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
               uint4 v;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                            : "r"(rd + k * 512 + ((piece ^ ((rrow >> 1) & 3)) << 4)));
-              if (h2 < p.H && w2 < p.W && ncol < p.Co) {
+              if (h2 < p.H && w2 < p.W && ncol < p.Co && c0 + piece * 8 < p.bn) {
                 const int64_t off = ((((int64_t)c.b * p.T + c.t) * p.H + h2) * p.W + w2) * p.Co + ncol;
                 if (p.epi.res) {
                   const uint4 rv = *reinterpret_cast<const uint4*>(p.epi.res + off);
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
             uint32_t r[32];
             tmem_ld_32x32b_x32(tl + c0, r);
             tmem_ld_wait();
-            if (row_ok) epi_chunk32<MODE>(p.epi, r, 32, c.n0 + c0, sbias + c.n0 + c0, c.b, c.t, h, w, row_base);
+            if (row_ok) epi_chunk32<MODE>(p.epi, r, min(32, p.bn - c0), c.n0 + c0, sbias + c.n0 + c0, c.b, c.t, h, w, row_base);
           }
         }
       }
@@ -315,6 +317,60 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
 }  // namespace mv2
 
 using namespace mv2;
+
+
+// ---- N-tile width for deep, wide layers (Co > 256, few positions) -------------------------------------------------------
+// With 128 x 256 tiles a 512-channel 16x16 layer has only 80 .. 320 tiles for 148 persistent CTAs, so up to half of the
+// SMs idle in the last wave.  Narrower, possibly ragged N tiles (e.g. 3 x 176 columns for Co = 512) trade a little MMA
+// efficiency for a full wave.  The choice comes from a small makespan model calibrated on profiles/r01_sweep_ragged.json:
+//   tile cost  = live frame taps(t) * kchunks * kh*kw * mw * 4 MMAs * max(bn/2, 1.28 * (32 + bn/4)) cycles
+//                (tensor pipe vs the shared-memory operand bandwidth of one 128 x bn x 16 MMA) + per-tile overhead,
+//   assignment = the kernel's static round robin (tile i -> CTA i mod grid), tiles ordered n, w, h, t, b.
+// A ragged candidate must beat the power-of-two default by 8 % in the model; results are cached per layer shape.
+static double slab_model_cycles(const mv2_tc_conv_args* a, int n_sm, int mw, int bn) {
+  const int tiles_per_frame = ceil_div(a->Ho, 16) * ceil_div(a->Wo, 8 * mw) * ceil_div(a->Co, bn);
+  const double t_mma = std::max(bn / 2.0, 1.28 * (32.0 + bn / 4.0));
+  const double per_tap_frame = (double)(a->Ci / 64) * a->kh * a->kw * mw * 4.0 * t_mma;
+  const double fixed = 3000.0 + (2 * mw * bn > 512 ? mw * bn * 10.0 : 0.0);   // + unoverlapped epilogue when single buffered
+  const int64_t total = (int64_t)a->B * a->To * tiles_per_frame;
+  const int G = (int)std::min<int64_t>(total, n_sm);
+  std::vector<double> load(G, 0.0);
+  int64_t idx = 0;
+  for (int b = 0; b < a->B; ++b)
+    for (int t = 0; t < a->To; ++t) {
+      const int live = a->kt - std::max(0, a->pt - t);
+      const double cost = live * per_tap_frame + fixed;
+      for (int i = 0; i < tiles_per_frame; ++i, ++idx) load[idx % G] += cost;
+    }
+  return *std::max_element(load.begin(), load.end());
+}
+
+static void choose_ragged_tiles(const mv2_tc_conv_args* a, int n_sm, int* mw_io, int* bn_io) {
+  struct Key { int v[10]; bool operator<(const Key& o) const { return memcmp(v, o.v, sizeof(v)) < 0; } };
+  static std::mutex mu;
+  static std::map<Key, std::pair<int, int>> cache;
+  const Key key = {{a->B, a->To, a->Ho, a->Wo, a->Ci, a->Co, a->kt, a->kh, a->kw, n_sm}};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    int mw = *mw_io, bn = *bn_io;
+    const double base = slab_model_cycles(a, n_sm, mw, bn);
+    double best = base * 0.92;
+    for (int j = ceil_div(a->Co, 256) + 1; j <= ceil_div(a->Co, 128); ++j) {
+      const int cbn = (ceil_div(a->Co, j) + 15) / 16 * 16;
+      if (cbn > 256 || cbn < 128) continue;
+      for (int cmw = 1; cmw <= 2; ++cmw) {
+        if (cmw == 2 && (a->Wo <= 8 || cmw * cbn > 512)) continue;
+        // two M-tiles per weight tile halve the weight stream, which the model does not see: worth ~3 %
+        const double c = slab_model_cycles(a, n_sm, cmw, cbn) * (cmw == 2 ? 0.97 : 1.0);
+        if (c < best) { best = c; mw = cmw; bn = cbn; }
+      }
+    }
+    it = cache.emplace(key, std::make_pair(mw, bn)).first;
+  }
+  *mw_io = it->second.first;
+  *bn_io = it->second.second;
+}
 
 extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
   if (!a) return 0;
@@ -351,7 +407,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   p.epi.act = a->act; p.epi.shuffle = a->shuffle; p.epi.mode = a->epi_mode; p.epi.Co = a->Co;
   p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo;
 
-  // ---- tiling (profiles/r01_sweep_slab_v2.json): widest N tile; two M-tiles per weight tile whenever both
+  // ---- tiling (profiles/r01_sweep_slab_v*.json): widest N tile; two M-tiles per weight tile whenever both
   //      accumulator sets still double-buffer in TMEM (2 * mw * bn <= 512), which also halves weight traffic ----
   const int tiles_h = ceil_div(a->Ho, 16);
   const int co_pad = (a->Co + 31) / 32 * 32;
@@ -360,13 +416,17 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
     if (bn <= co_pad && co_pad % bn == 0) { best_bn = bn; break; }
   int best_mw = (best_bn <= 128 && a->Wo > 8) ? 2 : 1;
   if (best_bn <= 64 && a->Wo > 16) best_mw = 4;   // narrow N: four M-tiles per weight tile still double-buffer in TMEM
+  // EPI_PLAIN guards every stored column, so N tiles need not divide Co: deep wide layers pick the width that fills
+  // the 148 SMs best (choose_ragged_tiles)
+  const bool ragged_ok = a->epi_mode == 0 && a->shuffle == MV2_SHUFFLE_NONE && a->Co % 8 == 0;
+  if (ragged_ok && a->Co > 256 && a->kt * a->kh * a->kw > 1) choose_ragged_tiles(a, n_sm, &best_mw, &best_bn);
   if (const char* env = getenv("MV2_SLAB_CFG")) {   // debug / tuning override: "mw,bn"
     int emw = 0, ebn = 0;
-    if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2 || emw == 4) && ebn >= 32 && ebn <= 256 &&
-        co_pad % ebn == 0 && emw * ebn <= 512 && !(emw >= 2 && a->Wo <= 8)) { best_mw = emw; best_bn = ebn; }
+    if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2 || emw == 4) && ebn >= 32 && ebn <= 256 && ebn % 16 == 0 &&
+        (co_pad % ebn == 0 || ragged_ok) && emw * ebn <= 512 && !(emw >= 2 && a->Wo <= 8)) { best_mw = emw; best_bn = ebn; }
   }
   p.mw = best_mw; p.bn = best_bn;
-  p.n_tiles_n = co_pad / p.bn;
+  p.n_tiles_n = (co_pad + p.bn - 1) / p.bn;   // a ragged last tile reads zero-filled weight rows and stores nothing for them
   // weight multicast across CTA pairs: when one M-tile per CTA cannot amortise the weight stream (mw == 1, deep
   // layers) two CTAs on neighbouring tiles fetch half of every weight tile each and multicast it to both
   // (measured: no gain on B200 at these shapes -- the deep layers are wave-quantisation bound, not weight-stream bound --
@@ -381,6 +441,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   p.slab_bytes = p.pitch * p.slab_h * p.row_bytes;
   p.slab_stride = (p.slab_bytes + 1023) / 1024 * 1024;
   p.nbuf = (2 * p.mw * p.bn <= 512) ? 2 : 1;
+  p.acc_stride = p.nbuf == 2 ? 256 : 0;
   // weight ring stage = tpw consecutive in-plane taps (fewer barrier round trips for small tiles), <= 32 KB
   const int taps2d = a->kh * a->kw;
   p.tpw = 1;
@@ -389,7 +450,8 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   if (p.cluster > 1) p.tpw = 1;
   if (const char* env = getenv("MV2_SLAB_TPW")) { const int v = atoi(env); if (v >= 1 && taps2d % v == 0 && v * p.bn * p.row_bytes <= 64 * 1024) p.tpw = v; }
   const int w_bytes = p.bn * p.row_bytes * p.tpw;
-  const int budget = 204 * 1024 - co_pad * 4;   // 227 KB minus 16 KB epilogue transpose buffers, barriers, alignment slack
+  const int nb_pad = p.n_tiles_n * p.bn;   // bias staging covers the padded column range
+  const int budget = 204 * 1024 - nb_pad * 4;   // 227 KB minus 16 KB epilogue transpose buffers, barriers, alignment slack
   p.slab_stages = p.slab_stride * 3 + w_bytes * 3 <= budget ? 3 : 2;
   p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
   if (p.w_stages < 2 && p.slab_stages > 2) { p.slab_stages = 2; p.w_stages = std::min(12, (budget - 2 * p.slab_stride) / w_bytes); }
@@ -427,7 +489,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights 2-D) failed: %d", (int)r); return MV2_E_CUDA; }
   }
-  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 32 + (size_t)co_pad * 4 + 8 * 2048 + 1024;
+  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 32 + (size_t)nb_pad * 4 + 8 * 2048 + 1024;
   MV2_CHECK_ARG(smem <= 227 * 1024);
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;

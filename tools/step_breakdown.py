@@ -72,5 +72,14 @@ rows = sorted(agg.items(), key=lambda kv: -kv[1][0])
 for k, (us, n) in rows:
     print(f"{k:48s} {us:9.1f} us  {n // STEPS:4d} launches  {100 * us / tot:5.1f} %")
 print(f"{'total kernel time / step':48s} {tot:9.1f} us")
+# per-launch durations (last step, launch order) of the small CUDA-core kernels
+last = evs[len(evs) * (STEPS - 1) // STEPS:]
+seqs = collections.defaultdict(list)
+for e in last:
+    name = ids.get(id(e)) or e.name.split("(")[0].replace("void ", "").replace("mv2::", "").split("<")[0]
+    seqs[name].append(round(e.device_time_total, 1))
+for k in ("se_pool_online_kernel", "se_hidden_kernel", "se_out_kernel", "gate_residual_bf16x8_kernel", "rmsnorm_bf16x8_kernel",
+          "pointwise c512->512 @16", "conv3x3x3 c512", "ff fc1+geglu", "strided conv (tap kernel)", "upsample conv"):
+    print(f"{k}: {seqs.get(k)}")
 if len(sys.argv) > 1:
     json.dump({"total_us": tot, "classes": {k: {"us": us, "launches": n // STEPS} for k, (us, n) in rows}}, open(sys.argv[1], "w"), indent=1)
