@@ -366,9 +366,11 @@ __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16
 #pragma unroll
       for (int u = 0; u < VEC / 8; ++u) raw[uu][u] = ok[uu] ? src[u] : make_uint4(0, 0, 0, 0);
     }
+    // the U rows are folded in together: one running-max update, one rescale of the accumulators and U + 1 exponentials
+    // per batch (the row-at-a-time recurrence serialised 2 exponentials and a full rescale per row)
+    float v[U][VEC], l[U];
 #pragma unroll
     for (int uu = 0; uu < U; ++uu) {
-      float v[VEC];
       float dot = 0.f;
 #pragma unroll
       for (int u = 0; u < VEC / 8; ++u) {
@@ -376,22 +378,32 @@ __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 fv = __bfloat1622float2(vb[q]);
-          v[u * 8 + 2 * q] = fv.x;
-          v[u * 8 + 2 * q + 1] = fv.y;
+          v[uu][u * 8 + 2 * q] = fv.x;
+          v[uu][u * 8 + 2 * q + 1] = fv.y;
         }
       }
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) dot = fmaf(v[q], wv[q], dot);
+      for (int q = 0; q < VEC; ++q) dot = fmaf(v[uu][q], wv[q], dot);
       for (int o = G >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      if (ok[uu]) {
-        const float l = dot + bk;
-        const float mn = fmaxf(m, l);
-        const float sc = __expf(m - mn), e = __expf(l - mn);
-        ssum = ssum * sc + e;
+      l[uu] = ok[uu] ? dot + bk : -INFINITY;
+    }
+    float mn = m;
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) acc[q] = fmaf(e, v[q], acc[q] * sc);
-        m = mn;
+    for (int uu = 0; uu < U; ++uu) mn = fmaxf(mn, l[uu]);
+    if (mn > -INFINITY) {
+      const float sc = __expf(m - mn);
+      float e[U], es = 0.f;
+#pragma unroll
+      for (int uu = 0; uu < U; ++uu) { e[uu] = __expf(l[uu] - mn); es += e[uu]; }
+      ssum = fmaf(ssum, sc, es);
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        float t = acc[q] * sc;
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu) t = fmaf(e[uu], v[uu][q], t);
+        acc[q] = t;
       }
+      m = mn;
     }
   }
   float* mine = dyn + (size_t)rsub * (C + 2);
@@ -399,24 +411,27 @@ __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16
 #pragma unroll
   for (int q = 0; q < VEC; ++q) mine[2 + g * VEC + q] = acc[q];
   __syncthreads();
-  float M = -INFINITY;
-  for (int r = 0; r < R; ++r) M = fmaxf(M, dyn[(size_t)r * (C + 2)]);
+  // merge the R row groups: warp 0 turns the group maxima into coefficients, then every thread sums its channels
+  float* coefs = dyn + (size_t)R * (C + 2);   // [R]
   float* out = ws + ((int64_t)f * n_chunks + chunk) * (C + 2);
-  if (tid == 0) {
-    float S = 0.f;
-    for (int r = 0; r < R; ++r) {
+  if (tid < 32) {   // R may exceed 32 (narrow layers: C = 16 -> 128 row groups)
+    float mx = -INFINITY;
+    for (int r = tid; r < R; r += 32) mx = fmaxf(mx, dyn[(size_t)r * (C + 2)]);
+    const float M = warp_max(mx);
+    float sp = 0.f;
+    for (int r = tid; r < R; r += 32) {
       const float mr = dyn[(size_t)r * (C + 2)];
-      if (mr > -INFINITY) S += dyn[(size_t)r * (C + 2) + 1] * __expf(mr - M);
+      const float cf = mr > -INFINITY ? __expf(mr - M) : 0.f;
+      coefs[r] = cf;
+      sp = fmaf(cf, dyn[(size_t)r * (C + 2) + 1], sp);
     }
-    out[0] = M;
-    out[1] = S;
+    const float S = warp_sum(sp);
+    if (tid == 0) { out[0] = M; out[1] = S; }
   }
+  __syncthreads();
   for (int c = tid; c < C; c += 256) {
     float t = 0.f;
-    for (int r = 0; r < R; ++r) {
-      const float mr = dyn[(size_t)r * (C + 2)];
-      if (mr > -INFINITY) t = fmaf(dyn[(size_t)r * (C + 2) + 2 + c], __expf(mr - M), t);
-    }
+    for (int r = 0; r < R; ++r) t = fmaf(dyn[(size_t)r * (C + 2) + 2 + c], coefs[r], t);
     out[2 + c] = t;
   }
 }
@@ -1617,6 +1632,7 @@ static int se_rows_per_block(int dtype, int F, int P, int C) {
   const int R = 256 / (C / se_online_vec(C));
   int rows = 512;
   while (rows > 4 * R && rows > SE_MIN_ROWS && (int64_t)F * ceil_div(P, rows) < 1184) rows >>= 1;
+  while (rows < 2048 && (int64_t)F * ceil_div(P, 2 * rows) >= 1184) rows <<= 1;   // big layers: amortise the per-block merge
   return rows;
 }
 
@@ -1630,7 +1646,7 @@ int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, 
   if (dtype == MV2_F32) launch_k(se_pool_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)y, P, C, wk, bk, (float*)workspace, nc);
   else if (dtype == MV2_BF16 && se_online_vec(C) != 0) {
     const int vec = se_online_vec(C);
-    const size_t dsm = (size_t)(256 / (C / vec)) * (C + 2) * sizeof(float);
+    const size_t dsm = (size_t)(256 / (C / vec)) * (C + 3) * sizeof(float);   // R records of (m, s, acc[C]) + R merge coefficients
     MV2_CHECK_ARG(dsm <= 48 * 1024);
     const __nv_bfloat16* yb = (const __nv_bfloat16*)y;
     if (vec == 8) launch_k(se_pool_online_kernel<8>, dim3(grid), dim3(256), dsm, st, yb, P, C, wk, bk, (float*)workspace, nc, rows);
