@@ -592,57 +592,79 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, T
 
 // bf16, C % 8 == 0: one warp per token, 16-byte accesses, the row is held in registers between the two phases
 // (C <= 1024: at most 4 uint4 per lane).
+// One warp normalises RN_TPW tokens: all of their 16-byte loads are issued before the first reduction (one token per
+// warp left a single load in flight per lane and ran at a third of the HBM rate).
+constexpr int RN_TPW = 4;
+template <int NU>   // 256-channel slabs per token: C <= 256 * NU
 __global__ void __launch_bounds__(256) rmsnorm_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                              const float* __restrict__ gamma, int64_t n_tok, int T_,
                                                              int P, int C, int token_shift) {
   pdl_wait();
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
-  const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (tok >= n_tok) return;
-  const int t = (int)((tok / P) % T_);
+  const int64_t tok0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * RN_TPW;
+  if (tok0 >= n_tok) return;
   const int half = C >> 1;
-  const __nv_bfloat16* row = x + tok * C;
-  const __nv_bfloat16* prow = row - (int64_t)P * C;
-  const bool has_prev = t > 0;
-  uint4 v[4];
-  float ss = 0.f;
+  uint4 v[RN_TPW][NU];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int c = (u * 32 + lane) * 8;
-    v[u] = make_uint4(0, 0, 0, 0);
-    if (c < C) {
-      if (token_shift && c >= half) { if (has_prev) v[u] = *reinterpret_cast<const uint4*>(prow + c); }
-      else v[u] = *reinterpret_cast<const uint4*>(row + c);
-      const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
+  for (int i = 0; i < RN_TPW; ++i) {
+    const int64_t tok = tok0 + i;
+    const bool valid = tok < n_tok;
+    const int t = valid ? (int)((tok / P) % T_) : 0;
+    const __nv_bfloat16* row = x + (valid ? tok : tok0) * C;
+    const __nv_bfloat16* prow = row - (int64_t)P * C;
+    const bool has_prev = t > 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 f = __bfloat1622float2(vb[q]);
-        ss = fmaf(f.x, f.x, ss);
-        ss = fmaf(f.y, f.y, ss);
+    for (int u = 0; u < NU; ++u) {
+      const int c = (u * 32 + lane) * 8;
+      v[i][u] = make_uint4(0, 0, 0, 0);
+      if (valid && c < C) {
+        if (token_shift && c >= half) { if (has_prev) v[i][u] = *reinterpret_cast<const uint4*>(prow + c); }
+        else v[i][u] = *reinterpret_cast<const uint4*>(row + c);
       }
     }
   }
-  ss = warp_sum(ss);
-  const float denom = fmaxf(sqrtf(ss), 1e-12f);
-  const float scale = sqrtf((float)C);
-  __nv_bfloat16* orow = out + tok * C;
+  float ss[RN_TPW];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int c = (u * 32 + lane) * 8;
-    if (c < C) {
-      const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v[u]);
-      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      uint4 o;
-      uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+  for (int i = 0; i < RN_TPW; ++i) {
+    float a = 0.f;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v[i][u]);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float2 f = __bfloat1622float2(vb[q]);
-        __nv_bfloat162 r = __floats2bfloat162_rn(((f.x / denom) * scale) * gg[2 * q], ((f.y / denom) * scale) * gg[2 * q + 1]);
-        ob[q] = *reinterpret_cast<uint32_t*>(&r);
+        a = fmaf(f.x, f.x, a);
+        a = fmaf(f.y, f.y, a);
       }
-      *reinterpret_cast<uint4*>(orow + c) = o;
+    }
+    ss[i] = a;
+  }
+#pragma unroll
+  for (int i = 0; i < RN_TPW; ++i) ss[i] = warp_sum(ss[i]);
+  const float scale = sqrtf((float)C);
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const int c = (u * 32 + lane) * 8;
+    if (c < C) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int i = 0; i < RN_TPW; ++i) {
+        if (tok0 + i < n_tok) {
+          const float rinv = 1.f / fmaxf(sqrtf(ss[i]), 1e-12f);   // x / max(|x|, eps) as one reciprocal per token
+          const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v[i][u]);
+          uint4 o;
+          uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = __bfloat1622float2(vb[q]);
+            __nv_bfloat162 r = __floats2bfloat162_rn(((f.x * rinv) * scale) * gg[2 * q], ((f.y * rinv) * scale) * gg[2 * q + 1]);
+            ob[q] = *reinterpret_cast<uint32_t*>(&r);
+          }
+          *reinterpret_cast<uint4*>(out + (tok0 + i) * C + c) = o;
+        }
+      }
     }
   }
 }
@@ -1703,7 +1725,14 @@ int mv2_rmsnorm(const void* x, void* out, int dtype, const float* gamma, int B, 
   if (dtype == MV2_F32)
     launch_k(rmsnorm_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)x, (float*)out, gamma, n_tok, T, P, C, token_shift);
   else if (dtype == MV2_BF16 && C % 8 == 0 && C <= 1024 && (!token_shift || (C / 2) % 8 == 0))
-    launch_k(rmsnorm_bf16x8_kernel, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, gamma, n_tok, T, P, C, token_shift);
+    {
+      const dim3 g(ceil_div(n_tok, 8 * RN_TPW));
+      const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+      __nv_bfloat16* ob = (__nv_bfloat16*)out;
+      if (C <= 256) launch_k(rmsnorm_bf16x8_kernel<1>, g, dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
+      else if (C <= 512) launch_k(rmsnorm_bf16x8_kernel<2>, g, dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
+      else launch_k(rmsnorm_bf16x8_kernel<4>, g, dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
+    }
   else if (dtype == MV2_BF16)
     launch_k(rmsnorm_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)out, gamma, n_tok, T, P, C, token_shift);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }

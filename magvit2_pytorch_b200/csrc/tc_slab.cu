@@ -420,10 +420,19 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   // the 148 SMs best (choose_ragged_tiles)
   const bool ragged_ok = a->epi_mode == 0 && a->shuffle == MV2_SHUFFLE_NONE && a->Co % 8 == 0;
   if (ragged_ok && a->Co > 256 && a->kt * a->kh * a->kw > 1) choose_ragged_tiles(a, n_sm, &best_mw, &best_bn);
+  // wide outputs whose width has no large power-of-two divisor (the GEGLU feed-forward: 2 * 1365 -> 2752 packed columns
+  // would run 43 tiles of 64): 64-column MMAs are shared-memory bound, so take wide tiles and let the last one be ragged
+  // (the GEGLU epilogue guards its 16-column groups against Co like the plain one guards its 8-column pieces)
+  if ((ragged_ok || a->epi_mode == 1) && best_bn <= 64 && co_pad >= 512) {
+    for (int bn : {256, 192, 128}) {
+      const int padded = (co_pad + bn - 1) / bn * bn;
+      if (padded * 100 <= co_pad * 108) { best_bn = bn; best_mw = (bn <= 128 && a->Wo > 8) ? 2 : 1; break; }
+    }
+  }
   if (const char* env = getenv("MV2_SLAB_CFG")) {   // debug / tuning override: "mw,bn"
     int emw = 0, ebn = 0;
     if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2 || emw == 4) && ebn >= 32 && ebn <= 256 && ebn % 16 == 0 &&
-        (co_pad % ebn == 0 || ragged_ok) && emw * ebn <= 512 && !(emw >= 2 && a->Wo <= 8)) { best_mw = emw; best_bn = ebn; }
+        (co_pad % ebn == 0 || ragged_ok || (a->epi_mode == 1 && ebn % 32 == 0)) && emw * ebn <= 512 && !(emw >= 2 && a->Wo <= 8)) { best_mw = emw; best_bn = ebn; }
   }
   p.mw = best_mw; p.bn = best_bn;
   p.n_tiles_n = (co_pad + p.bn - 1) / p.bn;   // a ragged last tile reads zero-filled weight rows and stores nothing for them
