@@ -258,6 +258,12 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
           const int rl = lane >> 2, piece = lane & 3;                 // read side: row within an 8-row group, 16-byte piece
           const int w2 = c.w0 + 8 * j + rl;
           const uint32_t rd = stg + rl * 64;
+          // output addressing is hoisted out of the chunk loop: element offset of (row k = 0, column piece) and the
+          // stride between the four h rows a warp stores per chunk
+          const int h20 = c.h0 + sub * 4;
+          const int64_t row0 = ((((int64_t)c.b * p.T + c.t) * p.H + h20) * p.W + w2) * p.Co + c.n0 + piece * 8;
+          const int64_t kstride = (int64_t)p.W * p.Co;
+          const int kmax = w2 < p.W ? p.H - h20 : 0;                   // rows k < kmax are inside the frame
           for (int c0 = ((j + half) & 1) * 32; c0 < p.bn; c0 += 64) {
             uint32_t r[32], pk[16];
             tmem_ld_32x32b_x32(tl + c0, r);
@@ -268,24 +274,24 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((g ^ wsw) << 4)), "r"(pk[4 * g]),
                            "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3]) : "memory");
             __syncwarp();
-            const int ncol = c.n0 + c0 + piece * 8;
+            const bool col_ok = c.n0 + c0 + piece * 8 < p.Co && c0 + piece * 8 < p.bn;
+            const int klim = col_ok ? kmax : 0;
+            __nv_bfloat16* yp = p.epi.y + row0 + c0;
+            const __nv_bfloat16* rp = p.epi.res ? p.epi.res + row0 + c0 : nullptr;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int h2 = c.h0 + sub * 4 + k;
-              const uint32_t rrow = 8 * k + rl;
               uint4 v;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                           : "r"(rd + k * 512 + ((piece ^ ((rrow >> 1) & 3)) << 4)));
-              if (h2 < p.H && w2 < p.W && ncol < p.Co && c0 + piece * 8 < p.bn) {
-                const int64_t off = ((((int64_t)c.b * p.T + c.t) * p.H + h2) * p.W + w2) * p.Co + ncol;
-                if (p.epi.res) {
-                  const uint4 rv = *reinterpret_cast<const uint4*>(p.epi.res + off);
+                           : "r"(rd + k * 512 + ((piece ^ (((8 * k + rl) >> 1) & 3)) << 4)));
+              if (k < klim) {
+                if (rp) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(rp + k * kstride);
                   __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(&v);
                   const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                   for (int q = 0; q < 4; ++q) a2[q] = __hadd2(a2[q], b2[q]);
                 }
-                *reinterpret_cast<uint4*>(p.epi.y + off) = v;
+                *reinterpret_cast<uint4*>(yp + k * kstride) = v;
               }
             }
             __syncwarp();

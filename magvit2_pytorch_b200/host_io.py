@@ -1,0 +1,84 @@
+"""Pinned-host-buffer front end of the tokenizer round trip.
+
+A caller that keeps its videos and results in host memory (a data loader on one side, a token store on the other) pays
+a host->device copy before and a device->host copy after every `tokenize` / `decode_from_code_indices` call of the
+reference API (magvit2_pytorch.py M:1651-1654, M:1590-1617).  `HostRoundTrip` issues the three phases on three CUDA
+streams with `depth` device staging slots, so the H2D copy of call i+1 and the D2H copy of call i-1 run under the
+kernels of call i.  Nothing is computed differently: the kernels are the ones `VideoTokenizer.tokenize` /
+`.decode_from_code_indices` launch, on the caller's current stream.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+
+class _Slot:
+    __slots__ = ("video", "codes", "recon", "h2d", "done", "d2h", "used")
+
+    def __init__(self):
+        self.video: Optional[torch.Tensor] = None
+        self.codes = self.recon = None
+        self.h2d = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        self.d2h = torch.cuda.Event()
+        self.used = False
+
+
+class HostRoundTrip:
+    """``submit(video_host, out_codes_host, out_video_host)`` enqueues copy-in -> tokenize -> decode -> copy-out and
+    returns a CUDA event that completes when both host outputs are written.  All host tensors must be pinned.  The
+    caller's buffers of a submit may be reused once its event has completed (``wait(event)``) or after
+    ``synchronize()``; at most `depth` submits are in flight on the device side."""
+
+    def __init__(self, model, depth: int = 2):
+        assert depth >= 1
+        self.model = model
+        self.device = model.device
+        if self.device.type != "cuda":
+            raise RuntimeError("HostRoundTrip needs the tokenizer on a CUDA device")
+        self.s_in = torch.cuda.Stream(self.device)
+        self.s_out = torch.cuda.Stream(self.device)
+        self.slots: List[_Slot] = [_Slot() for _ in range(depth)]
+        self.n = 0
+
+    def submit(self, video_host: torch.Tensor, out_codes_host: torch.Tensor, out_video_host: torch.Tensor) -> torch.cuda.Event:
+        for t in (video_host, out_codes_host, out_video_host):
+            if t.device.type != "cpu" or not t.is_pinned():
+                raise ValueError("HostRoundTrip takes pinned host tensors")
+        slot = self.slots[self.n % len(self.slots)]
+        self.n += 1
+        cur = torch.cuda.current_stream(self.device)
+        if slot.video is None or slot.video.shape != video_host.shape or slot.video.dtype != video_host.dtype:
+            if slot.used:
+                slot.done.synchronize()
+            slot.video = torch.empty(video_host.shape, dtype=video_host.dtype, device=self.device)
+        if slot.used:
+            self.s_in.wait_event(slot.done)          # the kernels that read this slot's staged input have finished
+        with torch.cuda.stream(self.s_in):
+            slot.video.copy_(video_host, non_blocking=True)
+            slot.h2d.record(self.s_in)
+        cur.wait_event(slot.h2d)
+        if slot.used:
+            cur.wait_event(slot.d2h)                 # the slot's previous results have left the device
+        codes = self.model.tokenize(slot.video)
+        recon = self.model.decode_from_code_indices(codes)
+        slot.codes, slot.recon = codes, recon        # keep the device results alive until their D2H copy is done
+        slot.done.record(cur)
+        self.s_out.wait_event(slot.done)
+        with torch.cuda.stream(self.s_out):
+            out_codes_host.copy_(codes, non_blocking=True)
+            out_video_host.copy_(recon, non_blocking=True)
+            slot.d2h.record(self.s_out)
+        slot.used = True
+        return slot.d2h
+
+    @staticmethod
+    def wait(event: torch.cuda.Event) -> None:
+        event.synchronize()
+
+    def synchronize(self) -> None:
+        for s in self.slots:
+            if s.used:
+                s.d2h.synchronize()

@@ -251,3 +251,30 @@ def test_wide_channel_config_vs_oracle(dtype):
     else:
         assert mism.float().mean().item() < 0.15
         assert rerr.mean().item() < 0.02 and rerr.max().item() < 0.2
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_host_round_trip_matches_direct_calls(graphs):
+    """HostRoundTrip (pinned host buffers, copies overlapped on side streams) returns exactly what tokenize /
+    decode_from_code_indices return for device inputs, for every in-flight slot and across slot reuse."""
+    _require_cuda()
+    from magvit2_pytorch_b200 import HostRoundTrip
+    g = load_golden("mini")
+    model = build_product(g["kwargs"], g["wseed"]).cuda().bfloat16()
+    vids = [(golden_video(g) + 0.05 * i).pin_memory() for i in range(5)]
+    want = []
+    for v in vids:
+        c = model.tokenize(v.cuda())
+        want.append((c.cpu(), model.decode_from_code_indices(c).cpu()))
+    model.cuda_graphs = graphs
+    hrt = HostRoundTrip(model, depth=2)
+    outs = [(torch.empty_like(want[0][0]).pin_memory(), torch.empty_like(want[0][1]).pin_memory()) for _ in vids]
+    for rep in range(2):
+        evs = [hrt.submit(v, oc, ov) for v, (oc, ov) in zip(vids, outs)]
+        hrt.wait(evs[-1])
+        hrt.synchronize()
+        for (oc, ov), (wc, wv) in zip(outs, want):
+            assert torch.equal(oc, wc)
+            assert torch.equal(ov, wv)
+    with pytest.raises(ValueError):
+        hrt.submit(vids[0].clone(), outs[0][0], outs[0][1])      # not pinned
