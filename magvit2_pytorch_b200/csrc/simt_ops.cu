@@ -106,40 +106,45 @@ static int dispatch_transpose(const void* src, int sd, void* dst, int dd, int B,
 // Video ingest for the tcgen05 conv_in: packs the k_w taps of the (tiny-channel) input into the channel axis so the
 // 7x7x7, C_in = 3 conv becomes a (7x7x1)-tap conv over 32 "channels":
 //   dst[b][t + t_pad][h][w][dw * C + c] = src[b][c][t][h][w + dw - pw]   (0 outside the image / for padded channels)
-// One thread writes 8 channels (16 B).
+// One block per (b, t, h) image row: the C source rows are staged in shared memory with a zero halo (coalesced
+// loads, each source element read once), then every thread assembles 16-byte groups of 8 packed channels from them.
 template <typename TS>
 __global__ void __launch_bounds__(256) ingest_kwpack_kernel(const TS* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                             int B, int C, int T, int H, int W, int t_pad, int kw, int pw,
                                                             int cpack) {
   pdl_wait();
   pdl_launch_dependents();
+  extern __shared__ float srow[];            // [C][W + kw - 1]
+  const int pitch = W + kw - 1;
   const int groups = cpack >> 3;
-  const int64_t total = (int64_t)B * (T + t_pad) * H * W * groups;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    int64_t r = idx / groups;
-    const int w = (int)(r % W); r /= W;
-    const int h = (int)(r % H); r /= H;
-    const int t = (int)(r % (T + t_pad)); r /= (T + t_pad);
-    const int b = (int)r;
-    const int ts = t - t_pad;
+  int r = blockIdx.x;
+  const int h = r % H; r /= H;
+  const int t = r % (T + t_pad);
+  const int b = r / (T + t_pad);
+  const int ts = t - t_pad;
+  for (int i = threadIdx.x; i < C * pitch; i += blockDim.x) {
+    const int c = i / pitch, ws = i - c * pitch - pw;
+    float x = 0.f;
+    if (ts >= 0 && ws >= 0 && ws < W) x = to_f32<TS>(src[((((int64_t)b * C + c) * T + ts) * H + h) * W + ws]);
+    srow[i] = x;
+  }
+  __syncthreads();
+  __nv_bfloat16* drow = dst + (((int64_t)b * (T + t_pad) + t) * H + h) * (int64_t)W * cpack;
+  for (int i = threadIdx.x; i < W * groups; i += blockDim.x) {
+    const int g = i % groups, w = i / groups;
+    int dw = (g * 8) / C, c = g * 8 - dw * C;
     float v[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int j = g * 8 + q;
-      const int dw = j / C, c = j - dw * C;
-      const int ws = w + dw - pw;
-      float x = 0.f;
-      if (ts >= 0 && dw < kw && ws >= 0 && ws < W)
-        x = to_f32<TS>(src[((((int64_t)b * C + c) * T + ts) * H + h) * W + ws]);
-      v[q] = x;
+      v[q] = dw < kw ? srow[c * pitch + w + dw] : 0.f;     // srow index w + dw  <->  source column w + dw - pw
+      if (++c == C) { c = 0; ++dw; }
     }
     uint4 o;
     __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
     __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
     o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
     o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-    *reinterpret_cast<uint4*>(dst + idx * 8) = o;
+    *reinterpret_cast<uint4*>(drow + (int64_t)i * 8) = o;
   }
 }
 
@@ -334,38 +339,95 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const T* __restrict__ y, i
 //   logit (lane-group shuffle reduce) -> running max / rescale -> acc[c] += exp(l - m) * y[c].
 // The row groups' partial (m, s, acc) are merged through shared memory and one (m, s, pooled[C]) record per chunk is
 // written, same workspace format as se_pool_kernel.
-template <int VEC>
+// exp for the online softmax: bare MUFU.EX2 (flush-to-zero; arguments are <= 0, and exp(-inf) = 0 as required)
+__device__ __forceinline__ float se_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
+// The chunk is streamed through shared memory by the bulk-copy engine (cp.async.bulk, one batch of R * U rows per ring
+// stage, SE_STAGES stages): loads run ahead of the arithmetic independently of how many registers / warps the SM
+// has left, which is what bounded the direct-load version to ~3.5 TB/s.
+constexpr int SE_STAGES = 3;
+__device__ __forceinline__ void se_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void se_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void se_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void se_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int VEC, int G>   // G = C / VEC lanes per row (compile time: the shuffle reductions unroll)
 __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16* __restrict__ y, int P, int C,
                                                              const float* __restrict__ wk, float bk,
                                                              float* __restrict__ ws, int n_chunks, int chunk_rows) {
-  pdl_wait();
-  pdl_launch_dependents();
-  extern __shared__ float dyn[];           // [R][C + 2]
+  extern __shared__ __align__(128) float dyn[];   // ring of SE_STAGES batches; reused as [R][C + 2] + [R] for the merge
+  __shared__ __align__(8) uint64_t full_bar[SE_STAGES];
   const int f = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x;
-  const int G = C / VEC, R = 256 / G;
+  constexpr int R = 256 / G;
   const int g = tid % G, rsub = tid / G;
   const int p0 = chunk * chunk_rows;
   const int cnt = min(chunk_rows, P - p0);
-  const __nv_bfloat16* yf = y + ((int64_t)f * P + p0) * C + g * VEC;
+  constexpr int U = (VEC == 8) ? 4 : 2;
+  const int batch_rows = R * U;
+  const uint32_t stage_bytes = (uint32_t)batch_rows * C * 2;
+  const int n_batches = (cnt + batch_rows - 1) / batch_rows;
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(dyn);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(full_bar);
+  const __nv_bfloat16* ychunk = y + ((int64_t)f * P + p0) * C;
+  if (tid == 0) {
+    for (int s_ = 0; s_ < SE_STAGES; ++s_) se_mbar_init(bar0 + 8 * s_, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
+  auto issue = [&](int bi) {     // thread 0 only
+    const int st_ = bi % SE_STAGES;
+    const int rows = min(batch_rows, cnt - bi * batch_rows);
+    const uint32_t bytes = (uint32_t)rows * C * 2;
+    se_mbar_expect_tx(bar0 + 8 * st_, bytes);
+    se_bulk_load(ring + st_ * stage_bytes, ychunk + (int64_t)bi * batch_rows * C, bytes, bar0 + 8 * st_);
+  };
+  if (tid == 0)
+    for (int bi = 0; bi < SE_STAGES && bi < n_batches; ++bi) issue(bi);
   float wv[VEC], acc[VEC];
 #pragma unroll
   for (int q = 0; q < VEC; ++q) { wv[q] = wk[g * VEC + q]; acc[q] = 0.f; }
   float m = -INFINITY, ssum = 0.f;
-  // rows are walked U at a time per row group: the U independent 16..64-byte loads are issued before any of them is
-  // consumed (memory-level parallelism), then the online-softmax updates run back to back.  Trip counts are warp uniform.
-  constexpr int U = (VEC == 8) ? 4 : 2;
-  for (int nb = 0; nb < cnt; nb += R * U) {
+  for (int bi = 0; bi < n_batches; ++bi) {
+    const int st_ = bi % SE_STAGES;
+    const int nb = bi * batch_rows;
+    se_mbar_wait(bar0 + 8 * st_, (uint32_t)(bi / SE_STAGES) & 1u);
+    const unsigned char* sbase = reinterpret_cast<const unsigned char*>(dyn) + (size_t)st_ * stage_bytes + (size_t)g * VEC * 2;
     uint4 raw[U][VEC / 8];
     bool ok[U];
 #pragma unroll
     for (int uu = 0; uu < U; ++uu) {
-      const int n = nb + uu * R + rsub;
-      ok[uu] = n < cnt;
-      const uint4* src = reinterpret_cast<const uint4*>(yf + (int64_t)(ok[uu] ? n : 0) * C);
+      const int rr = uu * R + rsub;                 // row inside the batch
+      ok[uu] = nb + rr < cnt;
+      const uint4* src = reinterpret_cast<const uint4*>(sbase + (size_t)rr * C * 2);
 #pragma unroll
       for (int u = 0; u < VEC / 8; ++u) raw[uu][u] = ok[uu] ? src[u] : make_uint4(0, 0, 0, 0);
     }
+    __syncthreads();                                // every thread has its rows in registers: the stage can be refilled
+    if (tid == 0 && bi + SE_STAGES < n_batches) issue(bi + SE_STAGES);
     // the U rows are folded in together: one running-max update, one rescale of the accumulators and U + 1 exponentials
     // per batch (the row-at-a-time recurrence serialised 2 exponentials and a full rescale per row)
     float v[U][VEC], l[U];
@@ -384,6 +446,7 @@ __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16
       }
 #pragma unroll
       for (int q = 0; q < VEC; ++q) dot = fmaf(v[uu][q], wv[q], dot);
+#pragma unroll
       for (int o = G >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
       l[uu] = ok[uu] ? dot + bk : -INFINITY;
     }
@@ -391,10 +454,10 @@ __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16
 #pragma unroll
     for (int uu = 0; uu < U; ++uu) mn = fmaxf(mn, l[uu]);
     if (mn > -INFINITY) {
-      const float sc = __expf(m - mn);
+      const float sc = se_exp(m - mn);
       float e[U], es = 0.f;
 #pragma unroll
-      for (int uu = 0; uu < U; ++uu) { e[uu] = __expf(l[uu] - mn); es += e[uu]; }
+      for (int uu = 0; uu < U; ++uu) { e[uu] = se_exp(l[uu] - mn); es += e[uu]; }
       ssum = fmaf(ssum, sc, es);
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
@@ -1603,13 +1666,15 @@ int mv2_ingest_kwpack(const void* src, int src_dtype, void* dst, int B, int C, i
                       int pw, int cpack, void* stream) {
   MV2_CHECK_ARG(src && dst && B > 0 && C > 0 && T > 0 && H > 0 && W > 0 && t_pad >= 0 && kw > 0);
   MV2_CHECK_ARG(cpack % 8 == 0 && kw * C <= cpack);
-  const int64_t total = (int64_t)B * (T + t_pad) * H * W * (cpack / 8);
-  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+  const int64_t rows = (int64_t)B * (T + t_pad) * H;
+  const size_t smem = (size_t)C * (W + kw - 1) * sizeof(float);
+  MV2_CHECK_ARG(rows <= 2147483647LL && smem <= 48 * 1024);
+  const int blocks = (int)rows;
   cudaStream_t st = (cudaStream_t)stream;
   if (src_dtype == MV2_F32)
-    launch_k(ingest_kwpack_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
+    launch_k(ingest_kwpack_kernel<float>, dim3(blocks), dim3(256), smem, st, (const float*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
   else if (src_dtype == MV2_BF16)
-    launch_k(ingest_kwpack_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
+    launch_k(ingest_kwpack_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), smem, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
   else { set_error("bad dtype %d", src_dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -1658,6 +1723,18 @@ static int se_rows_per_block(int dtype, int F, int P, int C) {
   return rows;
 }
 
+static cudaError_t se_pool_smem_optin() {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    auto set = [&](const void* fn) { if (err == cudaSuccess) err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); };
+    set((const void*)se_pool_online_kernel<8, 1>); set((const void*)se_pool_online_kernel<8, 2>); set((const void*)se_pool_online_kernel<8, 4>);
+    set((const void*)se_pool_online_kernel<8, 8>); set((const void*)se_pool_online_kernel<8, 16>); set((const void*)se_pool_online_kernel<8, 32>);
+    set((const void*)se_pool_online_kernel<16, 32>); set((const void*)se_pool_online_kernel<32, 32>);
+  });
+  return err;
+}
+
 int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, float bk, void* workspace,
                 void* stream) {
   MV2_CHECK_ARG(y && wk && workspace && F > 0 && P > 0 && C > 0);
@@ -1668,12 +1745,20 @@ int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, 
   if (dtype == MV2_F32) launch_k(se_pool_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)y, P, C, wk, bk, (float*)workspace, nc);
   else if (dtype == MV2_BF16 && se_online_vec(C) != 0) {
     const int vec = se_online_vec(C);
-    const size_t dsm = (size_t)(256 / (C / vec)) * (C + 3) * sizeof(float);   // R records of (m, s, acc[C]) + R merge coefficients
-    MV2_CHECK_ARG(dsm <= 48 * 1024);
+    const int R_ = 256 / (C / vec), U_ = vec == 8 ? 4 : 2;
+    // SE_STAGES batches of R * U rows, reused afterwards for R records of (m, s, acc[C]) + R merge coefficients
+    const size_t dsm = std::max((size_t)SE_STAGES * R_ * U_ * C * 2, (size_t)R_ * (C + 3) * sizeof(float));
+    MV2_CHECK_ARG(dsm <= 96 * 1024);
     const __nv_bfloat16* yb = (const __nv_bfloat16*)y;
-    if (vec == 8) launch_k(se_pool_online_kernel<8>, dim3(grid), dim3(256), dsm, st, yb, P, C, wk, bk, (float*)workspace, nc, rows);
-    else if (vec == 16) launch_k(se_pool_online_kernel<16>, dim3(grid), dim3(256), dsm, st, yb, P, C, wk, bk, (float*)workspace, nc, rows);
-    else launch_k(se_pool_online_kernel<32>, dim3(grid), dim3(256), dsm, st, yb, P, C, wk, bk, (float*)workspace, nc, rows);
+    MV2_CHECK_CUDA(se_pool_smem_optin());
+    const int G_ = C / vec;
+#define MV2_SE_POOL_CASE(V, GG) \
+    else if (vec == V && G_ == GG) launch_k(se_pool_online_kernel<V, GG>, dim3(grid), dim3(256), dsm, st, yb, P, C, wk, bk, (float*)workspace, nc, rows)
+    if (false) {}
+    MV2_SE_POOL_CASE(8, 1); MV2_SE_POOL_CASE(8, 2); MV2_SE_POOL_CASE(8, 4); MV2_SE_POOL_CASE(8, 8); MV2_SE_POOL_CASE(8, 16);
+    MV2_SE_POOL_CASE(8, 32); MV2_SE_POOL_CASE(16, 32); MV2_SE_POOL_CASE(32, 32);
+    else { set_error("se_pool: no kernel for C = %d", C); return MV2_E_UNSUPPORTED; }
+#undef MV2_SE_POOL_CASE
   } else if (dtype == MV2_BF16) launch_k(se_pool_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)y, P, C, wk, bk, (float*)workspace, nc);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
