@@ -25,7 +25,9 @@ for r in rows:
     if n == "gpu__time_duration.sum":
         v *= {"ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}.get(u, 1)
     per[i][n] = v
-order = order[len(order) // 2:]          # second step only
+# second step only: a step starts at its (single) ingest launch; everything before the last one is set-up + step 1
+starts = [k for k, i in enumerate(order) if per[i]["kernel"] == "ingest_kwpack_kernel"]
+order = order[starts[-1]:]
 TP = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"
 agg = collections.OrderedDict()
 for i in order:
