@@ -48,6 +48,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// Frames are enumerated most-expensive first: the B * (T - pt) frames that see all kt frame taps, then the frames
+// t = pt-1, pt-2, ..., 0 of every clip (their leading taps fall into the causal padding and are skipped, so their tiles
+// cost (kt-1)/kt ... 1/kt of a full one).  Together with the serpentine CTA assignment (slab_tile_of) a static schedule
+// then behaves like longest-processing-time-first list scheduling: with few tiles per CTA (C = 512 at T = 20: 320 tiles
+// for 148 CTAs) no CTA gets three full tiles while others get two.  Pure index arithmetic, so the tile id stays warp
+// uniform in the MMA-issuing warp (a schedule table read from memory does not: measured 5 % slower overall).
+__device__ __forceinline__ void slab_frame_of(const SlabParams& p, int slot, int& b, int& t) {
+  const int n_cheap = min(p.pt, p.T), n_full = p.T - n_cheap;
+  const int full_slots = p.B * n_full;
+  if (slot < full_slots) { b = slot / n_full; t = n_cheap + slot - b * n_full; }
+  else { const int r = slot - full_slots; const int level = r / p.B; b = r - level * p.B; t = n_cheap - 1 - level; }
+}
+// k-th tile of this CTA: waves alternate direction (serpentine) so the CTAs that finish a wave first start the next one first
+__device__ __forceinline__ int slab_tile_of(const SlabParams& p, int k) {
+  if (p.cluster > 1) { const int tile = blockIdx.x + k * gridDim.x; return tile < p.total_tiles ? tile : -1; }
+  const int tile = k * gridDim.x + ((k & 1) ? gridDim.x - 1 - blockIdx.x : blockIdx.x);
+  return tile < p.total_tiles ? tile : -1;
+}
+
 struct TileCoord { int b, t, h0, w0, n0; };
 __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) {
   TileCoord c;
@@ -61,8 +80,8 @@ __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) 
     th = tile % p.tiles_h; tile /= p.tiles_h;
     nt = tile % p.n_tiles_n; tile /= p.n_tiles_n;
   }
-  c.t = tile % p.T;
-  c.b = tile / p.T;
+  if (p.cluster == 1) slab_frame_of(p, tile, c.b, c.t);
+  else { c.t = tile % p.T; c.b = tile / p.T; }
   c.h0 = th * 16;
   c.w0 = tw * 8 * p.mw;
   c.n0 = nt * p.bn;
@@ -120,7 +139,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
     // ------------------------------ slab producer ------------------------------
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tk = 0, tile; (tile = slab_tile_of(p, tk)) >= 0; ++tk) {
         const TileCoord c = decode_tile(p, tile);
         const int dt0 = max(0, p.pt - c.t);
         for (int dt = dt0; dt < p.kt; ++dt)
@@ -137,7 +156,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
     // ------------------------------ weight producer ------------------------------
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tk = 0, tile; (tile = slab_tile_of(p, tk)) >= 0; ++tk) {
         const TileCoord c = decode_tile(p, tile);
         const int dt0 = max(0, p.pt - c.t);
         for (int dt = dt0; dt < p.kt; ++dt)
@@ -182,8 +201,15 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
       uint32_t t_idx = 0, t_par = 0;                               // TMEM accumulator ring
       int t_frame = -1, tile_in_frame = 0;
       const int tiles_per_frame = p.n_tiles_n * p.tiles_w * p.tiles_h;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int t_of_tile = (tile / tiles_per_frame) % p.T;      // once per tile (hundreds of taps)
+      // same sequence as slab_tile_of, written with plain induction variables: the compiler only keeps this warp's loop
+      // nest (descriptors, ring indices) in uniform registers when the tile id is an obviously uniform recurrence
+      const int fwd = blockIdx.x, rev = p.cluster == 1 ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
+      for (int tk = 0, base = 0;; ++tk, base += gridDim.x) {
+        const int tile = base + ((tk & 1) ? rev : fwd);
+        if (tile >= p.total_tiles) break;
+        int b_of_tile, t_of_tile;                                  // once per tile (hundreds of taps)
+        if (p.cluster == 1) slab_frame_of(p, tile / tiles_per_frame, b_of_tile, t_of_tile);
+        else t_of_tile = (tile / tiles_per_frame) % p.T;
         const int dt0 = max(0, p.pt - t_of_tile);
         mbar_wait(t_empty + 8 * t_idx, t_par ^ 1);
         tc_fence_after();
@@ -238,7 +264,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
     const int row = sub * 32 + lane;
     const int lh = row >> 3, lw = row & 7;
     uint32_t buf = 0, bpar = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tk = 0, tile; (tile = slab_tile_of(p, tk)) >= 0; ++tk) {
       const TileCoord c = decode_tile(p, tile);
       mbar_wait(t_full + 8 * buf, bpar);
       tc_fence_after();
@@ -331,7 +357,7 @@ using namespace mv2;
 // efficiency for a full wave.  The choice comes from a small makespan model calibrated on profiles/r01_sweep_ragged.json:
 //   tile cost  = live frame taps(t) * kchunks * kh*kw * mw * 4 MMAs * max(bn/2, 1.28 * (32 + bn/4)) cycles
 //                (tensor pipe vs the shared-memory operand bandwidth of one 128 x bn x 16 MMA) + per-tile overhead,
-//   assignment = the kernel's static round robin (tile i -> CTA i mod grid), tiles ordered n, w, h, t, b.
+//   assignment = the kernel's static schedule (slab_frame_of / slab_tile_of: cost-sorted frames, serpentine over the CTAs).
 // A ragged candidate must beat the power-of-two default by 8 % in the model; results are cached per layer shape.
 static double slab_model_cycles(const mv2_tc_conv_args* a, int n_sm, int mw, int bn) {
   const int tiles_per_frame = ceil_div(a->Ho, 16) * ceil_div(a->Wo, 8 * mw) * ceil_div(a->Co, bn);
@@ -342,12 +368,17 @@ static double slab_model_cycles(const mv2_tc_conv_args* a, int n_sm, int mw, int
   const int G = (int)std::min<int64_t>(total, n_sm);
   std::vector<double> load(G, 0.0);
   int64_t idx = 0;
-  for (int b = 0; b < a->B; ++b)
-    for (int t = 0; t < a->To; ++t) {
-      const int live = a->kt - std::max(0, a->pt - t);
-      const double cost = live * per_tap_frame + fixed;
-      for (int i = 0; i < tiles_per_frame; ++i, ++idx) load[idx % G] += cost;
+  // same enumeration as the kernel: full-cost frames first, then t = pt-1 ... 0 of every clip; serpentine over the CTAs
+  const int n_cheap = std::min(a->pt, a->To), n_full = a->To - n_cheap;
+  auto deal = [&](int frames, int live) {
+    const double cost = live * per_tap_frame + fixed;
+    for (int64_t i = 0; i < (int64_t)frames * tiles_per_frame; ++i, ++idx) {
+      const int64_t k = idx / G, pos = idx % G;
+      load[(k & 1) ? G - 1 - pos : pos] += cost;
     }
+  };
+  deal(a->B * n_full, a->kt);
+  for (int level = 0; level < n_cheap; ++level) deal(a->B, a->kt - (a->pt - (n_cheap - 1 - level)));
   return *std::max_element(load.begin(), load.end());
 }
 
