@@ -199,7 +199,6 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
       uint32_t s_idx = 0, s_par = 0;                               // slab ring
       uint32_t w_idx = 0, w_par = 0, b_lo = b_lo0;                 // weight ring
       uint32_t t_idx = 0, t_par = 0;                               // TMEM accumulator ring
-      int t_frame = -1, tile_in_frame = 0;
       const int tiles_per_frame = p.n_tiles_n * p.tiles_w * p.tiles_h;
       // same sequence as slab_tile_of, written with plain induction variables: the compiler only keeps this warp's loop
       // nest (descriptors, ring indices) in uniform registers when the tile id is an obviously uniform recurrence
@@ -255,7 +254,6 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         if (leader) umma_commit(t_full + 8 * t_idx);
         if (++t_idx == (uint32_t)p.nbuf) { t_idx = 0; t_par ^= 1; }
       }
-      (void)t_frame; (void)tile_in_frame;
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
