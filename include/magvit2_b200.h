@@ -210,6 +210,13 @@ int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream);
  * accumulators.  Requirements (mv2_tc_slab_supported): stride 1, Ci % 64 == 0, Co % 32 == 0, no shuffle.   */
 int mv2_tc_slab_supported(const mv2_tc_conv_args* a);
 int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream);
+/* Launch plan of mv2_tc_slab_forward for a layer shape on a device with n_sm SMs -- pure host arithmetic (no CUDA call,
+ * the pointers in `a` are not dereferenced), exposed so the tiling rule and the static tile schedule can be checked
+ * without a GPU.  mv2_tc_slab_plan: out6 = {M-tiles per weight tile (mw), N tile width (bn), N tiles, total tiles,
+ * grid size, TMEM accumulator buffers}.  mv2_tc_slab_tile: the k-th tile that persistent CTA `cta` processes:
+ * out6 = {tile id or -1 when the CTA has no k-th tile, clip b, frame t, h0, w0, first output column n0}. */
+int mv2_tc_slab_plan(const mv2_tc_conv_args* a, int n_sm, int* out6);
+int mv2_tc_slab_tile(const mv2_tc_conv_args* a, int n_sm, int cta, int k, int* out6);
 
 #ifdef __cplusplus
 }

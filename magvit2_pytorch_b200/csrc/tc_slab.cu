@@ -54,21 +54,23 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // then behaves like longest-processing-time-first list scheduling: with few tiles per CTA (C = 512 at T = 20: 320 tiles
 // for 148 CTAs) no CTA gets three full tiles while others get two.  Pure index arithmetic, so the tile id stays warp
 // uniform in the MMA-issuing warp (a schedule table read from memory does not: measured 5 % slower overall).
-__device__ __forceinline__ void slab_frame_of(const SlabParams& p, int slot, int& b, int& t) {
-  const int n_cheap = min(p.pt, p.T), n_full = p.T - n_cheap;
+__host__ __device__ __forceinline__ void slab_frame_of(const SlabParams& p, int slot, int& b, int& t) {
+  const int n_cheap = p.pt < p.T ? p.pt : p.T, n_full = p.T - n_cheap;
   const int full_slots = p.B * n_full;
   if (slot < full_slots) { b = slot / n_full; t = n_cheap + slot - b * n_full; }
   else { const int r = slot - full_slots; const int level = r / p.B; b = r - level * p.B; t = n_cheap - 1 - level; }
 }
-// k-th tile of this CTA: waves alternate direction (serpentine) so the CTAs that finish a wave first start the next one first
-__device__ __forceinline__ int slab_tile_of(const SlabParams& p, int k) {
-  if (p.cluster > 1) { const int tile = blockIdx.x + k * gridDim.x; return tile < p.total_tiles ? tile : -1; }
-  const int tile = k * gridDim.x + ((k & 1) ? gridDim.x - 1 - blockIdx.x : blockIdx.x);
+// k-th tile of CTA `cta` of `grid`: waves alternate direction (serpentine) so the CTAs that finish a wave first start the
+// next one first.  (mv2_tc_slab_tile exposes the same function to the host-side tests.)
+__host__ __device__ __forceinline__ int slab_tile_of_cta(const SlabParams& p, int k, int cta, int grid) {
+  if (p.cluster > 1) { const int tile = cta + k * grid; return tile < p.total_tiles ? tile : -1; }
+  const int tile = k * grid + ((k & 1) ? grid - 1 - cta : cta);
   return tile < p.total_tiles ? tile : -1;
 }
+__device__ __forceinline__ int slab_tile_of(const SlabParams& p, int k) { return slab_tile_of_cta(p, k, blockIdx.x, gridDim.x); }
 
 struct TileCoord { int b, t, h0, w0, n0; };
-__device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) {
+__host__ __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, int tile) {
   TileCoord c;
   int nt, tw, th;
   if (p.cluster == 1) {      // n-tile fastest: CTAs running side by side share the activation slab through L2
@@ -422,16 +424,9 @@ extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
   return 1;
 }
 
-extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
-  MV2_CHECK_ARG(a && a->x && a->w && a->y);
-  if (!mv2_tc_slab_supported(a)) { set_error("mv2_tc_slab_forward: unsupported shape"); return MV2_E_UNSUPPORTED; }
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MV2_E_CUDA; }
-  int dev = 0, n_sm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-
-  SlabParams p;
+// Everything the launch derives from the layer shape alone (tiling, ring depths, tile count): pure host arithmetic, no
+// CUDA calls -- also reachable through mv2_tc_slab_plan / mv2_tc_slab_tile for the CPU-side tests.
+static int slab_fill_plan(const mv2_tc_conv_args* a, int n_sm, SlabParams& p, int* bk_out, int* w_bytes_out, int* co_pad_out, int* nb_pad_out) {
   memset(&p, 0, sizeof(p));
   p.kt = a->kt; p.kh = a->kh; p.kw = a->kw; p.pt = a->pt; p.ph = a->ph; p.pw = a->pw;
   p.row_bytes = (a->Ci % 64 == 0) ? 128 : 64;
@@ -501,6 +496,57 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   if (p.w_stages < 2 && p.slab_stages > 2) { p.slab_stages = 2; p.w_stages = std::min(12, (budget - 2 * p.slab_stride) / w_bytes); }
   MV2_CHECK_ARG(p.w_stages >= 2);
 
+  *bk_out = bk; *w_bytes_out = w_bytes; *co_pad_out = co_pad; *nb_pad_out = nb_pad;
+  return MV2_OK;
+}
+
+extern "C" int mv2_tc_slab_plan(const mv2_tc_conv_args* a, int n_sm, int* out6) {
+  MV2_CHECK_ARG(a && out6 && n_sm > 0);
+  if (!mv2_tc_slab_supported(a)) { set_error("mv2_tc_slab_plan: unsupported shape"); return MV2_E_UNSUPPORTED; }
+  SlabParams p;
+  int bk, w_bytes, co_pad, nb_pad;
+  const int rc = slab_fill_plan(a, n_sm, p, &bk, &w_bytes, &co_pad, &nb_pad);
+  if (rc != MV2_OK) return rc;
+  int grid = std::min(p.total_tiles, n_sm);
+  if (p.cluster > 1) grid &= ~1;
+  out6[0] = p.mw; out6[1] = p.bn; out6[2] = p.n_tiles_n; out6[3] = p.total_tiles; out6[4] = grid; out6[5] = p.nbuf;
+  return MV2_OK;
+}
+
+extern "C" int mv2_tc_slab_tile(const mv2_tc_conv_args* a, int n_sm, int cta, int k, int* out6) {
+  MV2_CHECK_ARG(a && out6 && n_sm > 0 && cta >= 0 && k >= 0);
+  if (!mv2_tc_slab_supported(a)) { set_error("mv2_tc_slab_tile: unsupported shape"); return MV2_E_UNSUPPORTED; }
+  SlabParams p;
+  int bk, w_bytes, co_pad, nb_pad;
+  const int rc = slab_fill_plan(a, n_sm, p, &bk, &w_bytes, &co_pad, &nb_pad);
+  if (rc != MV2_OK) return rc;
+  int grid = std::min(p.total_tiles, n_sm);
+  if (p.cluster > 1) grid &= ~1;
+  MV2_CHECK_ARG(cta < grid);
+  const int tile = slab_tile_of_cta(p, k, cta, grid);
+  out6[0] = tile;                                // -1: this CTA has no k-th tile
+  if (tile >= 0) {
+    const TileCoord c = decode_tile(p, tile);
+    out6[1] = c.b; out6[2] = c.t; out6[3] = c.h0; out6[4] = c.w0; out6[5] = c.n0;
+  }
+  return MV2_OK;
+}
+
+extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
+  MV2_CHECK_ARG(a && a->x && a->w && a->y);
+  if (!mv2_tc_slab_supported(a)) { set_error("mv2_tc_slab_forward: unsupported shape"); return MV2_E_UNSUPPORTED; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MV2_E_CUDA; }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+
+  SlabParams p;
+  int bk, w_bytes, co_pad, nb_pad;
+  {
+    const int rc = slab_fill_plan(a, n_sm, p, &bk, &w_bytes, &co_pad, &nb_pad);
+    if (rc != MV2_OK) return rc;
+  }
   const CUtensorMapSwizzle swz = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   {
     const int64_t C = a->Ci, W = a->Wi, H = a->Hi, T = a->Ti;
