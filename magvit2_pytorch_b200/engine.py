@@ -272,11 +272,10 @@ class Engine:
                             B=B, Ti=Ti, Hi=Hi, Wi=Wi, Ci=Ci, To=To, Ho=Ho, Wo=Wo, Co=co_gemm,
                             kt=kt, kh=kh, kw=kw, st=stride[0], sh=stride[1], sw=stride[2],
                             pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle, epi_mode=pk.epi_mode)
+            # measured policy (profiles/r01_sweep_slab_v*.json): the persistent slab kernel wins on every layer it supports
+            # (incl. the 64-byte-row conv_in once it runs 4 M-tiles and 7 taps per weight stage); the tap-wise kernel
+            # keeps the strided down-samplers.  tc_variant = "tap" forces the tap-wise kernel (tests / sweeps).
             use_slab = self.tc_variant != "tap" and bool(self.lib.mv2_tc_slab_supported(C.byref(ta)))
-            if use_slab and self.tc_variant == "auto":
-                # measured policy (profiles/r01_sweep_slab_v*.json): the persistent slab kernel wins on every layer it
-                # supports (incl. the 64-byte-row conv_in once it runs 4 M-tiles and 7 taps per weight stage)
-                pass
             if use_slab or self.lib.mv2_tc_conv_supported(C.byref(ta)):
                 if self._prof is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
