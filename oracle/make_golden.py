@@ -46,6 +46,11 @@ CONFIGS = {
     # BASELINE.json configs[1] (README), one clip
     "readme": dict(kwargs=dict(image_size=128, init_dim=64, max_dim=512, codebook_size=1024, layers=README_LAYERS),
                    video=(1, 3, 17, 128, 128), wseed=0, vseed=1234, full=False, cs=16, ss=8),
+    # the one conditioned layer type that runs in the reference (cond_residual = ResidualUnitMod /
+    # Conv3DMod, M:680-753, M:946-988).  Conditioned layers must be the trailing ones (has_cond is never reset, M:1153).
+    "mini_cond": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, dim_cond=12,
+                                  layers=("residual", "compress_space", "compress_time", "cond_residual", "cond_residual")),
+                      video=(2, 3, 5, 32, 32), wseed=0, vseed=1249, cseed=77, full=True),   # vseed chosen for min |pre-sign| = 2.3e-4
 }
 
 
@@ -83,14 +88,21 @@ def make(name: str):
 
     hooks.append(model.quantizers.project_in.register_forward_hook(grab_proj))
 
+    cond = None
+    if kwargs.get("dim_cond") is not None:
+        g = torch.Generator(device="cpu")
+        g.manual_seed(cfg["cseed"])
+        cond = torch.randn(cfg["video"][0], kwargs["dim_cond"], generator=g)
+        hooks.append(model.encoder_cond_in.register_forward_hook(lambda m, i, o: taps.__setitem__("enc_cond_in", o.detach().clone())))
     t0 = time.time()
     with torch.no_grad():
-        codes = model.tokenize(video)
+        # tokenize() does not forward ``cond`` (M:1651-1654): conditioned specs use forward(return_codes=True)
+        codes = model.tokenize(video) if cond is None else model(video, cond=cond, return_codes=True)
         t1 = time.time()
-        recon = model.decode_from_code_indices(codes)
+        recon = model.decode_from_code_indices(codes, cond=cond)
         t2 = time.time()
         # README.md:85-90 round-trip statement
-        recon_fwd = model(video, return_recon=True)
+        recon_fwd = model(video, cond=cond, return_recon=True)
     assert torch.equal(recon, recon_fwd), "reference round-trip (README.md:87-90) does not hold"
     for h in hooks:
         h.remove()
@@ -108,6 +120,11 @@ def make(name: str):
         recon_mean=recon.mean(dim=(3, 4)).clone(),
         ref_seconds=dict(tokenize=t1 - t0, decode=t2 - t1),
         torch_version=torch.__version__,
+        cond=cond,
+        # generator state_dict layout of the reference (key -> shape; integer buffers by value): lets a checker rebuild the
+        # synthetic weights (oracle/weights.py) for specs the product does not construct yet
+        sd_shapes={k: tuple(v.shape) for k, v in model.state_dict().items() if W.is_generator_key(k) and v.is_floating_point()},
+        sd_buffers={k: v.clone() for k, v in model.state_dict().items() if W.is_generator_key(k) and not v.is_floating_point()},
         reference_commit="a00519fa (v0.5.1)",
         third_party="oracle/shims (restated LFQ/FSQ/TaylorSeriesLinearAttn; real packages unavailable)",
     )

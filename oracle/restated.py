@@ -36,7 +36,7 @@ import torch.nn.functional as F
 
 @dataclass
 class Stage:
-    kind: str                 # residual | compress_space | compress_time | attend_space | linear_attend_space | attend_time
+    kind: str                 # residual | cond_residual | compress_space | compress_time | attend_space | linear_attend_space | attend_time
     dim: int
     dim_out: int
     count: int = 1            # consecutive residual units
@@ -56,6 +56,8 @@ def schedule(layers, init_dim, max_dim) -> Tuple[List[Stage], int, int]:
             stages.append(Stage("residual", dim, dim, 1, False))
         elif kind == "consecutive_residual":
             stages.append(Stage("residual", dim, dim, int(params[0]), True))
+        elif kind == "cond_residual":                                   # M:1150-1157
+            stages.append(Stage("cond_residual", dim, dim))
         elif kind in ("compress_space", "compress_time"):
             dim_out = params[0] if len(params) > 0 else dim * 2      # M:1160-1162
             dim_out = int(min(dim_out, max_dim))
@@ -107,6 +109,30 @@ def residual_unit(x, sd, p):
     y = F.elu(causal_conv3d(x, sd[p + "fn.0.conv.weight"], sd[p + "fn.0.conv.bias"]))
     y = F.elu(F.conv3d(y, sd[p + "fn.2.weight"], sd[p + "fn.2.bias"]))
     y = squeeze_excite(y, sd, p + "fn.4.")
+    return y + x
+
+
+def conv3d_mod(x, cond, w, eps=1e-8):
+    """Conv3DMod.forward (M:718-753), StyleGAN2-style modulated causal conv, demod=True, zero padding.
+    x (B,C,T,H,W), cond (B,C) already through the unit's ``to_cond``; w (O,I,kt,kh,kw) shared by the batch.
+    Per-sample weights w_b = w * (cond_b + 1) over the input channels, demodulated by rsqrt(sum w_b^2) per output
+    channel (clamped at eps), applied as one grouped conv over the batch (groups = B) -- restated literally."""
+    b = x.shape[0]
+    o, i, kt, kh, kw = w.shape
+    wb = w[None] * (cond[:, None, :, None, None, None] + 1.)                                  # M:736-738
+    inv_norm = (wb ** 2).sum(dim=(2, 3, 4, 5), keepdim=True).clamp(min=eps).rsqrt()          # M:741
+    wb = wb * inv_norm                                                                        # M:742
+    xg = x.reshape(1, b * i, *x.shape[2:])                                                    # M:744
+    xg = F.pad(xg, (kw // 2, kw // 2, kh // 2, kh // 2, kt - 1, 0))                           # M:708-709, M:748 ('zeros' == constant 0)
+    y = F.conv3d(xg, wb.reshape(b * o, i, kt, kh, kw), groups=b)                              # M:746-749
+    return y.reshape(b, o, *y.shape[2:])                                                      # M:751
+
+
+def residual_unit_mod(x, cond, sd, p):
+    """ResidualUnitMod.forward (M:978-988): x + ELU(Conv1x1x1(ELU(Conv3DMod(x, to_cond(cond))))).  No SqueezeExcite."""
+    c = F.linear(cond, sd[p + "to_cond.weight"], sd[p + "to_cond.bias"])                      # M:983
+    y = F.elu(conv3d_mod(x, c, sd[p + "conv.weights"]))                                       # M:985-986
+    y = F.elu(F.conv3d(y, sd[p + "conv_out.weight"], sd[p + "conv_out.bias"]))                # M:987-988
     return y + x
 
 
@@ -357,7 +383,8 @@ class OracleTokenizer:
                  codebook_size=None, channels=3, init_dim=64, max_dim=float("inf"),
                  use_fsq=False, fsq_levels=None, attn_dim_head=32, attn_heads=8,
                  linear_attn_dim_head=8, linear_attn_heads=16, pad_mode="constant",
-                 lfq_soft_clamp_input_value=10., dtype=torch.float32, **unused):
+                 lfq_soft_clamp_input_value=10., dim_cond=None, dim_cond_expansion_factor=4.,
+                 dtype=torch.float32, **unused):
         self.dtype = dtype
         self.sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in state_dict.items()
                    if not k.startswith("discr.")}
@@ -374,11 +401,30 @@ class OracleTokenizer:
         self.pad_mode = pad_mode
         self.clamp = lfq_soft_clamp_input_value
         self.channels = channels
+        # conditioning (M:1134-1153, M:1318, M:1336-1352): ``has_cond`` is set by the first cond layer and never reset, so
+        # every later layer is called with ``cond=`` too -- the reference's plain layers then raise TypeError.  Only specs
+        # whose conditioned layers are the trailing ones run in the reference; anything else is rejected here as well.
+        kinds = [st.kind for st in self.stages]
+        self.has_cond = "cond_residual" in kinds
+        if self.has_cond:
+            first = kinds.index("cond_residual")
+            if any(k != "cond_residual" for k in kinds[first:]):
+                raise TypeError("a non-conditioned layer after a cond_* layer receives cond= in the reference (M:1153, M:1318) and fails")
+            assert dim_cond is not None, "dim_cond must be passed into VideoTokenizer, if tokenizer is to be conditioned"   # M:1151
+        self.dim_cond = dim_cond
+
+    def _cond_in(self, cond, which):
+        """encoder_cond_in / decoder_cond_in (M:1344-1352): Linear + SiLU stem."""
+        assert cond is not None, "`cond` must be passed into tokenizer forward method since conditionable layers were specified"  # M:1542
+        assert tuple(cond.shape[1:]) == (self.dim_cond,)                                     # M:1545
+        return F.silu(F.linear(cond.to(self.dtype), self.sd[f"{which}_cond_in.0.weight"], self.sd[f"{which}_cond_in.0.bias"]))
 
     # one encoder/decoder stage --------------------------------------------------
-    def _apply(self, x, st: Stage, p: str, decoder: bool, taps=None):
+    def _apply(self, x, st: Stage, p: str, decoder: bool, taps=None, cond=None):
         sd = self.sd
-        if st.kind == "residual":
+        if st.kind == "cond_residual":
+            x = residual_unit_mod(x, cond, sd, p)
+        elif st.kind == "residual":
             if st.nested:
                 for j in range(st.count):
                     x = residual_unit(x, sd, f"{p}{j}.")
@@ -402,7 +448,7 @@ class OracleTokenizer:
         return x
 
     @torch.no_grad()
-    def encode(self, video, taps=None):
+    def encode(self, video, taps=None, cond=None):
         """VideoTokenizer.encode (M:1523-1576).  NB the final LayerNorm (M:1322-1326) is never
         executed: zip() with has_cond_across_layers truncates it (M:1565)."""
         x = video.to(self.dtype)
@@ -410,20 +456,22 @@ class OracleTokenizer:
         x = causal_conv3d(x, self.sd["conv_in.conv.weight"], self.sd["conv_in.conv.bias"], self.pad_mode)
         if taps is not None:
             taps["conv_in"] = x
+        c = self._cond_in(cond, "encoder") if self.has_cond else None               # M:1544-1548
         for i, st in enumerate(self.stages):
-            x = self._apply(x, st, f"encoder_layers.{i}.", decoder=False)
+            x = self._apply(x, st, f"encoder_layers.{i}.", decoder=False, cond=c)
             if taps is not None:
                 taps[f"enc{i}"] = x
         return x
 
     @torch.no_grad()
-    def decode(self, quantized, taps=None):
+    def decode(self, quantized, taps=None, cond=None):
         """VideoTokenizer.decode (M:1598-1649): decoder layers are the encoder's in reverse
         (insert(0), M:1315); conv_out; drop the first time_padding frames (M:1646-1647)."""
         x = quantized.to(self.dtype)
         n = len(self.stages)
+        c = self._cond_in(cond, "decoder") if self.has_cond else None               # M:1612-1616
         for j, st in enumerate(reversed(self.stages)):
-            x = self._apply(x, st, f"decoder_layers.{j}.", decoder=True)
+            x = self._apply(x, st, f"decoder_layers.{j}.", decoder=True, cond=c)
             if taps is not None:
                 taps[f"dec{j}"] = x
         x = causal_conv3d(x, self.sd["conv_out.conv.weight"], self.sd["conv_out.conv.bias"], self.pad_mode)
@@ -444,15 +492,16 @@ class OracleTokenizer:
         return video
 
     @torch.no_grad()
-    def tokenize(self, video, taps=None, return_presign=False):
-        """VideoTokenizer.tokenize (M:1651-1654) = forward(return_codes=True) (M:1695-1708)."""
+    def tokenize(self, video, taps=None, return_presign=False, cond=None):
+        """VideoTokenizer.tokenize (M:1651-1654) = forward(return_codes=True) (M:1695-1708).  NB the reference's
+        tokenize() does not forward ``cond``; conditioned specs go through forward(video, cond, return_codes=True)."""
         video = self._check_video(video)
-        x = self.encode(video, taps)
+        x = self.encode(video, taps, cond=cond)
         _, idx, pre = self.quantize(x)
         return (idx, pre) if return_presign else idx
 
     @torch.no_grad()
-    def decode_from_code_indices(self, codes, taps=None):
+    def decode_from_code_indices(self, codes, taps=None, cond=None):
         """M:1579-1595: flat (b, f*h*w) ids are un-flattened with the fmap size."""
         assert codes.dtype in (torch.long, torch.int32)
         if codes.ndim == 2:
@@ -462,17 +511,17 @@ class OracleTokenizer:
             q = fsq_indices_to_codes(codes, self.sd, self.fsq_levels, self.dtype)
         else:
             q = lfq_indices_to_codes(codes, self.sd, self.dtype)
-        return self.decode(q, taps)
+        return self.decode(q, taps, cond=cond)
 
     @torch.no_grad()
-    def forward(self, video, return_codes=False, return_recon=False):
-        """forward up to M:1720 (inference returns only)."""
+    def forward(self, video, return_codes=False, return_recon=False, cond=None):
+        """forward up to M:1720 (inference returns only); ``cond`` reaches encode and decode (M:1695, M:1710)."""
         video = self._check_video(video)
-        x = self.encode(video)
+        x = self.encode(video, cond=cond)
         q, idx, _ = self.quantize(x)
         if return_codes and not return_recon:
             return idx
-        rec = self.decode(q)
+        rec = self.decode(q, cond=cond)
         if return_codes:
             return idx, rec
         return rec

@@ -4,7 +4,8 @@ behavioural properties SURVEY.md section 4 lists.  CPU only."""
 import pytest
 import torch
 
-from tests.util import build_oracle, build_product, golden_video, load_golden, sample_like_golden
+from tests.util import (build_oracle, build_oracle_from_golden, build_product, golden_video, load_golden,
+                        sample_like_golden)
 
 SMALL = ["cfg1", "mini", "mini_fsq"]
 
@@ -43,6 +44,60 @@ def test_restated_matches_reference_golden_readme():
     recon = orc.decode_from_code_indices(codes)
     assert torch.allclose(recon[:, :, :, ::4, ::4], g["recon_sample"], atol=5e-5, rtol=1e-5)
     assert torch.allclose(recon.mean(dim=(3, 4)), g["recon_mean"], atol=1e-5)
+
+
+def test_restated_cond_residual_matches_reference_golden():
+    """SURVEY 8f N1 groundwork: the conditioned residual unit (ResidualUnitMod / Conv3DMod, M:680-753, M:946-988) and the
+    conditioning stems (M:1344-1352), pinned to the reference before any kernel is written for it."""
+    g = load_golden("mini_cond")
+    orc = build_oracle_from_golden(g)
+    video, cond = golden_video(g), g["cond"]
+    taps = {}
+    codes = orc.tokenize(video, taps=taps, cond=cond)
+    assert torch.equal(codes, g["codes"])
+    for k, ref in g["taps"].items():
+        if k.startswith("enc") and k != "enc_cond_in":
+            assert torch.allclose(sample_like_golden(taps[k], g), ref, atol=2e-5, rtol=1e-5), k
+    assert torch.allclose(orc._cond_in(cond, "encoder"), g["taps"]["enc_cond_in"], atol=1e-6)
+    dtaps = {}
+    recon = orc.decode_from_code_indices(codes, taps=dtaps, cond=cond)
+    assert torch.allclose(recon, g["recon"], atol=2e-5, rtol=1e-5)
+    for k, ref in g["taps"].items():
+        if k.startswith("dec"):
+            assert torch.allclose(sample_like_golden(dtaps[k], g), ref, atol=2e-5, rtol=1e-5), k
+    assert torch.equal(orc.forward(video, return_recon=True, cond=cond), recon)          # README.md:85-90 with cond
+    # the modulation really depends on cond, per clip
+    other = orc.tokenize(video, cond=cond.flip(0))
+    assert not torch.equal(other, codes)
+    with pytest.raises(AssertionError):
+        orc.tokenize(video)                                                           # M:1542
+
+
+def test_modulated_conv_factorises_into_shared_weight_conv():
+    """The mapping the B200 path will use for Conv3DMod (M:736-751): per-clip weights w * (cond + 1) * inv_norm never need
+    to be materialised --  y[b, o] = inv_norm[b, o] * conv(x[b] * (cond[b] + 1), w)[o]  with
+    inv_norm[b, o] = rsqrt(max(sum_i (cond[b, i] + 1)^2 * S[o, i], eps)),  S[o, i] = sum_taps w[o, i, :]^2 --
+    i.e. the shared-weight causal conv with a per-(clip, channel) input scale and a per-(clip, channel) output scale."""
+    from oracle.restated import causal_conv3d, conv3d_mod
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 8, 4, 6, 6, generator=g)
+    cond = torch.randn(3, 8, generator=g)
+    w = torch.randn(16, 8, 3, 3, 3, generator=g)
+    ref = conv3d_mod(x, cond, w)
+    S = (w ** 2).sum(dim=(2, 3, 4))                                             # (O, I)
+    inv_norm = (((cond + 1.) ** 2) @ S.t()).clamp(min=1e-8).rsqrt()             # (B, O)
+    got = causal_conv3d(x * (cond + 1.)[:, :, None, None, None], w, None) * inv_norm[:, :, None, None, None]
+    assert torch.allclose(got, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_cond_layers_must_be_trailing_like_in_the_reference():
+    """has_cond is never reset (M:1153, M:1318): a plain layer after a cond layer gets cond= and raises in the reference."""
+    from oracle.restated import OracleTokenizer
+    with pytest.raises(TypeError):
+        OracleTokenizer({}, image_size=32, init_dim=16, codebook_size=1024, dim_cond=8,
+                        layers=("cond_residual", "residual"))
+    with pytest.raises(NotImplementedError):
+        build_product(dict(image_size=32, init_dim=16, codebook_size=1024, dim_cond=8, layers=("residual", "cond_residual")))
 
 
 def test_readme_roundtrip_property():

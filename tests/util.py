@@ -36,6 +36,14 @@ def build_oracle(model, kwargs, dtype=torch.float32):
     return OracleTokenizer(sd, dtype=dtype, **kwargs)
 
 
+def build_oracle_from_golden(g, dtype=torch.float32):
+    """Oracle for a golden whose spec the product does not construct (conditioned layers): the reference's state_dict
+    layout is stored in the golden, the synthetic weights are rebuilt from it."""
+    sd = {k: W.synth_tensor(k, shp, g["wseed"]) for k, shp in g["sd_shapes"].items()}
+    sd.update({k: v.clone() for k, v in g["sd_buffers"].items()})
+    return OracleTokenizer(sd, dtype=dtype, **g["kwargs"])
+
+
 def golden_video(g):
     b, c, t, s = g["video_shape"][:4]
     return W.synth_video(b, c, t, s, seed=g["vseed"])
