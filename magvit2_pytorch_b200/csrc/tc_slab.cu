@@ -9,12 +9,17 @@
 //     simply started (dh*pitch + dw) rows further into the slab (128-byte rows, hardware SWIZZLE_128B is a
 //     function of the absolute smem address, so row-shifted starts stay consistent with what TMA wrote;
 //     8-row core groups are 8 consecutive w positions, group stride (SBO) = slab row pitch);
-//   * a macro tile is mw (1|2) M-tiles of 16(h) x 8(w) positions side by side; both M-tiles consume the same
-//     weight tile from smem (two accumulators in TMEM), halving weight traffic;
-//   * CTAs are persistent (static round-robin over macro tiles), accumulators are double-buffered in TMEM
-//     when they fit (2 * mw * BN <= 512 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
-//   * causal frames in front of the clip (t + dt - pt < 0) are all-zero and are skipped outright.
-// Warp roles (256 threads): w0 slab TMA producer, w1 MMA issuer (+TMEM alloc), w2 weight TMA producer,
+//   * a macro tile is mw (1|2|4) M-tiles of 16(h) x 8(w) positions side by side; all of them consume the same
+//     weight tile from smem (mw accumulators in TMEM), dividing weight traffic by mw;
+//   * CTAs are persistent with a static, cost-sorted serpentine tile schedule (slab_frame_of / slab_tile_of);
+//     accumulators are double-buffered in TMEM when they fit (2 * mw * BN <= 512 columns) so the epilogue of
+//     tile i overlaps the MMAs of tile i+1;
+//   * causal frames in front of the clip (t + dt - pt < 0) are all-zero and are skipped outright;
+//   * N tiles need not divide Co (plain / GEGLU epilogues guard every stored column): deep wide layers choose
+//     their tile width with a makespan model (choose_ragged_tiles);
+//   * the kernel is instantiated per epilogue flavour (tc_common.cuh: EPI_*); the plain flavour transposes each
+//     32 x 32 chunk through shared memory so stores / residual loads are 64-byte contiguous per row.
+// Warp roles (384 threads): w0 slab TMA producer, w1 MMA issuer (+TMEM alloc), w2 weight TMA producer,
 // w4-11 epilogue (TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the column chunks).
 #include "common.cuh"
 #include "tc_common.cuh"
