@@ -49,3 +49,27 @@ def test_sass_is_sm100a():
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_tcgen05_issue_loops_stay_in_uniform_registers():
+    """Regression guard for the single most expensive lesson of the slab kernel: the warp that issues tcgen05.mma must
+    keep its loop nest (descriptors, ring indices, predicates) in uniform registers.  When the compiler cannot prove the
+    tile id / trip counts warp-uniform it re-materialises them with R2UR right in front of every UTCHMMA, which cost
+    5-8 % on every layer (profiles/r01_bench_v29.json vs the table-driven schedule).  Static check on the SASS."""
+    import re
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    kernels = re.split(r"\n\s*Function : ", sass)[1:]
+    checked = 0
+    for k in kernels:
+        name = k.split("\n", 1)[0]
+        if "tc_slab_kernel" not in name and "tc_conv_kernel" not in name:
+            continue
+        ins = [l for l in k.splitlines() if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l)]
+        mma = [i for i, l in enumerate(ins) if "UTCHMMA" in l]
+        assert mma, f"{name}: no tcgen05.mma (UTCHMMA) in the SASS"
+        window = ins[max(0, mma[0] - 45):mma[0]]
+        assert not any("R2UR" in l for l in window), f"{name}: MMA operands are converted from vector registers per issue"
+        assert any("UTMALDG" in l for l in ins), f"{name}: no TMA tensor loads (UTMALDG)"
+        checked += 1
+    assert checked >= 6          # 4 slab + >= 2 tap-kernel epilogue flavours
