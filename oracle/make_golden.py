@@ -51,6 +51,10 @@ CONFIGS = {
     "mini_cond": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, dim_cond=12,
                                   layers=("residual", "compress_space", "compress_time", "cond_residual", "cond_residual")),
                       video=(2, 3, 5, 32, 32), wseed=0, vseed=1249, cseed=77, full=True),   # vseed chosen for min |pre-sign| = 2.3e-4
+    # separate_first_frame_encoding (M:1113-1120, M:1553-1561, M:1633-1639)
+    "mini_sff": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, separate_first_frame_encoding=True,
+                                 layers=("residual", "compress_space", "compress_time", "residual")),
+                     video=(2, 3, 5, 32, 32), wseed=0, vseed=1234, full=True),
 }
 
 

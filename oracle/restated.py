@@ -384,7 +384,7 @@ class OracleTokenizer:
                  use_fsq=False, fsq_levels=None, attn_dim_head=32, attn_heads=8,
                  linear_attn_dim_head=8, linear_attn_heads=16, pad_mode="constant",
                  lfq_soft_clamp_input_value=10., dim_cond=None, dim_cond_expansion_factor=4.,
-                 dtype=torch.float32, **unused):
+                 separate_first_frame_encoding=False, dtype=torch.float32, **unused):
         self.dtype = dtype
         self.sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in state_dict.items()
                    if not k.startswith("discr.")}
@@ -412,6 +412,7 @@ class OracleTokenizer:
                 raise TypeError("a non-conditioned layer after a cond_* layer receives cond= in the reference (M:1153, M:1318) and fails")
             assert dim_cond is not None, "dim_cond must be passed into VideoTokenizer, if tokenizer is to be conditioned"   # M:1151
         self.dim_cond = dim_cond
+        self.sep_first = bool(separate_first_frame_encoding)                     # M:1113-1120
 
     def _cond_in(self, cond, which):
         """encoder_cond_in / decoder_cond_in (M:1344-1352): Linear + SiLU stem."""
@@ -452,8 +453,18 @@ class OracleTokenizer:
         """VideoTokenizer.encode (M:1523-1576).  NB the final LayerNorm (M:1322-1326) is never
         executed: zip() with has_cond_across_layers truncates it (M:1565)."""
         x = video.to(self.dtype)
-        x = F.pad(x, (0, 0, 0, 0, self.time_padding, 0))                      # M:1537
-        x = causal_conv3d(x, self.sd["conv_in.conv.weight"], self.sd["conv_in.conv.bias"], self.pad_mode)
+        if self.sep_first:
+            # M:1553-1561: the first frame goes through its own 2-D conv (SameConv2d, M:887-890), the remaining frames
+            # through the causal conv_in on their own (their causal padding starts at frame 1), then the feature map is
+            # re-padded with time_padding zero frames
+            w2, b2 = self.sd["conv_in_first_frame.weight"], self.sd["conv_in_first_frame.bias"]
+            first = F.conv2d(x[:, :, 0], w2, b2, padding=(w2.shape[2] // 2, w2.shape[3] // 2))
+            rest = causal_conv3d(x[:, :, 1:], self.sd["conv_in.conv.weight"], self.sd["conv_in.conv.bias"], self.pad_mode)
+            x = torch.cat((first[:, :, None], rest), dim=2)
+            x = F.pad(x, (0, 0, 0, 0, self.time_padding, 0))                  # M:1561
+        else:
+            x = F.pad(x, (0, 0, 0, 0, self.time_padding, 0))                  # M:1537
+            x = causal_conv3d(x, self.sd["conv_in.conv.weight"], self.sd["conv_in.conv.bias"], self.pad_mode)
         if taps is not None:
             taps["conv_in"] = x
         c = self._cond_in(cond, "encoder") if self.has_cond else None               # M:1544-1548
@@ -474,6 +485,12 @@ class OracleTokenizer:
             x = self._apply(x, st, f"decoder_layers.{j}.", decoder=True, cond=c)
             if taps is not None:
                 taps[f"dec{j}"] = x
+        if self.sep_first:                                                     # M:1633-1639
+            tp = self.time_padding
+            w2, b2 = self.sd["conv_out_first_frame.weight"], self.sd["conv_out_first_frame.bias"]
+            first = F.conv2d(x[:, :, tp], w2, b2, padding=(w2.shape[2] // 2, w2.shape[3] // 2))
+            rest = causal_conv3d(x[:, :, tp + 1:], self.sd["conv_out.conv.weight"], self.sd["conv_out.conv.bias"], self.pad_mode)
+            return torch.cat((first[:, :, None], rest), dim=2)
         x = causal_conv3d(x, self.sd["conv_out.conv.weight"], self.sd["conv_out.conv.bias"], self.pad_mode)
         return x[:, :, self.time_padding:]
 

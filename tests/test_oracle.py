@@ -73,6 +73,34 @@ def test_restated_cond_residual_matches_reference_golden():
         orc.tokenize(video)                                                           # M:1542
 
 
+def test_restated_separate_first_frame_encoding_matches_reference_golden():
+    """SURVEY 8f N3 groundwork: separate_first_frame_encoding (first frame through its own 2-D convs, M:1553-1561,
+    M:1633-1639), pinned to the reference."""
+    g = load_golden("mini_sff")
+    orc = build_oracle_from_golden(g)
+    video = golden_video(g)
+    taps, dtaps = {}, {}
+    codes = orc.tokenize(video, taps=taps)
+    assert torch.equal(codes, g["codes"])
+    recon = orc.decode_from_code_indices(codes, taps=dtaps)
+    assert torch.allclose(recon, g["recon"], atol=2e-5, rtol=1e-5)
+    for k, ref in g["taps"].items():
+        src = taps if (k.startswith("enc") or k == "conv_in") else dtaps
+        if k == "conv_in":
+            continue        # the reference's conv_in hook sees only frames 1.. (the first frame bypasses it)
+        assert torch.allclose(sample_like_golden(src[k], g), ref, atol=2e-5, rtol=1e-5), k
+    assert torch.equal(orc.forward(video, return_recon=True), recon)
+    # after the input convs the first real frame depends on the first input frame only (2-D path)
+    v2 = video.clone()
+    v2[:, :, 1:] += 1.0
+    t2 = {}
+    orc.encode(v2, taps=t2)
+    tp = orc.time_padding
+    assert torch.equal(t2["conv_in"][:, :, :tp + 1], taps["conv_in"][:, :, :tp + 1])
+    assert not torch.equal(t2["conv_in"][:, :, tp + 1:], taps["conv_in"][:, :, tp + 1:])
+    assert torch.count_nonzero(taps["conv_in"][:, :, :tp]) == 0                      # re-padded with zero frames (M:1561)
+
+
 def test_modulated_conv_factorises_into_shared_weight_conv():
     """The mapping the B200 path will use for Conv3DMod (M:736-751): per-clip weights w * (cond + 1) * inv_norm never need
     to be materialised --  y[b, o] = inv_norm[b, o] * conv(x[b] * (cond[b] + 1), w)[o]  with
