@@ -206,7 +206,10 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)
 // ~2300 SASS instructions per 32-column chunk and thrashed the instruction cache of the 8 epilogue warps).
 // EPI_PLAIN (slab kernel only) additionally requires Co % 8 == 0 and stores through a shared-memory transpose;
 // EPI_RAGGED is the direct per-row path with scalar tails (conv_out's 3 channels, and the tap kernel's plain mode).
-enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_SHUFFLE = 2, EPI_RAGGED = 3 };
+// EPI_PLAIN_RES is EPI_PLAIN with a residual input: the chunk is staged as fp32 so that act(conv + bias) + res is summed
+// in fp32 and rounded to bf16 ONCE (the reference's bf16 `fn(x) + x` rounds twice; the single rounding is strictly closer
+// to the fp32 result and costs only shared-memory staging width).
+enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_SHUFFLE = 2, EPI_RAGGED = 3, EPI_PLAIN_RES = 4 };
 
 // Branch-free activations on the bare MUFU approximations (ex2/rcp with flush-to-zero): the results are rounded to
 // bf16 right after, and __expf's denormal range handling costs ~5 extra instructions per element.
@@ -322,6 +325,23 @@ __device__ __forceinline__ void epi_pack32_t(const uint32_t (&r)[32], const floa
     pk[2 * g] = pack_bf16x2(act_ct<ACT>(__uint_as_float(r[4 * g]) + b.x), act_ct<ACT>(__uint_as_float(r[4 * g + 1]) + b.y));
     pk[2 * g + 1] = pack_bf16x2(act_ct<ACT>(__uint_as_float(r[4 * g + 2]) + b.z), act_ct<ACT>(__uint_as_float(r[4 * g + 3]) + b.w));
   }
+}
+// bias + activation of one 32-column chunk, kept in fp32 (for the fp32-staged residual epilogue)
+template <int ACT>
+__device__ __forceinline__ void epi_act32_t(uint32_t (&r)[32], const float* sb) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + g * 4);
+    r[4 * g] = __float_as_uint(act_ct<ACT>(__uint_as_float(r[4 * g]) + b.x));
+    r[4 * g + 1] = __float_as_uint(act_ct<ACT>(__uint_as_float(r[4 * g + 1]) + b.y));
+    r[4 * g + 2] = __float_as_uint(act_ct<ACT>(__uint_as_float(r[4 * g + 2]) + b.z));
+    r[4 * g + 3] = __float_as_uint(act_ct<ACT>(__uint_as_float(r[4 * g + 3]) + b.w));
+  }
+}
+__device__ __forceinline__ void epi_act32(int act, uint32_t (&r)[32], const float* sb) {
+  if (act == MV2_ACT_ELU) epi_act32_t<MV2_ACT_ELU>(r, sb);
+  else if (act == MV2_ACT_SILU) epi_act32_t<MV2_ACT_SILU>(r, sb);
+  else epi_act32_t<MV2_ACT_NONE>(r, sb);
 }
 __device__ __forceinline__ void epi_pack32(int act, const uint32_t (&r)[32], const float* sb, uint32_t (&pk)[16]) {
   if (act == MV2_ACT_ELU) epi_pack32_t<MV2_ACT_ELU>(r, sb, pk);

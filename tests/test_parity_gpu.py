@@ -9,8 +9,9 @@ from tests.util import build_oracle, build_product, golden_video, load_golden, s
 
 pytestmark = pytest.mark.gpu
 
-FP32_RECON_TOL = 1e-4     # fp32 path vs fp32 oracle, max-abs (outputs are O(1)); north-star goal is 1e-5
-FP32_TAP_TOL = 1e-4
+FP32_RECON_TOL = 1e-5     # fp32 path vs the fp32 reference, max-abs (outputs are O(1)): the north-star's 1e-5
+FP32_TAP_TOL = 1e-5       # per-layer activations of the small configs (measured 0.7 - 5.1e-6)
+FP32_README_TAP_TOL = 5e-5  # README config, 28 layers deep with O(10) activations near the bottleneck
 
 
 def _require_cuda():
@@ -63,19 +64,21 @@ def test_fp32_readme_config_vs_golden():
     x = eng.encode_cl(video)
     _, codes, pre = eng.quantize_cl(x, want_quantized=False, want_aux=True)
     taps, eng.taps = eng.taps, None
+    worst = 0.0
     for k, ref in g["taps"].items():
         if k in taps:
             err = (sample_like_golden(taps[k], g) - ref).abs().max().item()
-            assert err < 5e-4, (k, err)
+            worst = max(worst, err)
+            assert err < FP32_README_TAP_TOL, (k, err)
     pre_err = (pre.cpu().reshape(g["presign"].shape) - g["presign"]).abs().max().item()
     n_diff = (codes.cpu() != g["codes"]).sum().item()
     recon = model.decode_from_code_indices(g["codes"].cuda())
     rerr = (recon.cpu()[:, :, :, ::4, ::4] - g["recon_sample"]).abs().max().item()
     merr = (recon.cpu().mean(dim=(3, 4)) - g["recon_mean"]).abs().max().item()
     _report("fp32/readme", code_mismatches=n_diff, presign_maxabs=f"{pre_err:.3e}", recon_maxabs=f"{rerr:.3e}",
-            recon_mean_err=f"{merr:.3e}")
+            recon_mean_err=f"{merr:.3e}", worst_enc_tap=f"{worst:.3e}")
     assert n_diff == 0
-    assert rerr < 5e-4
+    assert rerr < FP32_RECON_TOL
 
 
 @pytest.mark.parametrize("name", ["mini", "mini_fsq"])
@@ -102,6 +105,10 @@ def test_roundtrip_and_api_properties(name):
     assert rec.shape == v.shape and loss.ndim == 0
 
 
+# measured on B200 (profiles/r02_parity.txt) + 50 %: (token mismatch rate, recon max-abs vs the fp32 reference)
+BF16_VS_FP32_BOUNDS = {"mini": (0.0625, 0.081), "mini_fsq": (0.125, 0.079)}
+
+
 @pytest.mark.parametrize("name", ["mini", "mini_fsq"])
 def test_bf16_path_vs_fp32_oracle(name):
     """bf16 storage / fp32 accumulate.  Protocol: tokens whose code differs from the fp32
@@ -120,11 +127,69 @@ def test_bf16_path_vs_fp32_oracle(name):
     rerr = (recon.float().cpu() - g["recon"]).abs().max().item()
     _report(f"bf16/{name}", token_mismatch_rate=f"{rate:.4f}", recon_maxabs=f"{rerr:.3e}")
     assert recon.dtype == torch.bfloat16
-    assert rate < 0.12, rate
-    assert rerr < 0.15, rerr
+    rate_max, rerr_max = BF16_VS_FP32_BOUNDS[name]
+    assert rate <= rate_max, rate
+    assert rerr <= rerr_max, rerr
     if not g["kwargs"].get("use_fsq", False) and mism.any():
         margin = g["presign"].reshape(*ref_codes.shape, -1).abs().min(dim=-1).values
-        assert margin[mism].max().item() < 0.15
+        assert margin[mism].max().item() < 0.07
+
+
+@pytest.mark.parametrize("name", ["mini", "readme"])
+def test_bf16_error_budget_vs_reference_bf16(name):
+    """SURVEY 8d protocol (ii): the bf16 product path against the REFERENCE ITSELF run as ``model.bfloat16()``
+    (tests/golden/<name>_bf16.pt, made by oracle/make_golden.py).  Both are compared with the fp32 reference golden,
+    layer by layer; the product's error must stay within 1.5x of the reference's own bf16 error at every tap, its
+    pre-sign deviation within 2x (max) / 1.5x (mean), its token mismatch rate and decode error (identical codes fed to both
+    sides) within 1.5x."""
+    _require_cuda()
+    g32, g16 = load_golden(name), load_golden(name + "_bf16")
+    assert g16["dtype"] == "bf16" and torch.equal(g16["codes_decoded"], g32["codes"])
+    model = build_product(g32["kwargs"], g32["wseed"]).cuda().bfloat16()
+    video = golden_video(g32).cuda()
+    eng = model.engine
+    eng.taps = {}
+    x = eng.encode_cl(video)
+    _, codes, pre = eng.quantize_cl(x, want_quantized=False, want_aux=True)
+    taps, eng.taps = eng.taps, {}
+    recon = model.decode_from_code_indices(g32["codes"].cuda())
+    taps.update(eng.taps)
+    eng.taps = None
+    lines, worst_ratio = [], 0.0
+    for k, ref32 in g32["taps"].items():
+        got = sample_like_golden(taps[k], g32)
+        e_prod, e_ref = (got - ref32).abs(), (g16["taps"][k] - ref32).abs()
+        ratio = e_prod.mean().item() / (e_ref.mean().item() + 1e-9)
+        worst_ratio = max(worst_ratio, ratio)
+        lines.append(f"{k}:{e_prod.mean().item():.2e}/{e_ref.mean().item():.2e}")
+        assert e_prod.mean().item() <= 1.5 * e_ref.mean().item() + 1e-5, (k, e_prod.mean().item(), e_ref.mean().item())
+        assert e_prod.max().item() <= 2.0 * e_ref.max().item() + 1e-4, (k, e_prod.max().item(), e_ref.max().item())
+    p32 = g32["presign"]
+    dp_prod = (pre.cpu().reshape(p32.shape) - p32).abs()
+    dp_ref = (g16["presign"] - p32).abs()
+    mism_prod = (codes.cpu() != g32["codes"]).float().mean().item()
+    mism_ref = (g16["codes"] != g32["codes"]).float().mean().item()
+    flipped = (pre.cpu().reshape(p32.shape) > 0) != (p32 > 0)
+    flip_margin = p32[flipped].abs().max().item() if flipped.any() else 0.0
+    flipped_ref = (g16["presign"] > 0) != (p32 > 0)
+    flip_margin_ref = p32[flipped_ref].abs().max().item() if flipped_ref.any() else 0.0
+    if "recon" in g32:
+        r_prod, r_ref = (recon.float().cpu() - g32["recon"]).abs(), (g16["recon"] - g32["recon"]).abs()
+    else:
+        r_prod = (recon.float().cpu()[:, :, :, ::4, ::4] - g32["recon_sample"]).abs()
+        r_ref = (g16["recon_sample"] - g32["recon_sample"]).abs()
+    _report(f"bf16-vs-ref-bf16/{name}", worst_tap_ratio=f"{worst_ratio:.2f}",
+            presign_max=f"{dp_prod.max().item():.3e}/{dp_ref.max().item():.3e}",
+            presign_mean=f"{dp_prod.mean().item():.3e}/{dp_ref.mean().item():.3e}",
+            token_mismatch=f"{mism_prod:.4f}/{mism_ref:.4f}", flipped_bit_margin=f"{flip_margin:.3e}/{flip_margin_ref:.3e}",
+            recon_max=f"{r_prod.max().item():.3e}/{r_ref.max().item():.3e}",
+            recon_mean=f"{r_prod.mean().item():.3e}/{r_ref.mean().item():.3e}", taps="(product/reference-bf16 mean-abs vs fp32) " + " ".join(lines))
+    assert dp_prod.max().item() <= 2.0 * dp_ref.max().item()
+    assert dp_prod.mean().item() <= 1.5 * dp_ref.mean().item()
+    assert mism_prod <= 1.5 * mism_ref + 1.0 / g32["codes"].numel()
+    assert flip_margin <= 2.0 * max(flip_margin_ref, dp_ref.max().item())
+    assert r_prod.max().item() <= 1.5 * r_ref.max().item()
+    assert r_prod.mean().item() <= 1.5 * r_ref.mean().item()
 
 
 def test_lfq_training_aux_terms_vs_oracle():
@@ -183,9 +248,10 @@ def test_bf16_readme_config_vs_reference_golden():
     rerr = (recon.float().cpu()[:, :, :, ::4, ::4] - g["recon_sample"]).abs()
     _report("bf16/readme", token_mismatch_rate=f"{rate:.4f}", worst_flipped_margin=f"{worst_margin:.3e}",
             recon_maxabs=f"{rerr.max().item():.3e}", recon_meanabs=f"{rerr.mean().item():.3e}")
-    assert rate < 0.08, rate
-    assert worst_margin < 0.25, worst_margin
-    assert rerr.max().item() < 0.12 and rerr.mean().item() < 0.01
+    # measured (profiles/r02_parity.txt) + 50 %; the reference's own bf16 run: 5.2 % of tokens, margin 6.1e-2, recon 4.6e-2 / 8.1e-3
+    assert rate < 0.04, rate
+    assert worst_margin < 0.094, worst_margin
+    assert rerr.max().item() < 0.057 and rerr.mean().item() < 0.0102
 
 
 def test_bf16_tensor_core_path_vs_bf16_cuda_core_path():
@@ -247,10 +313,10 @@ def test_wide_channel_config_vs_oracle(dtype):
     if dtype == torch.float32:
         margin = pre.reshape(*ref_codes.shape, -1).abs().min(dim=-1).values
         assert (not mism.any()) or margin[mism].max().item() < 2e-5      # only sign tests on a ~1e-5 margin may flip
-        assert rerr.max().item() < 2e-4
+        assert rerr.max().item() < 2e-5
     else:
-        assert mism.float().mean().item() < 0.15
-        assert rerr.mean().item() < 0.02 and rerr.max().item() < 0.2
+        assert mism.float().mean().item() < 0.0625       # measured 0.0417 (4 of 96 tokens) + 50 %
+        assert rerr.mean().item() < 0.012 and rerr.max().item() < 0.06
 
 
 @pytest.mark.parametrize("graphs", [False, True])

@@ -1,7 +1,11 @@
-"""tcgen05 implicit-GEMM convolution vs the CUDA-core kernel on identical bf16 inputs (both accumulate in
-fp32), shape by shape, through the engine's conv() entry (C ABI underneath)."""
+"""tcgen05 implicit-GEMM convolution, shape by shape, through the engine's conv() entry (C ABI underneath), against
+(a) the CPU oracle's building blocks (oracle/restated.py: plain torch fp32 functional ops on the same bf16-representable
+inputs and weights) and (b) the library's own CUDA-core kernel on identical bf16 inputs (both accumulate in fp32)."""
 import pytest
 import torch
+import torch.nn.functional as F
+
+from oracle import restated as R
 
 from magvit2_pytorch_b200 import VideoTokenizer
 from magvit2_pytorch_b200._lib import ACT_ELU, ACT_NONE, ACT_SILU, SHUFFLE_NONE, SHUFFLE_SPACE, SHUFFLE_TIME
@@ -32,6 +36,45 @@ CASES = [
     ("bk16_c48_tinyspatial", (64, 48, 3, 3, 3), None, (2, 3, 4, 4), dict(), 1),
     ("up_space_small_cy16", (64, 32, 1, 1), None, (1, 2, 8, 8), dict(act=ACT_SILU, shuffle=SHUFFLE_SPACE), 4),
 ]
+
+
+def _oracle_conv(w, bias, x_cl, k3, kw, res=None):
+    """fp32 CPU reference of one conv() call from the oracle's building blocks.  x_cl: (B,T,H,W,Ci) bf16 on the device;
+    w: torch-layout fp32 weight (rounded through bf16 here, as the engine packs it); returns channels-last fp32 (CPU)."""
+    x = x_cl.float().cpu().permute(0, 4, 1, 2, 3).contiguous()
+    wb = w.detach().to(torch.bfloat16).float().cpu()
+    b = bias.detach().float().cpu()
+    act, shuffle, stride = kw.get("act", ACT_NONE), kw.get("shuffle", SHUFFLE_NONE), kw.get("stride", (1, 1, 1))
+    if shuffle == SHUFFLE_SPACE:
+        y = R.spatial_up(x, {"net.0.weight": wb.reshape(wb.shape[0], wb.shape[1], 1, 1), "net.0.bias": b}, "")
+    elif shuffle == SHUFFLE_TIME:
+        y = R.time_up(x, {"net.0.weight": wb.reshape(wb.shape[0], wb.shape[1], 1), "net.0.bias": b}, "")
+    elif stride == (1, 2, 2):
+        y = R.spatial_down(x, {"conv.weight": wb, "conv.bias": b}, "")
+    elif stride == (2, 1, 1):
+        y = R.time_down(x, {"conv.weight": wb, "conv.bias": b}, "")
+    else:
+        k = tuple(k3) if k3 is not None else (1,) * (5 - wb.ndim) + tuple(wb.shape[2:])
+        y = R.causal_conv3d(x, wb.reshape(wb.shape[0], wb.shape[1], *k), b)
+        if act == ACT_ELU:
+            y = F.elu(y)
+        elif act == ACT_SILU:
+            y = F.silu(y)
+    if res is not None:
+        y = y + res.float().cpu().permute(0, 4, 1, 2, 3)
+    return y.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def _check_vs_oracle(name, y, ref):
+    """bf16 result vs the fp32 oracle: fp32 accumulation of bf16 products is exact to ~1e-6 relative, so the whole error
+    budget is the single rounding of the output to bf16 (half an ulp = 2^-9 relative) plus the MUFU activations."""
+    a = y.float().cpu()
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    err = (a - ref).abs()
+    bound = ref.abs() * 2.0 ** -8 + 2e-3
+    worst = (err - bound).max().item()
+    assert worst <= 0, f"{name}: |err| exceeds one bf16 ulp of the oracle value by {worst}"
+    assert err.mean().item() <= 0.0015 * ref.abs().mean().item() + 1e-4, (name, err.mean().item())
 
 
 def _engine():
@@ -76,6 +119,11 @@ def test_tc_matches_cuda_core(case):
     assert eng.tc_calls == 1, "tcgen05 path was not taken"
     y_ref = run(False)
     torch.cuda.synchronize()
+    res_o = None
+    if want_res:
+        To, Ho, Wo = kw.get("out_spatial", (T, H, W))
+        res_o = torch.randn((B, To, Ho, Wo, wshape[0]), generator=torch.Generator(device="cpu").manual_seed(7)).to(torch.bfloat16)
+    _check_vs_oracle(name, y_tc, _oracle_conv(w, bias, x, k3, kw, res_o))
     assert y_tc.shape == y_ref.shape
     a, b = y_tc.float(), y_ref.float()
     assert torch.isfinite(a).all()
@@ -120,7 +168,8 @@ def test_slab_matches_cuda_core(case):
     B, T, H, W = xshape
     x = torch.randn((B, T, H, W, wshape[1]), generator=g).cuda().to(torch.bfloat16)
     eng = _engine()
-    pk = pack_conv(w, bias, torch.bfloat16, k=kw.pop("k3", None), shuffle_q=kw.pop("q", 1))
+    k3 = kw.pop("k3", None)
+    pk = pack_conv(w, bias, torch.bfloat16, k=k3, shuffle_q=kw.pop("q", 1))
     want_res = kw.pop("res", False)
     res = torch.randn((B, T, H, W, wshape[0]), generator=g).cuda().to(torch.bfloat16) if want_res else None
     eng.use_tc, eng.tc_variant, eng.slab_calls = True, "slab", 0
@@ -131,6 +180,7 @@ def test_slab_matches_cuda_core(case):
     eng.use_tc = False
     y_ref = eng.conv(x, pk, res=res, **kw)
     torch.cuda.synchronize()
+    _check_vs_oracle(name, y_slab, _oracle_conv(w, bias, x, k3, kw, res))
     a, b, c = y_slab.float(), y_ref.float(), y_tap.float()
     assert torch.isfinite(a).all()
     tol = 0.008 * b.abs().max().item() + 1e-3
@@ -214,6 +264,15 @@ def test_attention_tensor_core_kernel_matches_fp32_cuda_core(L, D, heads, nseq):
     assert torch.isfinite(a_).all()
     assert (a_ - b_).abs().max().item() < 0.03 * b_.abs().max().item() + 5e-3
     assert (a_ - b_).abs().mean().item() < 0.006 * b_.abs().mean().item() + 1e-3
+    # the CPU oracle's Attend restatement (A:218-241 with the 4 memory key/values prepended, M:383-385) on the same inputs
+    t = qkv.float().cpu().reshape(nseq, L, 3, heads, D).permute(2, 0, 3, 1, 4)
+    memc = mem.cpu()
+    k_ = torch.cat((memc[0][None].expand(nseq, -1, -1, -1), t[1]), dim=-2)
+    v_ = torch.cat((memc[1][None].expand(nseq, -1, -1, -1), t[2]), dim=-2)
+    o_ = R.softmax_attention(t[0], k_, v_, causal=False).permute(0, 2, 1, 3).reshape(nseq * L, HD)
+    assert (b_.cpu() - o_).abs().max().item() < 2e-5 * o_.abs().max().item() + 2e-5          # fp32 kernel vs oracle
+    assert (a_.cpu() - o_).abs().max().item() < 0.03 * o_.abs().max().item() + 5e-3          # bf16 mma kernel vs oracle
+    assert (a_.cpu() - o_).abs().mean().item() < 0.006 * o_.abs().mean().item() + 1e-3
 
 
 @pytest.mark.parametrize("L,heads,nseq", [(1024, 16, 3), (200, 4, 2), (4096, 2, 1)])
@@ -241,3 +300,13 @@ def test_linear_attention_tensor_core_kernels_match_fp32_cuda_core(L, heads, nse
     assert torch.isfinite(a_).all()
     assert (a_ - b_).abs().max().item() < 0.04 * b_.abs().max().item() + 5e-3
     assert (a_ - b_).abs().mean().item() < 0.01 * b_.abs().mean().item() + 1e-3
+    # the CPU oracle's Taylor-attention restatement (Appendix A.3) with identity projections = the bare core
+    eye = torch.eye(HD)
+    sd = {"attn.to_q.0.weight": torch.cat((eye, torch.zeros(HD, 2 * HD)), dim=1),
+          "attn.to_kv.0.weight": torch.cat((torch.zeros(2 * HD, HD), torch.eye(2 * HD)), dim=1),
+          "attn.to_out.0.weight": eye}
+    xin = torch.cat((q.float().cpu(), kv.float().cpu()), dim=-1).reshape(nseq, L, 3 * HD)
+    o_ = R.taylor_linear_attention(xin, sd, "", heads, 8).reshape(nseq * L, HD)
+    assert (b_.cpu() - o_).abs().max().item() < 1e-4 * o_.abs().max().item() + 1e-4
+    assert (a_.cpu() - o_).abs().max().item() < 0.04 * o_.abs().max().item() + 5e-3
+    assert (a_.cpu() - o_).abs().mean().item() < 0.01 * o_.abs().mean().item() + 1e-3
