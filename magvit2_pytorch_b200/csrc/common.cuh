@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <mutex>
 #include "../../include/magvit2_b200.h"
 
 namespace mv2 {
@@ -67,6 +68,25 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- per-device one-time initialisation ----------------------------------------------------------------------
+// cudaFuncSetAttribute (the > 48 KB dynamic shared memory opt-in) applies to the CURRENT device only, so a process that
+// drives several GPUs must repeat it on each of them: the flag is kept per device ordinal, not per process.
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[64] = {};
+  cudaError_t err[64] = {};
+  template <typename F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done[dev]) { err[dev] = f(); done[dev] = true; }
+    return err[dev];
+  }
+};
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
 // Every kernel of the library starts with pdl_wait() (everything before it -- barrier init, TMEM allocation, bias

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const mv2_conv_args a) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const int ntaps = a.kt * a.kh * a.kw;
-  const int half_c = a.Ci >> 1;
+  const int half_c = (a.Ci + 1) >> 1;      // torch.chunk(2): the first (unshifted) half takes ceil(C / 2) channels (M:250)
   for (int tap = 0; tap < ntaps; ++tap) {
     const int dw = tap % a.kw, dh = (tap / a.kw) % a.kh, dt = tap / (a.kw * a.kh);
     const int ti = lto * a.st - a.pt + dt;
@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, T
   const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (tok >= n_tok) return;
   const int t = (int)((tok / P) % T_);
-  const int half = C >> 1;
+  const int half = (C + 1) >> 1;           // torch.chunk(2): the first (unshifted) half takes ceil(C / 2) channels (M:250)
   const T* row = x + tok * C;
   const T* prow = row - (int64_t)P * C;
   const bool has_prev = t > 0;
@@ -1690,7 +1690,6 @@ int mv2_conv_forward(const mv2_conv_args* a, void* stream) {
   MV2_CHECK_ARG(a->kt > 0 && a->kh > 0 && a->kw > 0 && a->st > 0 && a->sh > 0 && a->sw > 0);
   MV2_CHECK_ARG(a->shuffle != MV2_SHUFFLE_SPACE || a->Co % 4 == 0);
   MV2_CHECK_ARG(a->shuffle != MV2_SHUFFLE_TIME || a->Co % 2 == 0);
-  MV2_CHECK_ARG(!a->x_token_shift || a->Ci % 2 == 0);
   const int64_t M = (int64_t)a->B * a->To * a->Ho * a->Wo;
   dim3 grid(ceil_div(M, CBM), ceil_div(a->Co, CBN));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1727,15 +1726,15 @@ static int se_rows_per_block(int dtype, int F, int P, int C) {
 }
 
 static cudaError_t se_pool_smem_optin() {
-  static std::once_flag once;
-  static cudaError_t err = cudaSuccess;
-  std::call_once(once, [] {
+  static PerDeviceOnce once;
+  return once.run([] {
+    cudaError_t err = cudaSuccess;
     auto set = [&](const void* fn) { if (err == cudaSuccess) err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); };
     set((const void*)se_pool_online_kernel<8, 1>); set((const void*)se_pool_online_kernel<8, 2>); set((const void*)se_pool_online_kernel<8, 4>);
     set((const void*)se_pool_online_kernel<8, 8>); set((const void*)se_pool_online_kernel<8, 16>); set((const void*)se_pool_online_kernel<8, 32>);
     set((const void*)se_pool_online_kernel<16, 32>); set((const void*)se_pool_online_kernel<32, 32>);
+    return err;
   });
-  return err;
 }
 
 int mv2_se_pool(const void* y, int dtype, int F, int P, int C, const float* wk, float bk, void* workspace,
@@ -1806,7 +1805,6 @@ int mv2_gate_residual(const void* y, const void* x, const float* gates, void* ou
 int mv2_rmsnorm(const void* x, void* out, int dtype, const float* gamma, int B, int T, int P, int C, int token_shift,
                 void* stream) {
   MV2_CHECK_ARG(x && out && gamma && B > 0 && T > 0 && P > 0 && C > 0);
-  MV2_CHECK_ARG(!token_shift || C % 2 == 0);
   const int64_t n_tok = (int64_t)B * T * P;
   const int blocks = ceil_div(n_tok, 8);
   cudaStream_t st = (cudaStream_t)stream;

@@ -624,14 +624,14 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   }
   const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 32 + (size_t)nb_pad * 4 + 8 * ((a->res && a->epi_mode == 0 && a->shuffle == MV2_SHUFFLE_NONE && a->Co % 8 == 0) ? 4096 : 2048) + 1024;
   MV2_CHECK_ARG(smem <= 227 * 1024);
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_SHUFFLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(tc_slab_kernel<EPI_PLAIN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static PerDeviceOnce attr_once;
+  const cudaError_t attr_err = attr_once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(tc_slab_kernel<EPI_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_SHUFFLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_PLAIN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return e;
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
   int grid = std::min(p.total_tiles, n_sm);

@@ -45,6 +45,7 @@ class ConvPack:
     Co_tc: int = 0
     epi_mode: int = 0                        # 1: fused GEGLU (output has Co_tc // 2 channels)
     k_tc: Optional[Tuple[int, int, int]] = None
+    macs: int = 0                            # algorithmic multiply-accumulates per output position (Co * Ci * taps, unpadded)
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype, k=None, shuffle_q: int = 1) -> ConvPack:
@@ -59,6 +60,7 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype, k=None,
     w = w3.permute(2, 1, 0).contiguous().to(dtype)
     b = None if bias is None else bias.detach().float().contiguous()
     pk = ConvPack(w=w, bias=b, k=tuple(int(v) for v in k), Ci=int(Ci), Co=int(Co))
+    pk.macs = int(Co) * int(Ci) * int(w3.shape[2])
     if dtype == torch.bfloat16:
         wt = w3.permute(0, 2, 1).reshape(Co, -1)                      # [Co][tap*Ci + ci]
         bt = b
@@ -119,6 +121,7 @@ def pack_conv_in_kwpack(weight, bias, cpack=32):
     pk.bias_tc = None if bias is None else bias.detach().float().contiguous()
     pk.Ci_tc, pk.Co_tc, pk.k_tc = cpack, int(Co), (kt, kh, 1)
     pk.kw_orig, pk.cin_orig = int(kw), int(Cin)
+    pk.macs = int(Co) * int(Cin) * int(kt * kh * kw)          # the padded K (cpack x kt x kh) is not algorithmic work
     return pk
 
 
@@ -287,7 +290,7 @@ class Engine:
                     check(self.lib.mv2_tc_conv_forward(C.byref(ta), self._stream()), "mv2_tc_conv_forward")
                 if self._prof is not None:
                     e1.record()
-                    self._prof.append((e0, e1, 2.0 * B * To * Ho * Wo * pk.Co * pk.Ci * pk.k[0] * pk.k[1] * pk.k[2],
+                    self._prof.append((e0, e1, 2.0 * B * To * Ho * Wo * pk.macs,
                                        "slab" if use_slab else "tap", pk.k[1] * pk.k[2] * pk.k[0]))
                 if self.conv_log is not None:
                     self.conv_log.append(dict(kind="slab" if use_slab else "tap", Ci=Ci, Co=co_out, k=tuple(pk.k), out=(B, To, Ho, Wo),
@@ -346,7 +349,9 @@ class Engine:
         """Residual(FeedForward) (M:471-508, M:1191): x + fc2(geglu(fc1(rmsnorm(shift(x)))))."""
         B, T, H, W, Cc = x.shape
         xn = self.rmsnorm(x, p["gamma"], token_shift)
-        if self.dtype == torch.bfloat16 and self.use_tc and p["fc1"].epi_mode == 1:
+        # fused fc1 + GEGLU pack is tcgen05-only (K = C must be a multiple of 16); other widths take the unfused
+        # CUDA-core convs + mv2_geglu below, like the fp32 path
+        if self.dtype == torch.bfloat16 and self.use_tc and p["fc1"].epi_mode == 1 and Cc % 16 == 0:
             g = self.conv(xn, p["fc1"])                       # fc1 + bias + GEGLU fused, hidden width padded to 64
             return self.conv(g, p["fc2"], res=x)
         fc1 = p["fc1"]

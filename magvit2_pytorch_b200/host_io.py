@@ -54,6 +54,8 @@ class HostRoundTrip:
             if slot.used:
                 slot.done.synchronize()
             slot.video = torch.empty(video_host.shape, dtype=video_host.dtype, device=self.device)
+            # the block may have been freed on `cur` with kernels still queued there: order the first copy after them
+            self.s_in.wait_stream(cur)
         if slot.used:
             self.s_in.wait_event(slot.done)          # the kernels that read this slot's staged input have finished
         with torch.cuda.stream(self.s_in):

@@ -18,7 +18,9 @@ non-constant ``pad_mode``, the GAN / perceptual training losses (``return_loss``
 """
 from __future__ import annotations
 
+import contextlib
 import copy
+import functools
 import pickle
 from dataclasses import dataclass
 from pathlib import Path
@@ -40,6 +42,18 @@ class Stage:
     dim_out: int
     count: int = 1
     nested: bool = False
+
+
+def _on_model_device(fn):
+    """Runs the method with the model's CUDA device current: the C ABI launches on the current device (kernels, TMA
+    descriptors, function attributes), so a tokenizer on cuda:1 must not be driven while cuda:0 is current."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        dev = self.device
+        ctx = torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+        with ctx:
+            return fn(self, *a, **k)
+    return wrapper
 
 
 _UNSUPPORTED_LAYERS = {
@@ -252,7 +266,10 @@ class VideoTokenizer(nn.Module):
         return super().load_state_dict(sd, strict=strict, **kw)
 
     def __deepcopy__(self, memo):
+        # the engine (packed weights, ctypes handles) and captured CUDA graphs (static buffers, private pools) belong
+        # to THIS instance: a copy starts without them and re-packs / re-captures on first use
         eng, self._engine = self._engine, None
+        graphs, self._graphs = self._graphs, {}
         try:
             cls = self.__class__
             new = cls.__new__(cls)
@@ -261,11 +278,13 @@ class VideoTokenizer(nn.Module):
                 new.__dict__[k] = copy.deepcopy(v, memo)
         finally:
             self._engine = eng
+            self._graphs = graphs
         return new
 
     def __getstate__(self):
         st = dict(self.__dict__)
         st["_engine"] = None
+        st["_graphs"] = {}
         return st
 
     def copy_for_eval(self):
@@ -318,6 +337,8 @@ class VideoTokenizer(nn.Module):
             return fn(*tensors)
         eng = self.engine
         key = (name, eng._sig_id, tuple((tuple(t.shape), t.dtype) for t in tensors))
+        if any(k[1] != eng._sig_id for k in self._graphs):      # parameters were re-packed: old graphs read stale weights
+            self._graphs = {k: v for k, v in self._graphs.items() if k[1] == eng._sig_id}
         ent = self._graphs.get(key)
         if ent is None:                       # first call: plain run (warms up lazy init: attributes, entry points)
             self._graphs[key] = "warm"
@@ -364,6 +385,7 @@ class VideoTokenizer(nn.Module):
 
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
+    @_on_model_device
     def encode(self, video, quantize=False, cond=None, video_contains_first_frame=True):
         """M:1523-1576.  Returns (B, C, T', H', W') like the reference."""
         assert cond is None, "conditioning is not supported"
@@ -378,15 +400,24 @@ class VideoTokenizer(nn.Module):
             return out, idx, self.zero
         return eng.to_channels_first(x)
 
+    def _check_on_device(self, t, what):
+        if t.device != self.device:
+            raise RuntimeError(f"{what} is on {t.device} but the tokenizer is on {self.device}")
+
     @torch.no_grad()
+    @_on_model_device
     def decode(self, quantized, cond=None, video_contains_first_frame=True):
         """M:1598-1649.  quantized: (B, C, T', H', W')."""
         assert cond is None, "conditioning is not supported"
         assert video_contains_first_frame
+        assert quantized.ndim == 5 and quantized.shape[1] == self.quantizers.dim, \
+            f"quantized must be (B, {self.quantizers.dim}, T, H, W), got {tuple(quantized.shape)}"
+        self._check_on_device(quantized, "quantized")
         eng = self.engine
         return eng.decode_cl(eng.to_channels_last(quantized))
 
     @torch.no_grad()
+    @_on_model_device
     def decode_from_code_indices(self, codes, cond=None, video_contains_first_frame=True):
         """M:1579-1595."""
         assert cond is None, "conditioning is not supported"
@@ -398,10 +429,13 @@ class VideoTokenizer(nn.Module):
                 f"flattened video ids must have a length ({n}) that is divisible by the fmap size " \
                 f"({self.fmap_size}) squared ({self.fmap_size ** 2})"
             codes = codes.reshape(codes.shape[0], -1, self.fmap_size, self.fmap_size)
+        assert codes.ndim == 4, f"codes must be (B, T, H, W) or flat (B, N), got {tuple(codes.shape)}"
+        self._check_on_device(codes, "codes")
         eng = self.engine
         return self._graph_call("decode_codes", lambda c: eng.decode_cl(eng.codes_to_quantized_cl(c)), codes.contiguous())
 
     @torch.no_grad()
+    @_on_model_device
     def lfq_loss_breakdown(self, video, group=None):
         """Training-mode LFQ auxiliary terms the reference computes at M:1705 (``quantizer_loss_breakdown``):
         returns ``(codes, (per_sample_entropy, batch_entropy, commitment), aux_loss)``.  ``batch_entropy`` uses the
@@ -425,6 +459,7 @@ class VideoTokenizer(nn.Module):
         self.eval()
         return self.forward(video, return_codes=True)
 
+    @_on_model_device
     def forward(self, video_or_images, cond=None, return_loss=False, return_codes=False, return_recon=False,
                 return_discr_loss=False, return_recon_loss_only=False, apply_gradient_penalty=True,
                 video_contains_first_frame=True, adversarial_loss_weight=None,
