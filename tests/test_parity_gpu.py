@@ -344,3 +344,64 @@ def test_host_round_trip_matches_direct_calls(graphs):
             assert torch.equal(ov, wv)
     with pytest.raises(ValueError):
         hrt.submit(vids[0].clone(), outs[0][0], outs[0][1])      # not pinned
+
+
+def test_copy_for_eval_after_graph_capture_and_repack():
+    """Captured CUDA graphs (static buffers, private pools) belong to one instance and one parameter version:
+    copy_for_eval() / deepcopy / pickling start without them, and a re-pack drops the stale entries."""
+    _require_cuda()
+    import copy
+    import pickle
+    g = load_golden("mini")
+    model = build_product(g["kwargs"], g["wseed"]).cuda().bfloat16()
+    v = golden_video(g).cuda()
+    want = model.tokenize(v)
+    model.cuda_graphs = True
+    for _ in range(3):
+        assert torch.equal(model.tokenize(v), want)
+    assert any(isinstance(e, tuple) for e in model._graphs.values())
+    c = model.copy_for_eval()
+    assert c._graphs == {} and c._engine is None
+    assert torch.equal(c.tokenize(v), want)
+    d = copy.deepcopy(model)
+    assert d._graphs == {}
+    p = pickle.loads(pickle.dumps(model))
+    assert p._graphs == {} and torch.equal(p.tokenize(v), want)
+    # the cpu() / to(dev) round trip inside copy_for_eval re-packed the original: its old graphs must be gone after one call
+    sig_before = {k[1] for k in model._graphs}
+    assert torch.equal(model.tokenize(v), want)
+    assert all(k[1] == model.engine._sig_id for k in model._graphs), (sig_before, model.engine._sig_id)
+
+
+def test_device_mismatch_raises_cleanly():
+    """CPU (or other-device) inputs raise a RuntimeError instead of handing a foreign pointer to the kernels."""
+    _require_cuda()
+    g = load_golden("mini")
+    model = build_product(g["kwargs"], g["wseed"]).cuda()
+    with pytest.raises(RuntimeError):
+        model.decode_from_code_indices(g["codes"])                  # CPU codes
+    with pytest.raises(RuntimeError):
+        model.decode(torch.zeros(1, model.quantizers.dim, 3, 4, 4))  # CPU latents
+    with pytest.raises(AssertionError):
+        model.decode(torch.zeros(1, 7, 3, 4, 4, device="cuda"))      # wrong channel count
+    with pytest.raises(RuntimeError):
+        model.tokenize(golden_video(g))                             # CPU video
+
+
+def test_model_on_non_current_device():
+    """The C ABI launches on the current device: the host class must make its own device current (2+ GPUs only)."""
+    _require_cuda()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = load_golden("mini")
+    v = golden_video(g)
+    for dt in (torch.float32, torch.bfloat16):
+        m0 = build_product(g["kwargs"], g["wseed"]).to("cuda:0").to(dt)
+        m1 = build_product(g["kwargs"], g["wseed"]).to("cuda:1").to(dt)
+        torch.cuda.set_device(0)
+        c0 = m0.tokenize(v.to("cuda:0"))
+        c1 = m1.tokenize(v.to("cuda:1"))           # current device is 0
+        assert c1.device == torch.device("cuda:1")
+        assert torch.equal(c0.cpu(), c1.cpu())
+        r1 = m1.decode_from_code_indices(c1)
+        assert torch.equal(m0.decode_from_code_indices(c0).cpu(), r1.cpu())

@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import README_KW
 from magvit2_pytorch_b200 import VideoTokenizer
-from oracle import weights as Wt
+import synth_data as Wt
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2

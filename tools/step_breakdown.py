@@ -8,7 +8,7 @@ from torch.profiler import profile, ProfilerActivity
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import README_KW
 from magvit2_pytorch_b200 import VideoTokenizer
-from oracle import weights as Wt
+import synth_data as Wt
 
 STEPS = 3
 m = VideoTokenizer(**README_KW)
