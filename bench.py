@@ -373,7 +373,9 @@ def main():
         # timed region, no power cap seen), the sustained one once the run is long enough to be power limited
         pk_burst, pk_sus = peaks["bf16_tflops"], peaks["bf16_tflops_sustained"]
         sm_now, sm_max = (clocks or {}).get("sm_mhz"), (clocks or {}).get("sm_max_mhz")
-        power_limited = bool(sm_now and sm_max and sm_now < 0.97 * sm_max) or "sw_power_cap" in ((clocks or {}).get("reasons") or [])
+        # (sw_power_cap shows up within milliseconds on this path, but the clock only dips ~2 %: the cuBLAS "sustained" figure
+        #  was taken at a 1387 MHz median and does not describe that regime, so the decision is made on the clock itself)
+        power_limited = bool(sm_now and sm_max and sm_now < 0.90 * sm_max)
         pk = pk_sus if power_limited else pk_burst
         traffic = None
         try:     # dram__bytes_read + write per conv3d launch, from the committed ncu capture of one step (profiles/)
@@ -386,7 +388,7 @@ def main():
                     "kernel": "tc_slab_kernel on the causal 3x3x3 Conv3d layers (82% of the step's FLOPs)",
                     "launches_per_step": n3, "kernel_ms_per_step": ms3, "flop_per_launch_avg": fl3 / max(n3, 1),
                     "flops": "algorithmic: 2*B*T*H*W*Co*Ci*kt*kh*kw per launch (conv_in counted with its 3x7x7x7 taps, not the padded K)",
-                    "peak_source": f"MEASURED_PEAKS.json {'bf16_tflops_sustained (power-limited run)' if power_limited else 'bf16_tflops (burst: SM clock at max during the timed region)'} ({peaks_src})",
+                    "peak_source": f"MEASURED_PEAKS.json {'bf16_tflops_sustained (SM clock fell below 90% of max: power-limited run)' if power_limited else 'bf16_tflops (burst figure: the SM clock stayed within 10% of its maximum during the timed region)'} ({peaks_src})",
                     "all_tcgen05_launches": {"launches_per_step": na, "ms_per_step": msa,
                                              "achieved": fla / (msa / 1e3) / 1e12, "frac": fla / (msa / 1e3) / 1e12 / pk},
                     "whole_step_frac": (FLOP_PER_CLIP_ALL * CLIPS_PER_GPU * world * args.steps / (ms_max / 1e3) / 1e12)

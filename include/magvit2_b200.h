@@ -218,6 +218,35 @@ int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream);
 int mv2_tc_slab_plan(const mv2_tc_conv_args* a, int n_sm, int* out6);
 int mv2_tc_slab_tile(const mv2_tc_conv_args* a, int n_sm, int cta, int k, int* out6);
 
+
+/* ---- fused ResidualUnit front half (reference M:937-941 + the pooling half of SqueezeExcite M:229-233) ----------------
+ * One launch computes  y = ELU(Conv3d_1x1x1(ELU(CausalConv3d_ktxkhxkw(x))))  for C -> C channels (C = 64 or 128, the
+ * HBM-bound levels of the README config): the ELU'd 3x3x3 tile never leaves the SM -- it is written to shared memory as the
+ * A operand of a second tcgen05.mma against the 1x1x1 weights -- and the second epilogue emits, next to y, one SqueezeExcite
+ * pool record (max logit, sum e, sum e * y[C]; e = exp(logit - max), logit = <y, se_wk> + se_bk) per 32-position row group,
+ * which mv2_se_gate_records combines (replaces mv2_conv_forward x2 + mv2_se_pool for these layers).
+ * w3: bf16 [C][kt*kh*kw*C] (K-major, as mv2_tc_conv_args.w); w1: bf16 [C][C]; b3 / b1 / se_wk: fp32 [C].
+ * se_ws: workspace of mv2_tc_ru_workspace_bytes(a) bytes; records per frame = mv2_tc_ru_records(a).                     */
+typedef struct mv2_tc_ru_args {
+  const void* x;        /* bf16 (B, T, H, W, C) */
+  const void* w3; const float* b3;
+  const void* w1; const float* b1;
+  const float* se_wk; float se_bk;
+  void* y;              /* bf16 (B, T, H, W, C) */
+  float* se_ws;
+  int32_t B, T, H, W, C;
+  int32_t kt, kh, kw;
+} mv2_tc_ru_args;
+int mv2_tc_ru_supported(const mv2_tc_ru_args* a);
+int mv2_tc_ru_records(const mv2_tc_ru_args* a);
+size_t mv2_tc_ru_workspace_bytes(const mv2_tc_ru_args* a);
+int mv2_tc_ru_forward(const mv2_tc_ru_args* a, void* stream);
+/* SE gate from pool records in the (max, sum, acc[C]) format, nrec records per frame laid out [F][nrec][C + 2], with the
+ * hidden layer scratch (F * Hd floats) right behind them: gate[f,:] = sigmoid(W2 leaky_relu_0.1(W1 pooled + b1) + b2).   */
+int mv2_se_gate_records(const void* workspace, int nrec, int F, int C, int Hd,
+                        const float* w1, const float* b1, const float* w2, const float* b2,
+                        float* gates, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,16 @@ class TcConvArgs(C.Structure):
     ]
 
 
+class TcRuArgs(C.Structure):
+    """mv2_tc_ru_args (fused ResidualUnit front half; see include/magvit2_b200.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p),
+        ("se_wk", C.c_void_p), ("se_bk", C.c_float), ("y", C.c_void_p), ("se_ws", C.c_void_p),
+        ("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/magvit2_b200.h declares
 _VP, _I, _I64, _F, _SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 SIGNATURES = {
@@ -88,6 +98,11 @@ SIGNATURES = {
     "mv2_tc_slab_forward": (_I, [C.POINTER(TcConvArgs), _VP]),
     "mv2_tc_slab_plan": (_I, [C.POINTER(TcConvArgs), _I, C.POINTER(C.c_int32)]),
     "mv2_tc_slab_tile": (_I, [C.POINTER(TcConvArgs), _I, _I, _I, C.POINTER(C.c_int32)]),
+    "mv2_tc_ru_supported": (_I, [C.POINTER(TcRuArgs)]),
+    "mv2_tc_ru_records": (_I, [C.POINTER(TcRuArgs)]),
+    "mv2_tc_ru_workspace_bytes": (_SZ, [C.POINTER(TcRuArgs)]),
+    "mv2_tc_ru_forward": (_I, [C.POINTER(TcRuArgs), _VP]),
+    "mv2_se_gate_records": (_I, [_VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
 }
 
 _lib = None

@@ -1783,6 +1783,20 @@ int mv2_se_gate(const void* workspace, int dtype, int F, int P, int C, int Hd, c
   return MV2_OK;
 }
 
+int mv2_se_gate_records(const void* workspace, int nrec, int F, int C, int Hd, const float* w1, const float* b1,
+                        const float* w2, const float* b2, float* gates, void* stream) {
+  MV2_CHECK_ARG(workspace && w1 && b1 && w2 && b2 && gates && F > 0 && nrec > 0 && C > 0 && Hd > 0);
+  const size_t smem1 = (size_t)(C + nrec) * sizeof(float), smem2 = (size_t)Hd * sizeof(float);
+  MV2_CHECK_ARG(smem1 <= 48 * 1024 && smem2 <= 48 * 1024);
+  float* hidden = (float*)workspace + (size_t)F * nrec * (C + 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_k(se_hidden_kernel, dim3(dim3(F, ceil_div(Hd, 32))), dim3(256), smem1, st, (const float*)workspace, nrec, C, Hd, w1, b1, hidden);
+  MV2_CHECK_LAUNCH();
+  launch_k(se_out_kernel, dim3(dim3(F, ceil_div(C, 64))), dim3(256), smem2, st, hidden, C, Hd, w2, b2, gates);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
 int mv2_gate_residual(const void* y, const void* x, const float* gates, void* out, int dtype, int F, int P, int C,
                       void* stream) {
   MV2_CHECK_ARG(y && x && gates && out && F > 0 && P > 0 && C > 0);

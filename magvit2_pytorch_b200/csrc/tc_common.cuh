@@ -209,7 +209,10 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)
 // EPI_PLAIN_RES is EPI_PLAIN with a residual input: the chunk is staged as fp32 so that act(conv + bias) + res is summed
 // in fp32 and rounded to bf16 ONCE (the reference's bf16 `fn(x) + x` rounds twice; the single rounding is strictly closer
 // to the fp32 result and costs only shared-memory staging width).
-enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_SHUFFLE = 2, EPI_RAGGED = 3, EPI_PLAIN_RES = 4 };
+// EPI_FUSED_RU (slab kernel only): the whole conv half of a ResidualUnit in one launch -- the ELU'd 3x3x3 tile goes to
+// shared memory as the A operand of a second tcgen05.mma against the 1x1x1 weights, and the second epilogue emits the
+// SqueezeExcite online-softmax pool partials next to y (see tc_slab.cu).
+enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_SHUFFLE = 2, EPI_RAGGED = 3, EPI_PLAIN_RES = 4, EPI_FUSED_RU = 5 };
 
 // Branch-free activations on the bare MUFU approximations (ex2/rcp with flush-to-zero): the results are rounded to
 // bf16 right after, and __expf's denormal range handling costs ~5 extra instructions per element.

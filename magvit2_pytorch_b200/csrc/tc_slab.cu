@@ -47,6 +47,14 @@ struct alignas(64) SlabParams {
   int tpw;               // in-plane taps per weight stage (one 3-D TMA box {bk, bn, tpw})
   int cluster;           // 1, or 2: CTA pairs on neighbouring tiles multicast each other half of every weight tile
   TcEpi epi;
+  // ---- EPI_FUSED_RU only (mv2_tc_ru_forward) ----
+  CUtensorMap w1map;     // 1x1x1 weights [Co][Ci] as {ci, co}: 2-D boxes {64, bn}
+  const float* bias1;    // 1x1x1 bias [C]
+  const float* se_wk;    // SqueezeExcite to_k weight [C]
+  float se_bk;
+  float* se_ws;          // SE pool records [B*T][recs_per_frame][C + 2] = (max, sum, sum e*y[C]) per 32-position row group
+  int nh;                // shared-memory H buffers (ELU'd 3x3x3 tile of one M-tile, A operand of the second MMA): 1 or 2
+  int h_stride;          // bytes per H buffer = kchunks * 16 KB
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -95,6 +103,51 @@ __host__ __device__ __forceinline__ TileCoord decode_tile(const SlabParams& p, i
   return c;
 }
 
+// EPI_FUSED_RU, warp 3: issuer of the second GEMM (the 1x1x1 conv of a tile), which runs while the main MMA warp is already
+// issuing the next tile's 3x3x3 taps.  One M-tile at a time, as soon as the epilogue warps have written that M-tile's ELU'd
+// 3x3x3 result to shared memory (h_full): A = that H tile, B = the 1x1x1 weights (resident in shared memory, loaded once
+// here), D = the TMEM columns that held the M-tile's 3x3x3 accumulator (fully drained once h_full completes).
+// Lane 0 issues (no second elect.sync in the kernel): with a second elect_one() instance -- or a real call -- the compiler
+// moved the MAIN MMA warp's loop nest out of uniform registers (R2UR in front of every tcgen05.mma group; tests/test_abi.py
+// guards the SASS).
+__device__ __forceinline__ void ru_second_gemm_issuer(const SlabParams& p, uint32_t tmem_base, uint32_t h_full, uint32_t m2_done,
+                                                   uint32_t w1_full, uint32_t hbuf0, uint32_t w1buf, uint32_t w_tile, uint32_t bk,
+                                                   int lane) {
+  if (lane == 0) {
+    mbar_expect_tx(w1_full, (uint32_t)p.kchunks * w_tile);
+    for (int kc2 = 0; kc2 < p.kchunks; ++kc2) tma_load_2d(w1buf + kc2 * w_tile, &p.w1map, w1_full, kc2 * (int)bk, 0);
+  }
+  mbar_wait(w1_full, 0);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t d_hi = ((uint64_t)((8 * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 16) | ((uint64_t)2 << 61);
+  const uint32_t leader = lane == 0;
+  const uint32_t b0 = (w1buf & 0x3FFFF) >> 4;
+  uint32_t buf = 0;
+  for (int tk = 0; slab_tile_of(p, tk) >= 0; ++tk) {
+    const uint32_t par = (uint32_t)tk & 1u;
+    for (int j = 0; j < p.mw; ++j) {
+      mbar_wait(h_full + 8 * j, par);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t d2 = tmem_base + buf * p.acc_stride + (uint32_t)j * p.bn;
+        uint32_t a2 = ((hbuf0 + (uint32_t)((p.nh == 2) ? (j & 1) : 0) * p.h_stride) & 0x3FFFF) >> 4, b2 = b0;
+        for (int kc2 = 0; kc2 < p.kchunks; ++kc2) {
+          const uint64_t ad = d_hi | (uint64_t)a2, bd = d_hi | (uint64_t)b2;
+          umma_bf16(d2, ad, bd, idesc, kc2 > 0 ? 1u : 0u);
+          umma_bf16(d2, ad + 2, bd + 2, idesc, 1u);
+          umma_bf16(d2, ad + 4, bd + 4, idesc, 1u);
+          umma_bf16(d2, ad + 6, bd + 6, idesc, 1u);
+          a2 += 16384 >> 4;
+          b2 += w_tile >> 4;
+        }
+        umma_commit(m2_done + 8 * j);
+      }
+      __syncwarp();
+    }
+    if (++buf == (uint32_t)p.nbuf) buf = 0;
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__ SlabParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -111,24 +164,39 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
   const uint32_t slab_full = bar0, slab_empty = slab_full + 8 * p.slab_stages;
   const uint32_t w_full = slab_empty + 8 * p.slab_stages, w_empty = w_full + 8 * p.w_stages;
   const uint32_t t_full = w_empty + 8 * p.w_stages, t_empty = t_full + 8 * 2;
-  const uint32_t tslot = t_empty + 8 * 2;
+  const uint32_t h_full = t_empty + 8 * 2, m2_done = h_full + 8 * 4;       // EPI_FUSED_RU: per M-tile, once per tile each
+  const uint32_t w1_full = m2_done + 8 * 4;                                // EPI_FUSED_RU: 1x1x1 weights landed (once)
+  const uint32_t tslot = w1_full + 8;
   const uint32_t sbias_u = (tslot + 8 + 15) & ~15u;
   float* sbias = reinterpret_cast<float*>(smem_raw + (sbias_u - smem_u32(smem_raw)));   // Co floats, 16-byte aligned
   // EPI_PLAIN: one 2 KB transpose buffer per epilogue warp (32 rows x 64 B, 16-byte pieces XOR-swizzled)
-  const uint32_t stage0 = sbias_u + (uint32_t)(p.n_tiles_n * p.bn) * 4;
+  const uint32_t nbias = (uint32_t)(p.n_tiles_n * p.bn);
+  const uint32_t stage0 = sbias_u + nbias * 4 * (MODE == EPI_FUSED_RU ? 3 : 1);   // fused: [conv3 bias][conv1 bias][SE to_k weight]
+  // fused: no separate transpose buffers -- the H buffers double as them once every second GEMM of the tile is done
+  const uint32_t lpart_u = stage0;                                                 // fused: logit partials [2][8 warps][32] fp32
+  const uint32_t hbuf0 = (lpart_u + 2048 + 1023u) & ~1023u;                        // fused: H buffers (SWIZZLE_128B atoms: 1024-aligned)
+  const uint32_t w1buf = hbuf0 + (uint32_t)p.nh * p.h_stride;                      // fused: 1x1x1 weights, kchunks K-major tiles [bn][64]
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.slab_stages; ++s) { mbar_init(slab_full + 8 * s, 1); mbar_init(slab_empty + 8 * s, 1); }
     for (int s = 0; s < p.w_stages; ++s) { mbar_init(w_full + 8 * s, 1); mbar_init(w_empty + 8 * s, p.cluster); }
     for (int s = 0; s < 2; ++s) { mbar_init(t_full + 8 * s, 1); mbar_init(t_empty + 8 * s, 8); }
+    for (int s = 0; s < 4; ++s) { mbar_init(h_full + 8 * s, 8); mbar_init(m2_done + 8 * s, 1); }
+    mbar_init(w1_full, 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) tma_prefetch_desc(&p.amap);
   if (warp == 2 && lane == 0) { tma_prefetch_desc(&p.wmap); tma_prefetch_desc(&p.wmap2); }
+  if (MODE == EPI_FUSED_RU && warp == 3 && lane == 0) tma_prefetch_desc(&p.w1map);
   if (warp == 1) tmem_alloc(tslot, 512);
   if (warp >= 4) {
     const int nb = p.n_tiles_n * p.bn;   // >= Co; padded columns read zeros
     for (int i = threadIdx.x - 128; i < nb; i += 256) sbias[i] = (p.epi.bias && i < p.Co) ? p.epi.bias[i] : 0.f;
+    if (MODE == EPI_FUSED_RU)
+      for (int i = threadIdx.x - 128; i < nb; i += 256) {
+        sbias[nb + i] = (p.bias1 && i < p.Co) ? p.bias1[i] : 0.f;
+        sbias[2 * nb + i] = i < p.Co ? p.se_wk[i] : 0.f;
+      }
   }
   tc_fence_before();
   __syncthreads();
@@ -262,6 +330,15 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         if (++t_idx == (uint32_t)p.nbuf) { t_idx = 0; t_par ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------ EPI_FUSED_RU: second-GEMM issuer ------------------------------
+    // The 1x1x1 conv of a tile runs while the main MMA warp is already issuing the next tile's 3x3x3 taps: this warp
+    // issues it, one M-tile at a time, as soon as the epilogue warps have written that M-tile's ELU'd 3x3x3 result to
+    // shared memory (h_full).  A = that H tile, B = the 1x1x1 weights (resident in shared memory, loaded once below),
+    // D = the TMEM columns that held the M-tile's 3x3x3 accumulator (fully drained once h_full completes).  Keeping this
+    // out of the main MMA warp leaves that warp's loop nest (and its uniform-register allocation) exactly as in the
+    // plain kernel.
+    if (MODE == EPI_FUSED_RU) ru_second_gemm_issuer(p, tmem_base, h_full, m2_done, w1_full, hbuf0, w1buf, w_tile, bk, lane);
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
     // 8 epilogue warps: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 4) / 4
@@ -269,11 +346,141 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
     const int row = sub * 32 + lane;
     const int lh = row >> 3, lw = row & 7;
     uint32_t buf = 0, bpar = 0;
+    uint32_t ecount = 0;       // EPI_FUSED_RU: M-tiles processed (selects the logit exchange buffer)
     for (int tk = 0, tile; (tile = slab_tile_of(p, tk)) >= 0; ++tk) {
       const TileCoord c = decode_tile(p, tile);
       mbar_wait(t_full + 8 * buf, bpar);
       tc_fence_after();
       const int h = c.h0 + lh;
+      if (MODE == EPI_FUSED_RU) {
+        // ---------------- fused ResidualUnit epilogue (reference M:937-941 + the pooling half of M:229-233) ----------------
+        const uint32_t par = (uint32_t)tk & 1u;
+        // every epilogue warp has finished the previous tile's transposes (they alias the H buffers written below)
+        if (tk > 0) asm volatile("bar.sync 5, 256;" ::: "memory");
+        const float* sb1 = sbias + nbias;
+        const float* swk = sbias + 2 * nbias;
+        float* lpart = reinterpret_cast<float*>(smem_raw + (lpart_u - smem_u32(smem_raw)));
+        const uint32_t tl0 = tmem_base + buf * p.acc_stride + ((uint32_t)(sub * 32) << 16);
+        // E1: h = ELU(conv3 + b3) -> bf16 -> shared memory, K-major SWIZZLE_128B (128 rows x 64 channels per 16 KB K-chunk):
+        //     the A operand of the 1x1x1 GEMM.  One M-tile at a time; buffer j % nh is free once the GEMM of M-tile j - nh is done.
+        for (int j = 0; j < p.mw; ++j) {
+          if (j >= p.nh) mbar_wait(m2_done + 8 * (j - p.nh), par);
+          const uint32_t hb = hbuf0 + (uint32_t)((p.nh == 2) ? (j & 1) : 0) * p.h_stride + (uint32_t)row * 128;
+          for (int c0 = ((j + half) & 1) * 32; c0 < p.bn; c0 += 64) {
+            uint32_t r[32], pk[16];
+            tmem_ld_32x32b_x32(tl0 + j * p.bn + c0, r);
+            tmem_ld_wait();
+            epi_pack32_t<MV2_ACT_ELU>(r, sbias + c0, pk);
+            const uint32_t hrow = hb + (uint32_t)(c0 >> 6) * 16384;
+            const uint32_t p0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + (((p0 + g) ^ ((uint32_t)row & 7u)) << 4)),
+                           "r"(pk[4 * g]), "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3]) : "memory");
+          }
+          fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          tc_fence_before();        // this warp's TMEM reads of M-tile j are complete before the GEMM overwrites those columns
+          __syncwarp();
+          if (lane == 0) mbar_arrive(h_full + 8 * j);
+        }
+        // E2: y = ELU(conv1 + b1) -> bf16 -> global (64-byte row pieces through the transpose buffer), and per 32-position
+        //     row group (this warp's TMEM lane quarter) one SE pool record (max, sum e, sum e * y[C]) with e = exp(logit - max).
+        //     The transpose buffers live in the H region: free once the LAST second GEMM of the tile has completed
+        //     (tcgen05.commit covers every earlier MMA of the issuing thread).
+        mbar_wait(m2_done + 8 * (p.mw - 1), par);
+        const uint32_t stg = hbuf0 + (uint32_t)(warp - 4) * 2048;
+        const uint32_t wr = stg + lane * 64, wsw = (lane >> 1) & 3;
+        const int rl = lane >> 2, piece = lane & 3;
+        const uint32_t rd = stg + rl * 64;
+        const int h20 = c.h0 + sub * 4;
+        const int64_t kstride = (int64_t)p.W * p.Co;
+        const int recs_per_frame = p.tiles_h * p.tiles_w * p.mw * 4;
+        const int64_t rec_tile = ((int64_t)(c.b * p.T + c.t) * recs_per_frame + ((c.h0 >> 4) * p.tiles_w + c.w0 / (8 * p.mw)) * (p.mw * 4)) * (p.Co + 2);
+        for (int j = 0; j < p.mw; ++j) {
+          mbar_wait(m2_done + 8 * j, par);
+          tc_fence_after();
+          const int w = c.w0 + 8 * j + lw;
+          const bool row_ok = h < p.H && w < p.W;
+          uint32_t pk2[2][16];
+          float lp = 0.f;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c0 = ((j + half) & 1) * 32 + 64 * q;
+            if (c0 < p.bn) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(tl0 + j * p.bn + c0, r);
+              tmem_ld_wait();
+              epi_pack32_t<MV2_ACT_ELU>(r, sb1 + c0, pk2[q]);
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {          // SE logit on the bf16-rounded y, like the unfused path reads it
+                const float4 wv = *reinterpret_cast<const float4*>(swk + c0 + 2 * i);
+                lp = fmaf(__uint_as_float(pk2[q][i] << 16), wv.x, lp);
+                lp = fmaf(__uint_as_float(pk2[q][i] & 0xffff0000u), wv.y, lp);
+                lp = fmaf(__uint_as_float(pk2[q][i + 1] << 16), wv.z, lp);
+                lp = fmaf(__uint_as_float(pk2[q][i + 1] & 0xffff0000u), wv.w, lp);
+              }
+            }
+          }
+          // the two warps of this lane quarter hold the two halves of every row's channels: exchange the logit partials
+          float* lpb = lpart + (ecount & 1u) * 256;
+          ++ecount;
+          lpb[(warp - 4) * 32 + lane] = lp;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + sub) : "memory");
+          float lg = lpb[sub * 32 + lane] + lpb[(sub + 4) * 32 + lane] + p.se_bk;
+          lg = row_ok ? lg : -INFINITY;
+          const float mx = warp_max(lg);
+          const float ev = lg > -INFINITY ? ex2_approx((lg - mx) * 1.4426950408889634f) : 0.f;
+          const float es = warp_sum(ev);
+          float e4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) e4[k] = __shfl_sync(0xffffffffu, ev, 8 * k + rl);
+          float* rec = p.se_ws + rec_tile + (int64_t)(j * 4 + sub) * (p.Co + 2);
+          if (half == 0 && lane == 0) { rec[0] = mx; rec[1] = es; }
+          const int w2 = c.w0 + 8 * j + rl;
+          const int64_t row0 = ((((int64_t)c.b * p.T + c.t) * p.H + h20) * p.W + w2) * p.Co + piece * 8;
+          const int kmax = w2 < p.W ? p.H - h20 : 0;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c0 = ((j + half) & 1) * 32 + 64 * q;
+            if (c0 < p.bn) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((g ^ wsw) << 4)), "r"(pk2[q][4 * g]),
+                             "r"(pk2[q][4 * g + 1]), "r"(pk2[q][4 * g + 2]), "r"(pk2[q][4 * g + 3]) : "memory");
+              __syncwarp();
+              __nv_bfloat16* yp = p.epi.y + row0 + c0;
+              float t[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) t[i] = 0.f;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint4 v;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                             : "r"(rd + k * 512 + ((piece ^ (((8 * k + rl) >> 1) & 3)) << 4)));
+                if (k < kmax) *reinterpret_cast<uint4*>(yp + k * kstride) = v;
+                const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  t[2 * i] = fmaf(e4[k], __uint_as_float(vv[i] << 16), t[2 * i]);
+                  t[2 * i + 1] = fmaf(e4[k], __uint_as_float(vv[i] & 0xffff0000u), t[2 * i + 1]);
+                }
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                t[i] += __shfl_xor_sync(0xffffffffu, t[i], 4);
+                t[i] += __shfl_xor_sync(0xffffffffu, t[i], 8);
+                t[i] += __shfl_xor_sync(0xffffffffu, t[i], 16);
+              }
+              if (rl == 0) {
+                float2* dst = reinterpret_cast<float2*>(rec + 2 + c0 + piece * 8);
+                dst[0] = make_float2(t[0], t[1]); dst[1] = make_float2(t[2], t[3]);
+                dst[2] = make_float2(t[4], t[5]); dst[3] = make_float2(t[6], t[7]);
+              }
+            }
+          }
+        }
+      } else
       for (int j = 0; j < p.mw; ++j) {
         const int w = c.w0 + 8 * j + lw;
         const bool row_ok = h < p.H && w < p.W;
@@ -530,13 +737,20 @@ static int slab_fill_plan(const mv2_tc_conv_args* a, int n_sm, SlabParams& p, in
     if (taps2d % d == 0 && d * p.bn * p.row_bytes <= 32 * 1024) { p.tpw = d; break; }
   if (p.cluster > 1) p.tpw = 1;
   if (const char* env = getenv("MV2_SLAB_TPW")) { const int v = atoi(env); if (v >= 1 && taps2d % v == 0 && v * p.bn * p.row_bytes <= 64 * 1024) p.tpw = v; }
-  const int w_bytes = p.bn * p.row_bytes * p.tpw;
+  int w_bytes = p.bn * p.row_bytes * p.tpw;
   const int nb_pad = p.n_tiles_n * p.bn;   // bias staging covers the padded column range
   const bool res_stage = a->res != nullptr && a->epi_mode == 0 && a->shuffle == MV2_SHUFFLE_NONE && a->Co % 8 == 0;   // EPI_PLAIN_RES
   const int budget = 204 * 1024 - nb_pad * 4 - (res_stage ? 16 * 1024 : 0);   // 227 KB minus the epilogue transpose buffers (16 / 32 KB), barriers, alignment slack
   p.slab_stages = p.slab_stride * 3 + w_bytes * 3 <= budget ? 3 : 2;
   p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
   if (p.w_stages < 2 && p.slab_stages > 2) { p.slab_stages = 2; p.w_stages = std::min(12, (budget - 2 * p.slab_stride) / w_bytes); }
+  while (p.w_stages < 2 && p.tpw > 1) {   // wide slabs (mw = 4) + the fp32 residual staging: fall back to fewer taps per weight stage
+    int d = p.tpw - 1;
+    while (d > 1 && taps2d % d != 0) --d;
+    p.tpw = d;
+    w_bytes = p.bn * p.row_bytes * p.tpw;
+    p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
+  }
   MV2_CHECK_ARG(p.w_stages >= 2);
 
   *bk_out = bk; *w_bytes_out = w_bytes; *co_pad_out = co_pad; *nb_pad_out = nb_pad;
@@ -631,6 +845,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_SHUFFLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_PLAIN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_FUSED_RU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return e;
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
@@ -641,6 +856,150 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   else if (a->Co % 8 != 0) launch_kc(tc_slab_kernel<EPI_RAGGED>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   else if (a->res) launch_kc(tc_slab_kernel<EPI_PLAIN_RES>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   else launch_kc(tc_slab_kernel<EPI_PLAIN>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+
+// =====================================================================================================================
+// Fused ResidualUnit front half: y = ELU(conv1x1x1(ELU(causal_conv3x3x3(x)))) + SqueezeExcite pool partials, one launch.
+// =====================================================================================================================
+static void ru_as_conv_args(const mv2_tc_ru_args* a, mv2_tc_conv_args* c) {
+  memset(c, 0, sizeof(*c));
+  c->x = a->x; c->w = a->w3; c->bias = a->b3; c->res = nullptr; c->y = a->y;
+  c->B = a->B; c->Ti = c->To = a->T; c->Hi = c->Ho = a->H; c->Wi = c->Wo = a->W; c->Ci = c->Co = a->C;
+  c->kt = a->kt; c->kh = a->kh; c->kw = a->kw; c->st = c->sh = c->sw = 1;
+  c->pt = a->kt - 1; c->ph = a->kh / 2; c->pw = a->kw / 2;
+  c->act = MV2_ACT_ELU; c->shuffle = MV2_SHUFFLE_NONE; c->epi_mode = 0;
+}
+
+extern "C" int mv2_tc_ru_supported(const mv2_tc_ru_args* a) {
+  if (!a) return 0;
+  if (a->C != 64 && a->C != 128) return 0;            // all of Co in one N tile (bn = C), mw * C = 256 TMEM columns per buffer
+  if (a->W <= 8) return 0;                            // needs mw >= 2 M-tiles side by side
+  if (a->kt < 1 || a->kt > 8 || a->kh < 1 || a->kh > 7 || a->kw < 1 || a->kw > 3) return 0;
+  if ((a->kh & 1) == 0 || (a->kw & 1) == 0) return 0;
+  mv2_tc_conv_args c;
+  ru_as_conv_args(a, &c);
+  return mv2_tc_slab_supported(&c);
+}
+
+// tiling + shared-memory plan of the fused kernel (host arithmetic only)
+static int ru_fill_plan(const mv2_tc_ru_args* a, int n_sm, SlabParams& p, size_t* smem_out) {
+  mv2_tc_conv_args c;
+  ru_as_conv_args(a, &c);
+  int bk, w_bytes, co_pad, nb_pad;
+  const int rc = slab_fill_plan(&c, n_sm, p, &bk, &w_bytes, &co_pad, &nb_pad);
+  if (rc != MV2_OK) return rc;
+  MV2_CHECK_ARG(p.bn == a->C && p.n_tiles_n == 1 && p.cluster == 1 && p.row_bytes == 128);
+  // defaults (profiles/r02_sweep_ru.json): C = 128: 2 M-tiles, one H buffer; C = 64: 4 M-tiles (W > 16), two H buffers
+  int mw = (a->C == 64 && a->W > 16) ? 4 : 2, nh = a->C == 64 ? 2 : 1, tpw = 1, slab_stages = 2, w_stages = 0;
+  if (const char* env = getenv("MV2_RU_CFG")) {      // tuning override: "mw,nh,tpw,slab_stages,w_stages" (0 = derive)
+    int v[5] = {0, 0, 0, 0, 0};
+    if (sscanf(env, "%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4]) >= 1) {
+      if ((v[0] == 2 || v[0] == 4) && v[0] * a->C <= 256 && !(v[0] == 4 && a->W <= 16)) mw = v[0];
+      if (v[1] == 1 || v[1] == 2) nh = v[1];
+      if (v[2] >= 1 && (a->kh * a->kw) % v[2] == 0) tpw = v[2];
+      if (v[3] == 2 || v[3] == 3) slab_stages = v[3];
+      if (v[4] >= 2) w_stages = v[4];
+    }
+  }
+  p.mw = mw; p.nh = nh; p.tpw = tpw;
+  p.tiles_w = ceil_div(a->W, 8 * p.mw);
+  p.total_tiles = (int)((int64_t)a->B * a->T * p.tiles_h * p.tiles_w);
+  p.pitch = 8 * p.mw + a->kw - 1;
+  p.slab_bytes = p.pitch * p.slab_h * p.row_bytes;
+  p.slab_stride = (p.slab_bytes + 1023) / 1024 * 1024;
+  p.nbuf = 2; p.acc_stride = 256;
+  p.h_stride = p.kchunks * 16384;
+  const int wb = p.bn * p.row_bytes * p.tpw;
+  const size_t fixed = 1024 /* base alignment */ + 8 * (2 * 3 + 2 * 16 + 4 + 9) + 64 /* barriers, tmem slot */ + (size_t)3 * nb_pad * 4 +
+                       2048 /* logit partials */ + 1024 /* H alignment */ + (size_t)p.nh * p.h_stride /* H buffers = transpose buffers */ +
+                       (size_t)p.kchunks * p.bn * p.row_bytes /* resident 1x1x1 weights */;
+  MV2_CHECK_ARG(p.nh * p.h_stride >= 8 * 2048);
+  const size_t total = 227 * 1024;
+  p.slab_stages = slab_stages;
+  while (p.slab_stages > 2 && fixed + (size_t)p.slab_stages * p.slab_stride + 2 * (size_t)wb > total) --p.slab_stages;
+  const int64_t room = (int64_t)total - (int64_t)fixed - (int64_t)p.slab_stages * p.slab_stride;
+  p.w_stages = (int)std::min<int64_t>(12, room / wb);
+  if (w_stages >= 2 && w_stages <= p.w_stages) p.w_stages = w_stages;
+  MV2_CHECK_ARG(p.w_stages >= 2);
+  *smem_out = fixed + (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * wb;
+  p.bias1 = a->b1; p.se_wk = a->se_wk; p.se_bk = a->se_bk; p.se_ws = a->se_ws;
+  return MV2_OK;
+}
+
+extern "C" int mv2_tc_ru_records(const mv2_tc_ru_args* a) {
+  if (!mv2_tc_ru_supported(a)) { set_error("mv2_tc_ru_records: unsupported shape"); return MV2_E_UNSUPPORTED; }
+  SlabParams p;
+  size_t smem;
+  const int rc = ru_fill_plan(a, 148, p, &smem);
+  if (rc != MV2_OK) return rc;
+  return p.tiles_h * p.tiles_w * p.mw * 4;
+}
+
+extern "C" size_t mv2_tc_ru_workspace_bytes(const mv2_tc_ru_args* a) {
+  const int recs = mv2_tc_ru_records(a);
+  if (recs <= 0) return 0;
+  const size_t F = (size_t)a->B * a->T;
+  return (F * recs * (a->C + 2) + F * (a->C + 16)) * sizeof(float);    // pool records + the SE hidden layer (mv2_se_gate_records)
+}
+
+extern "C" int mv2_tc_ru_forward(const mv2_tc_ru_args* a, void* stream) {
+  MV2_CHECK_ARG(a && a->x && a->w3 && a->w1 && a->y && a->se_wk && a->se_ws);
+  if (!mv2_tc_ru_supported(a)) { set_error("mv2_tc_ru_forward: unsupported shape"); return MV2_E_UNSUPPORTED; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MV2_E_CUDA; }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  SlabParams p;
+  size_t smem = 0;
+  {
+    const int rc = ru_fill_plan(a, n_sm, p, &smem);
+    if (rc != MV2_OK) return rc;
+  }
+  MV2_CHECK_ARG(smem <= 227 * 1024);
+  const int bk = 64;
+  {
+    const int64_t C = a->C, W = a->W, H = a->H, T = a->T;
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T, (cuuint64_t)a->B};
+    cuuint64_t strides[4] = {(cuuint64_t)(C * 2), (cuuint64_t)(W * C * 2), (cuuint64_t)(H * W * C * 2), (cuuint64_t)(T * H * W * C * 2)};
+    cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)p.pitch, (cuuint32_t)p.slab_h, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&p.amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)a->x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(slab) failed: %d", (int)r); return MV2_E_CUDA; }
+  }
+  {
+    const int64_t ntaps = (int64_t)a->kt * a->kh * a->kw, K = ntaps * a->C;
+    cuuint64_t dims[3] = {(cuuint64_t)a->C, (cuuint64_t)a->C, (cuuint64_t)ntaps};
+    cuuint64_t strides[2] = {(cuuint64_t)(K * 2), (cuuint64_t)(a->C * 2)};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.bn, (cuuint32_t)p.tpw};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)a->w3, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(w3) failed: %d", (int)r); return MV2_E_CUDA; }
+    cuuint64_t dims2[2] = {(cuuint64_t)K, (cuuint64_t)a->C};
+    cuuint64_t strides2[1] = {(cuuint64_t)(K * 2)};
+    cuuint32_t box2[2] = {(cuuint32_t)bk, (cuuint32_t)p.bn};
+    cuuint32_t es2[2] = {1, 1};
+    r = enc(&p.wmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a->w3, dims2, strides2, box2, es2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(w3 2-D) failed: %d", (int)r); return MV2_E_CUDA; }
+    cuuint64_t dims1[2] = {(cuuint64_t)a->C, (cuuint64_t)a->C};
+    cuuint64_t strides1[1] = {(cuuint64_t)(a->C * 2)};
+    r = enc(&p.w1map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a->w1, dims1, strides1, box2, es2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(w1) failed: %d", (int)r); return MV2_E_CUDA; }
+  }
+  static PerDeviceOnce attr_once;
+  const cudaError_t attr_err = attr_once.run([] {
+    return cudaFuncSetAttribute(tc_slab_kernel<EPI_FUSED_RU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
+  const int grid = std::min(p.total_tiles, n_sm);
+  launch_kc(tc_slab_kernel<EPI_FUSED_RU>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, 1, p);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

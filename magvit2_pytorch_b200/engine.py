@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_ELU, ACT_NONE, ACT_SILU, MV2_BF16, MV2_F32, SHUFFLE_NONE, SHUFFLE_SPACE,
-                   SHUFFLE_TIME, AttnArgs, ConvArgs, TcConvArgs, check)
+                   SHUFFLE_TIME, AttnArgs, ConvArgs, TcConvArgs, TcRuArgs, check)
 
 
 def _dt(t: torch.dtype) -> int:
@@ -137,6 +137,8 @@ class Engine:
         self.launches = 0            # kernels launched through the C ABI (bench's gpu_launches)
         self.use_tc = True           # bf16: dense contractions on tcgen05 (False -> CUDA-core cross-check path)
         self.tc_variant = "auto"     # "auto" | "tap" (tc_conv.cu only) | "slab" (prefer tc_slab.cu)
+        self.fuse_ru = True          # bf16: conv3x3x3 + ELU + conv1x1x1 + ELU + SE pool partials in one tcgen05 launch (C = 64 / 128)
+        self.fused_ru_calls = 0
         self.tc_calls = 0
         self.slab_calls = 0
         self.simt_conv_calls = 0
@@ -322,13 +324,43 @@ class Engine:
     def residual_unit(self, x, p):
         """ResidualUnit (reference M:930-944): x + SE(ELU(conv1(ELU(causal_conv3(x)))))."""
         B, T, H, W, Cc = x.shape
-        h = self.conv(x, p["conv3"], act=ACT_ELU)
-        y = self.conv(h, p["conv1"], act=ACT_ELU)
         F_, Pn = B * T, H * W
-        ws = self._new((self.lib.mv2_se_workspace_bytes(F_, Pn, Cc) // 4,), torch.float32)
-        gates = self._new((F_, Cc), torch.float32)
         st = self._stream()
         dt = _dt(self.dtype)
+        c3, c1 = p["conv3"], p["conv1"]
+        if self.dtype == torch.bfloat16 and self.use_tc and self.fuse_ru and c3.w_tc is not None and self.tc_variant != "tap":
+            ra = TcRuArgs(x=_ptr(x), w3=_ptr(c3.w_tc), b3=_ptr(c3.bias_tc), w1=_ptr(c1.w_tc), b1=_ptr(c1.bias_tc),
+                          se_wk=_ptr(p["wk"]), se_bk=p["bk"], y=None, se_ws=None, B=B, T=T, H=H, W=W, C=Cc,
+                          kt=c3.k[0], kh=c3.k[1], kw=c3.k[2])
+            if self.lib.mv2_tc_ru_supported(C.byref(ra)):
+                y = self._new(x.shape)
+                ws = self._new((self.lib.mv2_tc_ru_workspace_bytes(C.byref(ra)) // 4,), torch.float32)
+                ra.y, ra.se_ws = _ptr(y), _ptr(ws)
+                nrec = self.lib.mv2_tc_ru_records(C.byref(ra))
+                if self._prof is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                check(self.lib.mv2_tc_ru_forward(C.byref(ra), st), "mv2_tc_ru_forward")
+                if self._prof is not None:
+                    e1.record()
+                    self._prof.append((e0, e1, 2.0 * B * T * H * W * (c3.macs + c1.macs), "slab", c3.k[0] * c3.k[1] * c3.k[2]))
+                if self.conv_log is not None:
+                    self.conv_log.append(dict(kind="slab", Ci=Cc, Co=Cc, k=tuple(c3.k), out=(B, T, H, W), geglu=False, shuffle=0,
+                                              res=False, fused_ru=True))
+                gates = self._new((F_, Cc), torch.float32)
+                check(self.lib.mv2_se_gate_records(_ptr(ws), nrec, F_, Cc, p["hidden"], _ptr(p["w1"]), _ptr(p["b1"]), _ptr(p["w2"]),
+                                                   _ptr(p["b2"]), _ptr(gates), st), "mv2_se_gate_records")
+                out = self._new(x.shape)
+                check(self.lib.mv2_gate_residual(_ptr(y), _ptr(x), _ptr(gates), _ptr(out), dt, F_, Pn, Cc, st), "mv2_gate_residual")
+                self.launches += 4
+                self.tc_calls += 1
+                self.slab_calls += 1
+                self.fused_ru_calls += 1
+                return out
+        h = self.conv(x, c3, act=ACT_ELU)
+        y = self.conv(h, c1, act=ACT_ELU)
+        ws = self._new((self.lib.mv2_se_workspace_bytes(F_, Pn, Cc) // 4,), torch.float32)
+        gates = self._new((F_, Cc), torch.float32)
         check(self.lib.mv2_se_pool(_ptr(y), dt, F_, Pn, Cc, _ptr(p["wk"]), p["bk"], _ptr(ws), st), "mv2_se_pool")
         check(self.lib.mv2_se_gate(_ptr(ws), dt, F_, Pn, Cc, p["hidden"], _ptr(p["w1"]), _ptr(p["b1"]), _ptr(p["w2"]),
                                    _ptr(p["b2"]), _ptr(gates), st), "mv2_se_gate")

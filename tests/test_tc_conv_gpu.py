@@ -310,3 +310,67 @@ def test_linear_attention_tensor_core_kernels_match_fp32_cuda_core(L, heads, nse
     assert (b_.cpu() - o_).abs().max().item() < 1e-4 * o_.abs().max().item() + 1e-4
     assert (a_.cpu() - o_).abs().max().item() < 0.04 * o_.abs().max().item() + 5e-3
     assert (a_.cpu() - o_).abs().mean().item() < 0.01 * o_.abs().mean().item() + 1e-3
+
+
+RU_CASES = [
+    # name, C, (B, T, H, W)
+    ("ru_c64_mw4_small", 64, (1, 3, 32, 32)),
+    ("ru_c64_mw2_w16", 64, (2, 3, 16, 16)),
+    ("ru_c128_small", 128, (1, 4, 16, 32)),
+    ("ru_c64_ragged_24x20", 64, (1, 3, 24, 20)),
+    ("ru_c128_ragged_20x24", 128, (2, 3, 20, 24)),
+    ("ru_c64_multi_tile_per_cta", 64, (1, 10, 128, 128)),      # 320 tiles: 2-3 tiles per persistent CTA
+    ("ru_c128_multi_tile_per_cta", 128, (2, 5, 64, 64)),       # 320 tiles
+]
+
+
+def _ru_pack(C_, g):
+    w3 = (torch.randn((C_, C_, 3, 3, 3), generator=g) * (27 * C_) ** -0.5).cuda()
+    b3 = (torch.randn(C_, generator=g) * 0.1).cuda()
+    w1 = (torch.randn((C_, C_, 1, 1, 1), generator=g) * C_ ** -0.5).cuda()
+    b1 = (torch.randn(C_, generator=g) * 0.1).cuda()
+    hd = max(16, C_ // 2)
+    wk = (torch.randn(C_, generator=g) * C_ ** -0.5).cuda()
+    bk = float(torch.randn(1, generator=g).item() * 0.1)
+    sw1 = (torch.randn((hd, C_), generator=g) * C_ ** -0.5).cuda()
+    sb1 = (torch.randn(hd, generator=g) * 0.1).cuda()
+    sw2 = (torch.randn((C_, hd), generator=g) * hd ** -0.5).cuda()
+    sb2 = (torch.randn(C_, generator=g) * 0.1).cuda()
+    p = dict(conv3=pack_conv(w3, b3, torch.bfloat16), conv1=pack_conv(w1, b1, torch.bfloat16), wk=wk.contiguous(), bk=bk,
+             w1=sw1.contiguous(), b1=sb1, w2=sw2.contiguous(), b2=sb2, hidden=hd)
+    sd = {"fn.0.conv.weight": w3.to(torch.bfloat16).float().cpu(), "fn.0.conv.bias": b3.cpu(),
+          "fn.2.weight": w1.to(torch.bfloat16).float().cpu(), "fn.2.bias": b1.cpu(),
+          "fn.4.to_k.weight": wk.cpu().reshape(1, C_, 1, 1), "fn.4.to_k.bias": torch.tensor([bk]),
+          "fn.4.net.0.weight": sw1.cpu().reshape(hd, C_, 1, 1), "fn.4.net.0.bias": sb1.cpu(),
+          "fn.4.net.2.weight": sw2.cpu().reshape(C_, hd, 1, 1), "fn.4.net.2.bias": sb2.cpu()}
+    return p, sd
+
+
+@pytest.mark.parametrize("case", RU_CASES, ids=[c[0] for c in RU_CASES])
+def test_fused_residual_unit(case):
+    """mv2_tc_ru_forward (conv3x3x3 + ELU + conv1x1x1 + ELU + SE pool records in one tcgen05 launch) + gate + residual
+    against (a) the unfused kernels on identical inputs and (b) the CPU oracle's residual_unit (M:930-944)."""
+    assert torch.cuda.is_available()
+    name, C_, (B, T, H, W) = case
+    g = torch.Generator(device="cpu").manual_seed(sum(map(ord, name)))
+    p, sd = _ru_pack(C_, g)
+    x = torch.randn((B, T, H, W, C_), generator=g).cuda().to(torch.bfloat16)
+    eng = _engine()
+    eng.use_tc, eng.tc_variant = True, "auto"
+    eng.fuse_ru, eng.fused_ru_calls = True, 0
+    out_f = eng.residual_unit(x, p)
+    assert eng.fused_ru_calls == 1, "fused kernel was not taken"
+    eng.fuse_ru = False
+    out_u = eng.residual_unit(x, p)
+    torch.cuda.synchronize()
+    eng.fuse_ru = True
+    a, b = out_f.float().cpu(), out_u.float().cpu()
+    assert torch.isfinite(a).all()
+    # same bf16 operands and fp32 accumulation in both paths; only the SE pooling order differs (fp32 round-off in the gate)
+    assert (a - b).abs().max().item() <= 2.0 ** -7 * b.abs().max().item() + 1e-3, (name, (a - b).abs().max().item())
+    assert (a != b).float().mean().item() < 0.02, (name, (a != b).float().mean().item())
+    ref = R.residual_unit(x.float().cpu().permute(0, 4, 1, 2, 3).contiguous(), sd, "").permute(0, 2, 3, 4, 1)
+    err = (a - ref).abs()
+    # three bf16 roundings along the unit (h, y, out) against the fp32 oracle
+    assert err.max().item() <= 0.02 * ref.abs().max().item() + 5e-3, (name, err.max().item())
+    assert err.mean().item() <= 0.004 * ref.abs().mean().item() + 2e-4, (name, err.mean().item())
