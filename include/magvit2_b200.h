@@ -223,7 +223,7 @@ int mv2_tc_slab_tile(const mv2_tc_conv_args* a, int n_sm, int cta, int k, int* o
  * One launch computes  y = ELU(Conv3d_1x1x1(ELU(CausalConv3d_ktxkhxkw(x))))  for C -> C channels (C = 64 or 128, the
  * HBM-bound levels of the README config): the ELU'd 3x3x3 tile never leaves the SM -- it is written to shared memory as the
  * A operand of a second tcgen05.mma against the 1x1x1 weights -- and the second epilogue emits, next to y, one SqueezeExcite
- * pool record (max logit, sum e, sum e * y[C]; e = exp(logit - max), logit = <y, se_wk> + se_bk) per 32-position row group,
+ * pool record (max logit, sum e, sum e * y[C]; e = exp(logit - max), logit = <y, se_wk> + se_bk) per TMEM lane quarter of a tile,
  * which mv2_se_gate_records combines (replaces mv2_conv_forward x2 + mv2_se_pool for these layers).
  * w3: bf16 [C][kt*kh*kw*C] (K-major, as mv2_tc_conv_args.w); w1: bf16 [C][C]; b3 / b1 / se_wk: fp32 [C].
  * se_ws: workspace of mv2_tc_ru_workspace_bytes(a) bytes; records per frame = mv2_tc_ru_records(a).                     */

@@ -525,10 +525,27 @@ __global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict_
     if (lane == 0) s_inv = 1.f / s;
   }
   __syncthreads();
-  for (int c = tid; c < C; c += 256) {
+  if (C <= 128 && (C & (C - 1)) == 0) {
+    // narrow layers: 256 / C thread groups each fold a strided subset of the chunk records (the fused ResidualUnit kernel
+    // writes hundreds of small records per frame), then the groups are summed through shared memory
+    float* part = sm + C + n_chunks;                  // [256]
+    const int nparts = 256 / C, c = tid & (C - 1), pi = tid / C;
     float acc = 0.f;
-    for (int k = 0; k < n_chunks; ++k) acc = fmaf(coef[k], wf[(int64_t)k * (C + 2) + 2 + c], acc);
-    pooled[c] = acc * s_inv;
+#pragma unroll 4
+    for (int k = pi; k < n_chunks; k += nparts) acc = fmaf(coef[k], wf[(int64_t)k * (C + 2) + 2 + c], acc);
+    part[tid] = acc;
+    __syncthreads();
+    if (tid < C) {
+      float t = 0.f;
+      for (int q = 0; q < nparts; ++q) t += part[q * C + tid];
+      pooled[tid] = t * s_inv;
+    }
+  } else {
+    for (int c = tid; c < C; c += 256) {
+      float acc = 0.f;
+      for (int k = 0; k < n_chunks; ++k) acc = fmaf(coef[k], wf[(int64_t)k * (C + 2) + 2 + c], acc);
+      pooled[c] = acc * s_inv;
+    }
   }
   __syncthreads();
   const int j0 = blockIdx.y * 32 + warp * 4;
@@ -1771,7 +1788,7 @@ int mv2_se_gate(const void* workspace, int dtype, int F, int P, int C, int Hd, c
                 const float* w2, const float* b2, float* gates, void* stream) {
   MV2_CHECK_ARG(workspace && w1 && b1 && w2 && b2 && gates && F > 0 && P > 0 && C > 0 && Hd > 0);
   const int nc = ceil_div(P, se_rows_per_block(dtype, F, P, C));   // chunk records se_pool wrote per frame
-  const size_t smem1 = (size_t)(C + nc) * sizeof(float), smem2 = (size_t)Hd * sizeof(float);
+  const size_t smem1 = (size_t)(C + nc + 256) * sizeof(float), smem2 = (size_t)Hd * sizeof(float);
   MV2_CHECK_ARG(smem1 <= 48 * 1024 && smem2 <= 48 * 1024);
   // hidden activations live behind the chunk partials (mv2_se_workspace_bytes reserves F*Hd_max floats)
   float* hidden = (float*)workspace + (size_t)F * ceil_div(P, SE_MIN_ROWS) * (C + 2);
@@ -1786,7 +1803,7 @@ int mv2_se_gate(const void* workspace, int dtype, int F, int P, int C, int Hd, c
 int mv2_se_gate_records(const void* workspace, int nrec, int F, int C, int Hd, const float* w1, const float* b1,
                         const float* w2, const float* b2, float* gates, void* stream) {
   MV2_CHECK_ARG(workspace && w1 && b1 && w2 && b2 && gates && F > 0 && nrec > 0 && C > 0 && Hd > 0);
-  const size_t smem1 = (size_t)(C + nrec) * sizeof(float), smem2 = (size_t)Hd * sizeof(float);
+  const size_t smem1 = (size_t)(C + nrec + 256) * sizeof(float), smem2 = (size_t)Hd * sizeof(float);
   MV2_CHECK_ARG(smem1 <= 48 * 1024 && smem2 <= 48 * 1024);
   float* hidden = (float*)workspace + (size_t)F * nrec * (C + 2);
   cudaStream_t st = (cudaStream_t)stream;

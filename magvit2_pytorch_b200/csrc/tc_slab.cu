@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         for (int j = 0; j < p.mw; ++j) {
           if (j >= p.nh) mbar_wait(m2_done + 8 * (j - p.nh), par);
           const uint32_t hb = hbuf0 + (uint32_t)((p.nh == 2) ? (j & 1) : 0) * p.h_stride + (uint32_t)row * 128;
-          for (int c0 = ((j + half) & 1) * 32; c0 < p.bn; c0 += 64) {
+          for (int c0 = half * 32; c0 < p.bn; c0 += 64) {      // fused: a warp owns the same columns in every M-tile
             uint32_t r[32], pk[16];
             tmem_ld_32x32b_x32(tl0 + j * p.bn + c0, r);
             tmem_ld_wait();
@@ -394,8 +394,14 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         const uint32_t rd = stg + rl * 64;
         const int h20 = c.h0 + sub * 4;
         const int64_t kstride = (int64_t)p.W * p.Co;
-        const int recs_per_frame = p.tiles_h * p.tiles_w * p.mw * 4;
-        const int64_t rec_tile = ((int64_t)(c.b * p.T + c.t) * recs_per_frame + ((c.h0 >> 4) * p.tiles_w + c.w0 / (8 * p.mw)) * (p.mw * 4)) * (p.Co + 2);
+        // one record per (tile, lane quarter): the M-tiles of the tile are folded in registers (online softmax over j)
+        const int recs_per_frame = p.tiles_h * p.tiles_w * 4;
+        float* rec = p.se_ws + ((int64_t)(c.b * p.T + c.t) * recs_per_frame + ((c.h0 >> 4) * p.tiles_w + c.w0 / (8 * p.mw)) * 4 + sub) * (p.Co + 2);
+        float run_m = -INFINITY, run_s = 0.f, run_acc[2][8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) run_acc[q][i] = 0.f;
         for (int j = 0; j < p.mw; ++j) {
           mbar_wait(m2_done + 8 * j, par);
           tc_fence_after();
@@ -405,7 +411,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
           float lp = 0.f;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const int c0 = ((j + half) & 1) * 32 + 64 * q;
+            const int c0 = half * 32 + 64 * q;
             if (c0 < p.bn) {
               uint32_t r[32];
               tmem_ld_32x32b_x32(tl0 + j * p.bn + c0, r);
@@ -434,14 +440,17 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
           float e4[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) e4[k] = __shfl_sync(0xffffffffu, ev, 8 * k + rl);
-          float* rec = p.se_ws + rec_tile + (int64_t)(j * 4 + sub) * (p.Co + 2);
-          if (half == 0 && lane == 0) { rec[0] = mx; rec[1] = es; }
+          const float new_m = fmaxf(run_m, mx);
+          const float ca = run_m > -INFINITY ? ex2_approx((run_m - new_m) * 1.4426950408889634f) : 0.f;   // rescales what is held
+          const float cb = mx > -INFINITY ? ex2_approx((mx - new_m) * 1.4426950408889634f) : 0.f;         // weights this M-tile
+          run_s = fmaf(run_s, ca, es * cb);
+          run_m = new_m;
           const int w2 = c.w0 + 8 * j + rl;
           const int64_t row0 = ((((int64_t)c.b * p.T + c.t) * p.H + h20) * p.W + w2) * p.Co + piece * 8;
           const int kmax = w2 < p.W ? p.H - h20 : 0;
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const int c0 = ((j + half) & 1) * 32 + 64 * q;
+            const int c0 = half * 32 + 64 * q;
             if (c0 < p.bn) {
 #pragma unroll
               for (int g = 0; g < 4; ++g)
@@ -472,11 +481,20 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
                 t[i] += __shfl_xor_sync(0xffffffffu, t[i], 8);
                 t[i] += __shfl_xor_sync(0xffffffffu, t[i], 16);
               }
-              if (rl == 0) {
-                float2* dst = reinterpret_cast<float2*>(rec + 2 + c0 + piece * 8);
-                dst[0] = make_float2(t[0], t[1]); dst[1] = make_float2(t[2], t[3]);
-                dst[2] = make_float2(t[4], t[5]); dst[3] = make_float2(t[6], t[7]);
-              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) run_acc[q][i] = fmaf(run_acc[q][i], ca, t[i] * cb);
+            }
+          }
+        }
+        if (half == 0 && lane == 0) { rec[0] = run_m; rec[1] = run_s; }
+        if (rl == 0) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c0 = half * 32 + 64 * q;
+            if (c0 < p.bn) {
+              float2* dst = reinterpret_cast<float2*>(rec + 2 + c0 + piece * 8);
+              dst[0] = make_float2(run_acc[q][0], run_acc[q][1]); dst[1] = make_float2(run_acc[q][2], run_acc[q][3]);
+              dst[2] = make_float2(run_acc[q][4], run_acc[q][5]); dst[3] = make_float2(run_acc[q][6], run_acc[q][7]);
             }
           }
         }
@@ -487,7 +505,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         const uint32_t tl = tmem_base + buf * p.acc_stride + j * p.bn + ((uint32_t)(sub * 32) << 16);
         const int64_t row_base = ((((int64_t)c.b * p.T + c.t) * p.H + h) * p.W + w) * p.Co;
         // column chunks are dealt round-robin to the two warps that share this lane quarter
-        if (MODE == EPI_PLAIN) {
+        if (MODE == EPI_PLAIN || MODE == EPI_SHUFFLE_ST) {
           // Row-per-lane results are transposed through shared memory so that every store instruction writes 8 rows
           // x 64 contiguous bytes (full sectors; the 8 rows are neighbours along w, i.e. one contiguous run when the
           // tile spans all of Co) instead of 32 scattered 16-byte pieces.  The residual is read with the same mapping.
@@ -514,13 +532,31 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
             __syncwarp();
             const bool col_ok = c.n0 + c0 + piece * 8 < p.Co && c0 + piece * 8 < p.bn;
             const int klim = col_ok ? kmax : 0;
-            __nv_bfloat16* yp = p.epi.y + row0 + c0;
+            __nv_bfloat16* yp;
+            int64_t ks;
+            if (MODE == EPI_SHUFFLE_ST) {
+              // packed GEMM columns are (q, c): this chunk's 32 columns share one sub-pixel phase q (Cy % 32 == 0), so a
+              // row's 64 bytes land contiguously at its shuffled position (reference M:824 / M:861 rearranges)
+              const int n = c.n0 + c0;
+              if (p.epi.shuffle == MV2_SHUFFLE_SPACE) {
+                const int cy = p.Co >> 2, qd = n / cy, cb = n - qd * cy;
+                yp = p.epi.y + ((((int64_t)c.b * p.T + c.t) * (2 * p.H) + (2 * h20 + (qd >> 1))) * (2 * p.W) + (2 * w2 + (qd & 1))) * cy + cb + piece * 8;
+                ks = (int64_t)4 * p.W * cy;          // next h row = two output rows further
+              } else {
+                const int cy = p.Co >> 1, qd = n / cy, cb = n - qd * cy;
+                yp = p.epi.y + ((((int64_t)c.b * (2 * p.T) + (2 * c.t + qd)) * p.H + h20) * p.W + w2) * cy + cb + piece * 8;
+                ks = (int64_t)p.W * cy;
+              }
+            } else {
+              yp = p.epi.y + row0 + c0;
+              ks = kstride;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               uint4 v;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                            : "r"(rd + k * 512 + ((piece ^ (((8 * k + rl) >> 1) & 3)) << 4)));
-              if (k < klim) *reinterpret_cast<uint4*>(yp + k * kstride) = v;
+              if (k < klim) *reinterpret_cast<uint4*>(yp + k * ks) = v;
             }
             __syncwarp();
           }
@@ -846,12 +882,15 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_RAGGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_PLAIN_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_FUSED_RU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_slab_kernel<EPI_SHUFFLE_ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     return e;
   });
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
   int grid = std::min(p.total_tiles, n_sm);
   if (p.cluster > 1) grid &= ~1;
   if (a->epi_mode == 1) launch_kc(tc_slab_kernel<EPI_GEGLU>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
+  else if (a->shuffle != MV2_SHUFFLE_NONE && (a->Co / (a->shuffle == MV2_SHUFFLE_SPACE ? 4 : 2)) % 32 == 0 && !getenv("MV2_NO_SHUFFLE_ST"))
+    launch_kc(tc_slab_kernel<EPI_SHUFFLE_ST>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   else if (a->shuffle != MV2_SHUFFLE_NONE) launch_kc(tc_slab_kernel<EPI_SHUFFLE>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   else if (a->Co % 8 != 0) launch_kc(tc_slab_kernel<EPI_RAGGED>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   else if (a->res) launch_kc(tc_slab_kernel<EPI_PLAIN_RES>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
@@ -935,7 +974,7 @@ extern "C" int mv2_tc_ru_records(const mv2_tc_ru_args* a) {
   size_t smem;
   const int rc = ru_fill_plan(a, 148, p, &smem);
   if (rc != MV2_OK) return rc;
-  return p.tiles_h * p.tiles_w * p.mw * 4;
+  return p.tiles_h * p.tiles_w * 4;
 }
 
 extern "C" size_t mv2_tc_ru_workspace_bytes(const mv2_tc_ru_args* a) {
