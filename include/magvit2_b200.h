@@ -201,6 +201,10 @@ typedef struct mv2_tc_conv_args {
   int32_t shuffle;
   int32_t epi_mode;    /* 0 plain; 1 fused GEGLU (M:466-469): packed columns come in groups of 16 = 8 x-columns then
                           their 8 gate-columns, output has Co/2 channels: y = gelu_erf(gate) * x */
+  int32_t out_layout;  /* 0: y is channels-last (B,To,Ho,Wo,Co).  1: y is torch's channels-first (B,Co,To,Ho,Wo) -- the slab
+                          kernel's conv_out (Co % 8 != 0) writes the reconstruction directly in the caller's layout; with
+                          To < Ti and pt = kt - 1 - (Ti - To) the leading time_padding frames are never computed
+                          (reference M:1642-1647: conv_out, then video[:, :, time_padding:]).                            */
 } mv2_tc_conv_args;
 int mv2_tc_conv_supported(const mv2_tc_conv_args* a);
 int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream);

@@ -53,7 +53,7 @@ class TcConvArgs(C.Structure):
         ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
         ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
         ("pt", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
-        ("act", C.c_int32), ("shuffle", C.c_int32), ("epi_mode", C.c_int32),
+        ("act", C.c_int32), ("shuffle", C.c_int32), ("epi_mode", C.c_int32), ("out_layout", C.c_int32),
     ]
 
 

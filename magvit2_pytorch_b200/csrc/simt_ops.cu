@@ -499,6 +499,9 @@ __global__ void __launch_bounds__(256) se_pool_online_kernel(const __nv_bfloat16
   }
 }
 
+// NARROW (C <= 128, a power of two): 256 / C thread groups each fold a strided subset of the chunk records (the fused
+// ResidualUnit kernel writes ~100 small records per frame), then the groups are summed through shared memory.
+template <bool NARROW>
 __global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict__ ws, int n_chunks, int C, int Hd,
                                                         const float* __restrict__ w1, const float* __restrict__ b1,
                                                         float* __restrict__ hidden_out) {
@@ -525,13 +528,10 @@ __global__ void __launch_bounds__(256) se_hidden_kernel(const float* __restrict_
     if (lane == 0) s_inv = 1.f / s;
   }
   __syncthreads();
-  if (C <= 128 && (C & (C - 1)) == 0) {
-    // narrow layers: 256 / C thread groups each fold a strided subset of the chunk records (the fused ResidualUnit kernel
-    // writes hundreds of small records per frame), then the groups are summed through shared memory
+  if (NARROW) {
     float* part = sm + C + n_chunks;                  // [256]
     const int nparts = 256 / C, c = tid & (C - 1), pi = tid / C;
     float acc = 0.f;
-#pragma unroll 4
     for (int k = pi; k < n_chunks; k += nparts) acc = fmaf(coef[k], wf[(int64_t)k * (C + 2) + 2 + c], acc);
     part[tid] = acc;
     __syncthreads();
@@ -1793,7 +1793,7 @@ int mv2_se_gate(const void* workspace, int dtype, int F, int P, int C, int Hd, c
   // hidden activations live behind the chunk partials (mv2_se_workspace_bytes reserves F*Hd_max floats)
   float* hidden = (float*)workspace + (size_t)F * ceil_div(P, SE_MIN_ROWS) * (C + 2);
   cudaStream_t st = (cudaStream_t)stream;
-  launch_k(se_hidden_kernel, dim3(dim3(F, ceil_div(Hd, 32))), dim3(256), smem1, st, (const float*)workspace, nc, C, Hd, w1, b1, hidden);
+  launch_k(se_hidden_kernel<false>, dim3(dim3(F, ceil_div(Hd, 32))), dim3(256), smem1, st, (const float*)workspace, nc, C, Hd, w1, b1, hidden);
   MV2_CHECK_LAUNCH();
   launch_k(se_out_kernel, dim3(dim3(F, ceil_div(C, 64))), dim3(256), smem2, st, hidden, C, Hd, w2, b2, gates);
   MV2_CHECK_LAUNCH();
@@ -1807,7 +1807,10 @@ int mv2_se_gate_records(const void* workspace, int nrec, int F, int C, int Hd, c
   MV2_CHECK_ARG(smem1 <= 48 * 1024 && smem2 <= 48 * 1024);
   float* hidden = (float*)workspace + (size_t)F * nrec * (C + 2);
   cudaStream_t st = (cudaStream_t)stream;
-  launch_k(se_hidden_kernel, dim3(dim3(F, ceil_div(Hd, 32))), dim3(256), smem1, st, (const float*)workspace, nrec, C, Hd, w1, b1, hidden);
+  if (C <= 128 && (C & (C - 1)) == 0 && nrec > 16)
+    launch_k(se_hidden_kernel<true>, dim3(dim3(F, ceil_div(Hd, 32))), dim3(256), smem1, st, (const float*)workspace, nrec, C, Hd, w1, b1, hidden);
+  else
+    launch_k(se_hidden_kernel<false>, dim3(dim3(F, ceil_div(Hd, 32))), dim3(256), smem1, st, (const float*)workspace, nrec, C, Hd, w1, b1, hidden);
   MV2_CHECK_LAUNCH();
   launch_k(se_out_kernel, dim3(dim3(F, ceil_div(C, 64))), dim3(256), smem2, st, hidden, C, Hd, w2, b2, gates);
   MV2_CHECK_LAUNCH();

@@ -193,6 +193,7 @@ struct TcEpi {
   int act, shuffle, mode;        // mode 0 plain; 1 GEGLU: packed cols [16g, 16g+8) = x, [16g+8, 16g+16) = gate (M:466-469)
   int Co;                        // packed GEMM output columns
   int To, Ho, Wo;                // output volume before any depth-to-space/time shuffle
+  int out_cf;                    // 1: y is channels-first (B, Co, To, Ho, Wo) -- EPI_RAGGED scalar stores only (conv_out)
 };
 
 __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)[8]) {
@@ -313,6 +314,11 @@ __device__ __forceinline__ void epi_chunk32_t(const TcEpi& e, const uint32_t (&r
       }
       store8_bf16(e.y + off, v);
     } else {
+      if (MODE == EPI_RAGGED && e.out_cf) {            // conv_out: the reconstruction goes out in torch's (B, C, T, H, W)
+        const int64_t plane = (int64_t)e.Ho * e.Wo;
+        const int64_t o0 = ((int64_t)b * e.Co * e.To + to) * plane + (int64_t)ho * e.Wo + wo;
+        for (int q = 0; q < 8 && ng + q < e.Co; ++q) e.y[o0 + (int64_t)(ng + q) * e.To * plane] = __float2bfloat16_rn(v[q]);
+      } else
       for (int q = 0; q < 8 && ng + q < e.Co; ++q) {   // scalar tail (Co % 8 != 0, e.g. conv_out's 3 channels)
         float x = v[q];
         if (e.res) x += __bfloat162float(e.res[off + q]);

@@ -68,7 +68,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // for 148 CTAs) no CTA gets three full tiles while others get two.  Pure index arithmetic, so the tile id stays warp
 // uniform in the MMA-issuing warp (a schedule table read from memory does not: measured 5 % slower overall).
 __host__ __device__ __forceinline__ void slab_frame_of(const SlabParams& p, int slot, int& b, int& t) {
-  const int n_cheap = p.pt < p.T ? p.pt : p.T, n_full = p.T - n_cheap;
+  const int ptc = p.pt > 0 ? p.pt : 0;          // pt < 0: cropped output (conv_out without the time_padding frames), no cheap frames
+  const int n_cheap = ptc < p.T ? ptc : p.T, n_full = p.T - n_cheap;
   const int full_slots = p.B * n_full;
   if (slot < full_slots) { b = slot / n_full; t = n_cheap + slot - b * n_full; }
   else { const int r = slot - full_slots; const int level = r / p.B; b = r - level * p.B; t = n_cheap - 1 - level; }
@@ -654,7 +655,7 @@ static double slab_model_cycles(const mv2_tc_conv_args* a, int n_sm, int mw, int
   std::vector<double> load(G, 0.0);
   int64_t idx = 0;
   // same enumeration as the kernel: full-cost frames first, then t = pt-1 ... 0 of every clip; serpentine over the CTAs
-  const int n_cheap = std::min(a->pt, a->To), n_full = a->To - n_cheap;
+  const int n_cheap = std::max(0, std::min(a->pt, a->To)), n_full = a->To - n_cheap;
   auto deal = [&](int frames, int live) {
     const double cost = live * per_tap_frame + fixed;
     for (int64_t i = 0; i < (int64_t)frames * tiles_per_frame; ++i, ++idx) {
@@ -705,7 +706,11 @@ extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
   if (a->res && a->Co % 8 != 0) return 0;
   if (a->shuffle != MV2_SHUFFLE_NONE && ((a->shuffle == MV2_SHUFFLE_SPACE ? a->Co / 4 : a->Co / 2) % 8 != 0 || a->Co % 32 != 0)) return 0;
   if (a->kh > 7 || a->kw > 3 || a->kt > 8) return 0;
-  if (a->To != a->Ti || a->Ho != a->Hi || a->Wo != a->Wi) return 0;
+  if (a->Ho != a->Hi || a->Wo != a->Wi) return 0;
+  if (a->out_layout == 1) {   // channels-first output: the ragged scalar-store epilogue only (conv_out); may drop leading frames
+    if (a->Co % 8 == 0 || a->res || a->shuffle != MV2_SHUFFLE_NONE || a->epi_mode != 0) return 0;
+    if (a->To > a->Ti || a->To < 1 || a->pt != a->kt - 1 - (a->Ti - a->To)) return 0;
+  } else if (a->out_layout != 0 || a->To != a->Ti) return 0;
   return 1;
 }
 
@@ -720,7 +725,7 @@ static int slab_fill_plan(const mv2_tc_conv_args* a, int n_sm, SlabParams& p, in
   p.B = a->B; p.T = a->To; p.H = a->Ho; p.W = a->Wo; p.Co = a->Co;
   p.epi.bias = a->bias; p.epi.res = (const __nv_bfloat16*)a->res; p.epi.y = (__nv_bfloat16*)a->y;
   p.epi.act = a->act; p.epi.shuffle = a->shuffle; p.epi.mode = a->epi_mode; p.epi.Co = a->Co;
-  p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo;
+  p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo; p.epi.out_cf = a->out_layout == 1;
 
   // ---- tiling (profiles/r01_sweep_slab_v*.json): widest N tile; two M-tiles per weight tile whenever both
   //      accumulator sets still double-buffer in TMEM (2 * mw * bn <= 512), which also halves weight traffic ----

@@ -139,6 +139,7 @@ class Engine:
         self.tc_variant = "auto"     # "auto" | "tap" (tc_conv.cu only) | "slab" (prefer tc_slab.cu)
         self.fuse_ru = True          # bf16: conv3x3x3 + ELU + conv1x1x1 + ELU + SE pool partials in one tcgen05 launch (C = 64 / 128)
         self.fused_ru_calls = 0
+        self.fuse_conv_out = True    # bf16: conv_out stores torch's (B,C,T,H,W) directly and skips the time_padding frames
         self.tc_calls = 0
         self.slab_calls = 0
         self.simt_conv_calls = 0
@@ -251,8 +252,9 @@ class Engine:
         return torch.empty(shape, device=self.device, dtype=dtype or self.dtype)
 
     def conv(self, x, pk: ConvPack, *, stride=(1, 1, 1), pad=None, out_spatial=None, act=ACT_NONE,
-             res=None, shuffle=SHUFFLE_NONE, token_shift=False):
-        """x: (B,T,H,W,Ci) channels-last.  `pad` = leading (pt,ph,pw); causal default (kt-1, kh//2, kw//2)."""
+             res=None, shuffle=SHUFFLE_NONE, token_shift=False, out_cf=False):
+        """x: (B,T,H,W,Ci) channels-last.  `pad` = leading (pt,ph,pw); causal default (kt-1, kh//2, kw//2).
+        out_cf (tcgen05 slab path, Co % 8 != 0 only): write torch's (B,Co,To,Ho,Wo) layout directly."""
         B, Ti, Hi, Wi, Ci = x.shape
         tc_ok = (self.dtype == torch.bfloat16 and self.use_tc and pk.w_tc is not None and not token_shift
                  and Ci == pk.Ci_tc)
@@ -269,6 +271,8 @@ class Engine:
                 y = self._new((B, To, 2 * Ho, 2 * Wo, co_out // 4))
             elif shuffle == SHUFFLE_TIME:
                 y = self._new((B, 2 * To, Ho, Wo, co_out // 2))
+            elif out_cf:
+                y = self._new((B, co_out, To, Ho, Wo))
             else:
                 y = self._new((B, To, Ho, Wo, co_out))
             if res is not None:
@@ -276,7 +280,8 @@ class Engine:
             ta = TcConvArgs(x=_ptr(x), w=_ptr(pk.w_tc), bias=_ptr(pk.bias_tc), res=_ptr(res), y=_ptr(y),
                             B=B, Ti=Ti, Hi=Hi, Wi=Wi, Ci=Ci, To=To, Ho=Ho, Wo=Wo, Co=co_gemm,
                             kt=kt, kh=kh, kw=kw, st=stride[0], sh=stride[1], sw=stride[2],
-                            pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle, epi_mode=pk.epi_mode)
+                            pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle, epi_mode=pk.epi_mode,
+                            out_layout=int(out_cf))
             # measured policy (profiles/r01_sweep_slab_v*.json): the persistent slab kernel wins on every layer it supports
             # (incl. the 64-byte-row conv_in once it runs 4 M-tiles and 7 taps per weight stage); the tap-wise kernel
             # keeps the strided down-samplers.  tc_variant = "tap" forces the tap-wise kernel (tests / sweeps).
@@ -300,10 +305,11 @@ class Engine:
                 self.launches += 1
                 self.tc_calls += 1
                 return y
+            assert not out_cf, "channels-first output is a tcgen05 slab-kernel feature"
             assert pk.w is not None and pk.epi_mode == 0 and Ci == pk.Ci, "tcgen05-only weight pack has no CUDA-core fallback"
             kt, kh, kw = pk.k
         assert Ci == pk.Ci, (Ci, pk.Ci)
-        assert pk.w is not None
+        assert pk.w is not None and not out_cf
         if shuffle == SHUFFLE_SPACE:
             y = self._new((B, To, 2 * Ho, 2 * Wo, pk.Co // 4))
         elif shuffle == SHUFFLE_TIME:
@@ -553,8 +559,16 @@ class Engine:
         for j, st in enumerate(reversed(m.stages)):
             x = self._stage(x, st, f"dec{j}", decoder=True)
             self._tap(f"dec{j}", x)
-        x = self.conv(x, self._packs["conv_out"])
-        return self.to_channels_first(x, t_crop=m.time_padding)
+        pk = self._packs["conv_out"]
+        B, T, H, W, Cc = x.shape
+        tp = m.time_padding
+        if (self.dtype == torch.bfloat16 and self.use_tc and self.tc_variant != "tap" and self.fuse_conv_out and pk.w_tc is not None
+                and pk.Co % 8 != 0 and Cc % 64 == 0 and pk.k[2] <= 3 and T > tp):
+            # conv_out writes the reconstruction in torch's (B,C,T,H,W) layout itself and never computes the time_padding
+            # frames the reference drops afterwards (M:1642-1647)
+            return self.conv(x, pk, pad=(pk.k[0] - 1 - tp, pk.k[1] // 2, pk.k[2] // 2), out_spatial=(T - tp, H, W), out_cf=True)
+        x = self.conv(x, pk)
+        return self.to_channels_first(x, t_crop=tp)
 
     def quantize_cl(self, x, want_quantized=True, want_aux=False):
         """x channels-last -> (quantized channels-last | None, indices (B,T,H,W), aux fp32 [N][d] | None)."""

@@ -60,6 +60,17 @@ CONFIGS = {
                         codes_from="readme"),
     "mini_bf16": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, layers=README_LAYERS),
                       video=(2, 3, 9, 32, 32), wseed=0, vseed=1234, full=True, dtype="bf16", codes_from="mini"),
+    # BASELINE.json configs[3]: image 256, max_dim 1024 (attention-heavy: space-attention seq 1024, linear-attention seq 4096)
+    "cfg4": dict(kwargs=dict(image_size=256, init_dim=64, max_dim=1024, codebook_size=1024, layers=README_LAYERS),
+                 video=(1, 3, 17, 256, 256), wseed=0, vseed=1234, full=False, cs=16, ss=16, rs=8),
+    "cfg4_bf16": dict(kwargs=dict(image_size=256, init_dim=64, max_dim=1024, codebook_size=1024, layers=README_LAYERS),
+                      video=(1, 3, 17, 256, 256), wseed=0, vseed=1234, full=False, cs=16, ss=16, rs=8, dtype="bf16",
+                      codes_from="cfg4"),
+    # BASELINE.json configs[4]: FSQ variant of the README config, levels [8,5,5,5]
+    "fsq": dict(kwargs=dict(image_size=128, init_dim=64, max_dim=512, use_fsq=True, fsq_levels=[8, 5, 5, 5], layers=README_LAYERS),
+                video=(1, 3, 17, 128, 128), wseed=0, vseed=1234, full=False, cs=16, ss=8),
+    "fsq_bf16": dict(kwargs=dict(image_size=128, init_dim=64, max_dim=512, use_fsq=True, fsq_levels=[8, 5, 5, 5], layers=README_LAYERS),
+                     video=(1, 3, 17, 128, 128), wseed=0, vseed=1234, full=False, cs=16, ss=8, dtype="bf16", codes_from="fsq"),
     "mini_sff": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, separate_first_frame_encoding=True,
                                  layers=("residual", "compress_space", "compress_time", "residual")),
                      video=(2, 3, 5, 32, 32), wseed=0, vseed=1234, full=True),
@@ -136,7 +147,7 @@ def make(name: str):
         name=name, kwargs=kwargs, video_shape=tuple(cfg["video"]), wseed=cfg["wseed"], vseed=cfg["vseed"],
         codes=codes.clone(), presign=pre.clone(),
         taps=taps, tap_strides=(cfg.get("cs", 7), cfg.get("ss", 5)),
-        recon_sample=recon[:, :, :, ::4, ::4].contiguous().clone(),
+        recon_sample=recon[:, :, :, ::cfg.get("rs", 4), ::cfg.get("rs", 4)].contiguous().clone(), recon_stride=cfg.get("rs", 4),
         recon_mean=recon.mean(dim=(3, 4)).clone(),
         ref_seconds=dict(tokenize=t1 - t0, decode=t2 - t1),
         torch_version=torch.__version__,

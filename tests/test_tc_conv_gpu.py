@@ -374,3 +374,24 @@ def test_fused_residual_unit(case):
     # three bf16 roundings along the unit (h, y, out) against the fp32 oracle
     assert err.max().item() <= 0.02 * ref.abs().max().item() + 5e-3, (name, err.max().item())
     assert err.mean().item() <= 0.004 * ref.abs().mean().item() + 2e-4, (name, err.mean().item())
+
+
+@pytest.mark.parametrize("T,tp,H,W", [(6, 3, 32, 32), (5, 1, 16, 24), (4, 0, 16, 16)])
+def test_conv_out_channels_first_with_cropped_frames(T, tp, H, W):
+    """conv_out (Co = 3) writing torch's (B,C,T,H,W) layout directly, without the leading time_padding frames the
+    reference drops after the conv (M:1642-1647), vs conv + mv2_to_channels_first crop and vs the CPU oracle."""
+    assert torch.cuda.is_available()
+    g = torch.Generator(device="cpu").manual_seed(T * 100 + tp)
+    w = (torch.randn((3, 64, 3, 3, 3), generator=g) * (27 * 64) ** -0.5).cuda()
+    bias = (torch.randn(3, generator=g) * 0.1).cuda()
+    x = torch.randn((2, T, H, W, 64), generator=g).cuda().to(torch.bfloat16)
+    eng = _engine()
+    pk = pack_conv(w, bias, torch.bfloat16)
+    eng.use_tc, eng.tc_variant, eng.slab_calls = True, "auto", 0
+    y_cf = eng.conv(x, pk, pad=(2 - tp, 1, 1), out_spatial=(T - tp, H, W), out_cf=True)
+    assert eng.slab_calls == 1 and y_cf.shape == (2, 3, T - tp, H, W)
+    y_ref = eng.to_channels_first(eng.conv(x, pk), t_crop=tp)
+    torch.cuda.synchronize()
+    assert torch.equal(y_cf, y_ref)
+    ref = _oracle_conv(w, bias, x, None, {}).permute(0, 4, 1, 2, 3)[:, :, tp:]
+    _check_vs_oracle("conv_out_cf", y_cf.permute(0, 2, 3, 4, 1), ref.permute(0, 2, 3, 4, 1).contiguous())
