@@ -39,6 +39,10 @@ WORKLOADS = {
     "readme": dict(kw=README_KW, clips=4, size=128, flop_clip=1.512e12,
                    name="README VideoTokenizer (BASELINE configs[1]): tokenize + decode_from_code_indices, "
                         "4 clips of 3x17x128x128 per GPU, batch sharded by clip"),
+    "cfg3": dict(kw=README_KW, clips=4, size=128, flop_clip=1.512e12, train_mode=True,
+                 name="BASELINE configs[2]: README VideoTokenizer in model.train(): forward(return_codes, return_recon) with the LFQ "
+                      "entropy terms and their cross-rank avg_prob all-reduce (NCCL, side stream, overlapped with the decoder), "
+                      "4 clips of 3x17x128x128 per GPU, batch sharded by clip"),
     "cfg4": dict(kw=dict(image_size=256, init_dim=64, max_dim=1024, codebook_size=1024, layers=README_LAYERS), clips=3,
                  size=256, flop_clip=8.944e12,
                  name="BASELINE configs[3]: image_size=256 max_dim=1024, tokenize + decode, 3 clips of 3x17x256x256 per GPU"),
@@ -292,7 +296,13 @@ def main():
     dev_batches = [hb.to(dev, non_blocking=True) for hb in host_batches]
     torch.cuda.synchronize()
 
+    train_mode = bool(wl.get("train_mode"))
+    if train_mode:
+        model.train()
+
     def step(v):
+        if train_mode:           # reference M:1705 in training mode: the LFQ aux terms + their all-reduce run inside the call
+            return model(v, return_codes=True, return_recon=True)
         codes = model.tokenize(v)
         return codes, model.decode_from_code_indices(codes)
 
@@ -335,7 +345,7 @@ def main():
     # copies of neighbouring steps overlap this step's kernels -- every step still copies its own input and results
     out_bufs = [(out_codes, out_video), (torch.empty_like(out_codes).pin_memory(), torch.empty_like(out_video).pin_memory())]
     from magvit2_pytorch_b200 import HostRoundTrip
-    hrt = HostRoundTrip(model, depth=2)
+    hrt = HostRoundTrip(model, depth=2, train_mode_forward=train_mode)
     cur = torch.cuda.current_stream()
 
     def step_e2e(i):

@@ -536,15 +536,17 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ the path
-    def encode_cl(self, video: torch.Tensor):
-        """video (B,C,T,H,W) on device -> encoder output, channels-last.  Reference encode M:1523-1576."""
+    def encode_cl(self, video: torch.Tensor, first_frame: bool = True):
+        """video (B,C,T,H,W) on device -> encoder output, channels-last.  Reference encode M:1523-1576; the time_padding
+        zero frames are only prepended when the clip starts with a first frame (video_contains_first_frame, M:1534-1537)."""
         m = self.model
+        t_pad = m.time_padding if first_frame else 0
         pin = self._packs.get("conv_in_tc")
         if self.dtype == torch.bfloat16 and self.use_tc and pin is not None:
-            x = self.ingest_kwpack(video, m.time_padding, pin)
+            x = self.ingest_kwpack(video, t_pad, pin)
             x = self.conv(x, pin, pad=(pin.k_tc[0] - 1, pin.k_tc[1] // 2, 0))
         else:
-            x = self.to_channels_last(video, m.time_padding)
+            x = self.to_channels_last(video, t_pad)
             x = self.conv(x, self._packs["conv_in"])
         self._tap("conv_in", x)
         for i, st in enumerate(m.stages):
@@ -552,8 +554,9 @@ class Engine:
             self._tap(f"enc{i}", x)
         return x
 
-    def decode_cl(self, q: torch.Tensor):
-        """quantized channels-last (B,T',H',W',C) -> video (B,3,T,H,W).  Reference decode M:1598-1649."""
+    def decode_cl(self, q: torch.Tensor, first_frame: bool = True):
+        """quantized channels-last (B,T',H',W',C) -> video (B,3,T,H,W).  Reference decode M:1598-1649; the leading
+        time_padding frames are dropped only for clips that contain a first frame (M:1646-1647)."""
         m = self.model
         x = q
         for j, st in enumerate(reversed(m.stages)):
@@ -561,7 +564,7 @@ class Engine:
             self._tap(f"dec{j}", x)
         pk = self._packs["conv_out"]
         B, T, H, W, Cc = x.shape
-        tp = m.time_padding
+        tp = m.time_padding if first_frame else 0
         if (self.dtype == torch.bfloat16 and self.use_tc and self.tc_variant != "tap" and self.fuse_conv_out and pk.w_tc is not None
                 and pk.Co % 8 != 0 and Cc % 64 == 0 and pk.k[2] <= 3 and T > tp):
             # conv_out writes the reconstruction in torch's (B,C,T,H,W) layout itself and never computes the time_padding

@@ -32,9 +32,12 @@ class HostRoundTrip:
     caller's buffers of a submit may be reused once its event has completed (``wait(event)``) or after
     ``synchronize()``; at most `depth` submits are in flight on the device side."""
 
-    def __init__(self, model, depth: int = 2):
+    def __init__(self, model, depth: int = 2, train_mode_forward: bool = False):
         assert depth >= 1
         self.model = model
+        # True: one ``model(video, return_codes=True, return_recon=True)`` call per submit (in ``model.train()`` this is the
+        # path with the LFQ batch-entropy all-reduce, BASELINE configs[2]) instead of tokenize + decode_from_code_indices
+        self.train_mode_forward = train_mode_forward
         self.device = model.device
         if self.device.type != "cuda":
             raise RuntimeError("HostRoundTrip needs the tokenizer on a CUDA device")
@@ -64,8 +67,11 @@ class HostRoundTrip:
         cur.wait_event(slot.h2d)
         if slot.used:
             cur.wait_event(slot.d2h)                 # the slot's previous results have left the device
-        codes = self.model.tokenize(slot.video)
-        recon = self.model.decode_from_code_indices(codes)
+        if self.train_mode_forward:
+            codes, recon = self.model(slot.video, return_codes=True, return_recon=True)
+        else:
+            codes = self.model.tokenize(slot.video)
+            recon = self.model.decode_from_code_indices(codes)
         slot.codes, slot.recon = codes, recon        # keep the device results alive until their D2H copy is done
         slot.done.record(cur)
         self.s_out.wait_event(slot.done)

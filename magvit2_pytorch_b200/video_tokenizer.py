@@ -237,6 +237,8 @@ class VideoTokenizer(nn.Module):
         self.grad_penalty_loss_weight = grad_penalty_loss_weight
         self.multiscale_adversarial_loss_weight = multiscale_adversarial_loss_weight
 
+        self.quantizer_loss_breakdown = None     # set by a train-mode forward (LFQ): (per_sample_entropy, batch_entropy, commitment)
+        self.quantizer_aux_loss = None
         self._engine: Optional[Engine] = None
         # opt-in: replay each (entry point, input shape) as one CUDA graph after a warm-up call -- the forward path is
         # a static launch plan (~170 kernels), so this removes the per-launch host overhead.  Outputs are cloned out
@@ -372,16 +374,15 @@ class VideoTokenizer(nn.Module):
         if v.ndim == 4:                                                           # M:1681-1685
             v = v[:, :, None]
             video_contains_first_frame = True
-        if not video_contains_first_frame:
-            raise NotImplementedError("video_contains_first_frame=False is not supported")
         frames = v.shape[2]
-        assert (frames - 1) % self.time_downsample_factor == 0, \
-            f"number of frames {frames} minus the first frame ({frames - 1}) must be divisible by the total " \
+        ff = int(bool(video_contains_first_frame))
+        assert (frames - ff) % self.time_downsample_factor == 0, \
+            f"number of frames {frames} minus the first frame ({frames - ff}) must be divisible by the total " \
             f"downsample factor across time {self.time_downsample_factor}"      # M:1691
         assert v.shape[1] == self.channels
         if v.device != self.device:
             raise RuntimeError(f"input is on {v.device} but the tokenizer is on {self.device}")
-        return v
+        return v, bool(ff)
 
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
@@ -389,9 +390,9 @@ class VideoTokenizer(nn.Module):
     def encode(self, video, quantize=False, cond=None, video_contains_first_frame=True):
         """M:1523-1576.  Returns (B, C, T', H', W') like the reference."""
         assert cond is None, "conditioning is not supported"
-        video = self._check_video(video, video_contains_first_frame)
+        video, ff = self._check_video(video, video_contains_first_frame)
         eng = self.engine
-        x = eng.encode_cl(video)
+        x = eng.encode_cl(video, ff)
         if quantize:
             q, idx, _ = eng.quantize_cl(x)
             out = eng.to_channels_first(q)
@@ -409,19 +410,17 @@ class VideoTokenizer(nn.Module):
     def decode(self, quantized, cond=None, video_contains_first_frame=True):
         """M:1598-1649.  quantized: (B, C, T', H', W')."""
         assert cond is None, "conditioning is not supported"
-        assert video_contains_first_frame
         assert quantized.ndim == 5 and quantized.shape[1] == self.quantizers.dim, \
             f"quantized must be (B, {self.quantizers.dim}, T, H, W), got {tuple(quantized.shape)}"
         self._check_on_device(quantized, "quantized")
         eng = self.engine
-        return eng.decode_cl(eng.to_channels_last(quantized))
+        return eng.decode_cl(eng.to_channels_last(quantized), bool(video_contains_first_frame))
 
     @torch.no_grad()
     @_on_model_device
     def decode_from_code_indices(self, codes, cond=None, video_contains_first_frame=True):
         """M:1579-1595."""
         assert cond is None, "conditioning is not supported"
-        assert video_contains_first_frame
         assert codes.dtype in (torch.long, torch.int32)                           # M:1585
         if codes.ndim == 2:                                                       # M:1587-1591
             n = codes.shape[-1]
@@ -432,7 +431,9 @@ class VideoTokenizer(nn.Module):
         assert codes.ndim == 4, f"codes must be (B, T, H, W) or flat (B, N), got {tuple(codes.shape)}"
         self._check_on_device(codes, "codes")
         eng = self.engine
-        return self._graph_call("decode_codes", lambda c: eng.decode_cl(eng.codes_to_quantized_cl(c)), codes.contiguous())
+        ff = bool(video_contains_first_frame)
+        return self._graph_call("decode_codes" if ff else "decode_codes_noff",
+                                lambda c: eng.decode_cl(eng.codes_to_quantized_cl(c), ff), codes.contiguous())
 
     @torch.no_grad()
     @_on_model_device
@@ -443,7 +444,7 @@ class VideoTokenizer(nn.Module):
         on a side stream.  (The losses' backward and the GAN/perceptual terms are out of scope)"""
         from .dist import LfqBatchEntropy
         assert not self.use_fsq, "FSQ has no auxiliary loss (reference M:1702)"
-        video = self._check_video(video)
+        video, _ = self._check_video(video)
         eng = self.engine
         x = eng.encode_cl(video)
         _, codes, pre = eng.quantize_cl(x, want_quantized=False, want_aux=True)
@@ -452,6 +453,33 @@ class VideoTokenizer(nn.Module):
         be.start(pre, group)
         ps, bent, commit, aux = be.finish(q.diversity_gamma, q.entropy_loss_weight, q.commitment_loss_weight)
         return codes, (ps, bent, commit), aux
+
+    def _forward_train_mode(self, eng, video, need_recon, ff=True, group=None):
+        """``model.train()`` forward of the LFQ tokenizer (reference M:1705: ``self.quantizers(x, return_loss_breakdown=True)``
+        in training mode): besides codes / reconstruction the quantiser's auxiliary terms are computed -- per-sample entropy,
+        batch (codebook) entropy of the CROSS-RANK mean code probability, commitment -- and kept in
+        ``self.quantizer_loss_breakdown`` = (per_sample_entropy, batch_entropy, commitment) / ``self.quantizer_aux_loss``.
+        The batch-entropy term needs the one collective of the path: a 4 KiB SUM all-reduce of avg_prob (A.1 step 7), issued
+        on a side stream so that it overlaps the decoder.  The decoder is fed the quantised value q itself; the reference's
+        straight-through ``x + (q - x).detach()`` equals q up to one rounding (SURVEY 8d cfg 3).  No autograd (N2)."""
+        from .dist import LfqBatchEntropy
+        qz = self.quantizers
+
+        def enc(v):
+            x = eng.encode_cl(v, ff)
+            q, codes_, pre = eng.quantize_cl(x, want_quantized=need_recon, want_aux=True)
+            return (codes_, pre, q) if need_recon else (codes_, pre)
+
+        sfx = "" if ff else "_noff"
+        res = self._graph_call(("train_enc_q" if need_recon else "train_enc") + sfx, enc, video)
+        codes, pre = res[0], res[1]
+        be = LfqBatchEntropy(eng)
+        be.start(pre, group)                                   # partial sums + all-reduce on the side stream ...
+        recon = self._graph_call("train_dec" + sfx, lambda t: eng.decode_cl(t, ff), res[2]) if need_recon else None   # ... under the decoder
+        ps, bent, commit, aux = be.finish(qz.diversity_gamma, qz.entropy_loss_weight, qz.commitment_loss_weight)
+        self.quantizer_loss_breakdown = (ps, bent, commit)
+        self.quantizer_aux_loss = aux
+        return (codes, recon) if need_recon else codes
 
     @torch.no_grad()
     def tokenize(self, video):
@@ -471,19 +499,22 @@ class VideoTokenizer(nn.Module):
             raise NotImplementedError(
                 "training losses (GAN / perceptual / adaptive weighting, reference M:1722-1896) are outside the "
                 "accelerated inference path (SURVEY.md 8f N2)")
-        video = self._check_video(video_or_images, video_contains_first_frame)
+        video, ff = self._check_video(video_or_images, video_contains_first_frame)
         with torch.no_grad():
             eng = self.engine
             need_recon = return_recon or return_recon_loss_only or not return_codes
 
             def run(v):
-                x = eng.encode_cl(v)
+                x = eng.encode_cl(v, ff)
                 q, codes_, _ = eng.quantize_cl(x, want_quantized=need_recon)
                 if not need_recon:
                     return codes_
-                return codes_, eng.decode_cl(q)
+                return codes_, eng.decode_cl(q, ff)
 
-            out = self._graph_call("fwd_recon" if need_recon else "fwd_codes", run, video.contiguous())
+            if self.training and not self.use_fsq:
+                out = self._forward_train_mode(eng, video.contiguous(), need_recon, ff)
+            else:
+                out = self._graph_call(("fwd_recon" if need_recon else "fwd_codes") + ("" if ff else "_noff"), run, video.contiguous())
             if return_codes and not return_recon:
                 return out                                                         # M:1707-1708
             codes, recon = out

@@ -71,6 +71,9 @@ CONFIGS = {
                 video=(1, 3, 17, 128, 128), wseed=0, vseed=1234, full=False, cs=16, ss=8),
     "fsq_bf16": dict(kwargs=dict(image_size=128, init_dim=64, max_dim=512, use_fsq=True, fsq_levels=[8, 5, 5, 5], layers=README_LAYERS),
                      video=(1, 3, 17, 128, 128), wseed=0, vseed=1234, full=False, cs=16, ss=8, dtype="bf16", codes_from="fsq"),
+    # video_contains_first_frame=False (M:1528-1537, M:1646-1647, M:1691): 8 frames, no front padding, no crop
+    "mini_noff": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, layers=README_LAYERS),
+                      video=(2, 3, 8, 32, 32), wseed=0, vseed=1235, full=True, first_frame=False),
     "mini_sff": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, separate_first_frame_encoding=True,
                                  layers=("residual", "compress_space", "compress_time", "residual")),
                      video=(2, 3, 5, 32, 32), wseed=0, vseed=1234, full=True),
@@ -124,14 +127,18 @@ def make(name: str):
     t0 = time.time()
     with torch.no_grad():
         # tokenize() does not forward ``cond`` (M:1651-1654): conditioned specs use forward(return_codes=True)
-        codes = model.tokenize(video) if cond is None else model(video, cond=cond, return_codes=True)
+        ff = cfg.get("first_frame", True)
+        if not ff:
+            codes = model(video, return_codes=True, video_contains_first_frame=False)
+        else:
+            codes = model.tokenize(video) if cond is None else model(video, cond=cond, return_codes=True)
         t1 = time.time()
         codes_dec = codes
         if cfg.get("codes_from"):      # decode the fp32 golden's codes, so both dtypes decode identical tokens
             codes_dec = torch.load(os.path.join(GOLDEN_DIR, cfg["codes_from"] + ".pt"), weights_only=False)["codes"]
-        recon = model.decode_from_code_indices(codes_dec, cond=cond).float()
+        recon = model.decode_from_code_indices(codes_dec, cond=cond, video_contains_first_frame=ff).float()
         t2 = time.time()
-        if not bf16:
+        if not bf16 and ff:
             # README.md:85-90 round-trip statement
             recon_fwd = model(video, cond=cond, return_recon=True)
             assert torch.equal(recon, recon_fwd), "reference round-trip (README.md:87-90) does not hold"
@@ -156,7 +163,7 @@ def make(name: str):
         # synthetic weights (oracle/weights.py) for specs the product does not construct yet
         sd_shapes={k: tuple(v.shape) for k, v in model.state_dict().items() if W.is_generator_key(k) and v.is_floating_point()},
         sd_buffers={k: v.clone() for k, v in model.state_dict().items() if W.is_generator_key(k) and not v.is_floating_point()},
-        dtype="bf16" if bf16 else "fp32", codes_decoded=codes_dec.clone(),
+        dtype="bf16" if bf16 else "fp32", codes_decoded=codes_dec.clone(), first_frame=ff,
         reference_commit="a00519fa (v0.5.1)",
         third_party="oracle/shims (restated LFQ/FSQ/TaylorSeriesLinearAttn; real packages unavailable)",
     )

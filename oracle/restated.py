@@ -449,11 +449,14 @@ class OracleTokenizer:
         return x
 
     @torch.no_grad()
-    def encode(self, video, taps=None, cond=None):
+    def encode(self, video, taps=None, cond=None, video_contains_first_frame=True):
         """VideoTokenizer.encode (M:1523-1576).  NB the final LayerNorm (M:1322-1326) is never
-        executed: zip() with has_cond_across_layers truncates it (M:1565)."""
+        executed: zip() with has_cond_across_layers truncates it (M:1565).  Without a first frame
+        (video_contains_first_frame=False) the clip is neither front-padded nor split (M:1530-1537)."""
         x = video.to(self.dtype)
-        if self.sep_first:
+        if not video_contains_first_frame:
+            x = causal_conv3d(x, self.sd["conv_in.conv.weight"], self.sd["conv_in.conv.bias"], self.pad_mode)
+        elif self.sep_first:
             # M:1553-1561: the first frame goes through its own 2-D conv (SameConv2d, M:887-890), the remaining frames
             # through the causal conv_in on their own (their causal padding starts at frame 1), then the feature map is
             # re-padded with time_padding zero frames
@@ -475,9 +478,9 @@ class OracleTokenizer:
         return x
 
     @torch.no_grad()
-    def decode(self, quantized, taps=None, cond=None):
+    def decode(self, quantized, taps=None, cond=None, video_contains_first_frame=True):
         """VideoTokenizer.decode (M:1598-1649): decoder layers are the encoder's in reverse
-        (insert(0), M:1315); conv_out; drop the first time_padding frames (M:1646-1647)."""
+        (insert(0), M:1315); conv_out; drop the first time_padding frames (M:1646-1647) when the clip had a first frame."""
         x = quantized.to(self.dtype)
         n = len(self.stages)
         c = self._cond_in(cond, "decoder") if self.has_cond else None               # M:1612-1616
@@ -485,14 +488,14 @@ class OracleTokenizer:
             x = self._apply(x, st, f"decoder_layers.{j}.", decoder=True, cond=c)
             if taps is not None:
                 taps[f"dec{j}"] = x
-        if self.sep_first:                                                     # M:1633-1639
+        if self.sep_first and video_contains_first_frame:                      # M:1633-1639
             tp = self.time_padding
             w2, b2 = self.sd["conv_out_first_frame.weight"], self.sd["conv_out_first_frame.bias"]
             first = F.conv2d(x[:, :, tp], w2, b2, padding=(w2.shape[2] // 2, w2.shape[3] // 2))
             rest = causal_conv3d(x[:, :, tp + 1:], self.sd["conv_out.conv.weight"], self.sd["conv_out.conv.bias"], self.pad_mode)
             return torch.cat((first[:, :, None], rest), dim=2)
         x = causal_conv3d(x, self.sd["conv_out.conv.weight"], self.sd["conv_out.conv.bias"], self.pad_mode)
-        return x[:, :, self.time_padding:]
+        return x[:, :, self.time_padding:] if video_contains_first_frame else x
 
     @torch.no_grad()
     def quantize(self, x):
@@ -500,25 +503,27 @@ class OracleTokenizer:
             return fsq_quantize(x, self.sd, self.fsq_levels)
         return lfq_quantize(x, self.sd, self.clamp)
 
-    def _check_video(self, video):
+    def _check_video(self, video, video_contains_first_frame=True):
         assert video.ndim in (4, 5)                                            # M:1675
         assert tuple(video.shape[-2:]) == (self.image_size, self.image_size)   # M:1677
         if video.ndim == 4:
             video = video[:, :, None]                                          # M:1684
-        assert (video.shape[2] - 1) % self.time_f == 0                        # M:1691
-        return video
+            video_contains_first_frame = True                                  # M:1685
+        assert (video.shape[2] - int(video_contains_first_frame)) % self.time_f == 0     # M:1691
+        return video, bool(video_contains_first_frame)
 
     @torch.no_grad()
-    def tokenize(self, video, taps=None, return_presign=False, cond=None):
+    def tokenize(self, video, taps=None, return_presign=False, cond=None, video_contains_first_frame=True):
         """VideoTokenizer.tokenize (M:1651-1654) = forward(return_codes=True) (M:1695-1708).  NB the reference's
-        tokenize() does not forward ``cond``; conditioned specs go through forward(video, cond, return_codes=True)."""
-        video = self._check_video(video)
-        x = self.encode(video, taps, cond=cond)
+        tokenize() does not forward ``cond`` / ``video_contains_first_frame``; such calls go through
+        forward(video, cond, return_codes=True, video_contains_first_frame=...)."""
+        video, ff = self._check_video(video, video_contains_first_frame)
+        x = self.encode(video, taps, cond=cond, video_contains_first_frame=ff)
         _, idx, pre = self.quantize(x)
         return (idx, pre) if return_presign else idx
 
     @torch.no_grad()
-    def decode_from_code_indices(self, codes, taps=None, cond=None):
+    def decode_from_code_indices(self, codes, taps=None, cond=None, video_contains_first_frame=True):
         """M:1579-1595: flat (b, f*h*w) ids are un-flattened with the fmap size."""
         assert codes.dtype in (torch.long, torch.int32)
         if codes.ndim == 2:
@@ -528,17 +533,17 @@ class OracleTokenizer:
             q = fsq_indices_to_codes(codes, self.sd, self.fsq_levels, self.dtype)
         else:
             q = lfq_indices_to_codes(codes, self.sd, self.dtype)
-        return self.decode(q, taps, cond=cond)
+        return self.decode(q, taps, cond=cond, video_contains_first_frame=video_contains_first_frame)
 
     @torch.no_grad()
-    def forward(self, video, return_codes=False, return_recon=False, cond=None):
+    def forward(self, video, return_codes=False, return_recon=False, cond=None, video_contains_first_frame=True):
         """forward up to M:1720 (inference returns only); ``cond`` reaches encode and decode (M:1695, M:1710)."""
-        video = self._check_video(video)
-        x = self.encode(video, cond=cond)
+        video, ff = self._check_video(video, video_contains_first_frame)
+        x = self.encode(video, cond=cond, video_contains_first_frame=ff)
         q, idx, _ = self.quantize(x)
         if return_codes and not return_recon:
             return idx
-        rec = self.decode(q, cond=cond)
+        rec = self.decode(q, cond=cond, video_contains_first_frame=ff)
         if return_codes:
             return idx, rec
         return rec

@@ -46,6 +46,52 @@ def test_restated_matches_reference_golden_readme():
     assert torch.allclose(recon.mean(dim=(3, 4)), g["recon_mean"], atol=1e-5)
 
 
+def test_restated_matches_reference_golden_fsq_full_size():
+    """BASELINE configs[4] (README layers, FSQ [8,5,5,5]) at full size, one clip."""
+    g = load_golden("fsq")
+    model = build_product(g["kwargs"], g["wseed"])
+    orc = build_oracle(model, g["kwargs"])
+    codes = orc.tokenize(golden_video(g))
+    assert codes.dtype == torch.int32 and torch.equal(codes, g["codes"])
+    recon = orc.decode_from_code_indices(codes)
+    assert torch.allclose(recon[:, :, :, ::4, ::4], g["recon_sample"], atol=5e-5, rtol=1e-5)
+
+
+def test_restated_matches_reference_golden_cfg4_tokenize():
+    """BASELINE configs[3] (image 256, max_dim 1024; space-attention seq 1024, linear-attention seq 4096): tokenize side
+    (~30 s of CPU; the decode side is pinned on the GPU box through the product, tests/test_parity_gpu.py)."""
+    g = load_golden("cfg4")
+    model = build_product(g["kwargs"], g["wseed"])
+    orc = build_oracle(model, g["kwargs"])
+    taps = {}
+    codes, pre = orc.tokenize(golden_video(g), taps=taps, return_presign=True)
+    assert torch.equal(codes, g["codes"])
+    assert torch.allclose(pre, g["presign"], atol=2e-4)
+    for k in ("enc5", "enc8", "enc13"):          # after the linear-attention, space-attention and time-attention blocks
+        assert torch.allclose(sample_like_golden(taps[k], g), g["taps"][k], atol=1e-4, rtol=1e-5), k
+
+
+def test_restated_no_first_frame_matches_reference_golden():
+    """video_contains_first_frame=False (M:1528-1537, M:1646-1647, M:1691): no front padding, no crop, frames % tdf == 0."""
+    g = load_golden("mini_noff")
+    assert g["first_frame"] is False
+    model = build_product(g["kwargs"], g["wseed"])
+    orc = build_oracle(model, g["kwargs"])
+    video = golden_video(g)
+    taps = {}
+    codes = orc.tokenize(video, taps=taps, video_contains_first_frame=False)
+    assert torch.equal(codes, g["codes"]) and codes.shape[1] == video.shape[2] // 4
+    dtaps = {}
+    recon = orc.decode_from_code_indices(codes, taps=dtaps, video_contains_first_frame=False)
+    assert recon.shape == video.shape
+    assert torch.allclose(recon, g["recon"], atol=2e-5, rtol=1e-5)
+    for k, ref in g["taps"].items():
+        got = taps.get(k, dtaps.get(k))
+        assert torch.allclose(sample_like_golden(got, g), ref, atol=2e-5, rtol=1e-5), k
+    with pytest.raises(AssertionError):
+        orc.tokenize(video)                      # 8 frames with a first frame: (8 - 1) % 4 != 0  (M:1691)
+
+
 def test_restated_cond_residual_matches_reference_golden():
     """SURVEY 8f N1 groundwork: the conditioned residual unit (ResidualUnitMod / Conv3DMod, M:680-753, M:946-988) and the
     conditioning stems (M:1344-1352), pinned to the reference before any kernel is written for it."""

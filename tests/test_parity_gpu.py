@@ -405,3 +405,106 @@ def test_model_on_non_current_device():
         assert torch.equal(c0.cpu(), c1.cpu())
         r1 = m1.decode_from_code_indices(c1)
         assert torch.equal(m0.decode_from_code_indices(c0).cpu(), r1.cpu())
+
+
+@pytest.mark.parametrize("name", ["cfg4", "fsq"])
+def test_full_size_configs_vs_reference_goldens(name):
+    """BASELINE configs[3] (image 256, max_dim 1024, attention-heavy) and configs[4] (FSQ) at FULL size against the
+    reference goldens: fp32 path bit-exact codes + recon within 1e-5-class tolerance; bf16 path inside the reference's own
+    bf16 error budget (1.5x, per tap and end to end), decode with identical codes."""
+    _require_cuda()
+    g32, g16 = load_golden(name), load_golden(name + "_bf16")
+    rs = g32.get("recon_stride", 4)
+    video = golden_video(g32).cuda()
+    # ---- fp32 path ----
+    model = build_product(g32["kwargs"], g32["wseed"]).cuda()
+    codes = model.tokenize(video)
+    n_diff = (codes.cpu() != g32["codes"]).sum().item()
+    recon = model.decode_from_code_indices(g32["codes"].cuda())
+    rerr = (recon.cpu()[:, :, :, ::rs, ::rs] - g32["recon_sample"]).abs().max().item()
+    _report(f"fp32/{name}", code_mismatches=n_diff, recon_maxabs=f"{rerr:.3e}")
+    assert codes.dtype == g32["codes"].dtype
+    if name == "fsq":
+        # FSQ rounds |bounded| values at half-integers: a 1e-6 fp32 difference can move a value across .5
+        assert n_diff <= 2, n_diff
+    else:
+        assert n_diff == 0, n_diff
+    assert rerr < 2e-5, rerr
+    del model
+    # ---- bf16 path vs the reference's own bf16 run ----
+    model = build_product(g32["kwargs"], g32["wseed"]).cuda().bfloat16()
+    eng = model.engine
+    eng.taps = {}
+    x = eng.encode_cl(video)
+    _, codes16, _ = eng.quantize_cl(x, want_quantized=False)
+    taps, eng.taps = eng.taps, {}
+    recon16 = model.decode_from_code_indices(g32["codes"].cuda())
+    taps.update(eng.taps)
+    eng.taps = None
+    assert eng.simt_conv_calls == 0, "a convolution fell back to the CUDA-core path"
+    worst = 0.0
+    for k, ref32 in g32["taps"].items():
+        e_prod = (sample_like_golden(taps[k], g32) - ref32).abs().mean().item()
+        e_ref = (g16["taps"][k] - ref32).abs().mean().item()
+        worst = max(worst, e_prod / (e_ref + 1e-9))
+        assert e_prod <= 1.5 * e_ref + 1e-5, (k, e_prod, e_ref)
+    mism_prod = (codes16.cpu() != g32["codes"]).float().mean().item()
+    mism_ref = (g16["codes"] != g32["codes"]).float().mean().item()
+    r_prod = (recon16.float().cpu()[:, :, :, ::rs, ::rs] - g32["recon_sample"]).abs()
+    r_ref = (g16["recon_sample"] - g32["recon_sample"]).abs()
+    _report(f"bf16-vs-ref-bf16/{name}", worst_tap_ratio=f"{worst:.2f}", token_mismatch=f"{mism_prod:.4f}/{mism_ref:.4f}",
+            recon_max=f"{r_prod.max().item():.3e}/{r_ref.max().item():.3e}", recon_mean=f"{r_prod.mean().item():.3e}/{r_ref.mean().item():.3e}")
+    assert mism_prod <= 1.5 * mism_ref + 2.0 / g32["codes"].numel()
+    assert r_prod.max().item() <= 1.5 * r_ref.max().item() and r_prod.mean().item() <= 1.5 * r_ref.mean().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_video_without_first_frame_vs_reference_golden(dtype):
+    """video_contains_first_frame=False (M:1528-1537, M:1646-1647, M:1691) through encode / forward / decode_from_code_indices."""
+    _require_cuda()
+    g = load_golden("mini_noff")
+    model = build_product(g["kwargs"], g["wseed"]).cuda().to(dtype)
+    v = golden_video(g).cuda()
+    codes = model(v, return_codes=True, video_contains_first_frame=False)
+    recon = model.decode_from_code_indices(g["codes"].cuda(), video_contains_first_frame=False)
+    assert recon.shape == v.shape and codes.shape == g["codes"].shape
+    c2, r2 = model(v, return_codes=True, return_recon=True, video_contains_first_frame=False)
+    assert torch.equal(c2, codes)
+    rerr = (recon.float().cpu() - g["recon"]).abs().max().item()
+    mism = (codes.cpu() != g["codes"]).float().mean().item()
+    _report(f"noff/{str(dtype).split('.')[-1]}", token_mismatch_rate=f"{mism:.4f}", recon_maxabs=f"{rerr:.3e}")
+    if dtype == torch.float32:
+        assert mism == 0 and rerr < FP32_RECON_TOL
+        assert torch.equal(r2, recon)
+    else:
+        assert mism <= 0.0625 and rerr < 0.081
+    with pytest.raises(AssertionError):
+        model.tokenize(v)                        # 8 frames WITH a first frame: (8 - 1) % 4 != 0
+    model.cuda_graphs = True
+    for _ in range(3):
+        assert torch.equal(model(v, return_codes=True, video_contains_first_frame=False), codes)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_train_mode_forward_world1(graphs):
+    """``model.train()`` forward (reference M:1705 in training mode): codes identical to eval, reconstruction from q, and the
+    LFQ auxiliary terms (world size 1 here; tests/test_dist_gpu.py runs the all-reduce over 2 GPUs) vs the oracle."""
+    _require_cuda()
+    from oracle.restated import lfq_train_losses
+    g = load_golden("mini")
+    model = build_product(g["kwargs"], g["wseed"]).cuda()
+    v = golden_video(g).cuda()
+    want_recon = model.decode_from_code_indices(g["codes"].cuda())
+    model.train()
+    model.cuda_graphs = graphs
+    for _ in range(3 if graphs else 1):
+        codes, recon = model(v, return_codes=True, return_recon=True)
+        ps, be, cm = model.quantizer_loss_breakdown
+    assert torch.equal(codes.cpu(), g["codes"])
+    assert torch.equal(recon, want_recon)
+    rps, rbe, rcm, raux, _ = lfq_train_losses(g["presign"], 10)
+    for got, ref in ((ps, rps), (be, rbe), (cm, rcm), (model.quantizer_aux_loss, raux)):
+        assert abs(got.item() - ref.item()) <= 2e-4 * max(1.0, abs(ref.item())), (got.item(), ref.item())
+    only_codes = model(v, return_codes=True)
+    assert torch.equal(only_codes, codes)
+    assert torch.equal(model.tokenize(v), codes) and not model.training          # tokenize() switches to eval (M:1653)
