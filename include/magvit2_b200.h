@@ -97,7 +97,9 @@ typedef struct mv2_conv_args {
   int32_t pt, ph, pw;        /* leading zero padding; trailing padding is implied by To/Ho/Wo */
   int32_t act;               /* MV2_ACT_* */
   int32_t shuffle;           /* MV2_SHUFFLE_*: SPACE: y (B,To,2Ho,2Wo,Co/4), co=(c,p1,p2); TIME: y (B,2To,Ho,Wo,Co/2), co=(c,p) */
-  int32_t x_token_shift;     /* 1: input channels >= Ci/2 are read from frame t-1 (zero at t = 0) */
+  int32_t x_token_shift;     /* 1: input channels >= ceil(Ci/2) are read from frame t-1 (zero at t = 0) */
+  const float* oscale;       /* fp32 [B][Co] or NULL: per-(clip, output channel) multiplier applied to the accumulator BEFORE
+                                bias / activation -- the demodulation factor of Conv3DMod (M:741-742), see mv2_mod_prepare */
 } mv2_conv_args;
 int mv2_conv_forward(const mv2_conv_args* a, void* stream);
 
@@ -116,6 +118,13 @@ int mv2_se_gate(const void* workspace, int dtype /* of the y passed to mv2_se_po
                 float* gates, void* stream);
 int mv2_gate_residual(const void* y, const void* x, const float* gates, void* out, int dtype,
                       int F, int P, int C, void* stream);
+
+/* SqueezeExcite + residual for small frames in ONE launch (bf16 activations; P * C <= 131072 elements per frame, C and Hd
+ * multiples of 8, <= 1024): pool, gate MLP and  out = gate * y + x  (M:221-240 + M:174) by one CTA per frame.  The gate MLP
+ * weights are passed as bf16 (w1 [Hd][C], w2 [C][Hd]; exact for a bf16 model); wk / b1 / b2 fp32.                          */
+int mv2_se_tail_supported(int F, int P, int C, int Hd);
+int mv2_se_tail(const void* y, const void* x, void* out, int F, int P, int C, int Hd, const float* wk, float bk,
+                const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2, void* stream);
 
 /* ---- RMSNorm (M:275-276): out = x / max(||x||_2, 1e-12) * sqrt(C) * gamma over the channel
  * axis of channels-last tokens; token_shift as in mv2_conv_args (M:250-254).               */
@@ -201,6 +210,7 @@ typedef struct mv2_tc_conv_args {
   int32_t shuffle;
   int32_t epi_mode;    /* 0 plain; 1 fused GEGLU (M:466-469): packed columns come in groups of 16 = 8 x-columns then
                           their 8 gate-columns, output has Co/2 channels: y = gelu_erf(gate) * x */
+  const float* oscale; /* as mv2_conv_args.oscale (plain / ragged epilogues only) */
   int32_t out_layout;  /* 0: y is channels-last (B,To,Ho,Wo,Co).  1: y is torch's channels-first (B,Co,To,Ho,Wo) -- the slab
                           kernel's conv_out (Co % 8 != 0) writes the reconstruction directly in the caller's layout; with
                           To < Ti and pt = kt - 1 - (Ti - To) the leading time_padding frames are never computed
@@ -222,6 +232,21 @@ int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream);
 int mv2_tc_slab_plan(const mv2_tc_conv_args* a, int n_sm, int* out6);
 int mv2_tc_slab_tile(const mv2_tc_conv_args* a, int n_sm, int cta, int k, int* out6);
 
+
+/* ---- conditioning (cond_residual = ResidualUnitMod / Conv3DMod, reference M:680-753, M:946-988; stems M:1344-1352) -------
+ * Conv3DMod applies per-clip weights  w_b = w * (cond_b + 1)  (over input channels), demodulated by
+ * rsqrt(max(sum_{i,taps} w_b^2, eps)) per output channel, as a grouped conv.  The per-clip weights never need to exist:
+ *     y[b, o] = inv_norm[b, o] * conv(x[b] * (cond[b] + 1), w)[o],   inv_norm[b,o] = rsqrt(max(sum_i (cond[b,i]+1)^2 S[o,i], eps)),
+ * with S[o, i] = sum_taps w[o, i, tap]^2 packed once by the host.  So the shared-weight conv kernels run unchanged with
+ *   mv2_dense_small   : y[b][n] = act(sum_k x[b][k] w[n][k] + bias[n])   (cond stems: Linear + SiLU; to_cond: Linear), fp32
+ *   mv2_mod_prepare   : scale_in[b][i] = cond[b][i] + 1,  inv_norm[b][o] as above                                  , fp32
+ *   mv2_scale_channels: out[b, pos, c] = x[b, pos, c] * scale[b][c]        (activation dtype)
+ * and mv2_*conv_args.oscale = inv_norm.                                                                                   */
+int mv2_dense_small(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act, void* stream);
+int mv2_mod_prepare(const float* cond, const float* S, float eps, float* scale_in, float* inv_norm, int B, int Ci, int Co,
+                    void* stream);
+int mv2_scale_channels(const void* x, const float* scale, void* out, int dtype, int B, int64_t positions_per_clip, int C,
+                       void* stream);
 
 /* ---- fused ResidualUnit front half (reference M:937-941 + the pooling half of SqueezeExcite M:229-233) ----------------
  * One launch computes  y = ELU(Conv3d_1x1x1(ELU(CausalConv3d_ktxkhxkw(x))))  for C -> C channels (C = 64 or 128, the

@@ -31,6 +31,7 @@ class ConvArgs(C.Structure):
         ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
         ("pt", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
         ("act", C.c_int32), ("shuffle", C.c_int32), ("x_token_shift", C.c_int32),
+        ("oscale", C.c_void_p),
     ]
 
 
@@ -53,7 +54,8 @@ class TcConvArgs(C.Structure):
         ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
         ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
         ("pt", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
-        ("act", C.c_int32), ("shuffle", C.c_int32), ("epi_mode", C.c_int32), ("out_layout", C.c_int32),
+        ("act", C.c_int32), ("shuffle", C.c_int32), ("epi_mode", C.c_int32),
+        ("oscale", C.c_void_p), ("out_layout", C.c_int32),
     ]
 
 
@@ -82,6 +84,8 @@ SIGNATURES = {
     "mv2_se_pool": (_I, [_VP, _I, _I, _I, _I, _VP, _F, _VP, _VP]),
     "mv2_se_gate": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mv2_gate_residual": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "mv2_se_tail_supported": (_I, [_I, _I, _I, _I]),
+    "mv2_se_tail": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _VP, _F, _VP, _VP, _VP, _VP, _VP]),
     "mv2_rmsnorm": (_I, [_VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP]),
     "mv2_attention": (_I, [C.POINTER(AttnArgs), _VP]),
     "mv2_linattn_workspace_bytes": (_SZ, [_I, _I, _I]),
@@ -98,6 +102,9 @@ SIGNATURES = {
     "mv2_tc_slab_forward": (_I, [C.POINTER(TcConvArgs), _VP]),
     "mv2_tc_slab_plan": (_I, [C.POINTER(TcConvArgs), _I, C.POINTER(C.c_int32)]),
     "mv2_tc_slab_tile": (_I, [C.POINTER(TcConvArgs), _I, _I, _I, C.POINTER(C.c_int32)]),
+    "mv2_dense_small": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "mv2_mod_prepare": (_I, [_VP, _VP, _F, _VP, _VP, _I, _I, _I, _VP]),
+    "mv2_scale_channels": (_I, [_VP, _VP, _VP, _I, _I, _I64, _I, _VP]),
     "mv2_tc_ru_supported": (_I, [C.POINTER(TcRuArgs)]),
     "mv2_tc_ru_records": (_I, [C.POINTER(TcRuArgs)]),
     "mv2_tc_ru_workspace_bytes": (_SZ, [C.POINTER(TcRuArgs)]),

@@ -254,7 +254,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const mv2_conv_args a) {
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= a.Co) continue;
-      float v = acc[i][j] + (a.bias ? a.bias[n] : 0.f);
+      float v = acc[i][j];
+      if (a.oscale) v *= a.oscale[(int64_t)b * a.Co + n];          // Conv3DMod demodulation (M:741-742)
+      v += a.bias ? a.bias[n] : 0.f;
       v = apply_act(v, a.act);
       int64_t off;
       if (a.shuffle == MV2_SHUFFLE_SPACE) {
@@ -633,6 +635,254 @@ __global__ void gate_residual_bf16x8_kernel(const uint4* __restrict__ y, const u
       ob[q] = *reinterpret_cast<uint32_t*>(&r);
     }
     out[i] = o;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// SqueezeExcite + residual for SMALL frames in one launch (the deep 16x16 levels: a frame of y is <= 256 KB and the four
+// launches of the general path -- pool, hidden, out, gate/residual -- are pure launch + L2 latency there).
+// One CTA (512 threads) per frame f:
+//   1. pooled[c] = sum_n softmax_n(<y[n,:], wk> + bk) y[n,c]     one warp per position row, online softmax, merged via smem
+//   2. hidden    = leaky_relu_0.1(W1 pooled + b1)                one warp per output, bf16 weight rows (exact: the SE
+//   3. gate      = sigmoid(W2 hidden + b2)                        weights of a bf16 model are bf16 values), fp32 accumulate
+//   4. out[n,c]  = gate[c] * y[n,c] + x[n,c]                      (M:240 + M:174), y re-read from L2
+// NU = 16-byte pieces per lane and row (C <= 256 * NU), HU likewise for the hidden width.
+// ------------------------------------------------------------------------------------------
+constexpr int ST_WARPS = 16;
+template <int NU, int HU>
+__global__ void __launch_bounds__(ST_WARPS * 32) se_tail_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ x,
+                                                                __nv_bfloat16* __restrict__ out, int P, int C, int Hd,
+                                                                const float* __restrict__ wk, float bk,
+                                                                const __nv_bfloat16* __restrict__ w1, const float* __restrict__ b1,
+                                                                const __nv_bfloat16* __restrict__ w2, const float* __restrict__ b2) {
+  extern __shared__ __align__(16) float st_sm[];
+  float* wacc = st_sm;                       // [ST_WARPS][C]
+  float* pooled = wacc + ST_WARPS * C;       // [C]
+  float* hidden = pooled + C;                // [Hd]
+  float* gates = hidden + Hd;                // [C]
+  __shared__ float wm[ST_WARPS], wsum[ST_WARPS];
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __nv_bfloat16* yf = y + (int64_t)f * P * C;
+  pdl_wait();
+  pdl_launch_dependents();
+  // ---- 1. pooling ----
+  float wv[NU][8];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const int c = (u * 32 + lane) * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) wv[u][q] = c + q < C ? wk[c + q] : 0.f;
+  }
+  float m = -INFINITY, ssum = 0.f, acc[NU][8];
+#pragma unroll
+  for (int u = 0; u < NU; ++u)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[u][q] = 0.f;
+  for (int n0 = warp; n0 < P; n0 += 2 * ST_WARPS) {      // two rows per iteration: both rows' loads are in flight together
+    const int n1 = n0 + ST_WARPS;
+    uint4 r0[NU], r1[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int c = (u * 32 + lane) * 8;
+      r0[u] = c < C ? *reinterpret_cast<const uint4*>(yf + (int64_t)n0 * C + c) : make_uint4(0, 0, 0, 0);
+      r1[u] = (c < C && n1 < P) ? *reinterpret_cast<const uint4*>(yf + (int64_t)n1 * C + c) : make_uint4(0, 0, 0, 0);
+    }
+    float v0[NU][8], v1[NU][8], d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const uint32_t a[4] = {r0[u].x, r0[u].y, r0[u].z, r0[u].w}, b[4] = {r1[u].x, r1[u].y, r1[u].z, r1[u].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v0[u][2 * q] = __uint_as_float(a[q] << 16); v0[u][2 * q + 1] = __uint_as_float(a[q] & 0xffff0000u);
+        v1[u][2 * q] = __uint_as_float(b[q] << 16); v1[u][2 * q + 1] = __uint_as_float(b[q] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { d0 = fmaf(v0[u][q], wv[u][q], d0); d1 = fmaf(v1[u][q], wv[u][q], d1); }
+    }
+    d0 = warp_sum(d0);
+    d1 = warp_sum(d1);
+    const float l0 = d0 + bk, l1 = n1 < P ? d1 + bk : -INFINITY;
+    const float mn = fmaxf(m, fmaxf(l0, l1));
+    const float sc = se_exp(m - mn), e0 = se_exp(l0 - mn), e1 = se_exp(l1 - mn);     // exp(-inf) = 0
+    ssum = fmaf(ssum, sc, e0 + e1);
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[u][q] = fmaf(e1, v1[u][q], fmaf(e0, v0[u][q], acc[u][q] * sc));
+    m = mn;
+  }
+  if (lane == 0) { wm[warp] = m; wsum[warp] = ssum; }
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const int c = (u * 32 + lane) * 8;
+    if (c < C) {
+      *reinterpret_cast<float4*>(wacc + warp * C + c) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+      *reinterpret_cast<float4*>(wacc + warp * C + c + 4) = make_float4(acc[u][4], acc[u][5], acc[u][6], acc[u][7]);
+    }
+  }
+  __syncthreads();
+  {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < ST_WARPS; ++w) M = fmaxf(M, wm[w]);
+    float cf[ST_WARPS], S = 0.f;
+#pragma unroll
+    for (int w = 0; w < ST_WARPS; ++w) { cf[w] = wm[w] > -INFINITY ? __expf(wm[w] - M) : 0.f; S = fmaf(cf[w], wsum[w], S); }
+    const float inv = 1.f / S;
+    for (int c = tid; c < C; c += ST_WARPS * 32) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < ST_WARPS; ++w) t = fmaf(cf[w], wacc[w * C + c], t);
+      pooled[c] = t * inv;
+    }
+  }
+  __syncthreads();
+  // ---- 2. hidden layer: warp per output, 4 outputs in flight ----
+  {
+    float pv[NU][8];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int c = (u * 32 + lane) * 8;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pv[u][q] = c + q < C ? pooled[c + q] : 0.f;
+    }
+    for (int j0 = warp * 4; j0 < Hd; j0 += ST_WARPS * 4) {
+      uint4 r[4][NU];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const int c = (u * 32 + lane) * 8;
+          r[t][u] = (j0 + t < Hd && c < C) ? *reinterpret_cast<const uint4*>(w1 + (int64_t)(j0 + t) * C + c) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float d = 0.f;
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const uint32_t a[4] = {r[t][u].x, r[t][u].y, r[t][u].z, r[t][u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            d = fmaf(__uint_as_float(a[q] << 16), pv[u][2 * q], d);
+            d = fmaf(__uint_as_float(a[q] & 0xffff0000u), pv[u][2 * q + 1], d);
+          }
+        }
+        d = warp_sum(d);
+        if (lane == 0 && j0 + t < Hd) {
+          const float h = d + b1[j0 + t];
+          hidden[j0 + t] = h > 0.f ? h : 0.1f * h;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 3. gates ----
+  {
+    float hv[HU][8];
+#pragma unroll
+    for (int u = 0; u < HU; ++u) {
+      const int j = (u * 32 + lane) * 8;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) hv[u][q] = j + q < Hd ? hidden[j + q] : 0.f;
+    }
+    for (int c0 = warp * 4; c0 < C; c0 += ST_WARPS * 4) {
+      uint4 r[4][HU];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+          const int j = (u * 32 + lane) * 8;
+          r[t][u] = (c0 + t < C && j < Hd) ? *reinterpret_cast<const uint4*>(w2 + (int64_t)(c0 + t) * Hd + j) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float d = 0.f;
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+          const uint32_t a[4] = {r[t][u].x, r[t][u].y, r[t][u].z, r[t][u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            d = fmaf(__uint_as_float(a[q] << 16), hv[u][2 * q], d);
+            d = fmaf(__uint_as_float(a[q] & 0xffff0000u), hv[u][2 * q + 1], d);
+          }
+        }
+        d = warp_sum(d);
+        if (lane == 0 && c0 + t < C) gates[c0 + t] = 1.f / (1.f + expf(-(d + b2[c0 + t])));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 4. out = gate * y + x ----
+  {
+    const uint4* y8 = reinterpret_cast<const uint4*>(yf);
+    const uint4* x8 = reinterpret_cast<const uint4*>(x + (int64_t)f * P * C);
+    uint4* o8 = reinterpret_cast<uint4*>(out + (int64_t)f * P * C);
+    const int C8 = C >> 3, total = P * C8;
+    for (int i = tid; i < total; i += ST_WARPS * 32) {
+      const int c = (i % C8) * 8;
+      const uint4 yv = y8[i], xv = x8[i];
+      const float4 g0 = *reinterpret_cast<const float4*>(gates + c), g1 = *reinterpret_cast<const float4*>(gates + c + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const __nv_bfloat162* yb = reinterpret_cast<const __nv_bfloat162*>(&yv);
+      const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xv);
+      uint4 o;
+      uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 yf2 = __bfloat1622float2(yb[q]), xf2 = __bfloat1622float2(xb[q]);
+        __nv_bfloat162 r = __floats2bfloat162_rn(fmaf(gg[2 * q], yf2.x, xf2.x), fmaf(gg[2 * q + 1], yf2.y, xf2.y));
+        ob[q] = *reinterpret_cast<uint32_t*>(&r);
+      }
+      o8[i] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// conditioning helpers (cond_residual; reference M:680-753, M:946-988, M:1344-1352)
+// ------------------------------------------------------------------------------------------
+// y[b][n] = act(sum_k x[b][k] w[n][k] + bias[n]); one warp per output, grid (ceil(N / 8), B)
+__global__ void __launch_bounds__(256) dense_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ y, int K, int N, int act) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.y, n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(x[(int64_t)b * K + k], w[(int64_t)n * K + k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) y[(int64_t)b * N + n] = apply_act(acc + (bias ? bias[n] : 0.f), act);
+}
+
+// scale_in[b][i] = cond[b][i] + 1;  inv_norm[b][o] = rsqrt(max(sum_i (cond[b][i] + 1)^2 S[o][i], eps))
+__global__ void __launch_bounds__(256) mod_prepare_kernel(const float* __restrict__ cond, const float* __restrict__ S, float eps,
+                                                          float* __restrict__ scale_in, float* __restrict__ inv_norm, int Ci, int Co) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < Ci; i += 256) scale_in[(int64_t)b * Ci + i] = cond[(int64_t)b * Ci + i] + 1.f;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (o >= Co) return;
+  float acc = 0.f;
+  for (int i = lane; i < Ci; i += 32) {
+    const float m = cond[(int64_t)b * Ci + i] + 1.f;
+    acc = fmaf(m * m, S[(int64_t)o * Ci + i], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) inv_norm[(int64_t)b * Co + o] = rsqrtf(fmaxf(acc, eps));
+}
+
+template <typename T>
+__global__ void scale_channels_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ out,
+                                      int64_t total, int64_t per_clip, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per_clip;
+    const int c = (int)(i % C);
+    out[i] = from_f32<T>(to_f32<T>(x[i]) * scale[b * C + c]);
   }
 }
 
@@ -1813,6 +2063,74 @@ int mv2_se_gate_records(const void* workspace, int nrec, int F, int C, int Hd, c
     launch_k(se_hidden_kernel<false>, dim3(dim3(F, ceil_div(Hd, 32))), dim3(256), smem1, st, (const float*)workspace, nrec, C, Hd, w1, b1, hidden);
   MV2_CHECK_LAUNCH();
   launch_k(se_out_kernel, dim3(dim3(F, ceil_div(C, 64))), dim3(256), smem2, st, hidden, C, Hd, w2, b2, gates);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_se_tail_supported(int F, int P, int C, int Hd) {
+  if (F <= 0 || P <= 0 || C <= 0 || Hd <= 0) return 0;
+  if (C % 8 != 0 || C > 1024 || Hd % 8 != 0 || Hd > 1024) return 0;
+  if ((int64_t)P * C > 131072) return 0;                 // frame of y <= 256 KB: the latency-bound deep levels
+  return 1;
+}
+
+int mv2_se_tail(const void* y, const void* x, void* out, int F, int P, int C, int Hd, const float* wk, float bk,
+                const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2, void* stream) {
+  MV2_CHECK_ARG(y && x && out && wk && w1_bf16 && b1 && w2_bf16 && b2);
+  if (!mv2_se_tail_supported(F, P, C, Hd)) { set_error("mv2_se_tail: unsupported shape F=%d P=%d C=%d Hd=%d", F, P, C, Hd); return MV2_E_UNSUPPORTED; }
+  const size_t smem = ((size_t)ST_WARPS * C + 2 * (size_t)C + Hd) * sizeof(float);
+  MV2_CHECK_ARG(smem <= 96 * 1024);
+  static PerDeviceOnce once;
+  const cudaError_t e = once.run([] {
+    cudaError_t err = cudaSuccess;
+    auto set = [&](const void* fn) { if (err == cudaSuccess) err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); };
+    set((const void*)se_tail_kernel<1, 1>); set((const void*)se_tail_kernel<2, 1>); set((const void*)se_tail_kernel<2, 2>);
+    set((const void*)se_tail_kernel<4, 1>); set((const void*)se_tail_kernel<4, 2>); set((const void*)se_tail_kernel<4, 4>);
+    set((const void*)se_tail_kernel<1, 2>); set((const void*)se_tail_kernel<1, 4>); set((const void*)se_tail_kernel<2, 4>);
+    return err;
+  });
+  MV2_CHECK_CUDA(e);
+  const int nu = C <= 256 ? 1 : (C <= 512 ? 2 : 4), hu = Hd <= 256 ? 1 : (Hd <= 512 ? 2 : 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* yb = (const __nv_bfloat16*)y;
+  const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+  __nv_bfloat16* ob = (__nv_bfloat16*)out;
+  const __nv_bfloat16* w1b = (const __nv_bfloat16*)w1_bf16;
+  const __nv_bfloat16* w2b = (const __nv_bfloat16*)w2_bf16;
+#define MV2_ST_CASE(N, H) \
+  else if (nu == N && hu == H) launch_k(se_tail_kernel<N, H>, dim3(F), dim3(ST_WARPS * 32), smem, st, yb, xb, ob, P, C, Hd, wk, bk, w1b, b1, w2b, b2)
+  if (false) {}
+  MV2_ST_CASE(1, 1); MV2_ST_CASE(1, 2); MV2_ST_CASE(1, 4); MV2_ST_CASE(2, 1); MV2_ST_CASE(2, 2); MV2_ST_CASE(2, 4);
+  MV2_ST_CASE(4, 1); MV2_ST_CASE(4, 2); MV2_ST_CASE(4, 4);
+#undef MV2_ST_CASE
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_dense_small(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act, void* stream) {
+  MV2_CHECK_ARG(x && w && y && B > 0 && K > 0 && N > 0 && B <= 65535);
+  launch_k(dense_small_kernel, dim3(ceil_div(N, 8), B), dim3(256), 0, (cudaStream_t)stream, x, w, bias, y, K, N, act);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_mod_prepare(const float* cond, const float* S, float eps, float* scale_in, float* inv_norm, int B, int Ci, int Co,
+                    void* stream) {
+  MV2_CHECK_ARG(cond && S && scale_in && inv_norm && B > 0 && Ci > 0 && Co > 0 && B <= 65535);
+  launch_k(mod_prepare_kernel, dim3(ceil_div(Co, 8), B), dim3(256), 0, (cudaStream_t)stream, cond, S, eps, scale_in, inv_norm, Ci, Co);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_scale_channels(const void* x, const float* scale, void* out, int dtype, int B, int64_t positions_per_clip, int C,
+                       void* stream) {
+  MV2_CHECK_ARG(x && scale && out && B > 0 && positions_per_clip > 0 && C > 0);
+  const int64_t per_clip = positions_per_clip * C, total = per_clip * B;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32) launch_k(scale_channels_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)x, scale, (float*)out, total, per_clip, C);
+  else if (dtype == MV2_BF16) launch_k(scale_channels_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, scale, (__nv_bfloat16*)out, total, per_clip, C);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

@@ -194,6 +194,7 @@ struct TcEpi {
   int Co;                        // packed GEMM output columns
   int To, Ho, Wo;                // output volume before any depth-to-space/time shuffle
   int out_cf;                    // 1: y is channels-first (B, Co, To, Ho, Wo) -- EPI_RAGGED scalar stores only (conv_out)
+  const float* oscale;           // [B][Co] or null: accumulator multiplier per (clip, output channel) before bias / activation
 };
 
 __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)[8]) {
@@ -286,6 +287,13 @@ __device__ __forceinline__ void epi_chunk32_t(const TcEpi& e, const uint32_t (&r
     {
       const float4 b0 = *reinterpret_cast<const float4*>(sb + g * 8), b1 = *reinterpret_cast<const float4*>(sb + g * 8 + 4);
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      if (MODE != EPI_SHUFFLE && e.oscale) {      // Conv3DMod demodulation (M:741-742)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float os = ng + q < e.Co ? e.oscale[(int64_t)b * e.Co + ng + q] : 0.f;
+          v[q] = act_ct<ACT>(__uint_as_float(r[g * 8 + q]) * os + bb[q]);
+        }
+      } else
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = act_ct<ACT>(__uint_as_float(r[g * 8 + q]) + bb[q]);
     }

@@ -182,6 +182,7 @@ int mv2_tc_conv_supported(const mv2_tc_conv_args* a) {
   if (a->epi_mode == 1 && (a->Co % 32 != 0 || a->shuffle != MV2_SHUFFLE_NONE || a->res)) return 0;   // GEGLU pairs
   if (a->epi_mode != 0 && a->epi_mode != 1) return 0;
   if (a->out_layout != 0) return 0;
+  if (a->oscale && (a->epi_mode != 0 || a->shuffle != MV2_SHUFFLE_NONE)) return 0;
   return 1;
 }
 
@@ -221,7 +222,7 @@ int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream) {
   p.stages = stages;
   p.epi.bias = a->bias; p.epi.res = (const __nv_bfloat16*)a->res; p.epi.y = (__nv_bfloat16*)a->y;
   p.epi.act = a->act; p.epi.shuffle = a->shuffle; p.epi.mode = a->epi_mode; p.epi.Co = a->Co;
-  p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo; p.epi.out_cf = 0;
+  p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo; p.epi.out_cf = 0; p.epi.oscale = a->oscale;
 
   // ---- activation tensor maps: one per stride-parity phase ----
   const int st = a->st, sh = a->sh, sw = a->sw;

@@ -525,6 +525,11 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
             uint32_t r[32], pk[16];
             tmem_ld_32x32b_x32(tl + c0, r);
             tmem_ld_wait();
+            if (MODE == EPI_PLAIN && p.epi.oscale) {      // Conv3DMod demodulation: per-(clip, channel) multiplier (M:741-742)
+              const float* os = p.epi.oscale + (int64_t)c.b * p.Co + c.n0 + c0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * (c.n0 + c0 + i < p.Co ? os[i] : 0.f));
+            }
             epi_pack32(p.epi.act, r, sbias + c.n0 + c0, pk);
 #pragma unroll
             for (int g = 0; g < 4; ++g)
@@ -576,6 +581,11 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
             uint32_t r[32];
             tmem_ld_32x32b_x32(tl + c0, r);
             tmem_ld_wait();
+            if (p.epi.oscale) {
+              const float* os = p.epi.oscale + (int64_t)c.b * p.Co + c.n0 + c0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * (c.n0 + c0 + i < p.Co ? os[i] : 0.f));
+            }
             epi_act32(p.epi.act, r, sbias + c.n0 + c0);
 #pragma unroll
             for (int g = 0; g < 8; ++g)
@@ -699,6 +709,7 @@ extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
   if (!a) return 0;
   if (a->st != 1 || a->sh != 1 || a->sw != 1) return 0;
   if (a->Ci % 32 != 0 || a->Co > 4096) return 0;
+  if (a->oscale && (a->epi_mode != 0 || a->shuffle != MV2_SHUFFLE_NONE)) return 0;   // demodulation: plain / ragged epilogues only
   if (a->epi_mode == 1 && (a->Co % 32 != 0 || a->shuffle != MV2_SHUFFLE_NONE || a->res)) return 0;   // fused GEGLU
   if (a->epi_mode != 0 && a->epi_mode != 1) return 0;
   if (a->Co % 32 != 0 && a->Co > 32) return 0;           // ragged N only as a single (zero padded) 32-column tile
@@ -725,7 +736,7 @@ static int slab_fill_plan(const mv2_tc_conv_args* a, int n_sm, SlabParams& p, in
   p.B = a->B; p.T = a->To; p.H = a->Ho; p.W = a->Wo; p.Co = a->Co;
   p.epi.bias = a->bias; p.epi.res = (const __nv_bfloat16*)a->res; p.epi.y = (__nv_bfloat16*)a->y;
   p.epi.act = a->act; p.epi.shuffle = a->shuffle; p.epi.mode = a->epi_mode; p.epi.Co = a->Co;
-  p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo; p.epi.out_cf = a->out_layout == 1;
+  p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo; p.epi.out_cf = a->out_layout == 1; p.epi.oscale = a->oscale;
 
   // ---- tiling (profiles/r01_sweep_slab_v*.json): widest N tile; two M-tiles per weight tile whenever both
   //      accumulator sets still double-buffer in TMEM (2 * mw * bn <= 512), which also halves weight traffic ----

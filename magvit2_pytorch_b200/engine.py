@@ -139,6 +139,8 @@ class Engine:
         self.tc_variant = "auto"     # "auto" | "tap" (tc_conv.cu only) | "slab" (prefer tc_slab.cu)
         self.fuse_ru = True          # bf16: conv3x3x3 + ELU + conv1x1x1 + ELU + SE pool partials in one tcgen05 launch (C = 64 / 128)
         self.fused_ru_calls = 0
+        self.se_tail = True          # bf16, small frames: SE pool + gate MLP + gate/residual in one launch
+        self.se_tail_calls = 0
         self.fuse_conv_out = True    # bf16: conv_out stores torch's (B,C,T,H,W) directly and skips the time_padding frames
         self.tc_calls = 0
         self.slab_calls = 0
@@ -190,6 +192,9 @@ class Engine:
                 w2=f32(se.net[2].weight.reshape(C_, -1)), b2=f32(se.net[2].bias),
                 hidden=int(se.net[0].weight.shape[0]),
             )
+            if dt == torch.bfloat16:      # bf16 copies of the gate MLP for the one-launch SE tail (exact: the parameters are bf16)
+                P[key]["w1b"] = P[key]["w1"].to(torch.bfloat16).contiguous()
+                P[key]["w2b"] = P[key]["w2"].to(torch.bfloat16).contiguous()
 
         def pack_ffn(ff, key):
             fc1, fc2 = pack_ff(ff.net[0].weight, ff.net[0].bias, ff.net[2].weight, ff.net[2].bias, dt)
@@ -217,6 +222,12 @@ class Engine:
                     units = list(mod) if st.nested else [mod]
                     for j, ru in enumerate(units):
                         pack_ru(ru, f"{key}.{j}")
+                elif st.kind == "cond_residual":
+                    w = mod.conv.weights
+                    wq = w.detach().to(dt).float()                  # the weights as the module holds them in this dtype
+                    P[key] = dict(conv3=pack_conv(w, None, dt), conv1=pack_conv(mod.conv_out.weight, mod.conv_out.bias, dt),
+                                  S=(wq * wq).sum(dim=(2, 3, 4)).contiguous(), eps=float(mod.conv.eps),
+                                  wc=f32(mod.to_cond.weight), bc=f32(mod.to_cond.bias))
                 elif st.kind == "compress_space":
                     if side == "enc":
                         P[key] = pack_conv(mod.conv.weight, mod.conv.bias, dt)                     # (Co,Ci,3,3) -> k=(1,3,3)
@@ -236,6 +247,9 @@ class Engine:
                 elif st.kind == "linear_attend_space":
                     pack_lin(mod[0].fn, key + ".attn")
                     pack_ffn(mod[1].fn, key + ".ff")
+        if m.has_cond:
+            for side, stem in (("enc", m.encoder_cond_in), ("dec", m.decoder_cond_in)):
+                P[f"{side}_cond_in"] = dict(w=f32(stem[0].weight), b=f32(stem[0].bias))
         q = m.quantizers
         # the reference applies the projections in the module dtype (bf16 weights in bf16 mode)
         P["quant"] = dict(win=q.project_in.weight.detach().to(dt).float().contiguous(), bin=q.project_in.bias.detach().to(dt).float().contiguous(),
@@ -252,7 +266,7 @@ class Engine:
         return torch.empty(shape, device=self.device, dtype=dtype or self.dtype)
 
     def conv(self, x, pk: ConvPack, *, stride=(1, 1, 1), pad=None, out_spatial=None, act=ACT_NONE,
-             res=None, shuffle=SHUFFLE_NONE, token_shift=False, out_cf=False):
+             res=None, shuffle=SHUFFLE_NONE, token_shift=False, out_cf=False, oscale=None):
         """x: (B,T,H,W,Ci) channels-last.  `pad` = leading (pt,ph,pw); causal default (kt-1, kh//2, kw//2).
         out_cf (tcgen05 slab path, Co % 8 != 0 only): write torch's (B,Co,To,Ho,Wo) layout directly."""
         B, Ti, Hi, Wi, Ci = x.shape
@@ -281,7 +295,7 @@ class Engine:
                             B=B, Ti=Ti, Hi=Hi, Wi=Wi, Ci=Ci, To=To, Ho=Ho, Wo=Wo, Co=co_gemm,
                             kt=kt, kh=kh, kw=kw, st=stride[0], sh=stride[1], sw=stride[2],
                             pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle, epi_mode=pk.epi_mode,
-                            out_layout=int(out_cf))
+                            oscale=_ptr(oscale), out_layout=int(out_cf))
             # measured policy (profiles/r01_sweep_slab_v*.json): the persistent slab kernel wins on every layer it supports
             # (incl. the 64-byte-row conv_in once it runs 4 M-tiles and 7 taps per weight stage); the tap-wise kernel
             # keeps the strided down-samplers.  tc_variant = "tap" forces the tap-wise kernel (tests / sweeps).
@@ -322,7 +336,8 @@ class Engine:
         a = ConvArgs(x=_ptr(x), w=_ptr(pk.w), bias=_ptr(pk.bias), res=_ptr(res), y=_ptr(y), dtype=_dt(self.dtype),
                      B=B, Ti=Ti, Hi=Hi, Wi=Wi, Ci=Ci, To=To, Ho=Ho, Wo=Wo, Co=pk.Co,
                      kt=kt, kh=kh, kw=kw, st=stride[0], sh=stride[1], sw=stride[2],
-                     pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle, x_token_shift=int(token_shift))
+                     pt=pad[0], ph=pad[1], pw=pad[2], act=act, shuffle=shuffle, x_token_shift=int(token_shift),
+                     oscale=_ptr(oscale))
         check(self.lib.mv2_conv_forward(C.byref(a), self._stream()), "mv2_conv_forward")
         self.launches += 1
         return y
@@ -365,6 +380,14 @@ class Engine:
                 return out
         h = self.conv(x, c3, act=ACT_ELU)
         y = self.conv(h, c1, act=ACT_ELU)
+        if (self.dtype == torch.bfloat16 and self.se_tail and "w1b" in p
+                and self.lib.mv2_se_tail_supported(F_, Pn, Cc, p["hidden"])):
+            out = self._new(x.shape)
+            check(self.lib.mv2_se_tail(_ptr(y), _ptr(x), _ptr(out), F_, Pn, Cc, p["hidden"], _ptr(p["wk"]), p["bk"],
+                                       _ptr(p["w1b"]), _ptr(p["b1"]), _ptr(p["w2b"]), _ptr(p["b2"]), st), "mv2_se_tail")
+            self.launches += 1
+            self.se_tail_calls += 1
+            return out
         ws = self._new((self.lib.mv2_se_workspace_bytes(F_, Pn, Cc) // 4,), torch.float32)
         gates = self._new((F_, Cc), torch.float32)
         check(self.lib.mv2_se_pool(_ptr(y), dt, F_, Pn, Cc, _ptr(p["wk"]), p["bk"], _ptr(ws), st), "mv2_se_pool")
@@ -374,6 +397,35 @@ class Engine:
         check(self.lib.mv2_gate_residual(_ptr(y), _ptr(x), _ptr(gates), _ptr(out), dt, F_, Pn, Cc, st), "mv2_gate_residual")
         self.launches += 3
         return out
+
+    def dense_small(self, x, w, b, act=ACT_NONE):
+        """fp32 y[b][n] = act(x[b] . w[n] + bias[n]) (cond stems M:1344-1352, to_cond M:983)."""
+        Bx, K = x.shape
+        N = w.shape[0]
+        y = self._new((Bx, N), torch.float32)
+        check(self.lib.mv2_dense_small(_ptr(x), _ptr(w), _ptr(b), _ptr(y), Bx, K, N, act, self._stream()), "mv2_dense_small")
+        self.launches += 1
+        return y
+
+    def cond_stem(self, cond, side):
+        p = self._packs[f"{side}_cond_in"]
+        return self.dense_small(cond.float().contiguous(), p["w"], p["b"], ACT_SILU)
+
+    def residual_unit_mod(self, x, p, cond_e):
+        """ResidualUnitMod (M:978-988): x + ELU(conv_out(ELU(Conv3DMod(x, to_cond(cond))))).  The per-clip modulated weights
+        are never built: input channels are scaled by (cond + 1), the shared-weight conv runs unchanged and the demodulation
+        rsqrt(sum w_b^2) multiplies the accumulator per (clip, output channel) in the epilogue (include/magvit2_b200.h)."""
+        B, T, H, W, Cc = x.shape
+        c = self.dense_small(cond_e, p["wc"], p["bc"])
+        scale_in = self._new((B, Cc), torch.float32)
+        inv_norm = self._new((B, Cc), torch.float32)
+        st = self._stream()
+        check(self.lib.mv2_mod_prepare(_ptr(c), _ptr(p["S"]), p["eps"], _ptr(scale_in), _ptr(inv_norm), B, Cc, Cc, st), "mv2_mod_prepare")
+        xs = self._new(x.shape)
+        check(self.lib.mv2_scale_channels(_ptr(x), _ptr(scale_in), _ptr(xs), _dt(self.dtype), B, T * H * W, Cc, st), "mv2_scale_channels")
+        self.launches += 2
+        h = self.conv(xs, p["conv3"], act=ACT_ELU, oscale=inv_norm)
+        return self.conv(h, p["conv1"], act=ACT_ELU, res=x)
 
     def rmsnorm(self, x, gamma, token_shift=False):
         B, T, H, W, Cc = x.shape
@@ -467,12 +519,14 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ stages
-    def _stage(self, x, st, key, decoder: bool):
+    def _stage(self, x, st, key, decoder: bool, cond_e=None):
         P = self._packs
         B, T, H, W, Cc = x.shape
         if st.kind == "residual":
             for j in range(st.count):
                 x = self.residual_unit(x, P[f"{key}.{j}"])
+        elif st.kind == "cond_residual":
+            x = self.residual_unit_mod(x, P[key], cond_e)
         elif st.kind == "compress_space":
             if decoder:   # SpatialUpsample2x (M:838-846)
                 x = self.conv(x, P[key], act=ACT_SILU, shuffle=SHUFFLE_SPACE)
@@ -536,7 +590,7 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ the path
-    def encode_cl(self, video: torch.Tensor, first_frame: bool = True):
+    def encode_cl(self, video: torch.Tensor, first_frame: bool = True, cond=None):
         """video (B,C,T,H,W) on device -> encoder output, channels-last.  Reference encode M:1523-1576; the time_padding
         zero frames are only prepended when the clip starts with a first frame (video_contains_first_frame, M:1534-1537)."""
         m = self.model
@@ -549,18 +603,20 @@ class Engine:
             x = self.to_channels_last(video, t_pad)
             x = self.conv(x, self._packs["conv_in"])
         self._tap("conv_in", x)
+        cond_e = self.cond_stem(cond, "enc") if (m.has_cond and cond is not None) else None     # M:1544-1548
         for i, st in enumerate(m.stages):
-            x = self._stage(x, st, f"enc{i}", decoder=False)
+            x = self._stage(x, st, f"enc{i}", decoder=False, cond_e=cond_e)
             self._tap(f"enc{i}", x)
         return x
 
-    def decode_cl(self, q: torch.Tensor, first_frame: bool = True):
+    def decode_cl(self, q: torch.Tensor, first_frame: bool = True, cond=None):
         """quantized channels-last (B,T',H',W',C) -> video (B,3,T,H,W).  Reference decode M:1598-1649; the leading
         time_padding frames are dropped only for clips that contain a first frame (M:1646-1647)."""
         m = self.model
         x = q
+        cond_e = self.cond_stem(cond, "dec") if (m.has_cond and cond is not None) else None     # M:1612-1616
         for j, st in enumerate(reversed(m.stages)):
-            x = self._stage(x, st, f"dec{j}", decoder=True)
+            x = self._stage(x, st, f"dec{j}", decoder=True, cond_e=cond_e)
             self._tap(f"dec{j}", x)
         pk = self._packs["conv_out"]
         B, T, H, W, Cc = x.shape

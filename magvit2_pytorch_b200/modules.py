@@ -84,6 +84,29 @@ def residual_unit(dim, kernel_size):
         SqueezeExcite(dim)))
 
 
+class Conv3DMod(_NoForward):
+    """M:680-716 -- StyleGAN2-style modulated causal conv: one ``weights`` Parameter (dim_out, dim, kt, ks, ks), demod=True."""
+
+    def __init__(self, dim, spatial_kernel, time_kernel, eps=1e-8):
+        super().__init__()
+        self.eps = eps
+        self.spatial_kernel, self.time_kernel = spatial_kernel, time_kernel
+        self.weights = nn.Parameter(torch.randn((dim, dim, time_kernel, spatial_kernel, spatial_kernel)))
+        nn.init.kaiming_normal_(self.weights, a=0, mode="fan_in", nonlinearity="selu")
+
+
+class ResidualUnitMod(_NoForward):
+    """M:946-976 -- to_cond: Linear(dim_cond -> dim), conv: Conv3DMod, conv_out: Conv3d 1x1x1 (no SqueezeExcite)."""
+
+    def __init__(self, dim, kernel_size, dim_cond):
+        super().__init__()
+        ks = kernel_size if isinstance(kernel_size, tuple) else (kernel_size,) * 3
+        assert ks[1] == ks[2]
+        self.to_cond = nn.Linear(dim_cond, dim)
+        self.conv = Conv3DMod(dim, spatial_kernel=ks[1], time_kernel=ks[0])
+        self.conv_out = nn.Conv3d(dim, dim, 1)
+
+
 class SpatialDownsample2x(_NoForward):
     """M:757-768 (antialias=False)."""
 

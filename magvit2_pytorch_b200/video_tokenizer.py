@@ -11,8 +11,9 @@ All arithmetic runs in hand-written sm_100a kernels behind the C ABI of libmagvi
 the compute dtype follows the parameters' dtype (``.float()`` -> fp32 CUDA-core path,
 ``.bfloat16()`` -> bf16 tcgen05 path).  There is no CPU / eager fallback.
 
-Out of scope (raise at construction / call): conditioning layers (``cond_*``),
-``gateloop_time``, ``separate_first_frame_encoding``, ``num_codebooks > 1``, ``lfq_spherical``,
+``cond_residual`` layers (ResidualUnitMod / Conv3DMod, M:680-753, M:946-988) run on the device through the
+factorisation in include/magvit2_b200.h; the other ``cond_*`` types raise in the reference itself.
+Out of scope (raise at construction / call): ``gateloop_time``, ``separate_first_frame_encoding``, ``num_codebooks > 1``, ``lfq_spherical``,
 non-constant ``pad_mode``, the GAN / perceptual training losses (``return_loss`` /
 ``return_discr_loss``), autograd.
 """
@@ -57,7 +58,6 @@ def _on_model_device(fn):
 
 
 _UNSUPPORTED_LAYERS = {
-    "cond_residual": "conditioning layers are outside the accelerated path (SURVEY.md 8f N1)",
     "cond_attend_space": "raises in the reference itself (SURVEY.md 2 row 9)",
     "cond_linear_attend_space": "raises in the reference itself (SURVEY.md 2 row 9)",
     "cond_attend_time": "raises in the reference itself (SURVEY.md 2 row 9)",
@@ -145,15 +145,26 @@ class VideoTokenizer(nn.Module):
         dim = init_dim
         fmap = image_size
         tdf = 1
+        has_cond = False
         stages: List[Stage] = []
         for layer_def in layers:
             kind, *params = layer_def if isinstance(layer_def, tuple) else (layer_def,)
             dim_out = dim
             if kind in _UNSUPPORTED_LAYERS:
                 raise NotImplementedError(f"layer type {kind!r}: {_UNSUPPORTED_LAYERS[kind]}")
+            if has_cond and kind != "cond_residual":
+                # has_cond is never reset in the reference (M:1153, M:1318): every later layer is called with cond=, and its
+                # plain layers then raise TypeError -- only specs whose conditioned layers are the trailing ones run there
+                raise TypeError(f"layer {kind!r} after a cond_* layer: the reference passes cond= to it and fails (M:1153, M:1318)")
             if kind == "residual":
                 enc, dec = M.residual_unit(dim, ks), M.residual_unit(dim, ks)
                 stages.append(Stage("residual", dim, dim, 1, False))
+            elif kind == "cond_residual":                                        # M:1150-1157
+                assert dim_cond is not None, "dim_cond must be passed into VideoTokenizer, if tokenizer is to be conditioned"
+                has_cond = True
+                dc = int(dim_cond * dim_cond_expansion_factor)
+                enc, dec = M.ResidualUnitMod(dim, ks, dc), M.ResidualUnitMod(dim, ks, dc)
+                stages.append(Stage("cond_residual", dim, dim))
             elif kind == "consecutive_residual":
                 n, = params
                 enc = nn.Sequential(*[M.residual_unit(dim, ks) for _ in range(n)])
@@ -205,10 +216,15 @@ class VideoTokenizer(nn.Module):
         self.time_downsample_factor = tdf
         self.time_padding = tdf - 1
         self.fmap_size = fmap
-        self.has_cond = False
-        self.has_cond_across_layers = [False] * len(stages)
+        self.has_cond = has_cond
+        self.has_cond_across_layers = [st.kind == "cond_residual" for st in stages]
+        self.dim_cond = dim_cond
         self.encoder_cond_in = nn.Identity()
         self.decoder_cond_in = nn.Identity()
+        if has_cond:                                                              # M:1340-1352: Linear + SiLU stems
+            dc = int(dim_cond * dim_cond_expansion_factor)
+            self.encoder_cond_in = nn.Sequential(nn.Linear(dim_cond, dc), M.Marker("SiLU"))
+            self.decoder_cond_in = nn.Sequential(nn.Linear(dim_cond, dc), M.Marker("SiLU"))
 
         # ---- quantiser (M:1356-1384) ----
         self.use_fsq = use_fsq
@@ -256,7 +272,8 @@ class VideoTokenizer(nn.Module):
     def parameters(self, recurse: bool = True):
         # list, as the reference returns (M:1460-1471)
         return [*self.conv_in.parameters(), *self.conv_out.parameters(), *self.encoder_layers.parameters(),
-                *self.decoder_layers.parameters(), *self.quantizers.parameters()]
+                *self.decoder_layers.parameters(), *self.encoder_cond_in.parameters(), *self.decoder_cond_in.parameters(),
+                *self.quantizers.parameters()]
 
     def discr_parameters(self):
         return []
@@ -389,10 +406,10 @@ class VideoTokenizer(nn.Module):
     @_on_model_device
     def encode(self, video, quantize=False, cond=None, video_contains_first_frame=True):
         """M:1523-1576.  Returns (B, C, T', H', W') like the reference."""
-        assert cond is None, "conditioning is not supported"
         video, ff = self._check_video(video, video_contains_first_frame)
+        cond = self._check_cond(cond, video.shape[0])
         eng = self.engine
-        x = eng.encode_cl(video, ff)
+        x = eng.encode_cl(video, ff, cond)
         if quantize:
             q, idx, _ = eng.quantize_cl(x)
             out = eng.to_channels_first(q)
@@ -400,6 +417,18 @@ class VideoTokenizer(nn.Module):
                 return out, idx
             return out, idx, self.zero
         return eng.to_channels_first(x)
+
+    def _check_cond(self, cond, batch):
+        """M:1542-1545 / M:1610-1613."""
+        assert (not self.has_cond) or cond is not None, \
+            "`cond` must be passed into tokenizer forward method since conditionable layers were specified"
+        if cond is None:
+            return None
+        if not self.has_cond:
+            return None                      # the reference runs the (Identity) stem and never uses the result
+        assert tuple(cond.shape) == (batch, self.dim_cond)
+        self._check_on_device(cond, "cond")
+        return cond
 
     def _check_on_device(self, t, what):
         if t.device != self.device:
@@ -409,18 +438,17 @@ class VideoTokenizer(nn.Module):
     @_on_model_device
     def decode(self, quantized, cond=None, video_contains_first_frame=True):
         """M:1598-1649.  quantized: (B, C, T', H', W')."""
-        assert cond is None, "conditioning is not supported"
         assert quantized.ndim == 5 and quantized.shape[1] == self.quantizers.dim, \
             f"quantized must be (B, {self.quantizers.dim}, T, H, W), got {tuple(quantized.shape)}"
         self._check_on_device(quantized, "quantized")
+        cond = self._check_cond(cond, quantized.shape[0])
         eng = self.engine
-        return eng.decode_cl(eng.to_channels_last(quantized), bool(video_contains_first_frame))
+        return eng.decode_cl(eng.to_channels_last(quantized), bool(video_contains_first_frame), cond)
 
     @torch.no_grad()
     @_on_model_device
     def decode_from_code_indices(self, codes, cond=None, video_contains_first_frame=True):
         """M:1579-1595."""
-        assert cond is None, "conditioning is not supported"
         assert codes.dtype in (torch.long, torch.int32)                           # M:1585
         if codes.ndim == 2:                                                       # M:1587-1591
             n = codes.shape[-1]
@@ -432,6 +460,10 @@ class VideoTokenizer(nn.Module):
         self._check_on_device(codes, "codes")
         eng = self.engine
         ff = bool(video_contains_first_frame)
+        cond = self._check_cond(cond, codes.shape[0])
+        if cond is not None:
+            return self._graph_call("decode_codes_cond" + ("" if ff else "_noff"),
+                                    lambda c, cd: eng.decode_cl(eng.codes_to_quantized_cl(c), ff, cd), codes.contiguous(), cond.contiguous())
         return self._graph_call("decode_codes" if ff else "decode_codes_noff",
                                 lambda c: eng.decode_cl(eng.codes_to_quantized_cl(c), ff), codes.contiguous())
 
@@ -494,24 +526,27 @@ class VideoTokenizer(nn.Module):
                 multiscale_adversarial_loss_weight=None):
         """Inference returns of the reference forward (M:1657-1720)."""
         assert (return_loss + return_codes + return_discr_loss) <= 1               # M:1674
-        assert cond is None, "conditioning is not supported"
         if return_loss or return_discr_loss:
             raise NotImplementedError(
                 "training losses (GAN / perceptual / adaptive weighting, reference M:1722-1896) are outside the "
                 "accelerated inference path (SURVEY.md 8f N2)")
         video, ff = self._check_video(video_or_images, video_contains_first_frame)
+        cond = self._check_cond(cond, video.shape[0])
         with torch.no_grad():
             eng = self.engine
             need_recon = return_recon or return_recon_loss_only or not return_codes
 
-            def run(v):
-                x = eng.encode_cl(v, ff)
+            def run(v, cd=None):
+                x = eng.encode_cl(v, ff, cd)
                 q, codes_, _ = eng.quantize_cl(x, want_quantized=need_recon)
                 if not need_recon:
                     return codes_
-                return codes_, eng.decode_cl(q, ff)
+                return codes_, eng.decode_cl(q, ff, cd)
 
-            if self.training and not self.use_fsq:
+            if cond is not None:
+                out = self._graph_call(("fwd_recon_cond" if need_recon else "fwd_codes_cond") + ("" if ff else "_noff"), run,
+                                       video.contiguous(), cond.contiguous())
+            elif self.training and not self.use_fsq:
                 out = self._forward_train_mode(eng, video.contiguous(), need_recon, ff)
             else:
                 out = self._graph_call(("fwd_recon" if need_recon else "fwd_codes") + ("" if ff else "_noff"), run, video.contiguous())

@@ -40,8 +40,8 @@ def test_load_and_version():
 
 def test_struct_sizes_match_header_layout():
     # 5 pointers + 22 int32 (conv), 3 pointers + 8 int32 + 3 int64 (attention)
-    assert ctypes.sizeof(_lib.ConvArgs) == 5 * 8 + 22 * 4
-    assert ctypes.sizeof(_lib.TcConvArgs) == 5 * 8 + 22 * 4          # 5 pointers + 22 int32 (incl. out_layout)
+    assert ctypes.sizeof(_lib.ConvArgs) == 5 * 8 + 22 * 4 + 8            # + oscale pointer
+    assert ctypes.sizeof(_lib.TcConvArgs) == 5 * 8 + 22 * 4 + 8 + 8      # + oscale pointer, out_layout (+ tail padding)
     assert ctypes.sizeof(_lib.AttnArgs) == 3 * 8 + 8 * 4 + 3 * 8
 
 

@@ -45,7 +45,16 @@ def test_constructor_errors():
     with pytest.raises(NotImplementedError):
         VideoTokenizer(image_size=32, codebook_size=1024, layers=("gateloop_time",))
     with pytest.raises(NotImplementedError):
-        VideoTokenizer(image_size=32, codebook_size=1024, dim_cond=8, layers=("cond_residual",))
+        VideoTokenizer(image_size=32, codebook_size=1024, dim_cond=8, layers=("cond_attend_space",))   # raises in the reference too
+    with pytest.raises(AssertionError):
+        VideoTokenizer(image_size=32, codebook_size=1024, layers=("cond_residual",))                   # no dim_cond (M:1151)
+    with pytest.raises(TypeError):     # a plain layer after a cond layer receives cond= in the reference and fails (M:1153, M:1318)
+        VideoTokenizer(image_size=32, codebook_size=1024, dim_cond=8, layers=("cond_residual", "residual"))
+    m = VideoTokenizer(image_size=32, codebook_size=1024, dim_cond=8, layers=("residual", "cond_residual"))
+    assert m.has_cond and m.has_cond_across_layers == [False, True]
+    keys = set(m.state_dict())
+    assert {"encoder_cond_in.0.weight", "decoder_cond_in.0.bias", "encoder_layers.1.to_cond.weight",
+            "encoder_layers.1.conv.weights", "decoder_layers.0.conv_out.bias"} <= keys
 
 
 def test_config_pickle_roundtrip_and_save_load(tmp_path):

@@ -508,3 +508,41 @@ def test_train_mode_forward_world1(graphs):
     only_codes = model(v, return_codes=True)
     assert torch.equal(only_codes, codes)
     assert torch.equal(model.tokenize(v), codes) and not model.training          # tokenize() switches to eval (M:1653)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cond_residual_vs_reference_golden(dtype):
+    """cond_residual (ResidualUnitMod / Conv3DMod, M:680-753, M:946-988) on the device -- input-channel
+    modulation + shared-weight conv + per-(clip, channel) demodulation in the epilogue -- against the reference golden."""
+    _require_cuda()
+    g = load_golden("mini_cond")
+    model = build_product(g["kwargs"], g["wseed"]).cuda().to(dtype)
+    v, cond = golden_video(g).cuda(), g["cond"].cuda()
+    eng = model.engine
+    eng.taps = {}
+    codes = model(v, cond=cond, return_codes=True)
+    enc_taps, eng.taps = eng.taps, {}
+    recon = model.decode_from_code_indices(g["codes"].cuda(), cond=cond)
+    dec_taps, eng.taps = eng.taps, None
+    mism = (codes.cpu() != g["codes"]).float().mean().item()
+    rerr = (recon.float().cpu() - g["recon"]).abs().max().item()
+    worst = 0.0
+    for k, ref in g["taps"].items():
+        got = enc_taps.get(k, dec_taps.get(k))
+        if got is None:
+            continue
+        worst = max(worst, (sample_like_golden(got, g) - ref).abs().max().item())
+    _report(f"cond/{str(dtype).split('.')[-1]}", token_mismatch_rate=f"{mism:.4f}", recon_maxabs=f"{rerr:.3e}", worst_tap=f"{worst:.3e}")
+    if dtype == torch.float32:
+        assert mism == 0 and rerr < FP32_RECON_TOL and worst < FP32_TAP_TOL
+        c2, r2 = model(v, cond=cond, return_codes=True, return_recon=True)
+        assert torch.equal(c2, codes) and torch.equal(r2, recon)
+        other = model(v, cond=cond.flip(0), return_codes=True)
+        assert not torch.equal(other, codes)                       # the modulation really depends on cond, per clip
+    else:
+        assert mism <= 0.1 and rerr < 0.1
+    with pytest.raises(AssertionError):
+        model(v, return_codes=True)                                # cond missing (M:1542)
+    model.cuda_graphs = True
+    for _ in range(3):
+        assert torch.equal(model(v, cond=cond, return_codes=True), codes)

@@ -395,3 +395,36 @@ def test_conv_out_channels_first_with_cropped_frames(T, tp, H, W):
     assert torch.equal(y_cf, y_ref)
     ref = _oracle_conv(w, bias, x, None, {}).permute(0, 4, 1, 2, 3)[:, :, tp:]
     _check_vs_oracle("conv_out_cf", y_cf.permute(0, 2, 3, 4, 1), ref.permute(0, 2, 3, 4, 1).contiguous())
+
+
+@pytest.mark.parametrize("C_,shape", [(512, (2, 3, 16, 16)), (256, (1, 4, 8, 8)), (64, (2, 2, 5, 7)), (1024, (1, 2, 8, 8)), (24, (1, 3, 6, 6))])
+def test_se_tail_one_launch_vs_general_path_and_oracle(C_, shape):
+    """mv2_se_tail (SE pool + gate MLP + gate/residual in one launch, small frames) inside the ResidualUnit against the
+    general 4-launch path on identical inputs and against the CPU oracle's residual_unit (M:930-944, M:221-240)."""
+    assert torch.cuda.is_available()
+    B, T, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(C_ + H)
+    p, sd = _ru_pack(C_, g)
+    p["w1b"], p["w2b"] = p["w1"].to(torch.bfloat16).contiguous(), p["w2"].to(torch.bfloat16).contiguous()
+    for k in ("w1", "w2"):                       # a bf16 model's SE weights are bf16 values
+        p[k] = p[k].to(torch.bfloat16).float().contiguous()
+    sd["fn.4.net.0.weight"] = p["w1"].cpu().reshape(-1, C_, 1, 1)
+    sd["fn.4.net.2.weight"] = p["w2"].cpu().reshape(C_, -1, 1, 1)
+    x = torch.randn((B, T, H, W, C_), generator=g).cuda().to(torch.bfloat16)
+    eng = _engine()
+    eng.use_tc, eng.tc_variant, eng.fuse_ru = True, "auto", False
+    eng.se_tail, eng.se_tail_calls = True, 0
+    out_t = eng.residual_unit(x, p)
+    assert eng.se_tail_calls == 1, "se_tail kernel was not taken"
+    eng.se_tail = False
+    out_g = eng.residual_unit(x, p)
+    torch.cuda.synchronize()
+    eng.se_tail, eng.fuse_ru = True, True
+    a, b = out_t.float().cpu(), out_g.float().cpu()
+    assert torch.isfinite(a).all()
+    assert (a - b).abs().max().item() <= 2.0 ** -7 * b.abs().max().item() + 1e-3
+    assert (a != b).float().mean().item() < 0.02
+    ref = R.residual_unit(x.float().cpu().permute(0, 4, 1, 2, 3).contiguous(), sd, "").permute(0, 2, 3, 4, 1)
+    err = (a - ref).abs()
+    assert err.max().item() <= 0.02 * ref.abs().max().item() + 5e-3, err.max().item()
+    assert err.mean().item() <= 0.004 * ref.abs().mean().item() + 2e-4, err.mean().item()
