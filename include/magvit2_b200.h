@@ -71,6 +71,13 @@ int mv2_to_channels_first(const void* src, int src_dtype, void* dst, int dst_dty
 int mv2_ingest_kwpack(const void* src, int src_dtype, void* dst, int B, int C, int T, int H, int W,
                       int t_pad, int kw, int pw, int cpack, void* stream);
 
+/* mv2_copy_frames: frame-range copy between channels-last clips (device memcpy2D, no kernel):
+ *   dst[b][dst_t0 + i] = src[b][src_t0 + i], i < n_frames; zero_front != 0 also zero-fills dst frames [0, dst_t0).
+ * Used to split off / re-attach the first frame for separate_first_frame_encoding (reference M:1553-1561, M:1633-1639:
+ * unpack / pack / pad_at_dim on the time axis).                                                                           */
+int mv2_copy_frames(const void* src, void* dst, int B, int src_T, int dst_T, int src_t0, int dst_t0, int n_frames,
+                    size_t frame_bytes, int zero_front, void* stream);
+
 /* ---- convolution family (CUDA-core fp32-accumulate path; any shape) -----------
  * One generic strided N-d convolution over channels-last activations with a fused
  * epilogue  y = shuffle(act(conv(x) + bias)) + res.   Replaces

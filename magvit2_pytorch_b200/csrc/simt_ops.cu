@@ -2135,6 +2135,19 @@ int mv2_scale_channels(const void* x, const float* scale, void* out, int dtype, 
   return MV2_OK;
 }
 
+int mv2_copy_frames(const void* src, void* dst, int B, int src_T, int dst_T, int src_t0, int dst_t0, int n_frames,
+                    size_t frame_bytes, int zero_front, void* stream) {
+  MV2_CHECK_ARG(src && dst && B > 0 && n_frames > 0 && frame_bytes > 0);
+  MV2_CHECK_ARG(src_t0 >= 0 && dst_t0 >= 0 && src_t0 + n_frames <= src_T && dst_t0 + n_frames <= dst_T);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zero_front && dst_t0 > 0)
+    MV2_CHECK_CUDA(cudaMemset2DAsync(dst, (size_t)dst_T * frame_bytes, 0, (size_t)dst_t0 * frame_bytes, B, st));
+  MV2_CHECK_CUDA(cudaMemcpy2DAsync((char*)dst + (size_t)dst_t0 * frame_bytes, (size_t)dst_T * frame_bytes,
+                                   (const char*)src + (size_t)src_t0 * frame_bytes, (size_t)src_T * frame_bytes,
+                                   (size_t)n_frames * frame_bytes, B, cudaMemcpyDeviceToDevice, st));
+  return MV2_OK;
+}
+
 int mv2_gate_residual(const void* y, const void* x, const float* gates, void* out, int dtype, int F, int P, int C,
                       void* stream) {
   MV2_CHECK_ARG(y && x && gates && out && F > 0 && P > 0 && C > 0);

@@ -176,6 +176,9 @@ class Engine:
         P["conv_in"] = pack_conv(m.conv_in.conv.weight, m.conv_in.conv.bias, dt)
         P["conv_in_tc"] = pack_conv_in_kwpack(m.conv_in.conv.weight, m.conv_in.conv.bias) if dt == torch.bfloat16 else None
         P["conv_out"] = pack_conv(m.conv_out.conv.weight, m.conv_out.conv.bias, dt)
+        if m.separate_first_frame_encoding:       # SameConv2d (M:887-890): a (1, kh, kw) conv on the single first frame
+            P["conv_in_ff"] = pack_conv(m.conv_in_first_frame.weight, m.conv_in_first_frame.bias, dt)
+            P["conv_out_ff"] = pack_conv(m.conv_out_first_frame.weight, m.conv_out_first_frame.bias, dt)
 
         def f32(t):
             return t.detach().float().contiguous()
@@ -580,6 +583,17 @@ class Engine:
         self.launches += 1
         return out
 
+    def copy_frames(self, src, t0, n, dst=None, dst_t0=0, zero_front=False):
+        """Frames [t0, t0 + n) of a channels-last clip tensor -> a new (B, n, ...) tensor, or into ``dst`` at ``dst_t0``."""
+        B, Ts = src.shape[:2]
+        if dst is None:
+            dst = self._new((B, n) + tuple(src.shape[2:]), src.dtype)
+        frame_bytes = src[0, 0].numel() * src.element_size()
+        assert dst[0, 0].numel() * dst.element_size() == frame_bytes and src.is_contiguous() and dst.is_contiguous()
+        check(self.lib.mv2_copy_frames(_ptr(src), _ptr(dst), B, Ts, dst.shape[1], t0, dst_t0, n, frame_bytes, int(zero_front),
+                                       self._stream()), "mv2_copy_frames")
+        return dst
+
     def to_channels_first(self, x: torch.Tensor, t_crop: int = 0, out_dtype=None):
         B, T, H, W, Cc = x.shape
         out_dtype = out_dtype or self.dtype
@@ -596,7 +610,18 @@ class Engine:
         m = self.model
         t_pad = m.time_padding if first_frame else 0
         pin = self._packs.get("conv_in_tc")
-        if self.dtype == torch.bfloat16 and self.use_tc and pin is not None:
+        if m.separate_first_frame_encoding and first_frame:
+            # M:1553-1561: the first frame goes through its own 2-D conv, frames 1.. through the causal conv_in on their own,
+            # then the feature map is [time_padding zero frames, first, rest]
+            B, _, T, H, W = video.shape
+            v_cl = self.to_channels_last(video, 0)
+            parts = [(self.conv(self.copy_frames(v_cl, 0, 1), self._packs["conv_in_ff"]), t_pad)]
+            if T > 1:
+                parts.append((self.conv(self.copy_frames(v_cl, 1, T - 1), self._packs["conv_in"]), t_pad + 1))
+            x = self._new((B, T + t_pad, H, W, parts[0][0].shape[-1]))
+            for i, (part, t0) in enumerate(parts):
+                self.copy_frames(part, 0, part.shape[1], dst=x, dst_t0=t0, zero_front=(i == 0))
+        elif self.dtype == torch.bfloat16 and self.use_tc and pin is not None:
             x = self.ingest_kwpack(video, t_pad, pin)
             x = self.conv(x, pin, pad=(pin.k_tc[0] - 1, pin.k_tc[1] // 2, 0))
         else:
@@ -621,6 +646,15 @@ class Engine:
         pk = self._packs["conv_out"]
         B, T, H, W, Cc = x.shape
         tp = m.time_padding if first_frame else 0
+        if m.separate_first_frame_encoding and first_frame:
+            # M:1633-1639: conv_out_first_frame on frame `tp`, the causal conv_out on the frames after it, re-attached
+            first = self.conv(self.copy_frames(x, tp, 1), self._packs["conv_out_ff"])
+            out = self._new((B, T - tp, H, W, first.shape[-1]))
+            self.copy_frames(first, 0, 1, dst=out, dst_t0=0)
+            if T - tp > 1:
+                rest = self.conv(self.copy_frames(x, tp + 1, T - tp - 1), pk)
+                self.copy_frames(rest, 0, T - tp - 1, dst=out, dst_t0=1)
+            return self.to_channels_first(out)
         if (self.dtype == torch.bfloat16 and self.use_tc and self.tc_variant != "tap" and self.fuse_conv_out and pk.w_tc is not None
                 and pk.Co % 8 != 0 and Cc % 64 == 0 and pk.k[2] <= 3 and T > tp):
             # conv_out writes the reconstruction in torch's (B,C,T,H,W) layout itself and never computes the time_padding

@@ -13,7 +13,8 @@ the compute dtype follows the parameters' dtype (``.float()`` -> fp32 CUDA-core 
 
 ``cond_residual`` layers (ResidualUnitMod / Conv3DMod, M:680-753, M:946-988) run on the device through the
 factorisation in include/magvit2_b200.h; the other ``cond_*`` types raise in the reference itself.
-Out of scope (raise at construction / call): ``gateloop_time``, ``separate_first_frame_encoding``, ``num_codebooks > 1``, ``lfq_spherical``,
+``separate_first_frame_encoding`` (M:1113-1120, M:1553-1561, M:1633-1639) runs through the same conv kernels.
+Out of scope (raise at construction / call): ``gateloop_time``, ``num_codebooks > 1``, ``lfq_spherical``,
 non-constant ``pad_mode``, the GAN / perceptual training losses (``return_loss`` /
 ``return_discr_loss``), autograd.
 """
@@ -123,8 +124,6 @@ class VideoTokenizer(nn.Module):
             raise NotImplementedError("num_codebooks > 1 is not supported")
         if lfq_spherical:
             raise NotImplementedError("lfq_spherical is not supported")
-        if separate_first_frame_encoding:
-            raise NotImplementedError("separate_first_frame_encoding is outside the accelerated path (SURVEY.md 8f N3)")
         if pad_mode != "constant":
             raise NotImplementedError("only pad_mode='constant' is supported")
         if attn_dropout != 0.:
@@ -136,7 +135,11 @@ class VideoTokenizer(nn.Module):
         self.conv_in = M.CausalConv3d(channels, init_dim, tuple(input_conv_kernel_size), pad_mode)
         self.conv_in_first_frame = nn.Identity()
         self.conv_out_first_frame = nn.Identity()
-        self.separate_first_frame_encoding = False
+        self.separate_first_frame_encoding = bool(separate_first_frame_encoding)
+        if separate_first_frame_encoding:                                          # M:1113-1120: SameConv2d (M:887-890)
+            ik, ok = tuple(input_conv_kernel_size)[-2:], tuple(output_conv_kernel_size)[-2:]
+            self.conv_in_first_frame = nn.Conv2d(channels, init_dim, ik, padding=(ik[0] // 2, ik[1] // 2))
+            self.conv_out_first_frame = nn.Conv2d(init_dim, channels, ok, padding=(ok[0] // 2, ok[1] // 2))
         self.encoder_layers = nn.ModuleList([])
         self.decoder_layers = nn.ModuleList([])
         self.conv_out = M.CausalConv3d(init_dim, channels, tuple(output_conv_kernel_size), pad_mode)
@@ -271,7 +274,8 @@ class VideoTokenizer(nn.Module):
 
     def parameters(self, recurse: bool = True):
         # list, as the reference returns (M:1460-1471)
-        return [*self.conv_in.parameters(), *self.conv_out.parameters(), *self.encoder_layers.parameters(),
+        return [*self.conv_in.parameters(), *self.conv_in_first_frame.parameters(), *self.conv_out_first_frame.parameters(),
+                *self.conv_out.parameters(), *self.encoder_layers.parameters(),
                 *self.decoder_layers.parameters(), *self.encoder_cond_in.parameters(), *self.decoder_cond_in.parameters(),
                 *self.quantizers.parameters()]
 

@@ -546,3 +546,34 @@ def test_cond_residual_vs_reference_golden(dtype):
     model.cuda_graphs = True
     for _ in range(3):
         assert torch.equal(model(v, cond=cond, return_codes=True), codes)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_separate_first_frame_encoding_vs_reference_golden(dtype):
+    """separate_first_frame_encoding (M:1113-1120, M:1553-1561, M:1633-1639) against the reference golden."""
+    _require_cuda()
+    g = load_golden("mini_sff")
+    model = build_product(g["kwargs"], g["wseed"]).cuda().to(dtype)
+    v = golden_video(g).cuda()
+    eng = model.engine
+    eng.taps = {}
+    codes = model.tokenize(v)
+    enc_taps, eng.taps = eng.taps, {}
+    recon = model.decode_from_code_indices(g["codes"].cuda())
+    dec_taps, eng.taps = eng.taps, None
+    mism = (codes.cpu() != g["codes"]).float().mean().item()
+    rerr = (recon.float().cpu() - g["recon"]).abs().max().item()
+    worst = 0.0
+    for k, ref in g["taps"].items():
+        got = enc_taps.get(k, dec_taps.get(k))
+        if got is not None:
+            worst = max(worst, (sample_like_golden(got, g) - ref).abs().max().item())
+    _report(f"sff/{str(dtype).split('.')[-1]}", token_mismatch_rate=f"{mism:.4f}", recon_maxabs=f"{rerr:.3e}", worst_tap=f"{worst:.3e}")
+    assert recon.shape == v.shape
+    if dtype == torch.float32:
+        assert mism == 0 and rerr < FP32_RECON_TOL and worst < FP32_TAP_TOL
+        assert torch.equal(model(v, return_recon=True), model.decode_from_code_indices(codes))
+        img = model.tokenize(v[:, :, 0])                  # single image: only the first-frame convs run
+        assert img.shape == (v.shape[0], 1, model.fmap_size, model.fmap_size)
+    else:
+        assert mism <= 0.1 and rerr < 0.1
