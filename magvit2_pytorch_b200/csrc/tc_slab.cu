@@ -38,6 +38,7 @@ struct alignas(64) SlabParams {
   CUtensorMap wmap;      // weights as {ci, co, tap} (3-D boxes of tpw taps)
   CUtensorMap wmap2;     // weights as {k, co} (2-D boxes, used when tpw == 1)
   int kt, kh, kw, pt, ph, pw;
+  int st;                // stride along t (1, or 2: TimeDownsample2x); spatial strides are always 1 in this kernel
   int Ci, kchunks, row_bytes;
   int B, T, H, W, Co;
   int mw, pitch, slab_h, slab_bytes, slab_stride;
@@ -68,7 +69,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // for 148 CTAs) no CTA gets three full tiles while others get two.  Pure index arithmetic, so the tile id stays warp
 // uniform in the MMA-issuing warp (a schedule table read from memory does not: measured 5 % slower overall).
 __host__ __device__ __forceinline__ void slab_frame_of(const SlabParams& p, int slot, int& b, int& t) {
-  const int ptc = p.pt > 0 ? p.pt : 0;          // pt < 0: cropped output (conv_out without the time_padding frames), no cheap frames
+  const int ptc = p.pt > 0 ? (p.pt + p.st - 1) / p.st : 0;   // output frames whose leading taps fall into the causal padding
+                                                              // (pt < 0: cropped conv_out output, none)
   const int n_cheap = ptc < p.T ? ptc : p.T, n_full = p.T - n_cheap;
   const int full_slots = p.B * n_full;
   if (slot < full_slots) { b = slot / n_full; t = n_cheap + slot - b * n_full; }
@@ -217,13 +219,13 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
       uint32_t s = 0, ph = 0;
       for (int tk = 0, tile; (tile = slab_tile_of(p, tk)) >= 0; ++tk) {
         const TileCoord c = decode_tile(p, tile);
-        const int dt0 = max(0, p.pt - c.t);
+        const int dt0 = max(0, p.pt - c.t * p.st);
         for (int dt = dt0; dt < p.kt; ++dt)
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(slab_empty + 8 * s, ph ^ 1);
             mbar_expect_tx(slab_full + 8 * s, p.slab_bytes);
             tma_load_5d(slab0 + s * p.slab_stride, &p.amap, slab_full + 8 * s, kc * bk, c.w0 - p.pw, c.h0 - p.ph,
-                        c.t + dt - p.pt, c.b);
+                        c.t * p.st + dt - p.pt, c.b);
             if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1; }
           }
       }
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
       uint32_t s = 0, ph = 0;
       for (int tk = 0, tile; (tile = slab_tile_of(p, tk)) >= 0; ++tk) {
         const TileCoord c = decode_tile(p, tile);
-        const int dt0 = max(0, p.pt - c.t);
+        const int dt0 = max(0, p.pt - c.t * p.st);
         for (int dt = dt0; dt < p.kt; ++dt)
           for (int kc = 0; kc < p.kchunks; ++kc)
             for (int tp = 0; tp < taps2d; tp += p.tpw) {
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         int b_of_tile, t_of_tile;                                  // once per tile (hundreds of taps)
         if (p.cluster == 1) slab_frame_of(p, tile / tiles_per_frame, b_of_tile, t_of_tile);
         else t_of_tile = (tile / tiles_per_frame) % p.T;
-        const int dt0 = max(0, p.pt - t_of_tile);
+        const int dt0 = max(0, p.pt - t_of_tile * p.st);
         mbar_wait(t_empty + 8 * t_idx, t_par ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + t_idx * p.acc_stride;
@@ -707,7 +709,11 @@ static void choose_ragged_tiles(const mv2_tc_conv_args* a, int n_sm, int* mw_io,
 
 extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
   if (!a) return 0;
-  if (a->st != 1 || a->sh != 1 || a->sw != 1) return 0;
+  if (a->sh != 1 || a->sw != 1) return 0;
+  if (a->st != 1) {      // TimeDownsample2x (M:796-807): stride 2 along t only, plain epilogue
+    if (a->st != 2 || a->out_layout != 0 || a->epi_mode != 0 || a->shuffle != MV2_SHUFFLE_NONE) return 0;
+    if (a->To != (a->Ti + a->pt - a->kt) / a->st + 1 || a->To < 1) return 0;
+  }
   if (a->Ci % 32 != 0 || a->Co > 4096) return 0;
   if (a->oscale && (a->epi_mode != 0 || a->shuffle != MV2_SHUFFLE_NONE)) return 0;   // demodulation: plain / ragged epilogues only
   if (a->epi_mode == 1 && (a->Co % 32 != 0 || a->shuffle != MV2_SHUFFLE_NONE || a->res)) return 0;   // fused GEGLU
@@ -721,7 +727,7 @@ extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
   if (a->out_layout == 1) {   // channels-first output: the ragged scalar-store epilogue only (conv_out); may drop leading frames
     if (a->Co % 8 == 0 || a->res || a->shuffle != MV2_SHUFFLE_NONE || a->epi_mode != 0) return 0;
     if (a->To > a->Ti || a->To < 1 || a->pt != a->kt - 1 - (a->Ti - a->To)) return 0;
-  } else if (a->out_layout != 0 || a->To != a->Ti) return 0;
+  } else if (a->out_layout != 0 || (a->st == 1 && a->To != a->Ti)) return 0;
   return 1;
 }
 
@@ -730,6 +736,7 @@ extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
 static int slab_fill_plan(const mv2_tc_conv_args* a, int n_sm, SlabParams& p, int* bk_out, int* w_bytes_out, int* co_pad_out, int* nb_pad_out) {
   memset(&p, 0, sizeof(p));
   p.kt = a->kt; p.kh = a->kh; p.kw = a->kw; p.pt = a->pt; p.ph = a->ph; p.pw = a->pw;
+  p.st = a->st;
   p.row_bytes = (a->Ci % 64 == 0) ? 128 : 64;
   const int bk = p.row_bytes / 2;
   p.Ci = a->Ci; p.kchunks = a->Ci / bk;
@@ -750,7 +757,7 @@ static int slab_fill_plan(const mv2_tc_conv_args* a, int n_sm, SlabParams& p, in
   // EPI_PLAIN guards every stored column, so N tiles need not divide Co: deep wide layers pick the width that fills
   // the 148 SMs best (choose_ragged_tiles)
   const bool ragged_ok = a->epi_mode == 0 && a->shuffle == MV2_SHUFFLE_NONE && a->Co % 8 == 0;
-  if (ragged_ok && a->Co > 256 && a->kt * a->kh * a->kw > 1) choose_ragged_tiles(a, n_sm, &best_mw, &best_bn);
+  if (ragged_ok && a->Co > 256 && a->kt * a->kh * a->kw > 1 && a->st == 1) choose_ragged_tiles(a, n_sm, &best_mw, &best_bn);
   // wide outputs whose width has no large power-of-two divisor (the GEGLU feed-forward: 2 * 1365 -> 2752 packed columns
   // would run 43 tiles of 64): 64-column MMAs are shared-memory bound, so take wide tiles and let the last one be ragged
   // (the GEGLU epilogue guards its 16-column groups against Co like the plain one guards its 8-column pieces)

@@ -428,3 +428,27 @@ def test_se_tail_one_launch_vs_general_path_and_oracle(C_, shape):
     err = (a - ref).abs()
     assert err.max().item() <= 0.02 * ref.abs().max().item() + 5e-3, err.max().item()
     assert err.mean().item() <= 0.004 * ref.abs().mean().item() + 2e-4, err.mean().item()
+
+
+@pytest.mark.parametrize("C_,Co,shape", [(512, 512, (2, 10, 16, 16)), (64, 128, (1, 5, 8, 16)), (128, 128, (2, 4, 16, 24)), (512, 512, (4, 20, 16, 16))])
+def test_slab_time_downsample(C_, Co, shape):
+    """TimeDownsample2x (F.pad(2,0) + Conv1d k3 s2 along t, M:796-807) on the slab kernel (t-strided slab loads) vs the
+    tap-wise kernel, the CUDA-core kernel and the CPU oracle."""
+    assert torch.cuda.is_available()
+    B, T, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(C_ + T)
+    w = (torch.randn((Co, C_, 3), generator=g) * (3 * C_) ** -0.5).cuda()
+    bias = (torch.randn(Co, generator=g) * 0.1).cuda()
+    x = torch.randn((B, T, H, W, C_), generator=g).cuda().to(torch.bfloat16)
+    eng = _engine()
+    pk = pack_conv(w, bias, torch.bfloat16, k=(3, 1, 1))
+    kw = dict(stride=(2, 1, 1), pad=(2, 0, 0), out_spatial=((T + 2 - 3) // 2 + 1, H, W))
+    eng.use_tc, eng.tc_variant, eng.slab_calls = True, "auto", 0
+    y_slab = eng.conv(x, pk, **kw)
+    assert eng.slab_calls == 1, "slab kernel was not taken"
+    eng.tc_variant = "tap"
+    y_tap = eng.conv(x, pk, **kw)
+    torch.cuda.synchronize()
+    eng.tc_variant = "auto"
+    _check_vs_oracle("slab_down_time", y_slab, _oracle_conv(w, bias, x, (3, 1, 1), dict(stride=(2, 1, 1))))
+    assert (y_slab.float() - y_tap.float()).abs().max().item() <= 0.008 * y_tap.float().abs().max().item() + 1e-3
