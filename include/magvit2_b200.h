@@ -231,6 +231,12 @@ int mv2_tc_conv_forward(const mv2_tc_conv_args* a, void* stream);
  * accumulators.  Requirements (mv2_tc_slab_supported): stride 1, Ci % 64 == 0, Co % 32 == 0, no shuffle.   */
 int mv2_tc_slab_supported(const mv2_tc_conv_args* a);
 int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream);
+/* SpatialDownsample2x (M:770-780: per-frame Conv2d k3 s2 p1) on the slab design: the input is read as (W/2) x (2C) with
+ * row-parity sub-slabs, so no tap reloads its tile from L2.  `a` describes the conv as usual (kh = kw = 3, sh = sw = 2,
+ * ph = pw = 1, kt = 1), but w is packed as bf16 [Co][6][2*Ci]: tap' = dh * 2 + q, q = 0: [zeros(Ci) | w[:, :, dh, 0]],
+ * q = 1: [w[:, :, dh, 1] | w[:, :, dh, 2]].  Requirements: Hi, Wi even, Ci % 64 == 0, Co % 32 == 0.                       */
+int mv2_tc_down_space_supported(const mv2_tc_conv_args* a);
+int mv2_tc_down_space_forward(const mv2_tc_conv_args* a, void* stream);
 /* Launch plan of mv2_tc_slab_forward for a layer shape on a device with n_sm SMs -- pure host arithmetic (no CUDA call,
  * the pointers in `a` are not dereferenced), exposed so the tiling rule and the static tile schedule can be checked
  * without a GPU.  mv2_tc_slab_plan: out6 = {M-tiles per weight tile (mw), N tile width (bn), N tiles, total tiles,

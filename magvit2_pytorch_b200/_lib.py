@@ -101,6 +101,8 @@ SIGNATURES = {
     "mv2_tc_conv_forward": (_I, [C.POINTER(TcConvArgs), _VP]),
     "mv2_tc_slab_supported": (_I, [C.POINTER(TcConvArgs)]),
     "mv2_tc_slab_forward": (_I, [C.POINTER(TcConvArgs), _VP]),
+    "mv2_tc_down_space_supported": (_I, [C.POINTER(TcConvArgs)]),
+    "mv2_tc_down_space_forward": (_I, [C.POINTER(TcConvArgs), _VP]),
     "mv2_tc_slab_plan": (_I, [C.POINTER(TcConvArgs), _I, C.POINTER(C.c_int32)]),
     "mv2_tc_slab_tile": (_I, [C.POINTER(TcConvArgs), _I, _I, _I, C.POINTER(C.c_int32)]),
     "mv2_dense_small": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),

@@ -217,7 +217,10 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)
 // EPI_SHUFFLE_ST (slab kernel only): depth-to-space / depth-to-time stores through the same shared-memory transpose as
 // EPI_PLAIN (64 contiguous bytes per output position and store instruction); needs Cy % 32 == 0 so that a 32-column chunk
 // stays inside one sub-pixel phase.  EPI_SHUFFLE is the direct 16-byte-piece path for the other widths.
-enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_SHUFFLE = 2, EPI_RAGGED = 3, EPI_PLAIN_RES = 4, EPI_FUSED_RU = 5, EPI_SHUFFLE_ST = 6 };
+// EPI_DOWN_SPACE (slab kernel only): SpatialDownsample2x (3x3, stride 2) -- plain epilogue, but the slab is two row-parity
+// sub-slabs of the input viewed as (W/2) x (2C) and the taps follow a small offset table (see tc_slab.cu).
+enum { EPI_PLAIN = 0, EPI_GEGLU = 1, EPI_SHUFFLE = 2, EPI_RAGGED = 3, EPI_PLAIN_RES = 4, EPI_FUSED_RU = 5, EPI_SHUFFLE_ST = 6,
+       EPI_DOWN_SPACE = 7 };
 
 // Branch-free activations on the bare MUFU approximations (ex2/rcp with flush-to-zero): the results are rounded to
 // bf16 right after, and __expf's denormal range handling costs ~5 extra instructions per element.

@@ -54,6 +54,11 @@ struct alignas(64) SlabParams {
   const float* se_wk;    // SqueezeExcite to_k weight [C]
   float se_bk;
   float* se_ws;          // SE pool records [B*T][recs_per_frame][C + 2] = (max, sum, sum e*y[C]) per 32-position row group
+  // ---- EPI_DOWN_SPACE only (mv2_tc_down_space_forward) ----
+  CUtensorMap amap_odd;  // odd input rows (amap: even rows), both over x viewed as {2C, W/2, H/2, T, B}
+  int dn_e_off;          // byte offset of the even-row sub-slab inside a slab stage
+  int dn_aoff[6];        // per tap' = dh * 2 + (dw2 + 1): A-descriptor start offset inside the stage, in 16-byte units
+  int dn_lower;          // K-chunks of the lower (pw = 0) half of the 2C axis: they only see the dw2 = 0 taps
   int nh;                // shared-memory H buffers (ELU'd 3x3x3 tile of one M-tile, A operand of the second MMA): 1 or 2
   int h_stride;          // bytes per H buffer = kchunks * 16 KB
 };
@@ -188,7 +193,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
     mbar_init(w1_full, 1);
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.amap);
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.amap); if (MODE == EPI_DOWN_SPACE) tma_prefetch_desc(&p.amap_odd); }
   if (warp == 2 && lane == 0) { tma_prefetch_desc(&p.wmap); tma_prefetch_desc(&p.wmap2); }
   if (MODE == EPI_FUSED_RU && warp == 3 && lane == 0) tma_prefetch_desc(&p.w1map);
   if (warp == 1) tmem_alloc(tslot, 512);
@@ -215,6 +220,23 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------ slab producer ------------------------------
+    if (MODE == EPI_DOWN_SPACE) {
+      // one stage = the odd-row sub-slab (input rows 2*ho - 1: 17 rows for 16 output rows) + the even-row sub-slab (rows 2*ho)
+      // of one 64-channel chunk of the (W/2) x (2C) view; w2 starts one position to the left (the dw = 0 tap), OOB = zero pad
+      if (lane == 0) {
+        uint32_t s = 0, ph = 0;
+        for (int tk = 0, tile; (tile = slab_tile_of(p, tk)) >= 0; ++tk) {
+          const TileCoord c = decode_tile(p, tile);
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(slab_empty + 8 * s, ph ^ 1);
+            mbar_expect_tx(slab_full + 8 * s, p.slab_bytes);
+            tma_load_5d(slab0 + s * p.slab_stride, &p.amap_odd, slab_full + 8 * s, kc * bk, c.w0 - 1, c.h0 - 1, c.t, c.b);
+            tma_load_5d(slab0 + s * p.slab_stride + p.dn_e_off, &p.amap, slab_full + 8 * s, kc * bk, c.w0 - 1, c.h0, c.t, c.b);
+            if (++s == (uint32_t)p.slab_stages) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    } else
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       for (int tk = 0, tile; (tile = slab_tile_of(p, tk)) >= 0; ++tk) {
@@ -232,6 +254,22 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
     }
   } else if (warp == 2) {
     // ------------------------------ weight producer ------------------------------
+    if (MODE == EPI_DOWN_SPACE) {
+      if (lane == 0) {
+        uint32_t s = 0, ph = 0;
+        const int C2 = p.Ci;                 // channels of the paired view (2C)
+        for (int tk = 0, tile; (tile = slab_tile_of(p, tk)) >= 0; ++tk) {
+          const TileCoord c = decode_tile(p, tile);
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            for (int tap = kc < p.dn_lower ? 1 : 0; tap < 6; tap += kc < p.dn_lower ? 2 : 1) {
+              mbar_wait(w_empty + 8 * s, ph ^ 1);
+              mbar_expect_tx(w_full + 8 * s, w_tile);
+              tma_load_2d(wst0 + s * w_bytes, &p.wmap2, w_full + 8 * s, tap * C2 + kc * (int)bk, c.n0);
+              if (++s == (uint32_t)p.w_stages) { s = 0; ph ^= 1; }
+            }
+        }
+      }
+    } else
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       for (int tk = 0, tile; (tile = slab_tile_of(p, tk)) >= 0; ++tk) {
@@ -281,6 +319,44 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
       // same sequence as slab_tile_of, written with plain induction variables: the compiler only keeps this warp's loop
       // nest (descriptors, ring indices) in uniform registers when the tile id is an obviously uniform recurrence
       const int fwd = blockIdx.x, rev = p.cluster == 1 ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
+      if (MODE == EPI_DOWN_SPACE) {
+        for (int tk = 0, base = 0;; ++tk, base += gridDim.x) {
+          const int tile = base + ((tk & 1) ? rev : fwd);
+          if (tile >= p.total_tiles) break;
+          mbar_wait(t_empty + 8 * t_idx, t_par ^ 1);
+          tc_fence_after();
+          const uint32_t acc = tmem_base + t_idx * p.acc_stride;
+          uint32_t accum = 0;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(slab_full + 8 * s_idx, s_par);
+            const uint32_t a_base = ((slab0 + s_idx * p.slab_stride) & 0x3FFFF) >> 4;
+            const int t0 = kc < p.dn_lower ? 1 : 0, tstep = kc < p.dn_lower ? 2 : 1;
+            for (int tap = t0; tap < 6; tap += tstep) {
+              mbar_wait(w_full + 8 * w_idx, w_par);
+              tc_fence_after();
+              if (leader) {
+                uint32_t a_j = a_base + (uint32_t)p.dn_aoff[tap], d = acc;
+                for (int j = 0; j < p.mw; ++j) {
+                  const uint64_t ad = a_hi | (uint64_t)a_j, bd = b_hi | (uint64_t)b_lo;
+                  umma_bf16(d, ad, bd, idesc, accum);
+                  umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                  umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                  umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                  a_j += a_mtile;
+                  d += p.bn;
+                }
+                umma_commit(w_empty + 8 * w_idx);
+              }
+              accum = 1;
+              if (++w_idx == (uint32_t)p.w_stages) { w_idx = 0; w_par ^= 1; b_lo = b_lo0; } else { b_lo += w_stage16; }
+            }
+            if (leader) umma_commit(slab_empty + 8 * s_idx);
+            if (++s_idx == (uint32_t)p.slab_stages) { s_idx = 0; s_par ^= 1; }
+          }
+          if (leader) umma_commit(t_full + 8 * t_idx);
+          if (++t_idx == (uint32_t)p.nbuf) { t_idx = 0; t_par ^= 1; }
+        }
+      } else
       for (int tk = 0, base = 0;; ++tk, base += gridDim.x) {
         const int tile = base + ((tk & 1) ? rev : fwd);
         if (tile >= p.total_tiles) break;
@@ -508,7 +584,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         const uint32_t tl = tmem_base + buf * p.acc_stride + j * p.bn + ((uint32_t)(sub * 32) << 16);
         const int64_t row_base = ((((int64_t)c.b * p.T + c.t) * p.H + h) * p.W + w) * p.Co;
         // column chunks are dealt round-robin to the two warps that share this lane quarter
-        if (MODE == EPI_PLAIN || MODE == EPI_SHUFFLE_ST) {
+        if (MODE == EPI_PLAIN || MODE == EPI_SHUFFLE_ST || MODE == EPI_DOWN_SPACE) {
           // Row-per-lane results are transposed through shared memory so that every store instruction writes 8 rows
           // x 64 contiguous bytes (full sectors; the 8 rows are neighbours along w, i.e. one contiguous run when the
           // tile spans all of Co) instead of 32 scattered 16-byte pieces.  The residual is read with the same mapping.
@@ -1062,6 +1138,104 @@ extern "C" int mv2_tc_ru_forward(const mv2_tc_ru_args* a, void* stream) {
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
   const int grid = std::min(p.total_tiles, n_sm);
   launch_kc(tc_slab_kernel<EPI_FUSED_RU>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, 1, p);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+
+// =====================================================================================================================
+// SpatialDownsample2x (reference M:770-780: per-frame Conv2d k3 s2 p1) on the slab design.
+// The input (H x W x C) is read as (H) x (W/2) x (2C): output column wo needs input columns 2wo-1, 2wo, 2wo+1 =
+// (w2 = wo-1, second half of the 2C axis), (w2 = wo, first half), (w2 = wo, second half), i.e. a 2-tap conv along w2 whose
+// dw2 = -1 tap only touches the upper C channels.  Rows: output row ho needs input rows 2ho-1, 2ho, 2ho+1: the slab stage
+// holds the odd rows and the even rows as two sub-slabs (two TMA box loads through row-parity tensor maps), and the three dh
+// taps start in (odd, row 0), (even, row 0), (odd, row 1).  Weights are packed by the host as w[co][tap'][2C],
+// tap' = dh * 2 + (dw2 + 1), lower half of the dw2 = -1 taps zero (and never loaded).
+// =====================================================================================================================
+extern "C" int mv2_tc_down_space_supported(const mv2_tc_conv_args* a) {
+  if (!a) return 0;
+  if (a->kt != 1 || a->kh != 3 || a->kw != 3 || a->st != 1 || a->sh != 2 || a->sw != 2) return 0;
+  if (a->pt != 0 || a->ph != 1 || a->pw != 1) return 0;
+  if ((a->Hi & 1) || (a->Wi & 1) || a->Ho != a->Hi / 2 || a->Wo != a->Wi / 2 || a->To != a->Ti) return 0;
+  if (a->Ci % 64 != 0 || a->Co % 32 != 0 || a->Co > 4096) return 0;
+  if (a->res || a->shuffle != MV2_SHUFFLE_NONE || a->epi_mode != 0 || a->out_layout != 0 || a->oscale) return 0;
+  return 1;
+}
+
+extern "C" int mv2_tc_down_space_forward(const mv2_tc_conv_args* a, void* stream) {
+  MV2_CHECK_ARG(a && a->x && a->w && a->y);
+  if (!mv2_tc_down_space_supported(a)) { set_error("mv2_tc_down_space_forward: unsupported shape"); return MV2_E_UNSUPPORTED; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return MV2_E_CUDA; }
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  SlabParams p;
+  memset(&p, 0, sizeof(p));
+  const int C2 = 2 * a->Ci, bk = 64;
+  p.kt = 1; p.kh = 3; p.kw = 2; p.pt = 0; p.ph = 1; p.pw = 1; p.st = 1;
+  p.row_bytes = 128; p.Ci = C2; p.kchunks = C2 / bk; p.dn_lower = a->Ci / bk;
+  p.B = a->B; p.T = a->To; p.H = a->Ho; p.W = a->Wo; p.Co = a->Co;
+  p.epi.bias = a->bias; p.epi.res = nullptr; p.epi.y = (__nv_bfloat16*)a->y; p.epi.act = a->act; p.epi.shuffle = MV2_SHUFFLE_NONE;
+  p.epi.mode = 0; p.epi.Co = a->Co; p.epi.To = a->To; p.epi.Ho = a->Ho; p.epi.Wo = a->Wo; p.epi.out_cf = 0; p.epi.oscale = nullptr;
+  int bn = 32;
+  for (int c = 256; c >= 32; c >>= 1) if (a->Co % c == 0) { bn = c; break; }
+  int mw = (bn <= 128 && a->Wo > 8) ? 2 : 1;
+  if (bn <= 64 && a->Wo > 16) mw = 4;
+  if (const char* env = getenv("MV2_DOWN_CFG")) {
+    int emw = 0, ebn = 0;
+    if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2 || emw == 4) && ebn >= 32 && ebn <= 256 && a->Co % ebn == 0 && emw * ebn <= 512 && !(emw >= 2 && a->Wo <= 8)) { mw = emw; bn = ebn; }
+  }
+  p.mw = mw; p.bn = bn; p.n_tiles_n = a->Co / bn; p.cluster = 1; p.tpw = 1;
+  p.tiles_h = ceil_div(a->Ho, 16); p.tiles_w = ceil_div(a->Wo, 8 * mw);
+  p.total_tiles = (int)((int64_t)a->B * a->To * p.tiles_h * p.tiles_w * p.n_tiles_n);
+  p.pitch = 8 * mw + 1; p.slab_h = 17;
+  const int o_bytes = 17 * p.pitch * 128, e_bytes = 16 * p.pitch * 128;
+  p.dn_e_off = (o_bytes + 1023) / 1024 * 1024;
+  p.slab_bytes = o_bytes + e_bytes;
+  p.slab_stride = p.dn_e_off + (e_bytes + 1023) / 1024 * 1024;
+  for (int dh = 0; dh < 3; ++dh)
+    for (int q = 0; q < 2; ++q)      // q = dw2 + 1
+      p.dn_aoff[dh * 2 + q] = ((dh == 1 ? p.dn_e_off : 0) + ((dh == 2 ? p.pitch : 0) + q) * 128) >> 4;
+  p.nbuf = (2 * mw * bn <= 512) ? 2 : 1;
+  p.acc_stride = p.nbuf == 2 ? 256 : 0;
+  const int w_bytes = bn * 128, nb_pad = p.n_tiles_n * bn;
+  const int budget = 204 * 1024 - nb_pad * 4;
+  p.slab_stages = p.slab_stride * 3 + w_bytes * 4 <= budget ? 3 : 2;
+  p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
+  MV2_CHECK_ARG(p.w_stages >= 2);
+  {
+    const int64_t W2 = a->Wi / 2, H2 = a->Hi / 2, T = a->Ti, rowb = (int64_t)a->Wi * a->Ci * 2;
+    cuuint64_t dims[5] = {(cuuint64_t)C2, (cuuint64_t)W2, (cuuint64_t)H2, (cuuint64_t)T, (cuuint64_t)a->B};
+    cuuint64_t strides[4] = {(cuuint64_t)(C2 * 2), (cuuint64_t)(2 * rowb), (cuuint64_t)(a->Hi * rowb), (cuuint64_t)(T * a->Hi * rowb)};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    cuuint32_t box_e[5] = {(cuuint32_t)bk, (cuuint32_t)p.pitch, 16, 1, 1}, box_o[5] = {(cuuint32_t)bk, (cuuint32_t)p.pitch, 17, 1, 1};
+    CUresult r = enc(&p.amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)a->x, dims, strides, box_e, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(even rows) failed: %d", (int)r); return MV2_E_CUDA; }
+    r = enc(&p.amap_odd, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (char*)a->x + rowb, dims, strides, box_o, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(odd rows) failed: %d", (int)r); return MV2_E_CUDA; }
+    const int64_t K = 6 * (int64_t)C2;
+    cuuint64_t dims2[2] = {(cuuint64_t)K, (cuuint64_t)a->Co};
+    cuuint64_t strides2[1] = {(cuuint64_t)(K * 2)};
+    cuuint32_t box2[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
+    cuuint32_t es2[2] = {1, 1};
+    r = enc(&p.wmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a->w, dims2, strides2, box2, es2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return MV2_E_CUDA; }
+    p.wmap = p.wmap2;
+  }
+  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4 + 9) + 32 +
+                      (size_t)nb_pad * 4 + 8 * 2048 + 1024;
+  MV2_CHECK_ARG(smem <= 227 * 1024);
+  static PerDeviceOnce attr_once;
+  const cudaError_t attr_err = attr_once.run([] {
+    return cudaFuncSetAttribute(tc_slab_kernel<EPI_DOWN_SPACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
+  const int grid = std::min(p.total_tiles, n_sm);
+  launch_kc(tc_slab_kernel<EPI_DOWN_SPACE>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, 1, p);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

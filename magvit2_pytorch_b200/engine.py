@@ -46,6 +46,7 @@ class ConvPack:
     epi_mode: int = 0                        # 1: fused GEGLU (output has Co_tc // 2 channels)
     k_tc: Optional[Tuple[int, int, int]] = None
     macs: int = 0                            # algorithmic multiply-accumulates per output position (Co * Ci * taps, unpadded)
+    w_down: Optional[torch.Tensor] = None    # SpatialDownsample2x pack for mv2_tc_down_space_forward ([Co][6][2*Ci] bf16)
 
 
 def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype, k=None, shuffle_q: int = 1) -> ConvPack:
@@ -72,6 +73,20 @@ def pack_conv(weight: torch.Tensor, bias: Optional[torch.Tensor], dtype, k=None,
         pk.bias_tc = bt
         pk.Ci_tc, pk.Co_tc, pk.k_tc = pk.Ci, pk.Co, pk.k
     return pk
+
+
+def pack_conv_down_space(pk: ConvPack, weight):
+    """SpatialDownsample2x (M:768: Conv2d k3 s2 p1) for mv2_tc_down_space_forward: w[co][tap'][2*Ci], tap' = dh * 2 + q,
+    q = 0 -> [zeros | w[:, :, dh, 0]] (the column left of the pair), q = 1 -> [w[:, :, dh, 1] | w[:, :, dh, 2]]."""
+    Co, Ci, kh, kw = weight.shape
+    if (kh, kw) != (3, 3) or Ci % 64 != 0 or Co % 32 != 0:
+        return
+    w = weight.detach().float()
+    wd = torch.zeros((Co, 3, 2, 2 * Ci), device=w.device)
+    wd[:, :, 0, Ci:] = w[:, :, :, 0].permute(0, 2, 1)
+    wd[:, :, 1, :Ci] = w[:, :, :, 1].permute(0, 2, 1)
+    wd[:, :, 1, Ci:] = w[:, :, :, 2].permute(0, 2, 1)
+    pk.w_down = wd.reshape(Co, 6 * 2 * Ci).contiguous().to(torch.bfloat16)
 
 
 def _round_up(v, m):
@@ -234,6 +249,8 @@ class Engine:
                 elif st.kind == "compress_space":
                     if side == "enc":
                         P[key] = pack_conv(mod.conv.weight, mod.conv.bias, dt)                     # (Co,Ci,3,3) -> k=(1,3,3)
+                        if dt == torch.bfloat16:
+                            pack_conv_down_space(P[key], mod.conv.weight)
                     else:
                         P[key] = pack_conv(mod.net[0].weight, mod.net[0].bias, dt, shuffle_q=4)    # (4Co,Ci,1,1)
                 elif st.kind == "compress_time":
@@ -303,11 +320,19 @@ class Engine:
             # (incl. the 64-byte-row conv_in once it runs 4 M-tiles and 7 taps per weight stage); the tap-wise kernel
             # keeps the strided down-samplers.  tc_variant = "tap" forces the tap-wise kernel (tests / sweeps).
             use_slab = self.tc_variant != "tap" and bool(self.lib.mv2_tc_slab_supported(C.byref(ta)))
+            use_down = (not use_slab and self.tc_variant != "tap" and pk.w_down is not None and stride == (1, 2, 2)
+                        and bool(self.lib.mv2_tc_down_space_supported(C.byref(ta))))
+            if use_down:
+                ta.w = _ptr(pk.w_down)
+                use_slab = True
             if use_slab or self.lib.mv2_tc_conv_supported(C.byref(ta)):
                 if self._prof is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                if use_slab:
+                if use_down:
+                    check(self.lib.mv2_tc_down_space_forward(C.byref(ta), self._stream()), "mv2_tc_down_space_forward")
+                    self.slab_calls += 1
+                elif use_slab:
                     check(self.lib.mv2_tc_slab_forward(C.byref(ta), self._stream()), "mv2_tc_slab_forward")
                     self.slab_calls += 1
                 else:

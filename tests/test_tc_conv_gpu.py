@@ -452,3 +452,32 @@ def test_slab_time_downsample(C_, Co, shape):
     eng.tc_variant = "auto"
     _check_vs_oracle("slab_down_time", y_slab, _oracle_conv(w, bias, x, (3, 1, 1), dict(stride=(2, 1, 1))))
     assert (y_slab.float() - y_tap.float()).abs().max().item() <= 0.008 * y_tap.float().abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("Ci,Co,shape", [(64, 128, (2, 3, 32, 32)), (128, 256, (1, 4, 64, 64)), (256, 512, (2, 3, 32, 32)),
+                                         (64, 128, (1, 2, 24, 40)), (64, 64, (1, 2, 16, 64)), (64, 128, (4, 20, 128, 128))])
+def test_slab_space_downsample(Ci, Co, shape):
+    """SpatialDownsample2x (Conv2d k3 s2 p1 per frame, M:770-780) on the slab kernel (row-parity sub-slabs of the (W/2) x (2C)
+    view, mv2_tc_down_space_forward) vs the tap-wise kernel and the CPU oracle."""
+    from magvit2_pytorch_b200.engine import pack_conv_down_space
+    assert torch.cuda.is_available()
+    B, T, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(Ci + Co + H)
+    w = (torch.randn((Co, Ci, 3, 3), generator=g) * (9 * Ci) ** -0.5).cuda()
+    bias = (torch.randn(Co, generator=g) * 0.1).cuda()
+    x = torch.randn((B, T, H, W, Ci), generator=g).cuda().to(torch.bfloat16)
+    eng = _engine()
+    pk = pack_conv(w, bias, torch.bfloat16)
+    pack_conv_down_space(pk, w)
+    assert pk.w_down is not None
+    kw = dict(stride=(1, 2, 2), pad=(0, 1, 1), out_spatial=(T, H // 2, W // 2))
+    eng.use_tc, eng.tc_variant, eng.slab_calls = True, "auto", 0
+    y_slab = eng.conv(x, pk, **kw)
+    assert eng.slab_calls == 1, "slab down-space kernel was not taken"
+    eng.tc_variant = "tap"
+    y_tap = eng.conv(x, pk, **kw)
+    torch.cuda.synchronize()
+    eng.tc_variant = "auto"
+    assert (y_slab.float() - y_tap.float()).abs().max().item() <= 0.008 * y_tap.float().abs().max().item() + 1e-3
+    if B * T * H * W <= 65536:       # the CPU oracle on the small cases
+        _check_vs_oracle("slab_down_space", y_slab, _oracle_conv(w, bias, x, None, dict(stride=(1, 2, 2))))
