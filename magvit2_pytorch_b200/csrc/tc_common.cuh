@@ -208,9 +208,9 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* dst, const float (&v)
 // ~2300 SASS instructions per 32-column chunk and thrashed the instruction cache of the 8 epilogue warps).
 // EPI_PLAIN (slab kernel only) additionally requires Co % 8 == 0 and stores through a shared-memory transpose;
 // EPI_RAGGED is the direct per-row path with scalar tails (conv_out's 3 channels, and the tap kernel's plain mode).
-// EPI_PLAIN_RES is EPI_PLAIN with a residual input: the chunk is staged as fp32 so that act(conv + bias) + res is summed
-// in fp32 and rounded to bf16 ONCE (the reference's bf16 `fn(x) + x` rounds twice; the single rounding is strictly closer
-// to the fp32 result and costs only shared-memory staging width).
+// EPI_PLAIN_RES is EPI_PLAIN with a residual input: each lane reads its own row's residual (64 contiguous bytes per chunk)
+// and act(conv + bias) + res is summed in fp32 and rounded to bf16 ONCE (the reference's bf16 `fn(x) + x` rounds twice; the
+// single rounding is strictly closer to the fp32 result).
 // EPI_FUSED_RU (slab kernel only): the whole conv half of a ResidualUnit in one launch -- the ELU'd 3x3x3 tile goes to
 // shared memory as the A operand of a second tcgen05.mma against the 1x1x1 weights, and the second epilogue emits the
 // SqueezeExcite online-softmax pool partials next to y (see tc_slab.cu).

@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
         const uint32_t tl = tmem_base + buf * p.acc_stride + j * p.bn + ((uint32_t)(sub * 32) << 16);
         const int64_t row_base = ((((int64_t)c.b * p.T + c.t) * p.H + h) * p.W + w) * p.Co;
         // column chunks are dealt round-robin to the two warps that share this lane quarter
-        if (MODE == EPI_PLAIN || MODE == EPI_SHUFFLE_ST || MODE == EPI_DOWN_SPACE) {
+        if (MODE == EPI_PLAIN || MODE == EPI_PLAIN_RES || MODE == EPI_SHUFFLE_ST || MODE == EPI_DOWN_SPACE) {
           // Row-per-lane results are transposed through shared memory so that every store instruction writes 8 rows
           // x 64 contiguous bytes (full sectors; the 8 rows are neighbours along w, i.e. one contiguous run when the
           // tile spans all of Co) instead of 32 scattered 16-byte pieces.  The residual is read with the same mapping.
@@ -601,13 +601,33 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
           const int kmax = w2 < p.W ? p.H - h20 : 0;                   // rows k < kmax are inside the frame
           for (int c0 = ((j + half) & 1) * 32; c0 < p.bn; c0 += 64) {
             uint32_t r[32], pk[16];
+            uint4 rv[4];
+            if (MODE == EPI_PLAIN_RES) {
+              // residual: this lane's own row, 64 contiguous bytes (two full sectors), requested before the TMEM load returns;
+              // it is added in fp32 BEFORE the single rounding to bf16 (the reference's bf16 `fn(x) + x` rounds twice)
+              const __nv_bfloat16* rr = p.epi.res + row_base + c.n0 + c0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                rv[g] = (row_ok && c.n0 + c0 + g * 8 < p.Co && c0 + g * 8 < p.bn) ? *reinterpret_cast<const uint4*>(rr + g * 8) : make_uint4(0, 0, 0, 0);
+            }
             tmem_ld_32x32b_x32(tl + c0, r);
             tmem_ld_wait();
-            if (MODE == EPI_PLAIN && p.epi.oscale) {      // Conv3DMod demodulation: per-(clip, channel) multiplier (M:741-742)
+            if ((MODE == EPI_PLAIN || MODE == EPI_PLAIN_RES) && p.epi.oscale) {   // Conv3DMod demodulation (M:741-742)
               const float* os = p.epi.oscale + (int64_t)c.b * p.Co + c.n0 + c0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * (c.n0 + c0 + i < p.Co ? os[i] : 0.f));
             }
+            if (MODE == EPI_PLAIN_RES) {
+              epi_act32(p.epi.act, r, sbias + c.n0 + c0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t w4[4] = {rv[g].x, rv[g].y, rv[g].z, rv[g].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  pk[4 * g + q] = pack_bf16x2(__uint_as_float(r[8 * g + 2 * q]) + __uint_as_float(w4[q] << 16),
+                                              __uint_as_float(r[8 * g + 2 * q + 1]) + __uint_as_float(w4[q] & 0xffff0000u));
+              }
+            } else
             epi_pack32(p.epi.act, r, sbias + c.n0 + c0, pk);
 #pragma unroll
             for (int g = 0; g < 4; ++g)
@@ -641,58 +661,6 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                            : "r"(rd + k * 512 + ((piece ^ (((8 * k + rl) >> 1) & 3)) << 4)));
               if (k < klim) *reinterpret_cast<uint4*>(yp + k * ks) = v;
-            }
-            __syncwarp();
-          }
-        } else if (MODE == EPI_PLAIN_RES) {
-          // Same store mapping as EPI_PLAIN, but the chunk is staged in fp32 (32 rows x 128 B per warp, 16-byte pieces
-          // XOR-swizzled by row) so that the residual is added in fp32 before the single rounding to bf16.
-          const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 4096;
-          const uint32_t wr = stg + lane * 128, wsw = lane & 7;
-          const int rl = lane >> 2, piece = lane & 3;
-          const int w2 = c.w0 + 8 * j + rl;
-          const int h20 = c.h0 + sub * 4;
-          const int64_t row0 = ((((int64_t)c.b * p.T + c.t) * p.H + h20) * p.W + w2) * p.Co + c.n0 + piece * 8;
-          const int64_t kstride = (int64_t)p.W * p.Co;
-          const int kmax = w2 < p.W ? p.H - h20 : 0;
-          for (int c0 = ((j + half) & 1) * 32; c0 < p.bn; c0 += 64) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tl + c0, r);
-            tmem_ld_wait();
-            if (p.epi.oscale) {
-              const float* os = p.epi.oscale + (int64_t)c.b * p.Co + c.n0 + c0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * (c.n0 + c0 + i < p.Co ? os[i] : 0.f));
-            }
-            epi_act32(p.epi.act, r, sbias + c.n0 + c0);
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((g ^ wsw) << 4)), "r"(r[4 * g]),
-                           "r"(r[4 * g + 1]), "r"(r[4 * g + 2]), "r"(r[4 * g + 3]) : "memory");
-            __syncwarp();
-            const bool col_ok = c.n0 + c0 + piece * 8 < p.Co && c0 + piece * 8 < p.bn;
-            const int klim = col_ok ? kmax : 0;
-            __nv_bfloat16* yp = p.epi.y + row0 + c0;
-            const __nv_bfloat16* rp = p.epi.res + row0 + c0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float4 a, b;
-              const uint32_t rrow = stg + (uint32_t)(8 * k + rl) * 128;
-              const uint32_t rsw = (uint32_t)rl;          // (8k + rl) & 7
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
-                           : "r"(rrow + (((2 * piece) ^ rsw) << 4)));
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                           : "r"(rrow + (((2 * piece + 1) ^ rsw) << 4)));
-              if (k < klim) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(rp + k * kstride);
-                const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-                const float2 r0 = __bfloat1622float2(b2[0]), r1 = __bfloat1622float2(b2[1]);
-                const float2 r2 = __bfloat1622float2(b2[2]), r3 = __bfloat1622float2(b2[3]);
-                uint4 o;
-                o.x = pack_bf16x2(a.x + r0.x, a.y + r0.y); o.y = pack_bf16x2(a.z + r1.x, a.w + r1.y);
-                o.z = pack_bf16x2(b.x + r2.x, b.y + r2.y); o.w = pack_bf16x2(b.z + r3.x, b.w + r3.y);
-                *reinterpret_cast<uint4*>(yp + k * kstride) = o;
-              }
             }
             __syncwarp();
           }
@@ -874,8 +842,7 @@ static int slab_fill_plan(const mv2_tc_conv_args* a, int n_sm, SlabParams& p, in
   if (const char* env = getenv("MV2_SLAB_TPW")) { const int v = atoi(env); if (v >= 1 && taps2d % v == 0 && v * p.bn * p.row_bytes <= 64 * 1024) p.tpw = v; }
   int w_bytes = p.bn * p.row_bytes * p.tpw;
   const int nb_pad = p.n_tiles_n * p.bn;   // bias staging covers the padded column range
-  const bool res_stage = a->res != nullptr && a->epi_mode == 0 && a->shuffle == MV2_SHUFFLE_NONE && a->Co % 8 == 0;   // EPI_PLAIN_RES
-  const int budget = 204 * 1024 - nb_pad * 4 - (res_stage ? 16 * 1024 : 0);   // 227 KB minus the epilogue transpose buffers (16 / 32 KB), barriers, alignment slack
+  const int budget = 204 * 1024 - nb_pad * 4;   // 227 KB minus 16 KB epilogue transpose buffers, barriers, alignment slack
   p.slab_stages = p.slab_stride * 3 + w_bytes * 3 <= budget ? 3 : 2;
   p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
   if (p.w_stages < 2 && p.slab_stages > 2) { p.slab_stages = 2; p.w_stages = std::min(12, (budget - 2 * p.slab_stride) / w_bytes); }
@@ -971,7 +938,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights 2-D) failed: %d", (int)r); return MV2_E_CUDA; }
   }
-  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 32 + (size_t)nb_pad * 4 + 8 * ((a->res && a->epi_mode == 0 && a->shuffle == MV2_SHUFFLE_NONE && a->Co % 8 == 0) ? 4096 : 2048) + 1024;
+  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 32 + (size_t)nb_pad * 4 + 8 * 2048 + 1024;
   MV2_CHECK_ARG(smem <= 227 * 1024);
   static PerDeviceOnce attr_once;
   const cudaError_t attr_err = attr_once.run([] {
