@@ -679,15 +679,25 @@ __global__ void __launch_bounds__(ST_WARPS * 32) se_tail_kernel(const __nv_bfloa
   for (int u = 0; u < NU; ++u)
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[u][q] = 0.f;
-  for (int n0 = warp; n0 < P; n0 += 2 * ST_WARPS) {      // two rows per iteration: both rows' loads are in flight together
+  // two rows per iteration, software pipelined: the loads of the next pair are issued before the current pair is folded, so
+  // every lane keeps 4 * NU 16-byte loads in flight (the whole kernel is a chain of L2 round trips otherwise)
+  uint4 q0[NU], q1[NU];
+  auto fetch = [&](int n0, uint4 (&a)[NU], uint4 (&b)[NU]) {
     const int n1 = n0 + ST_WARPS;
-    uint4 r0[NU], r1[NU];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       const int c = (u * 32 + lane) * 8;
-      r0[u] = c < C ? *reinterpret_cast<const uint4*>(yf + (int64_t)n0 * C + c) : make_uint4(0, 0, 0, 0);
-      r1[u] = (c < C && n1 < P) ? *reinterpret_cast<const uint4*>(yf + (int64_t)n1 * C + c) : make_uint4(0, 0, 0, 0);
+      a[u] = (c < C && n0 < P) ? *reinterpret_cast<const uint4*>(yf + (int64_t)n0 * C + c) : make_uint4(0, 0, 0, 0);
+      b[u] = (c < C && n1 < P) ? *reinterpret_cast<const uint4*>(yf + (int64_t)n1 * C + c) : make_uint4(0, 0, 0, 0);
     }
+  };
+  fetch(warp, q0, q1);
+  for (int n0 = warp; n0 < P; n0 += 2 * ST_WARPS) {
+    const int n1 = n0 + ST_WARPS;
+    uint4 r0[NU], r1[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) { r0[u] = q0[u]; r1[u] = q1[u]; }
+    fetch(n0 + 2 * ST_WARPS, q0, q1);
     float v0[NU][8], v1[NU][8], d0 = 0.f, d1 = 0.f;
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
@@ -786,17 +796,18 @@ __global__ void __launch_bounds__(ST_WARPS * 32) se_tail_kernel(const __nv_bfloa
 #pragma unroll
       for (int q = 0; q < 8; ++q) hv[u][q] = j + q < Hd ? hidden[j + q] : 0.f;
     }
-    for (int c0 = warp * 4; c0 < C; c0 += ST_WARPS * 4) {
-      uint4 r[4][HU];
+    constexpr int GB = HU == 1 ? 8 : 4;          // outputs per batch: GB * HU 16-byte loads in flight per lane
+    for (int c0 = warp * GB; c0 < C; c0 += ST_WARPS * GB) {
+      uint4 r[GB][HU];
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
+      for (int t = 0; t < GB; ++t)
 #pragma unroll
         for (int u = 0; u < HU; ++u) {
           const int j = (u * 32 + lane) * 8;
           r[t][u] = (c0 + t < C && j < Hd) ? *reinterpret_cast<const uint4*>(w2 + (int64_t)(c0 + t) * Hd + j) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < GB; ++t) {
         float d = 0.f;
 #pragma unroll
         for (int u = 0; u < HU; ++u) {
@@ -819,22 +830,34 @@ __global__ void __launch_bounds__(ST_WARPS * 32) se_tail_kernel(const __nv_bfloa
     const uint4* x8 = reinterpret_cast<const uint4*>(x + (int64_t)f * P * C);
     uint4* o8 = reinterpret_cast<uint4*>(out + (int64_t)f * P * C);
     const int C8 = C >> 3, total = P * C8;
-    for (int i = tid; i < total; i += ST_WARPS * 32) {
-      const int c = (i % C8) * 8;
-      const uint4 yv = y8[i], xv = x8[i];
-      const float4 g0 = *reinterpret_cast<const float4*>(gates + c), g1 = *reinterpret_cast<const float4*>(gates + c + 4);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const __nv_bfloat162* yb = reinterpret_cast<const __nv_bfloat162*>(&yv);
-      const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xv);
-      uint4 o;
-      uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+    constexpr int PB = 4, NT = ST_WARPS * 32;         // 2 * PB 16-byte loads in flight per thread
+    for (int i0 = tid; i0 < total; i0 += PB * NT) {
+      uint4 yv[PB], xv[PB];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 yf2 = __bfloat1622float2(yb[q]), xf2 = __bfloat1622float2(xb[q]);
-        __nv_bfloat162 r = __floats2bfloat162_rn(fmaf(gg[2 * q], yf2.x, xf2.x), fmaf(gg[2 * q + 1], yf2.y, xf2.y));
-        ob[q] = *reinterpret_cast<uint32_t*>(&r);
+      for (int b = 0; b < PB; ++b) {
+        const int i = i0 + b * NT;
+        yv[b] = i < total ? y8[i] : make_uint4(0, 0, 0, 0);
+        xv[b] = i < total ? x8[i] : make_uint4(0, 0, 0, 0);
       }
-      o8[i] = o;
+#pragma unroll
+      for (int b = 0; b < PB; ++b) {
+        const int i = i0 + b * NT;
+        if (i >= total) break;
+        const int c = (i % C8) * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(gates + c), g1 = *reinterpret_cast<const float4*>(gates + c + 4);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const __nv_bfloat162* yb = reinterpret_cast<const __nv_bfloat162*>(&yv[b]);
+        const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&xv[b]);
+        uint4 o;
+        uint32_t* ob = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 yf2 = __bfloat1622float2(yb[q]), xf2 = __bfloat1622float2(xb[q]);
+          __nv_bfloat162 r = __floats2bfloat162_rn(fmaf(gg[2 * q], yf2.x, xf2.x), fmaf(gg[2 * q + 1], yf2.y, xf2.y));
+          ob[q] = *reinterpret_cast<uint32_t*>(&r);
+        }
+        o8[i] = o;
+      }
     }
   }
 }

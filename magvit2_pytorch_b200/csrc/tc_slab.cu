@@ -1153,21 +1153,26 @@ extern "C" int mv2_tc_down_space_forward(const mv2_tc_conv_args* a, void* stream
     int emw = 0, ebn = 0;
     if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2 || emw == 4) && ebn >= 32 && ebn <= 256 && a->Co % ebn == 0 && emw * ebn <= 512 && !(emw >= 2 && a->Wo <= 8)) { mw = emw; bn = ebn; }
   }
+  const int w_bytes = bn * 128, nb_pad = (a->Co / bn) * bn;
+  const int budget = 204 * 1024 - nb_pad * 4;
+  int o_bytes, e_bytes;
+  for (;; mw >>= 1) {           // the two row-parity sub-slabs of a 4-M-tile macro tile do not fit twice: narrow the macro tile
+    p.pitch = 8 * mw + 1;
+    o_bytes = 17 * p.pitch * 128; e_bytes = 16 * p.pitch * 128;
+    p.dn_e_off = (o_bytes + 1023) / 1024 * 1024;
+    p.slab_stride = p.dn_e_off + (e_bytes + 1023) / 1024 * 1024;
+    if (mw == 1 || 2 * p.slab_stride + 3 * w_bytes <= budget) break;
+  }
   p.mw = mw; p.bn = bn; p.n_tiles_n = a->Co / bn; p.cluster = 1; p.tpw = 1;
   p.tiles_h = ceil_div(a->Ho, 16); p.tiles_w = ceil_div(a->Wo, 8 * mw);
   p.total_tiles = (int)((int64_t)a->B * a->To * p.tiles_h * p.tiles_w * p.n_tiles_n);
-  p.pitch = 8 * mw + 1; p.slab_h = 17;
-  const int o_bytes = 17 * p.pitch * 128, e_bytes = 16 * p.pitch * 128;
-  p.dn_e_off = (o_bytes + 1023) / 1024 * 1024;
+  p.slab_h = 17;
   p.slab_bytes = o_bytes + e_bytes;
-  p.slab_stride = p.dn_e_off + (e_bytes + 1023) / 1024 * 1024;
   for (int dh = 0; dh < 3; ++dh)
     for (int q = 0; q < 2; ++q)      // q = dw2 + 1
       p.dn_aoff[dh * 2 + q] = ((dh == 1 ? p.dn_e_off : 0) + ((dh == 2 ? p.pitch : 0) + q) * 128) >> 4;
   p.nbuf = (2 * mw * bn <= 512) ? 2 : 1;
   p.acc_stride = p.nbuf == 2 ? 256 : 0;
-  const int w_bytes = bn * 128, nb_pad = p.n_tiles_n * bn;
-  const int budget = 204 * 1024 - nb_pad * 4;
   p.slab_stages = p.slab_stride * 3 + w_bytes * 4 <= budget ? 3 : 2;
   p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
   MV2_CHECK_ARG(p.w_stages >= 2);
