@@ -757,7 +757,12 @@ __global__ void __launch_bounds__(ST_WARPS * 32) se_tail_kernel(const __nv_bfloa
 #pragma unroll
       for (int q = 0; q < 8; ++q) pv[u][q] = c + q < C ? pooled[c + q] : 0.f;
     }
-    for (int j0 = warp * 4; j0 < Hd; j0 += ST_WARPS * 4) {
+    // every CTA (frame) walks the same weight matrix: start each one at a different row group, so that the ~80 CTAs of a
+    // launch do not all pull the same L2 lines at the same moment
+    const int ng2 = (Hd + ST_WARPS * 4 - 1) / (ST_WARPS * 4);
+    for (int gi = 0; gi < ng2; ++gi) {
+      const int j0 = ((gi + f) % ng2) * (ST_WARPS * 4) + warp * 4;
+      if (j0 >= Hd) continue;
       uint4 r[4][NU];
 #pragma unroll
       for (int t = 0; t < 4; ++t)
@@ -797,7 +802,10 @@ __global__ void __launch_bounds__(ST_WARPS * 32) se_tail_kernel(const __nv_bfloa
       for (int q = 0; q < 8; ++q) hv[u][q] = j + q < Hd ? hidden[j + q] : 0.f;
     }
     constexpr int GB = HU == 1 ? 8 : 4;          // outputs per batch: GB * HU 16-byte loads in flight per lane
-    for (int c0 = warp * GB; c0 < C; c0 += ST_WARPS * GB) {
+    const int ng3 = (C + ST_WARPS * GB - 1) / (ST_WARPS * GB);
+    for (int gi = 0; gi < ng3; ++gi) {
+      const int c0 = ((gi + f) % ng3) * (ST_WARPS * GB) + warp * GB;
+      if (c0 >= C) continue;
       uint4 r[GB][HU];
 #pragma unroll
       for (int t = 0; t < GB; ++t)
