@@ -154,7 +154,10 @@ class Engine:
         self.tc_variant = "auto"     # "auto" | "tap" (tc_conv.cu only) | "slab" (prefer tc_slab.cu)
         self.fuse_ru = True          # bf16: conv3x3x3 + ELU + conv1x1x1 + ELU + SE pool partials in one tcgen05 launch (C = 64 / 128)
         self.fused_ru_calls = 0
-        self.se_tail = True          # bf16, small frames: SE pool + gate MLP + gate/residual in one launch
+        # bf16, small frames: SE pool + gate MLP + gate/residual in ONE launch (mv2_se_tail).  Off by default: measured 38 us per
+        # unit at C = 512 / 16x16 (one CTA per frame is instruction-issue bound: ncu issue-active 49 %, 7.7 k warp instructions
+        # per warp) against 36 us for the four small launches under graph replay (profiles/r02_se_tail.json)
+        self.se_tail = False
         self.se_tail_calls = 0
         self.fuse_conv_out = True    # bf16: conv_out stores torch's (B,C,T,H,W) directly and skips the time_padding frames
         self.tc_calls = 0
