@@ -1132,6 +1132,85 @@ __global__ void __launch_bounds__(128) attention_kernel(const mv2_attn_args a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// softmax attention core for SHORT sequences (time attention: L = T' = 5 tokens + 4 memory key/values per pixel, M:456-464):
+// one warp per (sequence, head), lane = head dimension; the whole (L x (n_mem + L)) score matrix lives in registers.  The
+// general kernel above spends a 128-thread block with 32 query slots and two shared-memory key tiles on 5 queries.
+// bf16 only (the fp32 path keeps the general kernel and its summation order).
+// ------------------------------------------------------------------------------------------
+constexpr int AS_L = 8, AS_M = 8;      // max tokens / memory slots
+template <int DPL>
+__global__ void __launch_bounds__(256) attention_small_kernel(const mv2_attn_args a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int D = DPL * 32;
+  const __nv_bfloat16* __restrict__ qkv = (const __nv_bfloat16*)a.qkv;
+  __nv_bfloat16* __restrict__ out = (__nv_bfloat16*)a.out;
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);       // (sequence, head)
+  const int64_t n_seq = (int64_t)a.n_outer * a.n_inner;
+  if (wid >= n_seq * a.heads) return;
+  const int h = (int)(wid % a.heads);
+  const int64_t seq = wid / a.heads;
+  const int64_t base = (seq / a.n_inner) * a.outer_stride + (seq % a.n_inner) * a.inner_stride;
+  const int HD = a.heads * D;
+  const int64_t row_stride = 3 * (int64_t)HD;
+  const float scale = rsqrtf((float)D);
+  const bool causal = a.causal && a.L > 1;
+  const int L = a.L, NM = a.n_mem;
+  float q[AS_L][DPL], k[AS_M + AS_L][DPL], v[AS_M + AS_L][DPL];
+#pragma unroll
+  for (int j = 0; j < AS_M; ++j)
+#pragma unroll
+    for (int dd = 0; dd < DPL; ++dd) {
+      const int d = lane + 32 * dd;
+      k[j][dd] = j < NM ? a.mem_kv[(((int64_t)0 * a.heads + h) * NM + j) * D + d] : 0.f;
+      v[j][dd] = j < NM ? a.mem_kv[(((int64_t)1 * a.heads + h) * NM + j) * D + d] : 0.f;
+    }
+#pragma unroll
+  for (int i = 0; i < AS_L; ++i)
+#pragma unroll
+    for (int dd = 0; dd < DPL; ++dd) {
+      const int d = lane + 32 * dd;
+      float qv = 0.f, kv = 0.f, vv = 0.f;
+      if (i < L) {
+        const int64_t row = (base + (int64_t)i * a.tok_stride) * row_stride + h * D + d;
+        qv = __bfloat162float(qkv[row]); kv = __bfloat162float(qkv[row + HD]); vv = __bfloat162float(qkv[row + 2 * HD]);
+      }
+      q[i][dd] = qv; k[AS_M + i][dd] = kv; v[AS_M + i][dd] = vv;
+    }
+#pragma unroll
+  for (int i = 0; i < AS_L; ++i) {
+    if (i >= L) break;
+    float sc[AS_M + AS_L], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < AS_M + AS_L; ++j) {
+      const int jk = j - AS_M;                               // key index among the tokens (memory slots: j < AS_M)
+      const bool valid = j < AS_M ? j < NM : (jk < L && (!causal || jk <= i));
+      float p = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < DPL; ++dd) p = fmaf(q[i][dd], k[j][dd], p);
+      p = warp_sum(p) * scale;
+      sc[j] = valid ? p : -INFINITY;
+      mx = fmaxf(mx, sc[j]);
+    }
+    float den = 0.f, o[DPL];
+#pragma unroll
+    for (int dd = 0; dd < DPL; ++dd) o[dd] = 0.f;
+#pragma unroll
+    for (int j = 0; j < AS_M + AS_L; ++j) {
+      const float e = sc[j] > -INFINITY ? __expf(sc[j] - mx) : 0.f;
+      den += e;
+#pragma unroll
+      for (int dd = 0; dd < DPL; ++dd) o[dd] = fmaf(e, v[j][dd], o[dd]);
+    }
+    const float inv = 1.f / den;
+    __nv_bfloat16* orow = out + (base + (int64_t)i * a.tok_stride) * HD + h * D;
+#pragma unroll
+    for (int dd = 0; dd < DPL; ++dd) orow[lane + 32 * dd] = __float2bfloat16_rn(o[dd] * inv);
+  }
+}
+
 
 // ------------------------------------------------------------------------------------------
 // softmax attention core on tensor cores (warp-level mma.sync m16n8k16, bf16 in / fp32 accumulate):
@@ -2233,6 +2312,13 @@ int mv2_attention(const mv2_attn_args* a, void* stream) {
     dim3 grid((unsigned)((int64_t)a->n_outer * a->n_inner), a->heads, ceil_div(a->L, FA_Q));
     if (a->dim_head == 32) launch_k(attention_mma_kernel<32>, dim3(grid), dim3(128), 0, st, *a);
     else launch_k(attention_mma_kernel<64>, dim3(grid), dim3(128), 0, st, *a);
+    MV2_CHECK_LAUNCH();
+    return MV2_OK;
+  }
+  if (a->dtype == MV2_BF16 && a->L <= AS_L && a->n_mem <= AS_M && (a->dim_head == 32 || a->dim_head == 64)) {
+    const int64_t warps = (int64_t)a->n_outer * a->n_inner * a->heads;
+    if (a->dim_head == 32) launch_k(attention_small_kernel<1>, dim3((unsigned)ceil_div(warps, 8)), dim3(256), 0, st, *a);
+    else launch_k(attention_small_kernel<2>, dim3((unsigned)ceil_div(warps, 8)), dim3(256), 0, st, *a);
     MV2_CHECK_LAUNCH();
     return MV2_OK;
   }

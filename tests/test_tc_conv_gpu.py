@@ -481,3 +481,37 @@ def test_slab_space_downsample(Ci, Co, shape):
     assert (y_slab.float() - y_tap.float()).abs().max().item() <= 0.008 * y_tap.float().abs().max().item() + 1e-3
     if B * T * H * W <= 65536:       # the CPU oracle on the small cases
         _check_vs_oracle("slab_down_space", y_slab, _oracle_conv(w, bias, x, None, dict(stride=(1, 2, 2))))
+
+
+@pytest.mark.parametrize("T,HW,D,heads,causal", [(5, 64, 32, 8, 1), (1, 16, 32, 4, 1), (8, 24, 64, 2, 1), (3, 10, 32, 3, 0)])
+def test_attention_small_sequences_kernel(T, HW, D, heads, causal):
+    """Short-sequence attention kernel (time attention: one warp per (pixel, head), right-aligned causal mask over 4 memory
+    key/values + the frames so far, A:46-47 / A:123-129; masking off when L == 1, A:209-210) vs the fp32 general kernel and
+    the CPU oracle, with the strided token addressing of TimeAttention (M:456-464)."""
+    import ctypes as C
+    from magvit2_pytorch_b200 import _lib
+    from magvit2_pytorch_b200._lib import AttnArgs, check
+    lib = _lib.load()
+    B = 2
+    g = torch.Generator(device="cpu").manual_seed(T * 10 + D)
+    HDm = heads * D
+    qkv = (torch.randn((B * T * HW, 3 * HDm), generator=g) * 1.2).to(torch.bfloat16).cuda()
+    mem = torch.randn((2, heads, 4, D), generator=g).to(torch.bfloat16).float().cuda()
+    outs = {}
+    for dt, code in ((torch.bfloat16, 1), (torch.float32, 0)):
+        x = qkv.to(dt).contiguous()
+        o = torch.zeros((B * T * HW, HDm), device="cuda", dtype=dt)
+        a = AttnArgs(qkv=x.data_ptr(), out=o.data_ptr(), mem_kv=mem.data_ptr(), dtype=code, heads=heads, dim_head=D, n_mem=4,
+                     causal=causal, n_outer=B, n_inner=HW, L=T, outer_stride=T * HW, inner_stride=1, tok_stride=HW)
+        check(lib.mv2_attention(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mv2_attention")
+        outs[dt] = o.float().cpu()
+    torch.cuda.synchronize()
+    t = qkv.float().cpu().reshape(B, T, HW, 3, heads, D).permute(3, 0, 2, 4, 1, 5).reshape(3, B * HW, heads, T, D)
+    memc = mem.cpu()
+    k_ = torch.cat((memc[0][None].expand(B * HW, -1, -1, -1), t[1]), dim=-2)
+    v_ = torch.cat((memc[1][None].expand(B * HW, -1, -1, -1), t[2]), dim=-2)
+    o_ = R.softmax_attention(t[0], k_, v_, causal=bool(causal))                    # (B*HW, heads, T, D)
+    o_ = o_.reshape(B, HW, heads, T, D).permute(0, 3, 1, 2, 4).reshape(B * T * HW, HDm)
+    a_, b_ = outs[torch.bfloat16], outs[torch.float32]
+    assert (b_ - o_).abs().max().item() < 2e-5 * o_.abs().max().item() + 2e-5
+    assert (a_ - o_).abs().max().item() < 2.0 ** -8 * o_.abs().max().item() + 2e-3     # one bf16 rounding of the output
