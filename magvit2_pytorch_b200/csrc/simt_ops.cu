@@ -958,7 +958,6 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, T
 // (C <= 1024: at most 4 uint4 per lane).
 // One warp normalises RN_TPW (template) tokens: all of their 16-byte loads are issued before the first reduction (one token per
 // warp left a single load in flight per lane and ran at a third of the HBM rate).
-// tokens per warp: 8 for C <= 256 (one 16-byte load per lane and token), 4 above
 template <int NU, int RN_TPW>   // 256-channel slabs per token: C <= 256 * NU
 __global__ void __launch_bounds__(256) rmsnorm_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                              const float* __restrict__ gamma, int64_t n_tok, int T_,
@@ -2289,7 +2288,8 @@ int mv2_rmsnorm(const void* x, void* out, int dtype, const float* gamma, int B, 
     {
       const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
       __nv_bfloat16* ob = (__nv_bfloat16*)out;
-      if (C <= 256) launch_k(rmsnorm_bf16x8_kernel<1, 8>, dim3(ceil_div(n_tok, 8 * 8)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
+      // (8 tokens per warp measured slower at C = 256: 188 -> 244 us per step, register pressure)
+      if (C <= 256) launch_k(rmsnorm_bf16x8_kernel<1, 4>, dim3(ceil_div(n_tok, 8 * 4)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
       else if (C <= 512) launch_k(rmsnorm_bf16x8_kernel<2, 4>, dim3(ceil_div(n_tok, 8 * 4)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
       else launch_k(rmsnorm_bf16x8_kernel<4, 4>, dim3(ceil_div(n_tok, 8 * 4)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
     }
