@@ -1214,10 +1214,10 @@ __global__ void __launch_bounds__(256) attention_small_kernel(const mv2_attn_arg
 // ------------------------------------------------------------------------------------------
 // softmax attention core on tensor cores (warp-level mma.sync m16n8k16, bf16 in / fp32 accumulate):
 // flash-style, non-causal, memory key/values prepended, sequences addressed through strides.
-// 4 warps x 16 queries per block; keys/values staged per 64-key tile (V transposed) in shared memory;
+// 8 warps x 16 queries per block; keys/values staged per 64-key tile (V transposed) in shared memory, loads prefetched one tile ahead;
 // online softmax with quad shuffles.  Used for bf16 sequences with L >= 64 (space attention).
 // ------------------------------------------------------------------------------------------
-constexpr int FA_Q = 64, FA_KT = 64;
+constexpr int FA_Q = 128, FA_KT = 64;     // 8 warps x 16 queries per block; keys / values staged 64 at a time
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -1231,7 +1231,7 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(128) attention_mma_kernel(const mv2_attn_args a) {
+__global__ void __launch_bounds__(256) attention_mma_kernel(const mv2_attn_args a) {
   pdl_wait();
   pdl_launch_dependents();
   constexpr int DK = D / 16, DN = D / 8;
@@ -1272,10 +1272,14 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const mv2_attn_args 
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int j0 = 0; j0 < Ltot; j0 += FA_KT) {
-    __syncthreads();
-    // ---- stage K (row major) and V (transposed) for keys j0 .. j0+63 ----
-    for (int idx = tid; idx < FA_KT * (D / 8); idx += 128) {
+  // K / V staging is software pipelined: the global loads of tile j0 + 64 are issued before tile j0 is consumed, so their
+  // latency hides under the MMAs / softmax of the current tile (each thread owns ITEMS 16-byte pieces of a tile)
+  constexpr int ITEMS = FA_KT * (D / 8) / 256;
+  uint4 kr[ITEMS], vr[ITEMS];
+  auto fetch = [&](int j0) {
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int idx = tid + it * 256;
       const int j = idx / (D / 8), c = (idx % (D / 8)) * 8;
       const int jg = j0 + j;
       uint4 kv4 = make_uint4(0, 0, 0, 0), vv4 = make_uint4(0, 0, 0, 0);
@@ -1291,12 +1295,25 @@ __global__ void __launch_bounds__(128) attention_mma_kernel(const mv2_attn_args 
         kv4 = *reinterpret_cast<const uint4*>(row + HD + h * D + c);
         vv4 = *reinterpret_cast<const uint4*>(row + 2 * HD + h * D + c);
       }
-      *reinterpret_cast<uint4*>(&Ks[j][c]) = kv4;
-      const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(&vv4);
+      kr[it] = kv4;
+      vr[it] = vv4;
+    }
+  };
+  fetch(0);
+  for (int j0 = 0; j0 < Ltot; j0 += FA_KT) {
+    __syncthreads();
+    // ---- stage K (row major) and V (transposed) for keys j0 .. j0+63 ----
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+      const int idx = tid + it * 256;
+      const int j = idx / (D / 8), c = (idx % (D / 8)) * 8;
+      *reinterpret_cast<uint4*>(&Ks[j][c]) = kr[it];
+      const __nv_bfloat16* vb = reinterpret_cast<const __nv_bfloat16*>(&vr[it]);
 #pragma unroll
       for (int q = 0; q < 8; ++q) Vt[c + q][j] = vb[q];
     }
     __syncthreads();
+    if (j0 + FA_KT < Ltot) fetch(j0 + FA_KT);
     // ---- S = Q K^T (16 x 64 per warp) ----
     float sfr[FA_KT / 8][4];
 #pragma unroll
@@ -2309,8 +2326,8 @@ int mv2_attention(const mv2_attn_args* a, void* stream) {
   if (a->dtype == MV2_F32) return launch_attention<float>(a, st);
   if (a->dtype == MV2_BF16 && !a->causal && a->L >= 64 && (a->dim_head == 32 || a->dim_head == 64) && a->heads * a->dim_head % 8 == 0) {
     dim3 grid((unsigned)((int64_t)a->n_outer * a->n_inner), a->heads, ceil_div(a->L, FA_Q));
-    if (a->dim_head == 32) launch_k(attention_mma_kernel<32>, dim3(grid), dim3(128), 0, st, *a);
-    else launch_k(attention_mma_kernel<64>, dim3(grid), dim3(128), 0, st, *a);
+    if (a->dim_head == 32) launch_k(attention_mma_kernel<32>, dim3(grid), dim3(256), 0, st, *a);
+    else launch_k(attention_mma_kernel<64>, dim3(grid), dim3(256), 0, st, *a);
     MV2_CHECK_LAUNCH();
     return MV2_OK;
   }
