@@ -1,21 +1,22 @@
 """Per-kernel-class time of one README tokenize+decode step (bf16, 4 clips), from a CUPTI trace (torch.profiler) of
 eager launches: warm-cache kernel durations, no launch gaps.  tcgen05 conv launches are matched in order with the
 engine's shape log so they can be grouped by layer class.
-Usage: python tools/step_breakdown.py [out.json]"""
+Usage: python tools/step_breakdown.py [out.json] [readme|cfg4|fsq]"""
 import json, os, sys, collections
 import torch
 from torch.profiler import profile, ProfilerActivity
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import README_KW
+from bench import README_KW, WORKLOADS
 from magvit2_pytorch_b200 import VideoTokenizer
 import synth_data as Wt
 
 STEPS = 3
-m = VideoTokenizer(**README_KW)
+WL = WORKLOADS[sys.argv[2]] if len(sys.argv) > 2 else WORKLOADS["readme"]
+m = VideoTokenizer(**WL["kw"])
 Wt.fill_state_dict_(m, 0)
 m = m.cuda().bfloat16().eval()
 m.cuda_graphs = False
-v = Wt.synth_video(4, 3, 17, 128, seed=5).cuda()
+v = Wt.synth_video(WL["clips"], 3, 17, WL["size"], seed=5).cuda()
 
 
 def step():
