@@ -78,6 +78,13 @@ int mv2_ingest_kwpack(const void* src, int src_dtype, void* dst, int B, int C, i
 int mv2_copy_frames(const void* src, void* dst, int B, int src_T, int dst_T, int src_t0, int dst_t0, int n_frames,
                     size_t frame_bytes, int zero_front, void* stream);
 
+/* mv2_pad_cl: explicit causal / spatial padding for CausalConv3d with pad_mode != 'constant' (reference M:925-927:
+ *   F.pad(x, (pw, pw, ph, ph, pt, 0), mode)): dst (B, T+pt, H+2ph, W+2pw, C) from src (B,T,H,W,C), channels-last;
+ *   mode 1 = 'reflect', 2 = 'replicate', 3 = 'circular'.  The conv then runs with zero leading padding on dst.
+ *   ('constant' never materialises its padding: TMA out-of-bounds fill / bounds checks.)                                   */
+int mv2_pad_cl(const void* src, void* dst, int dtype, int B, int T, int H, int W, int C, int pt, int ph, int pw, int mode,
+               void* stream);
+
 /* ---- convolution family (CUDA-core fp32-accumulate path; any shape) -----------
  * One generic strided N-d convolution over channels-last activations with a fused
  * epilogue  y = shuffle(act(conv(x) + bias)) + res.   Replaces

@@ -80,6 +80,7 @@ SIGNATURES = {
     "mv2_to_channels_first": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mv2_ingest_kwpack": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mv2_copy_frames": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _SZ, _I, _VP]),
+    "mv2_pad_cl": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "mv2_conv_forward": (_I, [C.POINTER(ConvArgs), _VP]),
     "mv2_se_workspace_bytes": (_SZ, [_I, _I, _I]),
     "mv2_se_pool": (_I, [_VP, _I, _I, _I, _I, _VP, _F, _VP, _VP]),

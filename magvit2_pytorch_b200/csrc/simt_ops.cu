@@ -918,6 +918,36 @@ __global__ void scale_channels_kernel(const T* __restrict__ x, const float* __re
 }
 
 // ------------------------------------------------------------------------------------------
+// explicit padding for CausalConv3d with pad_mode != 'constant' (M:925-927: F.pad(x, (pw, pw, ph, ph, kt-1, 0), mode))
+// dst (B, T + pt, H + 2 ph, W + 2 pw, C) <- src (B, T, H, W, C), channels-last; mode 1 reflect, 2 replicate, 3 circular
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pad_src_index(int i, int n, int mode) {
+  if (i >= 0 && i < n) return i;
+  if (mode == 1) { if (i < 0) i = -i; if (i >= n) i = 2 * (n - 1) - i; return i; }      // reflect (no edge repeat)
+  if (mode == 2) return i < 0 ? 0 : n - 1;                                             // replicate
+  i %= n;                                                                               // circular
+  return i < 0 ? i + n : i;
+}
+template <typename T>
+__global__ void pad_cl_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int Tn, int H, int W, int C, int pt, int ph,
+                              int pw, int mode) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int To = Tn + pt, Ho = H + 2 * ph, Wo = W + 2 * pw;
+  const int64_t total = (int64_t)B * To * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int c = (int)(r % C); r /= C;
+    const int w = (int)(r % Wo); r /= Wo;
+    const int h = (int)(r % Ho); r /= Ho;
+    const int t = (int)(r % To); r /= To;
+    const int b = (int)r;
+    const int ts = pad_src_index(t - pt, Tn, mode), hs = pad_src_index(h - ph, H, mode), ws = pad_src_index(w - pw, W, mode);
+    dst[i] = src[((((int64_t)b * Tn + ts) * H + hs) * W + ws) * C + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // RMSNorm (+ token shift addressing)
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -2271,6 +2301,22 @@ int mv2_copy_frames(const void* src, void* dst, int B, int src_T, int dst_T, int
   MV2_CHECK_CUDA(cudaMemcpy2DAsync((char*)dst + (size_t)dst_t0 * frame_bytes, (size_t)dst_T * frame_bytes,
                                    (const char*)src + (size_t)src_t0 * frame_bytes, (size_t)src_T * frame_bytes,
                                    (size_t)n_frames * frame_bytes, B, cudaMemcpyDeviceToDevice, st));
+  return MV2_OK;
+}
+
+int mv2_pad_cl(const void* src, void* dst, int dtype, int B, int T, int H, int W, int C, int pt, int ph, int pw, int mode,
+               void* stream) {
+  MV2_CHECK_ARG(src && dst && B > 0 && T > 0 && H > 0 && W > 0 && C > 0 && pt >= 0 && ph >= 0 && pw >= 0);
+  MV2_CHECK_ARG(mode >= 1 && mode <= 3);
+  if (mode == 1) MV2_CHECK_ARG(pt < T && ph < H && pw < W);          // torch's reflection padding requires pad < size
+  if (mode == 3) MV2_CHECK_ARG(pt <= T && ph <= H && pw <= W);
+  const int64_t total = (int64_t)B * (T + pt) * (H + 2 * ph) * (W + 2 * pw) * C;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32) launch_k(pad_cl_kernel<float>, dim3(blocks), dim3(256), 0, st, (const float*)src, (float*)dst, B, T, H, W, C, pt, ph, pw, mode);
+  else if (dtype == MV2_BF16) launch_k(pad_cl_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, B, T, H, W, C, pt, ph, pw, mode);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
+  MV2_CHECK_LAUNCH();
   return MV2_OK;
 }
 

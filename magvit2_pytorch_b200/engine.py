@@ -611,6 +611,21 @@ class Engine:
         self.launches += 1
         return out
 
+    _PAD_MODES = {"reflect": 1, "replicate": 2, "circular": 3}
+
+    def causal_conv_padded(self, x, pk, pad_mode):
+        """CausalConv3d with pad_mode != 'constant' (M:925-927): the padding is materialised by mv2_pad_cl, then the conv
+        runs without any implicit padding.  As in the reference the mode falls back to 'constant' when time_pad >= T."""
+        B, T, H, W, Cc = x.shape
+        kt, kh, kw = pk.k
+        if pad_mode == "constant" or kt - 1 >= T:
+            return self.conv(x, pk)
+        xp = self._new((B, T + kt - 1, H + 2 * (kh // 2), W + 2 * (kw // 2), Cc))
+        check(self.lib.mv2_pad_cl(_ptr(x), _ptr(xp), _dt(self.dtype), B, T, H, W, Cc, kt - 1, kh // 2, kw // 2,
+                                  self._PAD_MODES[pad_mode], self._stream()), "mv2_pad_cl")
+        self.launches += 1
+        return self.conv(xp, pk, pad=(0, 0, 0), out_spatial=(T, H, W))
+
     def copy_frames(self, src, t0, n, dst=None, dst_t0=0, zero_front=False):
         """Frames [t0, t0 + n) of a channels-last clip tensor -> a new (B, n, ...) tensor, or into ``dst`` at ``dst_t0``."""
         B, Ts = src.shape[:2]
@@ -645,10 +660,12 @@ class Engine:
             v_cl = self.to_channels_last(video, 0)
             parts = [(self.conv(self.copy_frames(v_cl, 0, 1), self._packs["conv_in_ff"]), t_pad)]
             if T > 1:
-                parts.append((self.conv(self.copy_frames(v_cl, 1, T - 1), self._packs["conv_in"]), t_pad + 1))
+                parts.append((self.causal_conv_padded(self.copy_frames(v_cl, 1, T - 1), self._packs["conv_in"], m.conv_in.pad_mode), t_pad + 1))
             x = self._new((B, T + t_pad, H, W, parts[0][0].shape[-1]))
             for i, (part, t0) in enumerate(parts):
                 self.copy_frames(part, 0, part.shape[1], dst=x, dst_t0=t0, zero_front=(i == 0))
+        elif m.conv_in.pad_mode != "constant":
+            x = self.causal_conv_padded(self.to_channels_last(video, t_pad), self._packs["conv_in"], m.conv_in.pad_mode)
         elif self.dtype == torch.bfloat16 and self.use_tc and pin is not None:
             x = self.ingest_kwpack(video, t_pad, pin)
             x = self.conv(x, pin, pad=(pin.k_tc[0] - 1, pin.k_tc[1] // 2, 0))
@@ -680,9 +697,11 @@ class Engine:
             out = self._new((B, T - tp, H, W, first.shape[-1]))
             self.copy_frames(first, 0, 1, dst=out, dst_t0=0)
             if T - tp > 1:
-                rest = self.conv(self.copy_frames(x, tp + 1, T - tp - 1), pk)
+                rest = self.causal_conv_padded(self.copy_frames(x, tp + 1, T - tp - 1), pk, m.conv_out.pad_mode)
                 self.copy_frames(rest, 0, T - tp - 1, dst=out, dst_t0=1)
             return self.to_channels_first(out)
+        if m.conv_out.pad_mode != "constant":
+            return self.to_channels_first(self.causal_conv_padded(x, pk, m.conv_out.pad_mode), t_crop=tp)
         if (self.dtype == torch.bfloat16 and self.use_tc and self.tc_variant != "tap" and self.fuse_conv_out and pk.w_tc is not None
                 and pk.Co % 8 != 0 and Cc % 64 == 0 and pk.k[2] <= 3 and T > tp):
             # conv_out writes the reconstruction in torch's (B,C,T,H,W) layout itself and never computes the time_padding

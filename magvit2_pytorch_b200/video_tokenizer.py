@@ -14,8 +14,7 @@ the compute dtype follows the parameters' dtype (``.float()`` -> fp32 CUDA-core 
 ``cond_residual`` layers (ResidualUnitMod / Conv3DMod, M:680-753, M:946-988) run on the device through the
 factorisation in include/magvit2_b200.h; the other ``cond_*`` types raise in the reference itself.
 ``separate_first_frame_encoding`` (M:1113-1120, M:1553-1561, M:1633-1639) runs through the same conv kernels.
-Out of scope (raise at construction / call): ``gateloop_time``, ``num_codebooks > 1``, ``lfq_spherical``,
-non-constant ``pad_mode``, the GAN / perceptual training losses (``return_loss`` /
+Out of scope (raise at construction / call): ``gateloop_time``, ``num_codebooks > 1``, ``lfq_spherical``, the GAN / perceptual training losses (``return_loss`` /
 ``return_discr_loss``), autograd.
 """
 from __future__ import annotations
@@ -124,8 +123,8 @@ class VideoTokenizer(nn.Module):
             raise NotImplementedError("num_codebooks > 1 is not supported")
         if lfq_spherical:
             raise NotImplementedError("lfq_spherical is not supported")
-        if pad_mode != "constant":
-            raise NotImplementedError("only pad_mode='constant' is supported")
+        if pad_mode not in ("constant", "reflect", "replicate", "circular"):
+            raise ValueError(f"unknown pad_mode {pad_mode!r}")
         if attn_dropout != 0.:
             raise NotImplementedError("attention dropout is a training feature")
         ks = residual_conv_kernel_size

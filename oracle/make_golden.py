@@ -74,6 +74,16 @@ CONFIGS = {
     # video_contains_first_frame=False (M:1528-1537, M:1646-1647, M:1691): 8 frames, no front padding, no crop
     "mini_noff": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, layers=README_LAYERS),
                       video=(2, 3, 8, 32, 32), wseed=0, vseed=1235, full=True, first_frame=False),
+    # pad_mode of conv_in / conv_out (M:925-927, M:1109, M:1127): F.pad modes other than 'constant'
+    "pad_reflect": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, pad_mode="reflect",
+                                    layers=("residual", "compress_space", "compress_time", "residual")),
+                        video=(2, 3, 9, 32, 32), wseed=0, vseed=1236, full=True),
+    "pad_replicate": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, pad_mode="replicate",
+                                      layers=("residual", "compress_space", "compress_time", "residual")),
+                          video=(2, 3, 9, 32, 32), wseed=0, vseed=1236, full=True),
+    "pad_circular": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, pad_mode="circular",
+                                     layers=("residual", "compress_space", "compress_time", "residual")),
+                         video=(2, 3, 9, 32, 32), wseed=0, vseed=1236, full=True),
     "mini_sff": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, separate_first_frame_encoding=True,
                                  layers=("residual", "compress_space", "compress_time", "residual")),
                      video=(2, 3, 5, 32, 32), wseed=0, vseed=1234, full=True),

@@ -92,6 +92,18 @@ def test_restated_no_first_frame_matches_reference_golden():
         orc.tokenize(video)                      # 8 frames with a first frame: (8 - 1) % 4 != 0  (M:1691)
 
 
+@pytest.mark.parametrize("mode", ["reflect", "replicate", "circular"])
+def test_restated_pad_modes_match_reference_goldens(mode):
+    """pad_mode of conv_in / conv_out (M:925-927, M:1109, M:1127)."""
+    g = load_golden("pad_" + mode)
+    assert g["kwargs"]["pad_mode"] == mode
+    model = build_product(g["kwargs"], g["wseed"])
+    orc = build_oracle(model, g["kwargs"])
+    codes = orc.tokenize(golden_video(g))
+    assert torch.equal(codes, g["codes"])
+    assert torch.allclose(orc.decode_from_code_indices(codes), g["recon"], atol=2e-5, rtol=1e-5)
+
+
 def test_restated_cond_residual_matches_reference_golden():
     """SURVEY 8f N1 groundwork: the conditioned residual unit (ResidualUnitMod / Conv3DMod, M:680-753, M:946-988) and the
     conditioning stems (M:1344-1352), pinned to the reference before any kernel is written for it."""

@@ -579,3 +579,22 @@ def test_separate_first_frame_encoding_vs_reference_golden(dtype):
         assert img.shape == (v.shape[0], 1, model.fmap_size, model.fmap_size)
     else:
         assert mism <= 0.1 and rerr < 0.1
+
+
+@pytest.mark.parametrize("mode", ["reflect", "replicate", "circular"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pad_modes_vs_reference_goldens(mode, dtype):
+    """pad_mode != 'constant' on conv_in / conv_out (M:925-927: F.pad(..., mode) before the conv) vs the reference goldens."""
+    _require_cuda()
+    g = load_golden("pad_" + mode)
+    model = build_product(g["kwargs"], g["wseed"]).cuda().to(dtype)
+    v = golden_video(g).cuda()
+    codes = model.tokenize(v)
+    recon = model.decode_from_code_indices(g["codes"].cuda())
+    mism = (codes.cpu() != g["codes"]).float().mean().item()
+    rerr = (recon.float().cpu() - g["recon"]).abs().max().item()
+    _report(f"pad_{mode}/{str(dtype).split('.')[-1]}", token_mismatch_rate=f"{mism:.4f}", recon_maxabs=f"{rerr:.3e}")
+    if dtype == torch.float32:
+        assert mism == 0 and rerr < FP32_RECON_TOL
+    else:
+        assert mism <= 0.08 and rerr < 0.08
