@@ -1611,14 +1611,30 @@ __device__ __forceinline__ void for_each_feature_pair(const float (&k)[LA_D], Fn
   }
 }
 
+// ldmatrix of four 8x8 b16 tiles, transposed: thread (g = lane / 4, t = lane % 4) receives, from the tile whose 8 row addresses
+// lanes 8j .. 8j+7 supplied, the elements [row 2t][col g] and [row 2t+1][col g]
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+constexpr int LAM_RS = LAM_F + 8;                                            // bf16 elements per token row (176 B: conflict-free)
+constexpr size_t LAM_REDUCE_SMEM = (size_t)2 * LAM_TB * LAM_RS * 2 + (size_t)16 * (LAM_TB + 8) * 2;   // phi hi + lo, v^T
+
 __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bfloat16* __restrict__ kv, float* __restrict__ ws,
                                                                  int L, int heads, int n_chunks) {
   pdl_wait();
   pdl_launch_dependents();
-  // phi is carried as a bf16 hi + lo pair (two MMAs) so the quadratic features keep ~16 mantissa bits; v is bf16 already
-  __shared__ __align__(16) __nv_bfloat16 phi_t[LAM_F][LAM_TB + 8];   // [feature][token] hi
-  __shared__ __align__(16) __nv_bfloat16 phi_l[LAM_F][LAM_TB + 8];   // lo = bf16(phi - hi)
-  __shared__ __align__(16) __nv_bfloat16 vt[16][LAM_TB + 8];         // [e][token]; e = 8 is the all-ones column
+  // phi is carried as a bf16 hi + lo pair (two MMAs) so the quadratic features keep ~16 mantissa bits; v is bf16 already.
+  // Token-major staging [token][feature] (one token per thread, 16-byte stores: a 176-byte row pitch puts the 32 rows of a warp
+  // in 8 distinct bank groups = the minimal 4 wavefronts per store); the MMA wants A = phi^T [feature][token], which
+  // ldmatrix.trans delivers straight from the token-major tile.  (The former feature-major layout needed 160 two-byte stores
+  // per token and was shared-memory wavefront bound: ncu L1/shared 80 %.)
+  extern __shared__ __align__(16) unsigned char lam_dyn[];
+  __nv_bfloat16 (*phi_s)[LAM_RS] = reinterpret_cast<__nv_bfloat16 (*)[LAM_RS]>(lam_dyn);                                // [token][feature] hi
+  __nv_bfloat16 (*phi_l)[LAM_RS] = reinterpret_cast<__nv_bfloat16 (*)[LAM_RS]>(lam_dyn + (size_t)LAM_TB * LAM_RS * 2);  // lo
+  __nv_bfloat16 (*vt)[LAM_TB + 8] = reinterpret_cast<__nv_bfloat16 (*)[LAM_TB + 8]>(lam_dyn + (size_t)2 * LAM_TB * LAM_RS * 2);   // [e][token]; e = 8: ones
   const int chunk = blockIdx.x, h = blockIdx.y;
   const int64_t seq = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1631,7 +1647,12 @@ __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bflo
     for (int b = 0; b < 2; ++b)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+#pragma unroll
+  for (int e = LA_D + 1; e < 16; ++e) vt[e][tid] = __float2bfloat16_rn(0.f);      // padding rows of the B operand: written once
   const int t_begin = chunk * LA_CHUNK, t_end = min(L, t_begin + LA_CHUNK);
+  // ldmatrix row address of this lane inside a 16-token x 16-feature block: tile j = lane / 8 covers tokens (j & 2 ? 8 : 0) + r,
+  // features (j & 1 ? 8 : 0) .. +7   ->   a[0], a[1], a[2], a[3] of the m16n8k16 A fragment (rows = features, k = tokens)
+  const int lm_tok = ((lane >> 3) & 2 ? 8 : 0) + (lane & 7), lm_feat = ((lane >> 3) & 1) ? 8 : 0;
   for (int t0 = t_begin; t0 < t_end; t0 += LAM_TB) {
     __syncthreads();
     {   // stage: thread = token
@@ -1653,20 +1674,23 @@ __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bflo
 #pragma unroll
         for (int q = 0; q < LA_D; ++q) { kk[q] = 0.f; vv[q] = 0.f; }
       }
+      uint32_t fh[LAM_F / 2], fl[LAM_F / 2];
       for_each_feature_pair<0>(kk, [&](int f, float a, float b) {
         a = ok ? a : 0.f;
         b = ok ? b : 0.f;
         const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-        phi_t[f][tid] = ah;
-        phi_t[f + 1][tid] = bh;
-        phi_l[f][tid] = __float2bfloat16_rn(a - __bfloat162float(ah));
-        phi_l[f + 1][tid] = __float2bfloat16_rn(b - __bfloat162float(bh));
+        __nv_bfloat162 hi; hi.x = ah; hi.y = bh;
+        fh[f >> 1] = *reinterpret_cast<uint32_t*>(&hi);
+        fl[f >> 1] = pack2_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
       });
+#pragma unroll
+      for (int v = 0; v < LAM_F / 8; ++v) {
+        *reinterpret_cast<uint4*>(&phi_s[tid][v * 8]) = make_uint4(fh[4 * v], fh[4 * v + 1], fh[4 * v + 2], fh[4 * v + 3]);
+        *reinterpret_cast<uint4*>(&phi_l[tid][v * 8]) = make_uint4(fl[4 * v], fl[4 * v + 1], fl[4 * v + 2], fl[4 * v + 3]);
+      }
 #pragma unroll
       for (int e = 0; e < LA_D; ++e) vt[e][tid] = __float2bfloat16_rn(vv[e]);
       vt[LA_D][tid] = __float2bfloat16_rn(ok ? 1.f : 0.f);
-#pragma unroll
-      for (int e = LA_D + 1; e < 16; ++e) vt[e][tid] = __float2bfloat16_rn(0.f);
     }
     __syncthreads();
     // each warp contracts its 32 tokens (2 k-steps of 16)
@@ -1682,24 +1706,18 @@ __global__ void __launch_bounds__(128) linattn_reduce_mma_kernel(const __nv_bflo
 #pragma unroll
       for (int mt = 0; mt < 5; ++mt) {
         uint32_t a[4];
-        a[0] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g][n0 + t * 2]);
-        a[1] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g + 8][n0 + t * 2]);
-        a[2] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g][n0 + 8 + t * 2]);
-        a[3] = *reinterpret_cast<const uint32_t*>(&phi_t[mt * 16 + g + 8][n0 + 8 + t * 2]);
+        ldmatrix_x4_trans(a, &phi_s[n0 + lm_tok][mt * 16 + lm_feat]);
         mma_bf16_16816(acc[mt][0], a, b[0][0], b[0][1]);
         mma_bf16_16816(acc[mt][1], a, b[1][0], b[1][1]);
-        a[0] = *reinterpret_cast<const uint32_t*>(&phi_l[mt * 16 + g][n0 + t * 2]);
-        a[1] = *reinterpret_cast<const uint32_t*>(&phi_l[mt * 16 + g + 8][n0 + t * 2]);
-        a[2] = *reinterpret_cast<const uint32_t*>(&phi_l[mt * 16 + g][n0 + 8 + t * 2]);
-        a[3] = *reinterpret_cast<const uint32_t*>(&phi_l[mt * 16 + g + 8][n0 + 8 + t * 2]);
+        ldmatrix_x4_trans(a, &phi_l[n0 + lm_tok][mt * 16 + lm_feat]);
         mma_bf16_16816(acc[mt][0], a, b[0][0], b[0][1]);
         mma_bf16_16816(acc[mt][1], a, b[1][0], b[1][1]);
       }
     }
   }
-  // cross-warp reduction through shared memory (reuse phi_t storage as fp32 [4][80*16]... too small: do it in 2 halves)
+  // cross-warp reduction through shared memory (the phi hi tile is reused as fp32 [4 warps][80 * 16]: 20480 B <= 22528 B)
   __syncthreads();
-  float* red = reinterpret_cast<float*>(&phi_t[0][0]);          // 80 * 136 * 2 B = 21760 B = 5440 floats >= 4 * 80 * 16 = 5120
+  float* red = reinterpret_cast<float*>(lam_dyn);
 #pragma unroll
   for (int mt = 0; mt < 5; ++mt)
 #pragma unroll
@@ -1744,6 +1762,7 @@ __global__ void __launch_bounds__(128) linattn_finalize_kernel(const float* __re
   }
 }
 
+constexpr int LAM_AB = 4;      // 64-token sub-blocks per apply block: the 5.6 KB state operand is loaded once per 256 tokens
 __global__ void __launch_bounds__(64) linattn_apply_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ sw,
                                                                __nv_bfloat16* __restrict__ out, int L, int heads) {
   pdl_wait();
@@ -1753,7 +1772,7 @@ __global__ void __launch_bounds__(64) linattn_apply_mma_kernel(const __nv_bfloat
   __shared__ __align__(16) __nv_bfloat16 phi_l[LAM_AT][LAM_F + 8];   // lo
   __shared__ __align__(16) __nv_bfloat16 st[16][LAM_F + 8];          // [e][feature] hi  (S transposed; e = 8 is the denominator)
   __shared__ __align__(16) __nv_bfloat16 sl[16][LAM_F + 8];          // lo
-  const int blk = blockIdx.x, h = blockIdx.y;
+  const int h = blockIdx.y;
   const int64_t seq = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -1765,67 +1784,81 @@ __global__ void __launch_bounds__(64) linattn_apply_mma_kernel(const __nv_bfloat
     constexpr int NV = LAM_SW / 8;
     for (int i = tid; i < NV; i += 64) { d0[i] = src[i]; d1[i] = src[NV + i]; }
   }
-  {
-    const int tok = blk * LAM_AT + tid;
-    const bool ok = tok < L;
-    float qq[LA_D];
-    if (ok) {
-      const uint4 qr = *reinterpret_cast<const uint4*>(q + (seq * L + tok) * HD + h * LA_D);
-      const __nv_bfloat162* qb = reinterpret_cast<const __nv_bfloat162*>(&qr);
-      const float qs = rsqrtf((float)LA_D);
+  for (int sb = 0; sb < LAM_AB; ++sb) {
+    const int blk = blockIdx.x * LAM_AB + sb;
+    if (blk * LAM_AT >= L) break;
+    __syncthreads();                 // the previous sub-block's fragment loads are done (first pass: state copy ordering below)
+    {
+      const int tok = blk * LAM_AT + tid;
+      const bool ok = tok < L;
+      float qq[LA_D];
+      if (ok) {
+        const uint4 qr = *reinterpret_cast<const uint4*>(q + (seq * L + tok) * HD + h * LA_D);
+        const __nv_bfloat162* qb = reinterpret_cast<const __nv_bfloat162*>(&qr);
+        const float qs = rsqrtf((float)LA_D);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 a = __bfloat1622float2(qb[i]);
-        qq[2 * i] = a.x * qs; qq[2 * i + 1] = a.y * qs;
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __bfloat1622float2(qb[i]);
+          qq[2 * i] = a.x * qs; qq[2 * i + 1] = a.y * qs;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < LA_D; ++i) qq[i] = 0.f;
       }
-    } else {
+      // the 80 features of this token, as 40 packed hi pairs + 40 packed lo pairs, written with 16-byte stores: a token row is
+      // 176 bytes, so the 32 rows of a warp start in 8 distinct bank groups and a 16-byte store takes the minimal 4 wavefronts
+      // (the former 4-byte stores were 4-way bank conflicted and dominated the kernel's shared-memory traffic)
+      uint32_t fh[LAM_F / 2], fl[LAM_F / 2];
+      for_each_feature_pair<0>(qq, [&](int f, float a, float b) {
+        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+        __nv_bfloat162 hi; hi.x = ah; hi.y = bh;
+        fh[f >> 1] = *reinterpret_cast<uint32_t*>(&hi);
+        fl[f >> 1] = pack2_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
+      });
 #pragma unroll
-      for (int i = 0; i < LA_D; ++i) qq[i] = 0.f;
-    }
-    for_each_feature_pair<0>(qq, [&](int f, float a, float b) {
-      const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-      __nv_bfloat162 hi; hi.x = ah; hi.y = bh;
-      *reinterpret_cast<__nv_bfloat162*>(&phi_s[tid][f]) = hi;
-      *reinterpret_cast<uint32_t*>(&phi_l[tid][f]) = pack2_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
-    });
-  }
-  __syncthreads();
-#pragma unroll
-  for (int mi = 0; mi < 2; ++mi) {
-    const int n0 = warp * 32 + mi * 16;
-    float c[2][4];
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) c[nt][j] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < LAM_F / 16; ++ks) {
-      uint32_t ah[4], al[4];
-      ah[0] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g][ks * 16 + t * 2]);
-      ah[1] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g + 8][ks * 16 + t * 2]);
-      ah[2] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g][ks * 16 + 8 + t * 2]);
-      ah[3] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g + 8][ks * 16 + 8 + t * 2]);
-      al[0] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g][ks * 16 + t * 2]);
-      al[1] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g + 8][ks * 16 + t * 2]);
-      al[2] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g][ks * 16 + 8 + t * 2]);
-      al[3] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g + 8][ks * 16 + 8 + t * 2]);
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&st[nt * 8 + g][ks * 16 + t * 2]);
-        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&st[nt * 8 + g][ks * 16 + 8 + t * 2]);
-        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&sl[nt * 8 + g][ks * 16 + t * 2]);
-        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&sl[nt * 8 + g][ks * 16 + 8 + t * 2]);
-        mma_bf16_16816(c[nt], ah, bh0, bh1);
-        mma_bf16_16816(c[nt], al, bh0, bh1);
-        mma_bf16_16816(c[nt], ah, bl0, bl1);
+      for (int v = 0; v < LAM_F / 8; ++v) {
+        *reinterpret_cast<uint4*>(&phi_s[tid][v * 8]) = make_uint4(fh[4 * v], fh[4 * v + 1], fh[4 * v + 2], fh[4 * v + 3]);
+        *reinterpret_cast<uint4*>(&phi_l[tid][v * 8]) = make_uint4(fl[4 * v], fl[4 * v + 1], fl[4 * v + 2], fl[4 * v + 3]);
       }
     }
-    // denominator = column 8 = c[1][0] (row g) / c[1][2] (row g+8) of the quad's t == 0 lane
-    const float d0 = fmaxf(__shfl_sync(0xffffffffu, c[1][0], lane & ~3), 1e-5f);
-    const float d1 = fmaxf(__shfl_sync(0xffffffffu, c[1][2], lane & ~3), 1e-5f);
-    const int r0 = blk * LAM_AT + n0 + g, r1 = r0 + 8;
-    if (r0 < L) *reinterpret_cast<uint32_t*>(out + (seq * L + r0) * HD + h * LA_D + t * 2) = pack2_bf16(c[0][0] / d0, c[0][1] / d0);
-    if (r1 < L) *reinterpret_cast<uint32_t*>(out + (seq * L + r1) * HD + h * LA_D + t * 2) = pack2_bf16(c[0][2] / d1, c[0][3] / d1);
+    __syncthreads();
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const int n0 = warp * 32 + mi * 16;
+      float c[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[nt][j] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < LAM_F / 16; ++ks) {
+        uint32_t ah[4], al[4];
+        ah[0] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g][ks * 16 + t * 2]);
+        ah[1] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g + 8][ks * 16 + t * 2]);
+        ah[2] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g][ks * 16 + 8 + t * 2]);
+        ah[3] = *reinterpret_cast<const uint32_t*>(&phi_s[n0 + g + 8][ks * 16 + 8 + t * 2]);
+        al[0] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g][ks * 16 + t * 2]);
+        al[1] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g + 8][ks * 16 + t * 2]);
+        al[2] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g][ks * 16 + 8 + t * 2]);
+        al[3] = *reinterpret_cast<const uint32_t*>(&phi_l[n0 + g + 8][ks * 16 + 8 + t * 2]);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&st[nt * 8 + g][ks * 16 + t * 2]);
+          const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&st[nt * 8 + g][ks * 16 + 8 + t * 2]);
+          const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&sl[nt * 8 + g][ks * 16 + t * 2]);
+          const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&sl[nt * 8 + g][ks * 16 + 8 + t * 2]);
+          mma_bf16_16816(c[nt], ah, bh0, bh1);
+          mma_bf16_16816(c[nt], al, bh0, bh1);
+          mma_bf16_16816(c[nt], ah, bl0, bl1);
+        }
+      }
+      // denominator = column 8 = c[1][0] (row g) / c[1][2] (row g+8) of the quad's t == 0 lane
+      const float d0 = fmaxf(__shfl_sync(0xffffffffu, c[1][0], lane & ~3), 1e-5f);
+      const float d1 = fmaxf(__shfl_sync(0xffffffffu, c[1][2], lane & ~3), 1e-5f);
+      const int r0 = blk * LAM_AT + n0 + g, r1 = r0 + 8;
+      if (r0 < L) *reinterpret_cast<uint32_t*>(out + (seq * L + r0) * HD + h * LA_D + t * 2) = pack2_bf16(c[0][0] / d0, c[0][1] / d0);
+      if (r1 < L) *reinterpret_cast<uint32_t*>(out + (seq * L + r1) * HD + h * LA_D + t * 2) = pack2_bf16(c[0][2] / d1, c[0][3] / d1);
+    }
   }
 }
 
@@ -2407,14 +2440,18 @@ int mv2_linear_attention(const void* q, const void* kv, void* out, int dtype, in
     MV2_CHECK_LAUNCH();
     launch_k(linattn_apply_kernel<float>, dim3(grid), dim3(64), 0, st, (const float*)q, (const float*)workspace, (float*)out, L, heads, nc);
   } else if (dtype == MV2_BF16 && (heads * LA_D) % 8 == 0) {
-    launch_k(linattn_reduce_mma_kernel, dim3(grid), dim3(128), 0, st, (const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
+    {
+      static PerDeviceOnce once;
+      MV2_CHECK_CUDA(once.run([] { return cudaFuncSetAttribute(linattn_reduce_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAM_REDUCE_SMEM); }));
+    }
+    launch_k(linattn_reduce_mma_kernel, dim3(grid), dim3(128), LAM_REDUCE_SMEM, st, (const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
     MV2_CHECK_LAUNCH();
     MV2_CHECK_LAUNCH();
     const size_t part_bytes = ((size_t)n_seq * heads * nc * LA_ST * sizeof(float) + 15) / 16 * 16;
     __nv_bfloat16* sw = reinterpret_cast<__nv_bfloat16*>((char*)workspace + part_bytes);
     launch_k(linattn_finalize_kernel, dim3(heads, n_seq), dim3(128), 0, st, (const float*)workspace, sw, heads, nc);
     MV2_CHECK_LAUNCH();
-    dim3 grid2(ceil_div(L, LAM_AT), heads, n_seq);
+    dim3 grid2(ceil_div(L, LAM_AT * LAM_AB), heads, n_seq);
     launch_k(linattn_apply_mma_kernel, dim3(grid2), dim3(64), 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)sw, (__nv_bfloat16*)out, L, heads);
   } else if (dtype == MV2_BF16) {
     launch_k(linattn_reduce_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)kv, (float*)workspace, L, heads, nc);
