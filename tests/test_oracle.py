@@ -182,8 +182,10 @@ def test_cond_layers_must_be_trailing_like_in_the_reference():
     with pytest.raises(TypeError):
         OracleTokenizer({}, image_size=32, init_dim=16, codebook_size=1024, dim_cond=8,
                         layers=("cond_residual", "residual"))
-    with pytest.raises(NotImplementedError):
-        build_product(dict(image_size=32, init_dim=16, codebook_size=1024, dim_cond=8, layers=("residual", "cond_residual")))
+    with pytest.raises(TypeError):       # the product rejects the same specs at construction
+        build_product(dict(image_size=32, init_dim=16, codebook_size=1024, dim_cond=8, layers=("cond_residual", "residual")))
+    m = build_product(dict(image_size=32, init_dim=16, codebook_size=1024, dim_cond=8, layers=("residual", "cond_residual")))
+    assert m.has_cond
 
 
 def test_readme_roundtrip_property():
