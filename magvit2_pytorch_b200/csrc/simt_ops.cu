@@ -9,6 +9,7 @@
 // Reference semantics are cited per entry point in include/magvit2_b200.h.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 #include <algorithm>
 
@@ -2175,6 +2176,10 @@ static int se_rows_per_block(int dtype, int F, int P, int C) {
   if (!(dtype == MV2_BF16 && se_online_vec(C) != 0)) return SE_CHUNK;
   // aim for >= ~8 blocks per SM while every row group still walks >= 4 rows (workspace holds ceil(P / SE_MIN_ROWS) records)
   const int R = 256 / (C / se_online_vec(C));
+  if (const char* env = getenv("MV2_SE_ROWS")) {     // tuning override (power of two, >= SE_MIN_ROWS)
+    const int v = atoi(env);
+    if (v >= SE_MIN_ROWS && v <= 4096 && (v & (v - 1)) == 0) return v;
+  }
   int rows = 512;
   while (rows > 4 * R && rows > SE_MIN_ROWS && (int64_t)F * ceil_div(P, rows) < 1184) rows >>= 1;
   while (rows < 2048 && (int64_t)F * ceil_div(P, 2 * rows) >= 1184) rows <<= 1;   // big layers: amortise the per-block merge
@@ -2385,7 +2390,13 @@ int mv2_rmsnorm(const void* x, void* out, int dtype, const float* gamma, int B, 
       const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
       __nv_bfloat16* ob = (__nv_bfloat16*)out;
       // (8 tokens per warp measured slower at C = 256: 188 -> 244 us per step, register pressure)
-      if (C <= 256) launch_k(rmsnorm_bf16x8_kernel<1, 4>, dim3(ceil_div(n_tok, 8 * 4)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
+      int tpw = 4;
+      if (const char* env = getenv("MV2_RN_TPW")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) tpw = v; }   // tuning override
+      if (C <= 256 && tpw == 1) launch_k(rmsnorm_bf16x8_kernel<1, 1>, dim3(ceil_div(n_tok, 8 * 1)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
+      else if (C <= 256 && tpw == 2) launch_k(rmsnorm_bf16x8_kernel<1, 2>, dim3(ceil_div(n_tok, 8 * 2)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
+      else if (C <= 256) launch_k(rmsnorm_bf16x8_kernel<1, 4>, dim3(ceil_div(n_tok, 8 * 4)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
+      else if (C <= 512 && tpw == 1) launch_k(rmsnorm_bf16x8_kernel<2, 1>, dim3(ceil_div(n_tok, 8 * 1)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
+      else if (C <= 512 && tpw == 2) launch_k(rmsnorm_bf16x8_kernel<2, 2>, dim3(ceil_div(n_tok, 8 * 2)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
       else if (C <= 512) launch_k(rmsnorm_bf16x8_kernel<2, 4>, dim3(ceil_div(n_tok, 8 * 4)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
       else launch_k(rmsnorm_bf16x8_kernel<4, 4>, dim3(ceil_div(n_tok, 8 * 4)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
     }
