@@ -97,3 +97,32 @@ def test_shape_asserts_follow_reference():
         m.decode_from_code_indices(torch.zeros(1, 3, 4, 4))   # float codes (M:1585)
     with pytest.raises(NotImplementedError):
         m(torch.randn(1, 3, 9, 32, 32), return_loss=True)
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: the product package, the neutral data helper and bench.py's product arm must not
+    import it (bench.py may, inside its CPU legs only)."""
+    import ast
+    import glob
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def oracle_imports(path):
+        tree = ast.parse(open(path).read())
+        hits = []
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in node.names):
+                hits.append(node.lineno)
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                hits.append(node.lineno)
+        return hits, tree
+
+    for path in glob.glob(os.path.join(root, "magvit2_pytorch_b200", "*.py")) + [os.path.join(root, "synth_data.py")]:
+        assert oracle_imports(path)[0] == [], path
+    hits, tree = oracle_imports(os.path.join(root, "bench.py"))
+    cpu_legs = {"_cpu_oracles", "run_reference_arm", "cpu_baseline_sample"}
+    allowed = set()
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in cpu_legs:
+            allowed.update(range(node.lineno, node.end_lineno + 1))
+    assert hits and all(h in allowed for h in hits), hits
