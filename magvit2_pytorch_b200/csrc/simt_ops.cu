@@ -2180,8 +2180,11 @@ static int se_rows_per_block(int dtype, int F, int P, int C) {
     const int v = atoi(env);
     if (v >= SE_MIN_ROWS && v <= 4096 && (v & (v - 1)) == 0) return v;
   }
+  // measured (profiles/r02_sweep_small.json; the inputs of these levels are L2 resident): chunks of 128 rows (64 when there are
+  // fewer than 40 frames) beat 32-row chunks by 15 - 30 %: fewer, longer bulk-copy pipelines and fewer records to merge
+  const int floor_rows = F >= 40 ? 128 : 64;
   int rows = 512;
-  while (rows > 4 * R && rows > SE_MIN_ROWS && (int64_t)F * ceil_div(P, rows) < 1184) rows >>= 1;
+  while (rows > 4 * R && rows > SE_MIN_ROWS && rows > floor_rows && (int64_t)F * ceil_div(P, rows) < 1184) rows >>= 1;
   while (rows < 2048 && (int64_t)F * ceil_div(P, 2 * rows) >= 1184) rows <<= 1;   // big layers: amortise the per-block merge
   return rows;
 }
@@ -2389,8 +2392,7 @@ int mv2_rmsnorm(const void* x, void* out, int dtype, const float* gamma, int B, 
     {
       const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
       __nv_bfloat16* ob = (__nv_bfloat16*)out;
-      // (8 tokens per warp measured slower at C = 256: 188 -> 244 us per step, register pressure)
-      int tpw = 4;
+      int tpw = 1;      // measured on the (L2-resident) README shapes, profiles/r02_sweep_small.json: 1 token per warp 23.7 / 14.4 us, 4: 27.7 / 20.3 us
       if (const char* env = getenv("MV2_RN_TPW")) { const int v = atoi(env); if (v == 1 || v == 2 || v == 4) tpw = v; }   // tuning override
       if (C <= 256 && tpw == 1) launch_k(rmsnorm_bf16x8_kernel<1, 1>, dim3(ceil_div(n_tok, 8 * 1)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
       else if (C <= 256 && tpw == 2) launch_k(rmsnorm_bf16x8_kernel<1, 2>, dim3(ceil_div(n_tok, 8 * 2)), dim3(256), 0, st, xb, ob, gamma, n_tok, T, P, C, token_shift);
