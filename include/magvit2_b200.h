@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MV2_ABI_VERSION 1
+#define MV2_ABI_VERSION 2   /* 2: mv2_conv_args.oscale, mv2_tc_conv_args.{oscale,out_layout}; round-2 entry points */
 
 enum { MV2_F32 = 0, MV2_BF16 = 1 };
 enum { MV2_ACT_NONE = 0, MV2_ACT_ELU = 1, MV2_ACT_SILU = 2 };

@@ -137,8 +137,8 @@ def load():
         fn.restype = res
         fn.argtypes = args
     ver = lib.mv2_abi_version()
-    if ver != 1:
-        raise Mv2Error(f"ABI version mismatch: library {ver}, binding 1")
+    if ver != 2:
+        raise Mv2Error(f"ABI version mismatch: library {ver}, binding 2")
     _lib = lib
     return lib
 
