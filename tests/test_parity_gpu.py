@@ -598,3 +598,20 @@ def test_pad_modes_vs_reference_goldens(mode, dtype):
         assert mism == 0 and rerr < FP32_RECON_TOL
     else:
         assert mism <= 0.08 and rerr < 0.08
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_readme_config_batch_independence(dtype):
+    """Eval forward has no cross-sample op: a 3-clip batch must give exactly the per-clip results, also for the
+    persistent-kernel tile schedules, the fused ResidualUnit records and the SE chunking, which all depend on the batch size."""
+    _require_cuda()
+    g = load_golden("readme")
+    model = build_product(g["kwargs"], g["wseed"]).cuda().to(dtype)
+    from oracle import weights as W
+    v = W.synth_video(3, 3, 17, 128, seed=4321).cuda()
+    codes = model.tokenize(v)
+    recon = model.decode_from_code_indices(codes)
+    for i in range(3):
+        ci = model.tokenize(v[i:i + 1])
+        assert torch.equal(ci, codes[i:i + 1]), i
+        assert torch.equal(model.decode_from_code_indices(ci), recon[i:i + 1]), i
