@@ -2173,20 +2173,19 @@ static int se_online_vec(int C) {
   return 0;
 }
 static int se_rows_per_block(int dtype, int F, int P, int C) {
+  (void)F;   // deliberately NOT a function of the frame count: the chunking fixes the summation order of the pooled vector, and
+             // a clip's tokens must not depend on how many other clips share its batch (tests: ..._batch_independence)
   if (!(dtype == MV2_BF16 && se_online_vec(C) != 0)) return SE_CHUNK;
-  // aim for >= ~8 blocks per SM while every row group still walks >= 4 rows (workspace holds ceil(P / SE_MIN_ROWS) records)
-  const int R = 256 / (C / se_online_vec(C));
   if (const char* env = getenv("MV2_SE_ROWS")) {     // tuning override (power of two, >= SE_MIN_ROWS)
     const int v = atoi(env);
     if (v >= SE_MIN_ROWS && v <= 4096 && (v & (v - 1)) == 0) return v;
   }
-  // measured (profiles/r02_sweep_small.json; the inputs of these levels are L2 resident): chunks of 128 rows (64 when there are
-  // fewer than 40 frames) beat 32-row chunks by 15 - 30 %: fewer, longer bulk-copy pipelines and fewer records to merge
-  const int floor_rows = F >= 40 ? 128 : 64;
-  int rows = 512;
-  while (rows > 4 * R && rows > SE_MIN_ROWS && rows > floor_rows && (int64_t)F * ceil_div(P, rows) < 1184) rows >>= 1;
-  while (rows < 2048 && (int64_t)F * ceil_div(P, 2 * rows) >= 1184) rows <<= 1;   // big layers: amortise the per-block merge
-  return rows;
+  // measured (profiles/r02_sweep_small.json, r01 se_pool notes): L2-resident small frames want 64 - 128-row chunks (fewer, longer
+  // bulk-copy pipelines, fewer records to merge than 32-row chunks: -15 .. -30 %); large frames amortise the per-block merge
+  if (P <= 256) return 64;
+  if (P <= 1024) return 128;
+  if (P <= 4096) return 512;
+  return 2048;
 }
 
 static cudaError_t se_pool_smem_optin() {
