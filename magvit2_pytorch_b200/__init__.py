@@ -4,7 +4,7 @@ Drop-in for ``magvit2_pytorch.VideoTokenizer`` inference (tokenize / decode_from
 forward) behind the C ABI of libmagvit2_b200.so.  See DESIGN.md / INTEGRATION.md.
 """
 from .video_tokenizer import VideoTokenizer, __version__  # noqa: F401
-from .host_io import HostRoundTrip  # noqa: F401
+from .host_io import HostRoundTrip, StreamLanes  # noqa: F401
 from . import _lib  # noqa: F401
 
-__all__ = ["VideoTokenizer", "HostRoundTrip"]
+__all__ = ["VideoTokenizer", "HostRoundTrip", "StreamLanes"]

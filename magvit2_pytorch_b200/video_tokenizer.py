@@ -263,6 +263,9 @@ class VideoTokenizer(nn.Module):
         # of the graph's static buffers.
         self.cuda_graphs = False
         self._graphs = {}
+        # graph-cache lane: calls issued under different lanes (host_io.StreamLanes: one CUDA stream per lane) replay
+        # separate graph instances with their own static buffers and memory pools, so they may overlap on the device
+        self._lane = 0
         # opt-in: programmatic dependent launch for every kernel of the path (mv2_set_pdl); process-wide library state
         self.pdl = False
 
@@ -358,7 +361,7 @@ class VideoTokenizer(nn.Module):
         if not self.cuda_graphs:
             return fn(*tensors)
         eng = self.engine
-        key = (name, eng._sig_id, tuple((tuple(t.shape), t.dtype) for t in tensors))
+        key = (name, eng._sig_id, tuple((tuple(t.shape), t.dtype) for t in tensors), self._lane)
         if any(k[1] != eng._sig_id for k in self._graphs):      # parameters were re-packed: old graphs read stale weights
             self._graphs = {k: v for k, v in self._graphs.items() if k[1] == eng._sig_id}
         ent = self._graphs.get(key)

@@ -321,8 +321,9 @@ def test_wide_channel_config_vs_oracle(dtype):
         assert rerr.mean().item() < 0.012 and rerr.max().item() < 0.06
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 3])
 @pytest.mark.parametrize("graphs", [False, True])
-def test_host_round_trip_matches_direct_calls(graphs):
+def test_host_round_trip_matches_direct_calls(graphs, lanes):
     """HostRoundTrip (pinned host buffers, copies overlapped on side streams) returns exactly what tokenize /
     decode_from_code_indices return for device inputs, for every in-flight slot and across slot reuse."""
     _require_cuda()
@@ -335,7 +336,7 @@ def test_host_round_trip_matches_direct_calls(graphs):
         c = model.tokenize(v.cuda())
         want.append((c.cpu(), model.decode_from_code_indices(c).cpu()))
     model.cuda_graphs = graphs
-    hrt = HostRoundTrip(model, depth=2)
+    hrt = HostRoundTrip(model, depth=max(2, lanes), lanes=lanes)
     outs = [(torch.empty_like(want[0][0]).pin_memory(), torch.empty_like(want[0][1]).pin_memory()) for _ in vids]
     for rep in range(2):
         evs = [hrt.submit(v, oc, ov) for v, (oc, ov) in zip(vids, outs)]
@@ -346,6 +347,35 @@ def test_host_round_trip_matches_direct_calls(graphs):
             assert torch.equal(ov, wv)
     with pytest.raises(ValueError):
         hrt.submit(vids[0].clone(), outs[0][0], outs[0][1])      # not pinned
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_stream_lanes_match_serial_calls(graphs):
+    """StreamLanes: calls issued round-robin on several CUDA streams (each lane replaying its own graph instances) return
+    exactly what the same calls return one after the other on the current stream."""
+    _require_cuda()
+    from magvit2_pytorch_b200 import StreamLanes
+    g = load_golden("mini")
+    model = build_product(g["kwargs"], g["wseed"]).cuda().bfloat16()
+    vids = [(golden_video(g) + 0.03 * i).cuda() for i in range(7)]
+
+    def step(v):
+        c = model.tokenize(v)
+        return c, model.decode_from_code_indices(c)
+
+    want = [step(v) for v in vids]
+    model.cuda_graphs = graphs
+    lanes = StreamLanes(model, 3)
+    for rep in range(3):                       # plain call, capture, replay on every lane
+        got = [lanes.run(step, v)[0] for v in vids]
+        lanes.join()
+        torch.cuda.synchronize()
+        for (gc, gv), (wc, wv) in zip(got, want):
+            assert torch.equal(gc, wc)
+            assert torch.equal(gv, wv)
+    if graphs:
+        assert len({k[3] for k in model._graphs}) == 3       # one set of graph instances per lane
+    assert model._lane == 0
 
 
 def test_copy_for_eval_after_graph_capture_and_repack():
