@@ -34,7 +34,8 @@ extern "C" {
 
 #define MV2_ABI_VERSION 2   /* 2: mv2_conv_args.oscale, mv2_tc_conv_args.{oscale,out_layout}; round-2 entry points */
 
-enum { MV2_F32 = 0, MV2_BF16 = 1 };
+enum { MV2_F32 = 0, MV2_BF16 = 1,
+       MV2_U8 = 2   /* source dtype of the two layout-in entry points only: decoded uint8 frames, normalised x / 255 */ };
 enum { MV2_ACT_NONE = 0, MV2_ACT_ELU = 1, MV2_ACT_SILU = 2 };
 enum { MV2_SHUFFLE_NONE = 0, MV2_SHUFFLE_SPACE = 1, MV2_SHUFFLE_TIME = 2 };
 enum {
@@ -200,6 +201,19 @@ int mv2_fsq_decode(const void* indices, int index_is_i64, int64_t N, int C, int 
  * stats and avg_prob must be zeroed by the caller.                                             */
 int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, float inv_temperature,
                              float* avg_prob, float* stats, void* stream);
+
+/* mv2_lfq_aux_finalize: out4 = {per_sample_entropy, batch_entropy, commitment, aux_loss} from the partial sums above
+ * (A.1 steps 7-10): per_sample = stats[0] / n_tokens, commitment = stats[1] / (n_tokens d),
+ * batch_entropy = sum_k -p_k log(max(p_k, 1e-5)), p = avg_prob_sum / n_tokens_global (avg_prob_sum = the cross-rank SUM),
+ * aux = (per_sample - diversity_gamma * batch_entropy) * entropy_weight + commitment * commitment_weight.             */
+int mv2_lfq_aux_finalize(const float* avg_prob_sum, const float* stats, int d, int64_t n_tokens, int64_t n_tokens_global,
+                         float diversity_gamma, float entropy_weight, float commitment_weight, float* out4, void* stream);
+
+/* ---- reconstruction loss (reference M:1722 F.mse_loss(video, recon_video)) ------------------
+ * out[0] = mean_i (a[i] - b[i])^2 over n elements of two same-layout tensors; a_dtype may be MV2_U8 (frames, x / 255).
+ * Deterministic (fixed-order two-stage reduction); workspace: mv2_mse_workspace_bytes() bytes.                          */
+int mv2_mse(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n, void* workspace, float* out, void* stream);
+size_t mv2_mse_workspace_bytes(void);
 
 /* ---- tcgen05 / TMA implicit-GEMM convolution (bf16 in, fp32 accumulate in TMEM) ------------
  * Same operator family and epilogue as mv2_conv_forward, for bf16 activations, executed on the

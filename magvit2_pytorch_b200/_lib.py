@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MV2_LIB_PATH") or os.path.join(_HERE, "libmagvit2_b200.so")   # env override: A/B builds
 
-MV2_F32, MV2_BF16 = 0, 1
+MV2_F32, MV2_BF16, MV2_U8 = 0, 1, 2
 ACT_NONE, ACT_ELU, ACT_SILU = 0, 1, 2
 SHUFFLE_NONE, SHUFFLE_SPACE, SHUFFLE_TIME = 0, 1, 2
 
@@ -98,6 +98,9 @@ SIGNATURES = {
     "mv2_fsq_forward": (_I, [_VP, _I, _I64, _I, _I, C.POINTER(C.c_int32), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mv2_fsq_decode": (_I, [_VP, _I, _I64, _I, _I, C.POINTER(C.c_int32), _VP, _VP, _VP, _I, _VP]),
     "mv2_lfq_entropy_partials": (_I, [_VP, _I64, _I, _F, _VP, _VP, _VP]),
+    "mv2_lfq_aux_finalize": (_I, [_VP, _VP, _I, _I64, _I64, _F, _F, _F, _VP, _VP]),
+    "mv2_mse": (_I, [_VP, _I, _VP, _I, _I64, _VP, _VP, _VP]),
+    "mv2_mse_workspace_bytes": (C.c_size_t, []),
     "mv2_tc_conv_supported": (_I, [C.POINTER(TcConvArgs)]),
     "mv2_tc_conv_forward": (_I, [C.POINTER(TcConvArgs), _VP]),
     "mv2_tc_slab_supported": (_I, [C.POINTER(TcConvArgs)]),

@@ -41,6 +41,9 @@ void set_error(const char* fmt, ...);
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+// MV2_U8 sources (decoded video frames): the data loaders' normalisation x / 255 (reference data.py:103 ToTensor,
+// data.py:188 `frames_torch /= 255.`) -- a correctly rounded fp32 division, so the result is bit-identical to theirs
+template <> __device__ __forceinline__ float to_f32<uint8_t>(uint8_t v) { return __fdiv_rn((float)v, 255.f); }
 
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }

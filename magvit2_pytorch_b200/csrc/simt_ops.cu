@@ -99,6 +99,10 @@ static int dispatch_transpose(const void* src, int sd, void* dst, int dd, int B,
     return launch_transpose<__nv_bfloat16, float>(src, dst, B, R, S, src_S_total, dst_S_total, s_off_src, s_off_dst, src_is_rs, st);
   if (sd == MV2_BF16 && dd == MV2_BF16)
     return launch_transpose<__nv_bfloat16, __nv_bfloat16>(src, dst, B, R, S, src_S_total, dst_S_total, s_off_src, s_off_dst, src_is_rs, st);
+  if (sd == MV2_U8 && dd == MV2_F32)
+    return launch_transpose<uint8_t, float>(src, dst, B, R, S, src_S_total, dst_S_total, s_off_src, s_off_dst, src_is_rs, st);
+  if (sd == MV2_U8 && dd == MV2_BF16)
+    return launch_transpose<uint8_t, __nv_bfloat16>(src, dst, B, R, S, src_S_total, dst_S_total, s_off_src, s_off_dst, src_is_rs, st);
   set_error("unsupported dtype pair %d -> %d", sd, dd);
   return MV2_E_ARG;
 }
@@ -2064,6 +2068,84 @@ __global__ void __launch_bounds__(256) lfq_entropy_kernel(const float* __restric
   if (tid == 0) atomicAdd(&stats[1], commit_sum);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// reconstruction loss F.mse_loss(video, recon_video) (reference M:1722): mean over all elements of (a - b)^2.
+// Deterministic two-stage reduction: MSE_BLOCKS blocks accumulate strided fp32 partial sums (one double per block),
+// then one warp folds the block partials in a fixed order.  a may be MV2_U8 (frames, x / 255).
+// ------------------------------------------------------------------------------------------
+constexpr int MSE_BLOCKS = 592;      // 4 per SM
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256) mse_partial_kernel(const TA* __restrict__ a, const TB* __restrict__ b, int64_t n,
+                                                          double* __restrict__ partials) {
+  pdl_wait();
+  pdl_launch_dependents();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float dlt = to_f32<TA>(a[i + u * stride]) - to_f32<TB>(b[i + u * stride]);
+      acc[u] = fmaf(dlt, dlt, acc[u]);
+    }
+  }
+  for (; i < n; i += stride) {
+    const float dlt = to_f32<TA>(a[i]) - to_f32<TB>(b[i]);
+    acc[0] = fmaf(dlt, dlt, acc[0]);
+  }
+  double t = (double)acc[0] + (double)acc[1] + (double)acc[2] + (double)acc[3];
+  __shared__ double sw[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += sw[w];
+    partials[blockIdx.x] = r;
+  }
+}
+
+__global__ void __launch_bounds__(32) mse_final_kernel(const double* __restrict__ partials, int nb, double inv_n, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  double t = 0.0;
+  for (int k = threadIdx.x; k < nb; k += 32) t += partials[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (threadIdx.x == 0) out[0] = (float)(t * inv_n);
+}
+
+// LFQ auxiliary loss from the (all-reduced) partial sums (A.1 steps 7-10):
+//   per_sample = stats[0] / N, commitment = stats[1] / (N d), batch_entropy = sum_k -p_k log(max(p_k, 1e-5)) with
+//   p = avg_prob_sum / (N_global), aux = (per_sample - gamma * batch_entropy) * w_entropy + commitment * w_commit.
+// out[0..3] = per_sample, batch_entropy, commitment, aux.
+__global__ void __launch_bounds__(256) lfq_aux_final_kernel(const float* __restrict__ avg_prob_sum, const float* __restrict__ stats, int K,
+                                                            float inv_tokens_global, float inv_tokens, float inv_elems, float gamma,
+                                                            float w_entropy, float w_commit, float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  float t = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    const float p = avg_prob_sum[k] * inv_tokens_global;
+    t += -p * logf(fmaxf(p, 1e-5f));
+  }
+  __shared__ float sw[8];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float be = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) be += sw[w];
+    const float ps = stats[0] * inv_tokens, cm = stats[1] * inv_elems;
+    out[0] = ps; out[1] = be; out[2] = cm;
+    out[3] = (ps - gamma * be) * w_entropy + cm * w_commit;
+  }
+}
+
 }  // namespace mv2
 
 // ==========================================================================================
@@ -2135,6 +2217,8 @@ int mv2_ingest_kwpack(const void* src, int src_dtype, void* dst, int B, int C, i
     launch_k(ingest_kwpack_kernel<float>, dim3(blocks), dim3(256), smem, st, (const float*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
   else if (src_dtype == MV2_BF16)
     launch_k(ingest_kwpack_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), smem, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
+  else if (src_dtype == MV2_U8)
+    launch_k(ingest_kwpack_kernel<uint8_t>, dim3(blocks), dim3(256), smem, st, (const uint8_t*)src, (__nv_bfloat16*)dst, B, C, T, H, W, t_pad, kw, pw, cpack);
   else { set_error("bad dtype %d", src_dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
@@ -2558,6 +2642,36 @@ int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, float inv_t
   const int K = 1 << d;
   const int blocks = ceil_div(N, LE_TOK);
   launch_k(lfq_entropy_kernel, dim3(blocks), dim3(256), K * sizeof(float), (cudaStream_t)stream, presign, N, d, inv_temperature, avg_prob, stats);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_mse(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n, void* workspace, float* out, void* stream) {
+  MV2_CHECK_ARG(a && b && workspace && out && n > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* part = (double*)workspace;
+  const int nb = (int)std::min<int64_t>(MSE_BLOCKS, ceil_div(n, (int64_t)256));
+#define MV2_MSE_CASE(DA, TA, DB, TB) \
+  else if (a_dtype == DA && b_dtype == DB) launch_k(mse_partial_kernel<TA, TB>, dim3(nb), dim3(256), 0, st, (const TA*)a, (const TB*)b, n, part)
+  if (false) {}
+  MV2_MSE_CASE(MV2_F32, float, MV2_F32, float); MV2_MSE_CASE(MV2_F32, float, MV2_BF16, __nv_bfloat16);
+  MV2_MSE_CASE(MV2_BF16, __nv_bfloat16, MV2_F32, float); MV2_MSE_CASE(MV2_BF16, __nv_bfloat16, MV2_BF16, __nv_bfloat16);
+  MV2_MSE_CASE(MV2_U8, uint8_t, MV2_F32, float); MV2_MSE_CASE(MV2_U8, uint8_t, MV2_BF16, __nv_bfloat16);
+  else { set_error("mse: unsupported dtype pair %d, %d", a_dtype, b_dtype); return MV2_E_ARG; }
+#undef MV2_MSE_CASE
+  MV2_CHECK_LAUNCH();
+  launch_k(mse_final_kernel, dim3(1), dim3(32), 0, st, (const double*)part, nb, 1.0 / (double)n, out);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+size_t mv2_mse_workspace_bytes(void) { return (size_t)MSE_BLOCKS * sizeof(double); }
+
+int mv2_lfq_aux_finalize(const float* avg_prob_sum, const float* stats, int d, int64_t n_tokens, int64_t n_tokens_global,
+                         float diversity_gamma, float entropy_weight, float commitment_weight, float* out4, void* stream) {
+  MV2_CHECK_ARG(avg_prob_sum && stats && out4 && d > 0 && d <= 12 && n_tokens > 0 && n_tokens_global > 0);
+  launch_k(lfq_aux_final_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, avg_prob_sum, stats, 1 << d,
+           (float)(1.0 / (double)n_tokens_global), (float)(1.0 / (double)n_tokens), (float)(1.0 / ((double)n_tokens * d)),
+           diversity_gamma, entropy_weight, commitment_weight, out4);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

@@ -78,16 +78,25 @@ class LfqBatchEntropy:
                   "mv2_lfq_entropy_partials")
             eng.launches += 1
             avg.div_(N)                       # local mean code probability
-            allreduce_mean_(avg, group)       # the one collective of the path (NCCL, 4 KiB)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                dist.all_reduce(avg, op=dist.ReduceOp.SUM, group=group)    # the one collective of the path (NCCL, 4 KiB)
         presign.record_stream(self.side)
         self._pending = (avg, stats, N, d)
 
-    def finish(self, diversity_gamma=2.5, entropy_w=0.1, commit_w=1.0):
+    def finish(self, diversity_gamma=2.5, entropy_w=0.1, commit_w=1.0, group=None):
+        """-> (per_sample_entropy, batch_entropy, commitment, aux_loss) as 0-d fp32 tensors (views of one 4-float result of
+        mv2_lfq_aux_finalize).  `avg` holds the SUM over ranks of the per-rank mean code probabilities (start() divides by the
+        local token count before the all-reduce, as the reference's maybe_distributed_mean does), so p = avg / world."""
+        from ._lib import check
         avg, stats, N, d = self._pending
-        torch.cuda.current_stream(self.eng.device).wait_stream(self.side)
-        per_sample = stats[0] / N
-        commitment = stats[1] / (N * d)
-        batch_entropy = entropy_from_avg_prob(avg)
-        aux = (per_sample - diversity_gamma * batch_entropy) * entropy_w + commitment * commit_w
+        eng = self.eng
+        cur = torch.cuda.current_stream(eng.device)
+        cur.wait_stream(self.side)
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        out = torch.empty(4, device=avg.device, dtype=torch.float32)
+        # avg is already a per-rank mean: "tokens_global" = number of ranks summed; per-rank terms use the local N
+        check(eng.lib.mv2_lfq_aux_finalize(avg.data_ptr(), stats.data_ptr(), d, N, world, float(diversity_gamma), float(entropy_w),
+                                           float(commit_w), out.data_ptr(), C.c_void_p(cur.cuda_stream)), "mv2_lfq_aux_finalize")
+        eng.launches += 1
         self._pending = None
-        return per_sample, batch_entropy, commitment, aux
+        return out[0], out[1], out[2], out[3]

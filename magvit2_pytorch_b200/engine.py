@@ -15,7 +15,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_ELU, ACT_NONE, ACT_SILU, MV2_BF16, MV2_F32, SHUFFLE_NONE, SHUFFLE_SPACE,
+from ._lib import (ACT_ELU, ACT_NONE, ACT_SILU, MV2_BF16, MV2_F32, MV2_U8, SHUFFLE_NONE, SHUFFLE_SPACE,
                    SHUFFLE_TIME, AttnArgs, ConvArgs, TcConvArgs, TcRuArgs, check)
 
 
@@ -25,6 +25,11 @@ def _dt(t: torch.dtype) -> int:
     if t == torch.bfloat16:
         return MV2_BF16
     raise TypeError(f"unsupported dtype {t} (only float32 and bfloat16)")
+
+
+def _src_dt(t: torch.dtype) -> int:
+    """dtype code of a layout-in SOURCE tensor: uint8 frames are accepted there (normalised x / 255 on the fly)."""
+    return MV2_U8 if t == torch.uint8 else _dt(t)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -588,25 +593,26 @@ class Engine:
 
     # ------------------------------------------------------------------ layout
     def to_channels_last(self, v: torch.Tensor, t_pad: int = 0):
-        """(B,C,T,H,W) torch tensor (fp32 or bf16) -> (B,T+t_pad,H,W,C) compute dtype."""
-        if v.dtype not in (torch.float32, torch.bfloat16):
+        """(B,C,T,H,W) torch tensor (fp32, bf16, or uint8 frames: normalised x / 255 as the reference's data loaders do,
+        D:103, D:188) -> (B,T+t_pad,H,W,C) compute dtype."""
+        if v.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
             v = v.float()
         v = v.contiguous()
         B, Cc, T, H, W = v.shape
         out = self._new((B, T + t_pad, H, W, Cc))
-        check(self.lib.mv2_to_channels_last(_ptr(v), _dt(v.dtype), _ptr(out), _dt(self.dtype), B, Cc, T, H, W, t_pad,
+        check(self.lib.mv2_to_channels_last(_ptr(v), _src_dt(v.dtype), _ptr(out), _dt(self.dtype), B, Cc, T, H, W, t_pad,
                                             self._stream()), "mv2_to_channels_last")
         self.launches += 1
         return out
 
     def ingest_kwpack(self, v: torch.Tensor, t_pad: int, pin):
         """(B,C,T,H,W) -> (B,T+t_pad,H,W,32) bf16 with the k_w taps packed into channels (mv2_ingest_kwpack)."""
-        if v.dtype not in (torch.float32, torch.bfloat16):
+        if v.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
             v = v.float()
         v = v.contiguous()
         B, Cc, T, H, W = v.shape
         out = self._new((B, T + t_pad, H, W, pin.Ci_tc), torch.bfloat16)
-        check(self.lib.mv2_ingest_kwpack(_ptr(v), _dt(v.dtype), _ptr(out), B, Cc, T, H, W, t_pad, pin.kw_orig,
+        check(self.lib.mv2_ingest_kwpack(_ptr(v), _src_dt(v.dtype), _ptr(out), B, Cc, T, H, W, t_pad, pin.kw_orig,
                                          pin.kw_orig // 2, pin.Ci_tc, self._stream()), "mv2_ingest_kwpack")
         self.launches += 1
         return out
@@ -645,6 +651,19 @@ class Engine:
                                              self._stream()), "mv2_to_channels_first")
         self.launches += 1
         return out
+
+    def mse(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """F.mse_loss(a, b) of two same-layout tensors (reference M:1722: video vs reconstruction, both (B,C,T,H,W)) as a 0-d
+        fp32 tensor; `a` may hold uint8 frames (x / 255)."""
+        assert a.shape == b.shape, (a.shape, b.shape)
+        if a.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
+            a = a.float()
+        a, b = a.contiguous(), b.contiguous()
+        ws = self._new((self.lib.mv2_mse_workspace_bytes() // 4,), torch.float32)
+        out = self._new((1,), torch.float32)
+        check(self.lib.mv2_mse(_ptr(a), _src_dt(a.dtype), _ptr(b), _dt(b.dtype), a.numel(), _ptr(ws), _ptr(out), self._stream()), "mv2_mse")
+        self.launches += 2
+        return out[0]
 
     # ------------------------------------------------------------------ the path
     def encode_cl(self, video: torch.Tensor, first_frame: bool = True, cond=None):

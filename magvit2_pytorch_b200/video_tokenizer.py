@@ -23,6 +23,7 @@ import contextlib
 import copy
 import functools
 import pickle
+from collections import namedtuple
 from dataclasses import dataclass
 from pathlib import Path
 from typing import List, Optional, Tuple
@@ -34,6 +35,12 @@ from . import modules as M
 from .engine import Engine
 
 __version__ = "0.1.0"
+
+
+# reference M:1028-1037
+LossBreakdown = namedtuple("LossBreakdown", [
+    "recon_loss", "lfq_aux_loss", "quantizer_loss_breakdown", "perceptual_loss", "adversarial_gen_loss",
+    "adaptive_adversarial_weight", "multiscale_gen_losses", "multiscale_gen_adaptive_weights"])
 
 
 @dataclass
@@ -489,7 +496,7 @@ class VideoTokenizer(nn.Module):
         q = self.quantizers
         be = LfqBatchEntropy(eng)
         be.start(pre, group)
-        ps, bent, commit, aux = be.finish(q.diversity_gamma, q.entropy_loss_weight, q.commitment_loss_weight)
+        ps, bent, commit, aux = be.finish(q.diversity_gamma, q.entropy_loss_weight, q.commitment_loss_weight, group)
         return codes, (ps, bent, commit), aux
 
     def _forward_train_mode(self, eng, video, need_recon, ff=True, group=None):
@@ -514,7 +521,7 @@ class VideoTokenizer(nn.Module):
         be = LfqBatchEntropy(eng)
         be.start(pre, group)                                   # partial sums + all-reduce on the side stream ...
         recon = self._graph_call("train_dec" + sfx, lambda t: eng.decode_cl(t, ff), res[2]) if need_recon else None   # ... under the decoder
-        ps, bent, commit, aux = be.finish(qz.diversity_gamma, qz.entropy_loss_weight, qz.commitment_loss_weight)
+        ps, bent, commit, aux = be.finish(qz.diversity_gamma, qz.entropy_loss_weight, qz.commitment_loss_weight, group)
         self.quantizer_loss_breakdown = (ps, bent, commit)
         self.quantizer_aux_loss = aux
         return (codes, recon) if need_recon else codes
@@ -530,17 +537,23 @@ class VideoTokenizer(nn.Module):
                 return_discr_loss=False, return_recon_loss_only=False, apply_gradient_penalty=True,
                 video_contains_first_frame=True, adversarial_loss_weight=None,
                 multiscale_adversarial_loss_weight=None):
-        """Inference returns of the reference forward (M:1657-1720)."""
+        """The reference forward (M:1657-1896): inference returns (codes / reconstruction), ``return_recon_loss_only`` and --
+        for models without the GAN / perceptual branches (``use_gan=False, perceptual_loss_weight=0``) -- ``return_loss``:
+        ``(total_loss, LossBreakdown)`` with ``total_loss = recon_loss + aux_loss * quantizer_aux_loss_weight`` (M:1868-1896)."""
         assert (return_loss + return_codes + return_discr_loss) <= 1               # M:1674
-        if return_loss or return_discr_loss:
+        if return_discr_loss:
+            raise NotImplementedError("the GAN discriminator losses (reference M:1728-1786) are outside the accelerated path "
+                                      "(SURVEY.md 8f N2)")
+        if return_loss and self._needs_gan_or_vgg():
             raise NotImplementedError(
-                "training losses (GAN / perceptual / adaptive weighting, reference M:1722-1896) are outside the "
-                "accelerated inference path (SURVEY.md 8f N2)")
+                "return_loss with the GAN / perceptual / adaptive-weighting terms (reference M:1788-1866) is outside the "
+                "accelerated path (SURVEY.md 8f N2): construct with use_gan=False, perceptual_loss_weight=0.")
         video, ff = self._check_video(video_or_images, video_contains_first_frame)
         cond = self._check_cond(cond, video.shape[0])
         with torch.no_grad():
             eng = self.engine
-            need_recon = return_recon or return_recon_loss_only or not return_codes
+            need_recon = return_recon or return_recon_loss_only or return_loss or not return_codes
+            aux = None
 
             def run(v, cd=None):
                 x = eng.encode_cl(v, ff, cd)
@@ -554,6 +567,7 @@ class VideoTokenizer(nn.Module):
                                        video.contiguous(), cond.contiguous())
             elif self.training and not self.use_fsq:
                 out = self._forward_train_mode(eng, video.contiguous(), need_recon, ff)
+                aux = self.quantizer_aux_loss
             else:
                 out = self._graph_call(("fwd_recon" if need_recon else "fwd_codes") + ("" if ff else "_noff"), run, video.contiguous())
             if return_codes and not return_recon:
@@ -561,7 +575,23 @@ class VideoTokenizer(nn.Module):
             codes, recon = out
             if return_codes:
                 return codes, recon                                                # M:1714-1715
-            if return_recon_loss_only:                                             # M:1722-1727
-                loss = torch.nn.functional.mse_loss(video.float(), recon.float())
-                return loss, recon
-            return recon                                                           # M:1719-1720
+            if not (return_loss or return_recon_loss_only):
+                return recon                                                       # M:1719-1720
+            recon_loss = eng.mse(video, recon).to(self.dtype)                      # M:1722
+            if return_recon_loss_only:                                             # M:1726-1727
+                return recon_loss, recon
+            # M:1868-1896 with perceptual_loss = gen_loss = zero, adaptive_weight = 0., no multiscale discriminators
+            zero = self.zero
+            aux_losses = zero if aux is None else aux.to(recon_loss.dtype)         # eval mode / FSQ: M:1700-1703
+            total_loss = recon_loss + aux_losses * self.quantizer_aux_loss_weight
+            qlb = None if (self.use_fsq or aux is None) else self.quantizer_loss_breakdown
+            return total_loss, LossBreakdown(recon_loss, aux_losses, qlb, zero, zero, 0., [], [])
+
+    def _needs_gan_or_vgg(self) -> bool:
+        """True when the reference constructor would have built a VGG (M:1392) or discriminators (M:1427, M:1435)."""
+        return bool((self.channels in {1, 3, 4} and self.perceptual_loss_weight > 0.)
+                    or (self.use_gan and self.adversarial_loss_weight > 0.) or self.has_multiscale_discrs)
+
+    @property
+    def dtype(self):
+        return self.conv_in.conv.weight.dtype

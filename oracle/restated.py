@@ -448,8 +448,7 @@ class OracleTokenizer:
             raise ValueError(st.kind)
         return x
 
-    @torch.no_grad()
-    def encode(self, video, taps=None, cond=None, video_contains_first_frame=True):
+    def _encode(self, video, taps=None, cond=None, video_contains_first_frame=True):
         """VideoTokenizer.encode (M:1523-1576).  NB the final LayerNorm (M:1322-1326) is never
         executed: zip() with has_cond_across_layers truncates it (M:1565).  Without a first frame
         (video_contains_first_frame=False) the clip is neither front-padded nor split (M:1530-1537)."""
@@ -477,8 +476,7 @@ class OracleTokenizer:
                 taps[f"enc{i}"] = x
         return x
 
-    @torch.no_grad()
-    def decode(self, quantized, taps=None, cond=None, video_contains_first_frame=True):
+    def _decode(self, quantized, taps=None, cond=None, video_contains_first_frame=True):
         """VideoTokenizer.decode (M:1598-1649): decoder layers are the encoder's in reverse
         (insert(0), M:1315); conv_out; drop the first time_padding frames (M:1646-1647) when the clip had a first frame."""
         x = quantized.to(self.dtype)
@@ -496,6 +494,45 @@ class OracleTokenizer:
             return torch.cat((first[:, :, None], rest), dim=2)
         x = causal_conv3d(x, self.sd["conv_out.conv.weight"], self.sd["conv_out.conv.bias"], self.pad_mode)
         return x[:, :, self.time_padding:] if video_contains_first_frame else x
+
+    @torch.no_grad()
+    def encode(self, *a, **k):
+        return self._encode(*a, **k)
+
+    @torch.no_grad()
+    def decode(self, *a, **k):
+        return self._decode(*a, **k)
+
+    def loss_forward(self, video, train: bool, world_reduce=None, lfq_entropy_loss_weight=0.1, lfq_commitment_loss_weight=1.,
+                     lfq_diversity_gamma=2.5, quantizer_aux_loss_weight=1.):
+        """forward(video, return_loss=True) of a tokenizer built with use_gan=False, perceptual_loss_weight=0 (M:1695-1727,
+        M:1868-1896): total_loss = recon_loss + aux_loss * quantizer_aux_loss_weight.  Differentiable: with state_dict tensors
+        that require grad, ``out["total_loss"].backward()`` yields the parameter gradients the trainer consumes (T:356-363).
+        train=True is the LFQ training branch (M:1705; A.1 steps 6-8, 10: straight-through output, entropy + commitment terms);
+        train=False (and FSQ) has zero auxiliary loss (M:1700-1703)."""
+        video, ff = self._check_video(video, True)
+        x = self._encode(video, video_contains_first_frame=ff)
+        out = {}
+        if self.use_fsq or not train:
+            q, idx, _ = (fsq_quantize if self.use_fsq else lfq_quantize)(x, self.sd, *( (self.fsq_levels,) if self.use_fsq else (self.clamp,) ))
+            aux = torch.zeros((), dtype=video.dtype)
+        else:
+            b, c, t, h, w = x.shape
+            p = lfq_presign(x, self.sd, self.clamp)                          # (B, N, d) fp32, differentiable
+            qd = torch.where(p > 0, torch.ones_like(p), -torch.ones_like(p))
+            st = p + (qd - p).detach()                                       # straight-through (A.1 step 6)
+            d_bits = p.shape[-1]
+            ps, be, cm, aux, _ = lfq_train_losses(p, d_bits, world_reduce, 100., lfq_diversity_gamma, lfq_entropy_loss_weight,
+                                                  lfq_commitment_loss_weight)
+            out.update(per_sample_entropy=ps, batch_entropy=be, commitment=cm)
+            q = F.linear(st.to(x.dtype), self.sd["quantizers.project_out.weight"], self.sd["quantizers.project_out.bias"])
+            q = q.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
+            mask = self.sd["quantizers.mask"].to(torch.int32)
+            idx = ((qd > 0).int() * mask).sum(dim=-1).reshape(b, t, h, w)
+        recon = self._decode(q, video_contains_first_frame=ff)
+        recon_loss = F.mse_loss(video.to(recon.dtype), recon)                # M:1722
+        out.update(codes=idx, recon=recon, recon_loss=recon_loss, aux=aux, total_loss=recon_loss + aux * quantizer_aux_loss_weight)
+        return out
 
     @torch.no_grad()
     def quantize(self, x):

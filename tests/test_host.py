@@ -95,8 +95,14 @@ def test_shape_asserts_follow_reference():
         m.tokenize(torch.randn(1, 3, 9, 16, 16))     # wrong image size (M:1677)
     with pytest.raises(AssertionError):
         m.decode_from_code_indices(torch.zeros(1, 3, 4, 4))   # float codes (M:1585)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):         # default ctor: use_gan=True, perceptual_loss_weight=0.1 -> GAN / VGG terms
         m(torch.randn(1, 3, 9, 32, 32), return_loss=True)
+    with pytest.raises(NotImplementedError):
+        m(torch.randn(1, 3, 9, 32, 32), return_discr_loss=True)
+    m2 = build_product(dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, layers=README_LAYERS, use_gan=False,
+                            perceptual_loss_weight=0.))
+    with pytest.raises(RuntimeError):                # supported there, but a CPU-resident model has no kernels to run
+        m2(torch.randn(1, 3, 9, 32, 32), return_loss=True)
 
 
 def test_product_code_never_imports_the_oracle():

@@ -233,3 +233,49 @@ def test_dead_layernorm_never_applied():
     from oracle.restated import OracleTokenizer
     orc = OracleTokenizer(sd, **g["kwargs"])
     assert torch.equal(orc.tokenize(golden_video(g)), g["codes"])
+
+
+def grad_digest_close(g, dg, rtol, what, atol=0.0):
+    """g: a gradient tensor; dg: the golden's digest of the reference's gradient (oracle/make_train_golden.grad_digest).
+    atol: absolute slack for gradients that are mathematically zero (the bias of a softmax logit: SE to_k.bias) and hold
+    only round-off noise in the reference."""
+    flat = g.detach().reshape(-1).double().cpu()
+    assert tuple(g.shape) == tuple(dg["shape"]), what
+    n_err = max(0.0, abs(float(flat.norm()) - dg["norm"]) - atol) / max(dg["norm"], 1e-30)
+    samp = flat[::dg["stride"]]
+    s_err = max(0.0, float((samp - dg["sample"].double()).abs().max()) - atol) / (float(dg["sample"].double().abs().max()) + 1e-30)
+    assert n_err < rtol and s_err < rtol, (what, n_err, s_err, dg["norm"])
+    return max(n_err, s_err)
+
+
+def test_restated_loss_forward_and_gradients_match_reference_golden():
+    """the differentiable restatement of forward(return_loss=True) reproduces the reference's loss values (eval and
+    train mode) and, through autograd, the reference's gradient of every parameter (tests/golden/mini_train.pt, made by the
+    unmodified reference: oracle/make_train_golden.py)."""
+    g = load_golden("mini_train")
+    model = build_product(g["kwargs"], g["wseed"])
+    video = golden_video(g)
+    orc = build_oracle(model, g["kwargs"])
+    with torch.no_grad():
+        ev = orc.loss_forward(video, train=False)
+    assert abs(ev["total_loss"].item() - g["eval"]["total_loss"].item()) < 1e-6
+    assert abs(ev["recon_loss"].item() - g["eval"]["recon_loss_only"].item()) < 1e-6
+    assert ev["aux"].item() == 0.0 and g["eval"]["aux"].item() == 0.0
+    assert (ev["recon"].mean(dim=(3, 4)) - g["eval"]["recon_mean"]).abs().max().item() < 1e-5
+
+    for v in orc.sd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    tr = orc.loss_forward(video, train=True)
+    gt = g["train"]
+    for k in ("total_loss", "recon_loss", "aux", "per_sample_entropy", "batch_entropy", "commitment"):
+        assert abs(tr[k].item() - gt[k].item()) < 2e-6 * max(1.0, abs(gt[k].item())), k
+    tr["total_loss"].backward()
+    worst = 0.0
+    gnorm = sum(d["norm"] ** 2 for d in gt["grads"].values() if d is not None) ** 0.5
+    for k, dg in gt["grads"].items():
+        if dg is None:                    # parameters the reference's forward never touches (dead LayerNorm, ...)
+            assert k not in orc.sd or orc.sd[k].grad is None or float(orc.sd[k].grad.abs().max()) == 0.0, k
+            continue
+        worst = max(worst, grad_digest_close(orc.sd[k].grad, dg, 2e-3, k, atol=1e-7 * gnorm))   # fp32 round-off through 28 layers and the inv_temperature = 100 softmax
+    print(f"worst relative gradient deviation vs the reference: {worst:.2e}")

@@ -645,3 +645,60 @@ def test_readme_config_batch_independence(dtype):
         ci = model.tokenize(v[i:i + 1])
         assert torch.equal(ci, codes[i:i + 1]), i
         assert torch.equal(model.decode_from_code_indices(ci), recon[i:i + 1]), i
+
+
+@pytest.mark.gpu
+def test_return_loss_forward_vs_reference_golden():
+    """forward(video, return_loss=True) / return_recon_loss_only (reference M:1722-1727, M:1868-1896; use_gan=False,
+    perceptual_loss_weight=0) against the values the unmodified reference produced (tests/golden/mini_train.pt), eval and
+    train mode, fp32; bf16 against the same values at the bf16 error budget."""
+    _require_cuda()
+    from magvit2_pytorch_b200.video_tokenizer import LossBreakdown
+    g = load_golden("mini_train")
+    video = golden_video(g).cuda()
+    model = build_product(g["kwargs"], g["wseed"]).cuda()
+    total, bd = model(video, return_loss=True)
+    assert isinstance(bd, LossBreakdown) and bd.quantizer_loss_breakdown is None and bd.multiscale_gen_losses == []
+    assert abs(total.item() - g["eval"]["total_loss"].item()) < 2e-6
+    assert abs(bd.recon_loss.item() - g["eval"]["recon_loss"].item()) < 2e-6 and float(bd.lfq_aux_loss) == 0.0
+    rl, recon = model(video, return_recon_loss_only=True)
+    assert abs(rl.item() - g["eval"]["recon_loss_only"].item()) < 2e-6
+    assert (recon.mean(dim=(3, 4)).cpu() - g["eval"]["recon_mean"]).abs().max().item() < 1e-5
+    assert abs(rl.item() - torch.nn.functional.mse_loss(video, recon).item()) < 1e-6
+
+    model.train()
+    with torch.no_grad():
+        total, bd = model(video, return_loss=True)
+    gt = g["train"]
+    assert abs(total.item() - gt["total_loss"].item()) < 1e-5
+    assert abs(bd.recon_loss.item() - gt["recon_loss"].item()) < 1e-5
+    assert abs(bd.lfq_aux_loss.item() - gt["aux"].item()) < 1e-5
+    ps, be, cm = bd.quantizer_loss_breakdown
+    assert abs(ps.item() - gt["per_sample_entropy"].item()) < 1e-5
+    assert abs(be.item() - gt["batch_entropy"].item()) < 1e-5
+    assert abs(cm.item() - gt["commitment"].item()) < 1e-5
+
+    m16 = build_product(g["kwargs"], g["wseed"]).cuda().bfloat16().eval()
+    t16, bd16 = m16(video.bfloat16(), return_loss=True)
+    assert t16.dtype == torch.bfloat16
+    assert abs(t16.float().item() - g["eval"]["total_loss"].item()) < 0.05 * g["eval"]["total_loss"].item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_uint8_frames_are_normalised_like_the_data_loaders(dtype):
+    """uint8 frames (what a video decoder delivers) are accepted by the layout-in kernels and normalised x / 255 there, exactly as
+    the reference's loaders do on the host (data.py:103 ToTensor, data.py:188): tokens and reconstruction are bit-identical to
+    feeding ``frames.float() / 255``."""
+    _require_cuda()
+    g = load_golden("mini")
+    model = build_product(g["kwargs"], g["wseed"]).cuda().to(dtype)
+    gen = torch.Generator().manual_seed(3)
+    frames = torch.randint(0, 256, tuple(g["video_shape"]), generator=gen, dtype=torch.uint8).cuda()
+    as_float = frames.float() / 255.
+    c8, r8 = model(frames, return_codes=True, return_recon=True)
+    cf, rf = model(as_float, return_codes=True, return_recon=True)
+    assert torch.equal(c8, cf) and torch.equal(r8, rf)
+    l8, _ = model(frames, return_recon_loss_only=True)
+    lf, _ = model(as_float, return_recon_loss_only=True)
+    assert l8.item() == lf.item()
