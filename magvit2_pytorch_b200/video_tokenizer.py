@@ -14,8 +14,11 @@ the compute dtype follows the parameters' dtype (``.float()`` -> fp32 CUDA-core 
 ``cond_residual`` layers (ResidualUnitMod / Conv3DMod, M:680-753, M:946-988) run on the device through the
 factorisation in include/magvit2_b200.h; the other ``cond_*`` types raise in the reference itself.
 ``separate_first_frame_encoding`` (M:1113-1120, M:1553-1561, M:1633-1639) runs through the same conv kernels.
-Out of scope (raise at construction / call): ``gateloop_time``, ``num_codebooks > 1``, ``lfq_spherical``, the GAN / perceptual training losses (``return_loss`` /
-``return_discr_loss``), autograd.
+``forward(return_loss=True)`` (reconstruction + quantiser auxiliary loss; models built with ``use_gan=False,
+perceptual_loss_weight=0``) runs on the device; in ``model.train()`` with gradients enabled it returns a loss with a
+``grad_fn`` (train.py: forward by the same kernels, backward by library code).
+Out of scope (raise at construction / call): ``gateloop_time``, ``num_codebooks > 1``, ``lfq_spherical``, the
+GAN / perceptual training losses (``return_discr_loss``, ``return_loss`` with a discriminator or VGG).
 """
 from __future__ import annotations
 
@@ -550,6 +553,16 @@ class VideoTokenizer(nn.Module):
                 "accelerated path (SURVEY.md 8f N2): construct with use_gan=False, perceptual_loss_weight=0.")
         video, ff = self._check_video(video_or_images, video_contains_first_frame)
         cond = self._check_cond(cond, video.shape[0])
+        if return_loss and self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # the trainer's generator step (T:356-363): loss with a grad_fn.  Forward = the same kernels; backward = train.py
+            from .train import train_forward
+            recon, aux, _, qlb = train_forward(self, video.contiguous(), ff)
+            target = video.float() / 255. if video.dtype == torch.uint8 else video
+            recon_loss = torch.nn.functional.mse_loss(target.to(recon.dtype), recon)          # M:1722
+            self.quantizer_loss_breakdown, self.quantizer_aux_loss = qlb, aux.detach()
+            aux_losses = aux.to(recon_loss.dtype)
+            total_loss = recon_loss + aux_losses * self.quantizer_aux_loss_weight                # M:1868-1871
+            return total_loss, LossBreakdown(recon_loss, aux_losses, qlb, self.zero, self.zero, 0., [], [])
         with torch.no_grad():
             eng = self.engine
             need_recon = return_recon or return_recon_loss_only or return_loss or not return_codes

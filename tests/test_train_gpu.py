@@ -1,0 +1,94 @@
+"""SURVEY 8f N2 (first slice): ``model.train(); loss, _ = model(video, return_loss=True); loss.backward()`` -- the generator step of
+the reference trainer (T:356-363) -- against the loss values and parameter gradients the UNMODIFIED reference produced on the same
+weights and clip (tests/golden/mini_train.pt, oracle/make_train_golden.py)."""
+import pytest
+import torch
+
+from tests.test_oracle import grad_digest_close
+from tests.util import build_product, golden_video, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _train_step(model, video):
+    model.train()
+    for p in model.parameters():
+        p.grad = None
+    total, bd = model(video, return_loss=True)
+    assert total.requires_grad and total.grad_fn is not None
+    total.backward()
+    return total, bd
+
+
+def test_fp32_losses_and_gradients_vs_reference_golden():
+    _require_cuda()
+    g = load_golden("mini_train")
+    gt = g["train"]
+    model = build_product(g["kwargs"], g["wseed"]).cuda()
+    total, bd = _train_step(model, golden_video(g).cuda())
+    assert abs(total.item() - gt["total_loss"].item()) < 1e-5
+    assert abs(bd.recon_loss.item() - gt["recon_loss"].item()) < 1e-5
+    assert abs(bd.lfq_aux_loss.item() - gt["aux"].item()) < 1e-5
+    ps, be, cm = bd.quantizer_loss_breakdown
+    for got, k in ((ps, "per_sample_entropy"), (be, "batch_entropy"), (cm, "commitment")):
+        assert abs(got.item() - gt[k].item()) < 1e-5, k
+    named = dict(model.named_parameters())
+    gnorm = sum(d["norm"] ** 2 for d in gt["grads"].values() if d is not None) ** 0.5
+    worst, checked = 0.0, 0
+    for k, dg in gt["grads"].items():
+        if k not in named:
+            continue
+        p = named[k]
+        if dg is None:      # parameters the reference's forward never touches
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        worst = max(worst, grad_digest_close(p.grad, dg, 5e-3, k, atol=1e-7 * gnorm))
+        checked += 1
+    assert checked >= 250, checked
+    print(f"{checked} parameter gradients checked, worst relative deviation vs the reference {worst:.2e}")
+
+
+def test_optimizer_step_changes_the_loss_and_repacks_the_weights():
+    """Trainer-shaped loop: backward, optimizer step, forward again -- the engine re-packs the updated parameters and the loss
+    goes down along the negative gradient (|grad|^2 ~ 2e3 on these synthetic weights: lr 1e-5 predicts -0.02 per step)."""
+    _require_cuda()
+    g = load_golden("mini_train")
+    model = build_product(g["kwargs"], g["wseed"]).cuda()
+    video = golden_video(g).cuda()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-5)
+    losses = []
+    for _ in range(3):
+        total, _ = _train_step(model, video)
+        opt.step()
+        losses.append(total.item())
+    assert losses[1] < losses[0] and losses[2] < losses[1], losses
+    model.eval()
+    with torch.no_grad():
+        codes = model.tokenize(video)            # the inference path still runs on the updated weights
+    assert codes.dtype == torch.int64
+
+
+def test_bf16_gradients_agree_with_fp32():
+    _require_cuda()
+    g = load_golden("mini_train")
+    video = golden_video(g).cuda()
+    m32 = build_product(g["kwargs"], g["wseed"]).cuda()
+    m16 = build_product(g["kwargs"], g["wseed"]).cuda().bfloat16()
+    t32, _ = _train_step(m32, video)
+    t16, _ = _train_step(m16, video.bfloat16())
+    assert abs(t16.float().item() - t32.item()) < 0.05 * abs(t32.item()) + 0.05
+    num = den_a = den_b = 0.0
+    for (k, a), (_, b) in zip(m32.named_parameters(), m16.named_parameters()):
+        if a.grad is None or b.grad is None:
+            continue
+        ga, gb = a.grad.double().flatten(), b.grad.double().flatten()
+        num += float(ga @ gb); den_a += float(ga @ ga); den_b += float(gb @ gb)
+    cos = num / (den_a ** 0.5 * den_b ** 0.5)
+    print(f"cosine(fp32 grads, bf16 grads) = {cos:.4f}")
+    assert cos > 0.9, cos
