@@ -240,3 +240,67 @@ class FSQ(_NoForward):
             raise NotImplementedError("FSQ without projections is not supported")
         self.project_in = nn.Linear(dim, len(levels))
         self.project_out = nn.Linear(len(levels), dim)
+
+
+class CausalConvTranspose3d(nn.Module):
+    """M:990-1024 -- ``nn.ConvTranspose3d`` with stride (time_stride, 1, 1), padding (0, kh//2, kw//2), output cut to
+    ``t * time_stride`` frames.  The reference never instantiates it inside ``VideoTokenizer`` (dead code there); it is kept
+    as a standalone, *computing* module for API completeness.
+
+    On the device a transposed conv with time stride s is s causal convs interleaved in time:
+        out[s t' + r] = sum_m  x[t' - m] * W[:, :, r + m s]        (spatially: a stride-1 conv with the flipped kernel)
+    so it runs as ONE causal conv with s * C_out output channels in the reference's '(c p)' order and ceil(kt / s) taps,
+    followed by the depth-to-time store the TimeUpsample2x kernels already have (time_stride 1 or 2)."""
+
+    def __init__(self, chan_in, chan_out, kernel_size, *, time_stride, **kwargs):
+        super().__init__()
+        ks = kernel_size if isinstance(kernel_size, tuple) else (kernel_size,) * 3
+        assert ks[1] % 2 == 1 and ks[2] % 2 == 1
+        if time_stride not in (1, 2):
+            raise NotImplementedError("CausalConvTranspose3d on the device supports time_stride 1 and 2")
+        self.upsample_factor = time_stride
+        self.conv = nn.ConvTranspose3d(chan_in, chan_out, ks, (time_stride, 1, 1), padding=(0, ks[1] // 2, ks[2] // 2), **kwargs)
+        self._pack = None
+
+    def equivalent_conv_weight(self):
+        """-> (weight (s*Co, Ci, ceil(kt/s), kh, kw), bias (s*Co) | None) of the causal conv described above."""
+        w = self.conv.weight.detach()                      # (Ci, Co, kt, kh, kw)
+        s = self.upsample_factor
+        Ci, Co, kt, kh, kw = w.shape
+        ktp = -(-kt // s)
+        wf = w.flip(3, 4).permute(1, 0, 2, 3, 4)           # (Co, Ci, kt, kh, kw), spatially flipped
+        weq = w.new_zeros((Co, s, Ci, ktp, kh, kw))
+        for r in range(s):
+            for dt in range(ktp):
+                j = r + (ktp - 1 - dt) * s
+                if j < kt:
+                    weq[:, r, :, dt] = wf[:, :, j]
+        beq = None if self.conv.bias is None else self.conv.bias.detach().repeat_interleave(s)
+        return weq.reshape(Co * s, Ci, ktp, kh, kw), beq
+
+    def forward(self, x):
+        from .engine import Engine, pack_conv
+        from ._lib import SHUFFLE_NONE, SHUFFLE_TIME
+        assert x.ndim == 5
+        w = self.conv.weight
+        if w.device.type != "cuda" or x.device != w.device:
+            raise RuntimeError("CausalConvTranspose3d runs on CUDA (sm_100a) only, input and parameters on the same device")
+        if w.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("parameters must be float32 or bfloat16")
+        sig = (w.data_ptr(), w._version, w.dtype, w.device, None if self.conv.bias is None else self.conv.bias._version)
+        with torch.no_grad(), torch.cuda.device(w.device):
+            if self._pack is None or self._pack[0] != sig:
+                eng = Engine(None)
+                eng.dtype, eng.device = w.dtype, w.device
+                weq, beq = self.equivalent_conv_weight()
+                self._pack = (sig, eng, pack_conv(weq, beq, w.dtype, shuffle_q=self.upsample_factor))
+            _, eng, pk = self._pack
+            y = eng.conv(eng.to_channels_last(x), pk, shuffle=SHUFFLE_TIME if self.upsample_factor == 2 else SHUFFLE_NONE)
+            out = eng.to_channels_first(y)
+            n = self.output_frames(x.shape[2])
+            return out if n == out.shape[2] else out[:, :, :n].contiguous()
+
+    def output_frames(self, t: int) -> int:
+        """min(t * s, (t - 1) * s + kt): a kernel shorter than the stride leaves the transposed conv's output shorter than the cut."""
+        s, kt = self.upsample_factor, self.conv.weight.shape[2]
+        return min(t * s, (t - 1) * s + kt)

@@ -88,6 +88,14 @@ def causal_conv3d(x, w, b, pad_mode="constant"):
     return F.conv3d(x, w, b)
 
 
+def causal_conv_transpose3d(x, w, b, time_stride):
+    """CausalConvTranspose3d.forward (M:990-1024): ConvTranspose3d stride (s, 1, 1), padding (0, k_h//2, k_w//2), then the
+    output is cut to t * s frames.  w: (C_in, C_out, k_t, k_h, k_w)."""
+    kh, kw = w.shape[3:]
+    out = F.conv_transpose3d(x, w, b, stride=(time_stride, 1, 1), padding=(0, kh // 2, kw // 2))
+    return out[:, :, :x.shape[2] * time_stride]
+
+
 def squeeze_excite(x, sd, p):
     """SqueezeExcite.forward on video (M:221-240): per (b, f) frame, softmax over h*w of
     a 1x1 conv logit, pooled C-vector, 2-layer MLP with LeakyReLU(0.1), sigmoid gate."""

@@ -132,3 +132,26 @@ def test_product_code_never_imports_the_oracle():
         if isinstance(node, ast.FunctionDef) and node.name in cpu_legs:
             allowed.update(range(node.lineno, node.end_lineno + 1))
     assert hits and all(h in allowed for h in hits), hits
+
+
+@pytest.mark.parametrize("kt,stride", [(3, 2), (4, 2), (2, 2), (3, 1), (1, 2)])
+def test_causal_conv_transpose3d_equivalent_causal_conv(kt, stride):
+    """CausalConvTranspose3d (M:990-1024) = one causal conv with s * C_out channels + depth-to-time: the weight mapping the device
+    path packs, checked on CPU against the reference semantics (oracle.restated.causal_conv_transpose3d)."""
+    import torch.nn.functional as F
+    from magvit2_pytorch_b200.modules import CausalConvTranspose3d
+    from oracle.restated import causal_conv_transpose3d, causal_conv3d
+    torch.manual_seed(kt * 10 + stride)
+    m = CausalConvTranspose3d(5, 4, (kt, 3, 3), time_stride=stride)
+    x = torch.randn(2, 5, 6, 7, 7)
+    want = causal_conv_transpose3d(x, m.conv.weight.detach(), m.conv.bias.detach(), stride)
+    weq, beq = m.equivalent_conv_weight()
+    o = causal_conv3d(x, weq, beq)                                  # (B, (c p), T, H, W)
+    b, cp, t, h, w = o.shape
+    got = o.reshape(b, cp // stride, stride, t, h, w).permute(0, 1, 3, 2, 4, 5).reshape(b, cp // stride, t * stride, h, w)
+    got = got[:, :, :m.output_frames(x.shape[2])]
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < 1e-5
+    assert set(m.state_dict()) == {"conv.weight", "conv.bias"}
+    with pytest.raises(RuntimeError):
+        m(x)                                                        # CPU-resident: no kernels to run, no eager fallback
