@@ -209,6 +209,12 @@ int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, float inv_t
 int mv2_lfq_aux_finalize(const float* avg_prob_sum, const float* stats, int d, int64_t n_tokens, int64_t n_tokens_global,
                          float diversity_gamma, float entropy_weight, float commitment_weight, float* out4, void* stream);
 
+/* ---- gateloop_time (reference M:1216-1222: ToTimeSequence(Residual(SimpleGateLoopLayer(dim)))) -----------
+ * qkva [B][T][P][3C] = Linear(dim, 3 dim) of the RMSNorm'ed activations (q | kv | a thirds), res / out [B][T][P][C]:
+ *   s_t = sigmoid(a_t) * s_{t-1} + kv_t  (s_{-1} = 0, fp32 state),   out_t = q_t * s_t + res_t
+ * per (b, pixel p, channel).  The norm and the projection run through mv2_rmsnorm and the conv entry points.   */
+int mv2_gateloop_scan(const void* qkva, const void* res, void* out, int dtype, int B, int T, int P, int C, void* stream);
+
 /* ---- reconstruction loss (reference M:1722 F.mse_loss(video, recon_video)) ------------------
  * out[0] = mean_i (a[i] - b[i])^2 over n elements of two same-layout tensors; a_dtype may be MV2_U8 (frames, x / 255).
  * Deterministic (fixed-order two-stage reduction); workspace: mv2_mse_workspace_bytes() bytes.                          */

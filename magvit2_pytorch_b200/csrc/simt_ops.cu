@@ -2070,6 +2070,33 @@ __global__ void __launch_bounds__(256) lfq_entropy_kernel(const float* __restric
 
 
 // ------------------------------------------------------------------------------------------
+// gateloop_time (reference M:1216-1222: ToTimeSequence(Residual(SimpleGateLoopLayer))): per (clip, pixel, channel) the gated
+// recurrence over time  s_t = sigmoid(a_t) s_{t-1} + kv_t,  out_t = q_t s_t + x_t  (residual fused), with q / kv / a the three
+// channel thirds of the Linear(dim, 3 dim) output.  One thread per (b, pixel, channel); consecutive threads = consecutive
+// channels, so every time step is a coalesced row access.  State in fp32.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gateloop_scan_kernel(const T* __restrict__ qkva, const T* __restrict__ res, T* __restrict__ out,
+                                                            int Tn, int64_t PC, int C, int64_t total) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;      // over B * P * C
+  if (i >= total) return;
+  const int64_t b = i / PC, pc = i - b * PC;
+  const int64_t p = pc / C;
+  const int c = (int)(pc - p * C);
+  const int64_t P = PC / C;
+  float s = 0.f;
+  for (int t = 0; t < Tn; ++t) {
+    const int64_t pos = (b * Tn + t) * P + p;
+    const T* row = qkva + pos * 3 * C;
+    const float q = to_f32<T>(row[c]), kv = to_f32<T>(row[C + c]), a = to_f32<T>(row[2 * C + c]);
+    s = fmaf(1.f / (1.f + expf(-a)), s, kv);
+    out[pos * C + c] = from_f32<T>(fmaf(q, s, to_f32<T>(res[pos * C + c])));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // reconstruction loss F.mse_loss(video, recon_video) (reference M:1722): mean over all elements of (a - b)^2.
 // Deterministic two-stage reduction: MSE_BLOCKS blocks accumulate strided fp32 partial sums (one double per block),
 // then one warp folds the block partials in a fixed order.  a may be MV2_U8 (frames, x / 255).
@@ -2672,6 +2699,21 @@ int mv2_lfq_aux_finalize(const float* avg_prob_sum, const float* stats, int d, i
   launch_k(lfq_aux_final_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, avg_prob_sum, stats, 1 << d,
            (float)(1.0 / (double)n_tokens_global), (float)(1.0 / (double)n_tokens), (float)(1.0 / ((double)n_tokens * d)),
            diversity_gamma, entropy_weight, commitment_weight, out4);
+  MV2_CHECK_LAUNCH();
+  return MV2_OK;
+}
+
+int mv2_gateloop_scan(const void* qkva, const void* res, void* out, int dtype, int B, int T, int P, int C, void* stream) {
+  MV2_CHECK_ARG(qkva && res && out && B > 0 && T > 0 && P > 0 && C > 0);
+  const int64_t total = (int64_t)B * P * C;
+  const int64_t blocks = ceil_div(total, (int64_t)256);
+  MV2_CHECK_ARG(blocks <= 2147483647LL);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == MV2_F32)
+    launch_k(gateloop_scan_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, st, (const float*)qkva, (const float*)res, (float*)out, T, (int64_t)P * C, C, total);
+  else if (dtype == MV2_BF16)
+    launch_k(gateloop_scan_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, st, (const __nv_bfloat16*)qkva, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, T, (int64_t)P * C, C, total);
+  else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }

@@ -275,6 +275,9 @@ class Engine:
                 elif st.kind == "linear_attend_space":
                     pack_lin(mod[0].fn, key + ".attn")
                     pack_ffn(mod[1].fn, key + ".ff")
+                elif st.kind == "gateloop_time":
+                    gl = mod.fn.fn
+                    P[key] = dict(gamma=f32(gl.norm.gamma), qkva=pack_conv(gl.to_qkva[0].weight[:, :, None, None, None], None, dt))
         if m.has_cond:
             for side, stem in (("enc", m.encoder_cond_in), ("dec", m.decoder_cond_in)):
                 P[f"{side}_cond_in"] = dict(w=f32(stem[0].weight), b=f32(stem[0].bias))
@@ -531,6 +534,17 @@ class Engine:
         self.launches += 2
         return self.conv(o, p["out"], res=x)
 
+    def gateloop(self, x, p):
+        """ToTimeSequence(Residual(SimpleGateLoopLayer)) (M:178-191, M:1216-1222): RMSNorm, Linear(dim, 3 dim), then the gated
+        recurrence over time per (pixel, channel) with the residual add fused (mv2_gateloop_scan)."""
+        B, T, H, W, Cc = x.shape
+        qkva = self.conv(self.rmsnorm(x, p["gamma"]), p["qkva"])
+        out = self._new(x.shape)
+        check(self.lib.mv2_gateloop_scan(_ptr(qkva), _ptr(x), _ptr(out), _dt(self.dtype), B, T, H * W, Cc, self._stream()),
+              "mv2_gateloop_scan")
+        self.launches += 1
+        return out
+
     def profile_convs(self, fn, steps: int = 3):
         """Runs fn() `steps` times with CUDA events around every tcgen05 conv launch (on the launching stream).
         A long spin kernel is queued first so the host runs ahead of the GPU and the event pairs bracket pure
@@ -583,6 +597,8 @@ class Engine:
         elif st.kind == "linear_attend_space":
             x = self.linear_attention(x, P[key + ".attn"])
             x = self.feed_forward(x, P[key + ".ff"])
+        elif st.kind == "gateloop_time":
+            x = self.gateloop(x, P[key])
         else:
             raise ValueError(st.kind)
         return x

@@ -196,6 +196,25 @@ class LinearSpaceAttention(_NoForward):
         self.attn = TaylorSeriesLinearAttn(dim, dim_head, heads)
 
 
+class SimpleGateLoopLayer(_NoForward):
+    """Parameter layout of gateloop_transformer.SimpleGateLoopLayer(dim) with its defaults (prenorm RMSNorm, no post-LN), as
+    the reference constructs it at M:1220-1221: ``norm.gamma`` (dim,), ``to_qkva.0.weight`` (3 dim, dim), no bias."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+        self.norm = RMSNorm(dim)
+        self.to_qkva = nn.Sequential(nn.Linear(dim, dim * 3, bias=False), Marker("'b n (qkva d) -> qkva (b d) n 1'"))
+
+
+class ToTimeSequence(_NoForward):
+    """M:178-191."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
 class FeedForward(_NoForward):
     """M:471-496: channel-first RMSNorm, Conv3d C->2I 1x1x1, GEGLU, Conv3d I->C; I = int(C*4*2/3)."""
 

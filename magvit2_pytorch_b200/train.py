@@ -109,6 +109,18 @@ def _linear_attention_block(x, la):
     return F.linear(o, la.attn.to_out[0].weight).reshape(x.shape) + x
 
 
+def _gateloop_block(x, gl):
+    """ToTimeSequence(Residual(SimpleGateLoopLayer)) (M:178-191, M:1216-1222): s_t = sigmoid(a_t) s_{t-1} + kv_t, out_t = q_t s_t."""
+    q, kv, a = F.linear(_rmsnorm(x, gl.norm.gamma), gl.to_qkva[0].weight).chunk(3, dim=-1)
+    a = a.sigmoid()
+    s = torch.zeros_like(kv[:, 0])
+    outs = []
+    for t in range(x.shape[1]):
+        s = a[:, t] * s + kv[:, t]
+        outs.append(q[:, t] * s)
+    return torch.stack(outs, dim=1) + x
+
+
 def _feed_forward_block(x, ff, shift):
     """Residual(FeedForward) / Residual(TokenShift(FeedForward)) (M:466-508, M:1191, M:1236)."""
     xs = _token_shift(x) if shift else x
@@ -305,6 +317,9 @@ class TrainRunner:
         if st.kind == "compress_time":
             conv = mod.net[0]
             return self._block(x, run, lambda t: _upsample_time(t, conv), list(conv.parameters()))
+        if st.kind == "gateloop_time":
+            gl = mod.fn.fn
+            return self._block(x, run, lambda t: _gateloop_block(t, gl), list(gl.parameters()))
         if st.kind in ("attend_space", "attend_time", "linear_attend_space"):
             time_axis = st.kind == "attend_time"
             at = mod[0].fn.fn if time_axis else mod[0].fn

@@ -17,7 +17,7 @@ factorisation in include/magvit2_b200.h; the other ``cond_*`` types raise in the
 ``forward(return_loss=True)`` (reconstruction + quantiser auxiliary loss; models built with ``use_gan=False,
 perceptual_loss_weight=0``) runs on the device; in ``model.train()`` with gradients enabled it returns a loss with a
 ``grad_fn`` (train.py: forward by the same kernels, backward by library code).
-Out of scope (raise at construction / call): ``gateloop_time``, ``num_codebooks > 1``, ``lfq_spherical``, the
+Out of scope (raise at construction / call): ``num_codebooks > 1``, ``lfq_spherical``, the
 GAN / perceptual training losses (``return_discr_loss``, ``return_loss`` with a discriminator or VGG).
 """
 from __future__ import annotations
@@ -71,7 +71,6 @@ _UNSUPPORTED_LAYERS = {
     "cond_attend_space": "raises in the reference itself (SURVEY.md 2 row 9)",
     "cond_linear_attend_space": "raises in the reference itself (SURVEY.md 2 row 9)",
     "cond_attend_time": "raises in the reference itself (SURVEY.md 2 row 9)",
-    "gateloop_time": "gateloop_time is outside the accelerated path (SURVEY.md 8f N3)",
 }
 
 
@@ -206,6 +205,10 @@ class VideoTokenizer(nn.Module):
                     return nn.Sequential(M.Residual(M.LinearSpaceAttention(dim, linear_attn_dim_head, linear_attn_heads)),
                                          M.Residual(M.FeedForward(dim)))
                 enc, dec = mk(), mk()
+                stages.append(Stage(kind, dim, dim))
+            elif kind == "gateloop_time":                                        # M:1216-1222
+                enc = M.ToTimeSequence(M.Residual(M.SimpleGateLoopLayer(dim)))
+                dec = M.ToTimeSequence(M.Residual(M.SimpleGateLoopLayer(dim)))
                 stages.append(Stage(kind, dim, dim))
             elif kind == "attend_time":
                 def mk():

@@ -84,6 +84,10 @@ CONFIGS = {
     "pad_circular": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, pad_mode="circular",
                                      layers=("residual", "compress_space", "compress_time", "residual")),
                          video=(2, 3, 9, 32, 32), wseed=0, vseed=1236, full=True),
+    # gateloop_time (M:1216-1222; SimpleGateLoopLayer through oracle/shims/gateloop.py)
+    "mini_gateloop": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024,
+                                      layers=("residual", "compress_space", "gateloop_time", "compress_time", "gateloop_time", "residual")),
+                          video=(2, 3, 9, 32, 32), wseed=0, vseed=1237, full=True),
     "mini_sff": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, separate_first_frame_encoding=True,
                                  layers=("residual", "compress_space", "compress_time", "residual")),
                      video=(2, 3, 5, 32, 32), wseed=0, vseed=1234, full=True),

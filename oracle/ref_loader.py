@@ -13,7 +13,7 @@ CPU tests that are skipped when the reference tree is absent.
 trainer and five PyPI packages that are not installed.  We
 register a synthetic package whose ``__path__`` is the reference directory and
 import the model module directly, after installing restated stand-ins for the
-four model-side third-party modules (oracle/shims/).
+model-side third-party modules (oracle/shims/).
 """
 from __future__ import annotations
 
@@ -43,13 +43,9 @@ def _install_shims():
         m.__shim__ = True
         sys.modules["taylor_series_linear_attention"] = m
     if "gateloop_transformer" not in sys.modules:
+        from oracle.shims import gateloop
         m = types.ModuleType("gateloop_transformer")
-
-        class SimpleGateLoopLayer:  # out of scope
-            def __init__(self, *a, **k):
-                raise NotImplementedError("gateloop_time is out of scope for the oracle")
-
-        m.SimpleGateLoopLayer = SimpleGateLoopLayer
+        m.SimpleGateLoopLayer = gateloop.SimpleGateLoopLayer
         m.__shim__ = True
         sys.modules["gateloop_transformer"] = m
     if "kornia" not in sys.modules:

@@ -66,7 +66,7 @@ def schedule(layers, init_dim, max_dim) -> Tuple[List[Stage], int, int]:
                 space_f *= 2
             else:
                 time_f *= 2
-        elif kind in ("attend_space", "linear_attend_space", "attend_time"):
+        elif kind in ("attend_space", "linear_attend_space", "attend_time", "gateloop_time"):
             stages.append(Stage(kind, dim, dim))
         else:
             raise ValueError(f"oracle: unsupported layer type {kind}")
@@ -273,6 +273,24 @@ def linear_space_attention(x, sd, p, heads, dim_head):
     return o.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
 
 
+def gateloop_time(x, sd, p):
+    """ToTimeSequence(SimpleGateLoopLayer) (M:178-191, M:1220; un-vendored dependency gateloop-transformer, restated in
+    oracle/shims/gateloop.py): per pixel, over time: RMSNorm, q / kv / a = Linear(dim, 3 dim) chunks, the gated recurrence
+    s_t = sigmoid(a_t) s_{t-1} + kv_t, out_t = q_t s_t."""
+    b, c, t, h, w = x.shape
+    tok = x.permute(0, 3, 4, 2, 1).reshape(b * h * w, t, c)
+    tok = rmsnorm_last(tok, sd[p + "norm.gamma"])
+    q, kv, a = F.linear(tok, sd[p + "to_qkva.0.weight"]).chunk(3, dim=-1)
+    a = a.sigmoid()
+    s = torch.zeros_like(kv[:, 0])
+    outs = []
+    for i in range(t):
+        s = a[:, i] * s + kv[:, i]
+        outs.append(q[:, i] * s)
+    o = torch.stack(outs, dim=1)
+    return o.reshape(b, h, w, t, c).permute(0, 4, 3, 1, 2)
+
+
 def feed_forward(x, sd, p):
     """FeedForward (M:471-508): channel-first RMSNorm, Conv3d 1x1x1 C->2I, GEGLU
     (x, gate = chunk; gelu(gate) * x, M:466-469), Conv3d 1x1x1 I->C."""
@@ -449,6 +467,8 @@ class OracleTokenizer:
         elif st.kind == "linear_attend_space":                               # M:1206-1214
             x = linear_space_attention(x, sd, p + "0.fn.", self.lin_heads, self.lin_dim_head) + x
             x = feed_forward(x, sd, p + "1.fn.") + x
+        elif st.kind == "gateloop_time":                                     # M:1216-1222
+            x = gateloop_time(x, sd, p + "fn.fn.") + x
         elif st.kind == "attend_time":                                       # M:1234-1242
             x = time_attention(token_shift(x), sd, p + "0.fn.fn.", self.heads) + x
             x = feed_forward(token_shift(x), sd, p + "1.fn.fn.") + x

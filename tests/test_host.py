@@ -42,8 +42,9 @@ def test_constructor_errors():
         VideoTokenizer(image_size=32, layers=("residual",))                       # no codebook_size (M:1359)
     with pytest.raises(AssertionError):
         VideoTokenizer(image_size=32, use_fsq=True, codebook_size=1024, layers=("residual",))  # M:1376
-    with pytest.raises(NotImplementedError):
-        VideoTokenizer(image_size=32, codebook_size=1024, layers=("gateloop_time",))
+    gl = VideoTokenizer(image_size=32, codebook_size=1024, layers=("gateloop_time",))                 # M:1216-1222
+    assert {"encoder_layers.0.fn.fn.norm.gamma", "encoder_layers.0.fn.fn.to_qkva.0.weight",
+            "decoder_layers.0.fn.fn.to_qkva.0.weight"} <= set(gl.state_dict())
     with pytest.raises(NotImplementedError):
         VideoTokenizer(image_size=32, codebook_size=1024, dim_cond=8, layers=("cond_attend_space",))   # raises in the reference too
     with pytest.raises(AssertionError):

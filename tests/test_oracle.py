@@ -7,7 +7,7 @@ import torch
 from tests.util import (build_oracle, build_oracle_from_golden, build_product, golden_video, load_golden,
                         sample_like_golden)
 
-SMALL = ["cfg1", "mini", "mini_fsq"]
+SMALL = ["cfg1", "mini", "mini_fsq", "mini_gateloop"]
 
 
 @pytest.mark.parametrize("name", SMALL)

@@ -702,3 +702,37 @@ def test_uint8_frames_are_normalised_like_the_data_loaders(dtype):
     l8, _ = model(frames, return_recon_loss_only=True)
     lf, _ = model(as_float, return_recon_loss_only=True)
     assert l8.item() == lf.item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gateloop_time_vs_reference_golden(dtype):
+    """gateloop_time (ToTimeSequence(Residual(SimpleGateLoopLayer)), M:178-191, M:1216-1222) on the device -- RMSNorm,
+    the 1x1x1 projection kernels and mv2_gateloop_scan -- against the golden the reference produced (through the restated
+    SimpleGateLoopLayer of oracle/shims/gateloop.py: the dependency's arithmetic is "parity unpinned")."""
+    _require_cuda()
+    g = load_golden("mini_gateloop")
+    model = build_product(g["kwargs"], g["wseed"]).cuda().to(dtype)
+    v = golden_video(g).cuda()
+    eng = model.engine
+    eng.taps = {}
+    codes = model.tokenize(v)
+    enc_taps, eng.taps = eng.taps, {}
+    recon = model.decode_from_code_indices(g["codes"].cuda())
+    dec_taps, eng.taps = eng.taps, None
+    mism = (codes.cpu() != g["codes"]).float().mean().item()
+    rerr = (recon.float().cpu() - g["recon"]).abs().max().item()
+    worst = 0.0
+    for k, ref in g["taps"].items():
+        got = enc_taps.get(k, dec_taps.get(k))
+        if got is None:
+            continue
+        worst = max(worst, (sample_like_golden(got, g) - ref).abs().max().item())
+    _report(f"gateloop/{str(dtype).split('.')[-1]}", token_mismatch_rate=f"{mism:.4f}", recon_maxabs=f"{rerr:.3e}", worst_tap=f"{worst:.3e}")
+    if dtype == torch.float32:
+        assert mism == 0 and rerr < FP32_RECON_TOL and worst < FP32_TAP_TOL
+    else:
+        assert mism <= 0.1 and rerr < 0.1
+    model.cuda_graphs = True
+    for _ in range(3):
+        assert torch.equal(model.tokenize(v), codes)
