@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MV2_ABI_VERSION 2   /* 2: mv2_conv_args.oscale, mv2_tc_conv_args.{oscale,out_layout}; round-2 entry points */
+#define MV2_ABI_VERSION 3   /* 2: mv2_conv_args.oscale, mv2_tc_conv_args.{oscale,out_layout}; 3: num_codebooks / spherical in the quantiser entry points */
 
 enum { MV2_F32 = 0, MV2_BF16 = 1,
        MV2_U8 = 2   /* source dtype of the two layout-in entry points only: decoded uint8 frames, normalised x / 255 */ };
@@ -175,39 +175,43 @@ int mv2_linear_attention(const void* q, const void* kv, void* out, int dtype,
 int mv2_geglu(const void* in, void* out, int dtype, int64_t N, int I, void* stream);
 
 /* ---- quantisers (un-vendored vector-quantize-pytorch LFQ / FSQ; SURVEY.md Appendix A.1/A.2;
- * reference call sites M:1576, M:1593, M:1700, M:1705) ---------------------------------------
- * lfq_forward : x [N][C] -> p = tanh((Win x + bin)/clamp)*clamp (fp32), bit_i = p_i > 0,
- *               index = sum bit_i << (d-1-i) (int64), quantized [N][C] = Wout (+-1) + bout.
- *               presign (fp32 [N][d]) is optional (diagnostics / training losses).
+ * reference call sites M:1576, M:1593, M:1700, M:1705; constructor kwargs num_codebooks M:1057, lfq_spherical M:1070) ------
+ * d = dims per codebook, num_codebooks = nc, D = d * nc <= 16 projected dims; one index per (token, codebook):
+ *   indices [N][nc].
+ * lfq_forward : x [N][C] -> p = tanh((Win x + bin)/clamp)*clamp (fp32), per codebook (L2-normalised first when
+ *               spherical != 0): bit_j = p_j > 0, index = sum bit_j << (d-1-j) (int64), quantized [N][C] = Wout (+-1) + bout.
+ *               presign (fp32 [N][D], after the optional normalisation) is optional (diagnostics / training losses).
  * lfq_decode  : indices -> quantized (LFQ.indices_to_codes).
- * fsq_*       : same with tanh-bound + round-half-even + mixed-radix int32 index.
- * win [d][C], bin [d], wout [C][d], bout [C] are fp32.                                         */
-int mv2_lfq_forward(const void* x, int dtype, int64_t N, int C, int d,
+ * fsq_*       : same with tanh-bound + round-half-even + mixed-radix int32 index (levels[d], shared by the codebooks).
+ * win [D][C], bin [D], wout [C][D], bout [C] are fp32.                                         */
+int mv2_lfq_forward(const void* x, int dtype, int64_t N, int C, int d, int num_codebooks,
                     const float* win, const float* bin, const float* wout, const float* bout,
-                    float clamp, int64_t* indices, void* quantized, float* presign, void* stream);
-int mv2_lfq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d,
+                    float clamp, int spherical, int64_t* indices, void* quantized, float* presign, void* stream);
+int mv2_lfq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d, int num_codebooks,
                    const float* wout, const float* bout, void* quantized, int dtype, void* stream);
-int mv2_fsq_forward(const void* x, int dtype, int64_t N, int C, int d, const int32_t* levels /* host */,
+int mv2_fsq_forward(const void* x, int dtype, int64_t N, int C, int d, int num_codebooks, const int32_t* levels /* host */,
                     const float* win, const float* bin, const float* wout, const float* bout,
                     int32_t* indices, void* quantized, float* bounded, void* stream);
-int mv2_fsq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d, const int32_t* levels /* host */,
+int mv2_fsq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d, int num_codebooks, const int32_t* levels /* host */,
                    const float* wout, const float* bout, void* quantized, int dtype, void* stream);
 
 /* ---- LFQ training-mode auxiliary terms (A.1 steps 7-8; the one collective on the path) -------
- * lfq_entropy_partials: from presign [N][d] (d <= 12) accumulates, for this rank,
- *   stats[0] = sum_tokens H(softmax_K(2*inv_temp*<p, code_k>)), stats[1] = sum (p - sign p)^2,
- *   avg_prob[K] += sum_tokens prob (un-normalised; caller divides by the global token count after
- *   the cross-rank SUM all-reduce of avg_prob -- the 4 KiB NCCL all-reduce of cfg 3).
+ * lfq_entropy_partials: from presign [N][nc][d] (d <= 12) accumulates, for this rank,
+ *   stats[0] = sum_{tokens, codebooks} H(softmax_K(2*inv_temp*<p, code_k>)), stats[1] = sum (p - sign p)^2,
+ *   avg_prob[nc][K] += sum_tokens prob (un-normalised; caller divides by the token count, then the cross-rank SUM
+ *   all-reduce of avg_prob -- the 4 KiB NCCL all-reduce of cfg 3).
  * stats and avg_prob must be zeroed by the caller.                                             */
-int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, float inv_temperature,
+int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, int num_codebooks, float inv_temperature,
                              float* avg_prob, float* stats, void* stream);
 
 /* mv2_lfq_aux_finalize: out4 = {per_sample_entropy, batch_entropy, commitment, aux_loss} from the partial sums above
- * (A.1 steps 7-10): per_sample = stats[0] / n_tokens, commitment = stats[1] / (n_tokens d),
- * batch_entropy = sum_k -p_k log(max(p_k, 1e-5)), p = avg_prob_sum / n_tokens_global (avg_prob_sum = the cross-rank SUM),
- * aux = (per_sample - diversity_gamma * batch_entropy) * entropy_weight + commitment * commitment_weight.             */
-int mv2_lfq_aux_finalize(const float* avg_prob_sum, const float* stats, int d, int64_t n_tokens, int64_t n_tokens_global,
-                         float diversity_gamma, float entropy_weight, float commitment_weight, float* out4, void* stream);
+ * (A.1 steps 7-10): per_sample = stats[0] / (n_tokens nc), commitment = stats[1] / (n_tokens nc d),
+ * batch_entropy = mean over codebooks of sum_k -p_k log(max(p_k, 1e-5)), p = avg_prob_sum / n_tokens_global
+ * (avg_prob_sum = the cross-rank SUM), aux = (per_sample - diversity_gamma * batch_entropy) * entropy_weight
+ * + commitment * commitment_weight.                                                                                    */
+int mv2_lfq_aux_finalize(const float* avg_prob_sum, const float* stats, int d, int num_codebooks, int64_t n_tokens,
+                         int64_t n_tokens_global, float diversity_gamma, float entropy_weight, float commitment_weight,
+                         float* out4, void* stream);
 
 /* ---- gateloop_time (reference M:1216-1222: ToTimeSequence(Residual(SimpleGateLoopLayer(dim)))) -----------
  * qkva [B][T][P][3C] = Linear(dim, 3 dim) of the RMSNorm'ed activations (q | kv | a thirds), res / out [B][T][P][C]:

@@ -93,12 +93,12 @@ SIGNATURES = {
     "mv2_linattn_workspace_bytes": (_SZ, [_I, _I, _I]),
     "mv2_linear_attention": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP, _VP]),
     "mv2_geglu": (_I, [_VP, _VP, _I, _I64, _I, _VP]),
-    "mv2_lfq_forward": (_I, [_VP, _I, _I64, _I, _I, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP, _VP]),
-    "mv2_lfq_decode": (_I, [_VP, _I, _I64, _I, _I, _VP, _VP, _VP, _I, _VP]),
-    "mv2_fsq_forward": (_I, [_VP, _I, _I64, _I, _I, C.POINTER(C.c_int32), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
-    "mv2_fsq_decode": (_I, [_VP, _I, _I64, _I, _I, C.POINTER(C.c_int32), _VP, _VP, _VP, _I, _VP]),
-    "mv2_lfq_entropy_partials": (_I, [_VP, _I64, _I, _F, _VP, _VP, _VP]),
-    "mv2_lfq_aux_finalize": (_I, [_VP, _VP, _I, _I64, _I64, _F, _F, _F, _VP, _VP]),
+    "mv2_lfq_forward": (_I, [_VP, _I, _I64, _I, _I, _I, _VP, _VP, _VP, _VP, _F, _I, _VP, _VP, _VP, _VP]),
+    "mv2_lfq_decode": (_I, [_VP, _I, _I64, _I, _I, _I, _VP, _VP, _VP, _I, _VP]),
+    "mv2_fsq_forward": (_I, [_VP, _I, _I64, _I, _I, _I, C.POINTER(C.c_int32), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "mv2_fsq_decode": (_I, [_VP, _I, _I64, _I, _I, _I, C.POINTER(C.c_int32), _VP, _VP, _VP, _I, _VP]),
+    "mv2_lfq_entropy_partials": (_I, [_VP, _I64, _I, _I, _F, _VP, _VP, _VP]),
+    "mv2_lfq_aux_finalize": (_I, [_VP, _VP, _I, _I, _I64, _I64, _F, _F, _F, _VP, _VP]),
     "mv2_gateloop_scan": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "mv2_mse": (_I, [_VP, _I, _VP, _I, _I64, _VP, _VP, _VP]),
     "mv2_mse_workspace_bytes": (C.c_size_t, []),
@@ -141,8 +141,8 @@ def load():
         fn.restype = res
         fn.argtypes = args
     ver = lib.mv2_abi_version()
-    if ver != 2:
-        raise Mv2Error(f"ABI version mismatch: library {ver}, binding 2")
+    if ver != 3:
+        raise Mv2Error(f"ABI version mismatch: library {ver}, binding 3")
     _lib = lib
     return lib
 

@@ -1891,12 +1891,15 @@ __global__ void geglu_kernel(const T* __restrict__ in, T* __restrict__ out, int6
 constexpr int Q_MAXD = 16;
 struct FsqLevels { int32_t lv[Q_MAXD]; };
 
-// mode 0: LFQ, mode 1: FSQ.  One warp per token.
+// mode 0: LFQ, mode 1: FSQ.  One warp per token.  `d` = dims per codebook, `nc` codebooks (d * nc <= Q_MAXD projected dims,
+// reference kwarg num_codebooks M:1057 -> M:1367 / M:1381): one index per (token, codebook), idx[tok * nc + cb].
+// spherical (LFQ, M:1070 -> A.1 step 4): the per-codebook d-vector is L2-normalised before the sign / the auxiliary terms; the
+// quantised output (+-1) and the indices do not depend on it.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256) quant_forward_kernel(const T* __restrict__ x, int64_t N, int C, int d,
+__global__ void __launch_bounds__(256) quant_forward_kernel(const T* __restrict__ x, int64_t N, int C, int d, int nc,
                                                             const float* __restrict__ win, const float* __restrict__ bin,
                                                             const float* __restrict__ wout, const float* __restrict__ bout,
-                                                            float clamp, FsqLevels lv, int64_t* __restrict__ idx64,
+                                                            float clamp, int spherical, FsqLevels lv, int64_t* __restrict__ idx64,
                                                             int32_t* __restrict__ idx32, T* __restrict__ quant,
                                                             float* __restrict__ aux) {
   pdl_wait();
@@ -1904,6 +1907,7 @@ __global__ void __launch_bounds__(256) quant_forward_kernel(const T* __restrict_
   const int lane = threadIdx.x & 31;
   const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (tok >= N) return;
+  const int D = d * nc;
   const T* row = x + tok * C;
   float acc[Q_MAXD];
 #pragma unroll
@@ -1912,24 +1916,45 @@ __global__ void __launch_bounds__(256) quant_forward_kernel(const T* __restrict_
     const float xv = to_f32<T>(row[c]);
 #pragma unroll
     for (int i = 0; i < Q_MAXD; ++i)
-      if (i < d) acc[i] = fmaf(xv, win[(int64_t)i * C + c], acc[i]);
+      if (i < D) acc[i] = fmaf(xv, win[(int64_t)i * C + c], acc[i]);
   }
-  float code[Q_MAXD];
+  float code[Q_MAXD], pv[Q_MAXD];
+#pragma unroll
+  for (int i = 0; i < Q_MAXD; ++i) {
+    pv[i] = 0.f;
+    if (i < D) {
+      float p = warp_sum(acc[i]) + bin[i];
+      if (MODE == 0 && clamp > 0.f) p = tanhf(p / clamp) * clamp;
+      pv[i] = p;
+    }
+  }
+  if (MODE == 0 && spherical) {          // F.normalize(x, dim = -1) per codebook: x / max(||x||, 1e-12)
+    for (int cb = 0; cb < nc; ++cb) {
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < Q_MAXD; ++i)
+        if (i >= cb * d && i < (cb + 1) * d) ss = fmaf(pv[i], pv[i], ss);
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int i = 0; i < Q_MAXD; ++i)
+        if (i >= cb * d && i < (cb + 1) * d) pv[i] *= inv;
+    }
+  }
   int64_t index = 0;
   int32_t basis = 1;
+  int j = 0, cb = 0;                      // position inside the current codebook
 #pragma unroll
   for (int i = 0; i < Q_MAXD; ++i) {
     code[i] = 0.f;
-    if (i < d) {
-      float p = warp_sum(acc[i]) + bin[i];
+    if (i < D) {
+      const float p = pv[i];
       if (MODE == 0) {
-        if (clamp > 0.f) p = tanhf(p / clamp) * clamp;
         const bool bit = p > 0.f;
         code[i] = bit ? 1.f : -1.f;
-        if (bit) index |= (int64_t)1 << (d - 1 - i);
-        if (aux && lane == 0) aux[tok * d + i] = p;
+        if (bit) index |= (int64_t)1 << (d - 1 - j);
+        if (aux && lane == 0) aux[tok * D + i] = p;
       } else {
-        const int L = lv.lv[i];
+        const int L = lv.lv[j];
         const float half_l = (float)(L - 1) * (1.f + 1e-3f) * 0.5f;
         const float offset = (L % 2 == 0) ? 0.5f : 0.f;
         const float shift = atanhf(offset / half_l);
@@ -1939,13 +1964,16 @@ __global__ void __launch_bounds__(256) quant_forward_kernel(const T* __restrict_
         code[i] = q / (float)half_w;
         index += (int64_t)((int)q + half_w) * basis;
         basis *= L;
-        if (aux && lane == 0) aux[tok * d + i] = bnd;
+        if (aux && lane == 0) aux[tok * D + i] = bnd;
+      }
+      if (++j == d) {
+        if (lane == 0) {
+          if (idx64) idx64[tok * nc + cb] = index;
+          if (idx32) idx32[tok * nc + cb] = (int32_t)index;
+        }
+        j = 0; ++cb; index = 0; basis = 1;
       }
     }
-  }
-  if (lane == 0) {
-    if (idx64) idx64[tok] = index;
-    if (idx32) idx32[tok] = (int32_t)index;
   }
   if (quant) {
     T* qrow = quant + tok * C;
@@ -1953,7 +1981,7 @@ __global__ void __launch_bounds__(256) quant_forward_kernel(const T* __restrict_
       float o = bout[c];
 #pragma unroll
       for (int i = 0; i < Q_MAXD; ++i)
-        if (i < d) o = fmaf(code[i], wout[(int64_t)c * d + i], o);
+        if (i < D) o = fmaf(code[i], wout[(int64_t)c * D + i], o);
       qrow[c] = from_f32<T>(o);
     }
   }
@@ -1961,29 +1989,35 @@ __global__ void __launch_bounds__(256) quant_forward_kernel(const T* __restrict_
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) quant_decode_kernel(const void* __restrict__ indices, int is64, int64_t N, int C,
-                                                           int d, FsqLevels lv, const float* __restrict__ wout,
+                                                           int d, int nc, FsqLevels lv, const float* __restrict__ wout,
                                                            const float* __restrict__ bout, T* __restrict__ quant) {
   pdl_wait();
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t tok = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (tok >= N) return;
-  int64_t index = is64 ? ((const int64_t*)indices)[tok] : (int64_t)((const int32_t*)indices)[tok];
+  const int D = d * nc;
   float code[Q_MAXD];
-  int64_t rem = index;
+  int64_t index = 0, rem = 0;
+  int j = 0, cb = 0;
 #pragma unroll
   for (int i = 0; i < Q_MAXD; ++i) {
     code[i] = 0.f;
-    if (i < d) {
+    if (i < D) {
+      if (j == 0) {
+        index = is64 ? ((const int64_t*)indices)[tok * nc + cb] : (int64_t)((const int32_t*)indices)[tok * nc + cb];
+        rem = index;
+      }
       if (MODE == 0) {
-        code[i] = ((index >> (d - 1 - i)) & 1) ? 1.f : -1.f;
+        code[i] = ((index >> (d - 1 - j)) & 1) ? 1.f : -1.f;
       } else {
-        const int L = lv.lv[i];
+        const int L = lv.lv[j];
         const int digit = (int)(rem % L);
         rem /= L;
         const int half_w = L / 2;
         code[i] = (float)(digit - half_w) / (float)half_w;
       }
+      if (++j == d) { j = 0; ++cb; }
     }
   }
   T* qrow = quant + tok * C;
@@ -1991,15 +2025,16 @@ __global__ void __launch_bounds__(256) quant_decode_kernel(const void* __restric
     float o = bout[c];
 #pragma unroll
     for (int i = 0; i < Q_MAXD; ++i)
-      if (i < d) o = fmaf(code[i], wout[(int64_t)c * d + i], o);
+      if (i < D) o = fmaf(code[i], wout[(int64_t)c * D + i], o);
     qrow[c] = from_f32<T>(o);
   }
 }
 
-// LFQ training-mode entropy / commitment partial sums.  One block handles LE_TOK tokens.
+// LFQ training-mode entropy / commitment partial sums.  One block handles LE_TOK tokens of ONE codebook (blockIdx.y):
+// presign is [N][nc][d], avg_prob [nc][K].
 constexpr int LE_TOK = 32;
-__global__ void __launch_bounds__(256) lfq_entropy_kernel(const float* __restrict__ presign, int64_t N, int d,
-                                                          float inv_temp, float* __restrict__ avg_prob,
+__global__ void __launch_bounds__(256) lfq_entropy_kernel(const float* __restrict__ presign_all, int64_t N, int d, int nc,
+                                                          float inv_temp, float* __restrict__ avg_prob_all,
                                                           float* __restrict__ stats) {
   pdl_wait();
   pdl_launch_dependents();
@@ -2007,6 +2042,9 @@ __global__ void __launch_bounds__(256) lfq_entropy_kernel(const float* __restric
   __shared__ float red[8];
   __shared__ float bc;
   const int K = 1 << d;
+  const float* presign = presign_all + (int64_t)blockIdx.y * d;     // token stride below is nc * d
+  float* avg_prob = avg_prob_all + (int64_t)blockIdx.y * K;
+  const int tstride = nc * d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float ent_sum = 0.f, commit_sum = 0.f;
   const int64_t t0 = (int64_t)blockIdx.x * LE_TOK;
@@ -2017,7 +2055,7 @@ __global__ void __launch_bounds__(256) lfq_entropy_kernel(const float* __restric
   for (int64_t t = t0; t < min(N, t0 + LE_TOK); ++t) {
     float p[12];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) p[i] = (i < d) ? presign[t * d + i] : 0.f;
+    for (int i = 0; i < 12; ++i) p[i] = (i < d) ? presign[t * tstride + i] : 0.f;
     float mx = -INFINITY;
     for (int k = tid; k < K; k += 256) {
       float s = 0.f;
@@ -2150,12 +2188,12 @@ __global__ void __launch_bounds__(32) mse_final_kernel(const double* __restrict_
 //   p = avg_prob_sum / (N_global), aux = (per_sample - gamma * batch_entropy) * w_entropy + commitment * w_commit.
 // out[0..3] = per_sample, batch_entropy, commitment, aux.
 __global__ void __launch_bounds__(256) lfq_aux_final_kernel(const float* __restrict__ avg_prob_sum, const float* __restrict__ stats, int K,
-                                                            float inv_tokens_global, float inv_tokens, float inv_elems, float gamma,
+                                                            int nc, float inv_tokens_global, float inv_tokens, float inv_elems, float gamma,
                                                             float w_entropy, float w_commit, float* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
   float t = 0.f;
-  for (int k = threadIdx.x; k < K; k += 256) {
+  for (int k = threadIdx.x; k < K * nc; k += 256) {     // codebook entropy: mean over the codebooks of sum_k -p log p
     const float p = avg_prob_sum[k] * inv_tokens_global;
     t += -p * logf(fmaxf(p, 1e-5f));
   }
@@ -2167,6 +2205,7 @@ __global__ void __launch_bounds__(256) lfq_aux_final_kernel(const float* __restr
     float be = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) be += sw[w];
+    be /= (float)nc;
     const float ps = stats[0] * inv_tokens, cm = stats[1] * inv_elems;
     out[0] = ps; out[1] = be; out[2] = cm;
     out[3] = (ps - gamma * be) * w_entropy + cm * w_commit;
@@ -2597,78 +2636,83 @@ int mv2_geglu(const void* in, void* out, int dtype, int64_t N, int I, void* stre
   return MV2_OK;
 }
 
-int mv2_lfq_forward(const void* x, int dtype, int64_t N, int C, int d, const float* win, const float* bin,
-                    const float* wout, const float* bout, float clamp, int64_t* indices, void* quantized,
+int mv2_lfq_forward(const void* x, int dtype, int64_t N, int C, int d, int num_codebooks, const float* win, const float* bin,
+                    const float* wout, const float* bout, float clamp, int spherical, int64_t* indices, void* quantized,
                     float* presign, void* stream) {
-  MV2_CHECK_ARG(x && win && bin && N > 0 && C > 0 && d > 0 && d <= Q_MAXD);
+  const int nc = num_codebooks;
+  MV2_CHECK_ARG(x && win && bin && N > 0 && C > 0 && d > 0 && nc > 0 && d * nc <= Q_MAXD);
   MV2_CHECK_ARG(!quantized || (wout && bout));
   FsqLevels lv = {};
   const int blocks = ceil_div(N, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
-    launch_k(quant_forward_kernel<float, 0>, dim3(blocks), dim3(256), 0, st, (const float*)x, N, C, d, win, bin, wout, bout, clamp, lv, indices, nullptr, (float*)quantized, presign);
+    launch_k(quant_forward_kernel<float, 0>, dim3(blocks), dim3(256), 0, st, (const float*)x, N, C, d, nc, win, bin, wout, bout, clamp, spherical, lv, indices, nullptr, (float*)quantized, presign);
   else if (dtype == MV2_BF16)
-    launch_k(quant_forward_kernel<__nv_bfloat16, 0>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, N, C, d, win, bin, wout, bout, clamp, lv, indices, nullptr, (__nv_bfloat16*)quantized, presign);
+    launch_k(quant_forward_kernel<__nv_bfloat16, 0>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, N, C, d, nc, win, bin, wout, bout, clamp, spherical, lv, indices, nullptr, (__nv_bfloat16*)quantized, presign);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }
 
-int mv2_lfq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d, const float* wout,
+int mv2_lfq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d, int num_codebooks, const float* wout,
                    const float* bout, void* quantized, int dtype, void* stream) {
-  MV2_CHECK_ARG(indices && wout && bout && quantized && N > 0 && C > 0 && d > 0 && d <= Q_MAXD);
+  const int nc = num_codebooks;
+  MV2_CHECK_ARG(indices && wout && bout && quantized && N > 0 && C > 0 && d > 0 && nc > 0 && d * nc <= Q_MAXD);
   FsqLevels lv = {};
   const int blocks = ceil_div(N, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
-    launch_k(quant_decode_kernel<float, 0>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, lv, wout, bout, (float*)quantized);
+    launch_k(quant_decode_kernel<float, 0>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, nc, lv, wout, bout, (float*)quantized);
   else if (dtype == MV2_BF16)
-    launch_k(quant_decode_kernel<__nv_bfloat16, 0>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, lv, wout, bout, (__nv_bfloat16*)quantized);
+    launch_k(quant_decode_kernel<__nv_bfloat16, 0>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, nc, lv, wout, bout, (__nv_bfloat16*)quantized);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }
 
-int mv2_fsq_forward(const void* x, int dtype, int64_t N, int C, int d, const int32_t* levels, const float* win,
+int mv2_fsq_forward(const void* x, int dtype, int64_t N, int C, int d, int num_codebooks, const int32_t* levels, const float* win,
                     const float* bin, const float* wout, const float* bout, int32_t* indices, void* quantized,
                     float* bounded, void* stream) {
-  MV2_CHECK_ARG(x && levels && win && bin && N > 0 && C > 0 && d > 0 && d <= Q_MAXD);
+  const int nc = num_codebooks;
+  MV2_CHECK_ARG(x && levels && win && bin && N > 0 && C > 0 && d > 0 && nc > 0 && d * nc <= Q_MAXD);
   MV2_CHECK_ARG(!quantized || (wout && bout));
   FsqLevels lv = {};
   for (int i = 0; i < d; ++i) { MV2_CHECK_ARG(levels[i] >= 2); lv.lv[i] = levels[i]; }
   const int blocks = ceil_div(N, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
-    launch_k(quant_forward_kernel<float, 1>, dim3(blocks), dim3(256), 0, st, (const float*)x, N, C, d, win, bin, wout, bout, 0.f, lv, nullptr, indices, (float*)quantized, bounded);
+    launch_k(quant_forward_kernel<float, 1>, dim3(blocks), dim3(256), 0, st, (const float*)x, N, C, d, nc, win, bin, wout, bout, 0.f, 0, lv, nullptr, indices, (float*)quantized, bounded);
   else if (dtype == MV2_BF16)
-    launch_k(quant_forward_kernel<__nv_bfloat16, 1>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, N, C, d, win, bin, wout, bout, 0.f, lv, nullptr, indices, (__nv_bfloat16*)quantized, bounded);
+    launch_k(quant_forward_kernel<__nv_bfloat16, 1>, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)x, N, C, d, nc, win, bin, wout, bout, 0.f, 0, lv, nullptr, indices, (__nv_bfloat16*)quantized, bounded);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }
 
-int mv2_fsq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d, const int32_t* levels,
+int mv2_fsq_decode(const void* indices, int index_is_i64, int64_t N, int C, int d, int num_codebooks, const int32_t* levels,
                    const float* wout, const float* bout, void* quantized, int dtype, void* stream) {
-  MV2_CHECK_ARG(indices && levels && wout && bout && quantized && N > 0 && C > 0 && d > 0 && d <= Q_MAXD);
+  const int nc = num_codebooks;
+  MV2_CHECK_ARG(indices && levels && wout && bout && quantized && N > 0 && C > 0 && d > 0 && nc > 0 && d * nc <= Q_MAXD);
   FsqLevels lv = {};
   for (int i = 0; i < d; ++i) { MV2_CHECK_ARG(levels[i] >= 2); lv.lv[i] = levels[i]; }
   const int blocks = ceil_div(N, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == MV2_F32)
-    launch_k(quant_decode_kernel<float, 1>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, lv, wout, bout, (float*)quantized);
+    launch_k(quant_decode_kernel<float, 1>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, nc, lv, wout, bout, (float*)quantized);
   else if (dtype == MV2_BF16)
-    launch_k(quant_decode_kernel<__nv_bfloat16, 1>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, lv, wout, bout, (__nv_bfloat16*)quantized);
+    launch_k(quant_decode_kernel<__nv_bfloat16, 1>, dim3(blocks), dim3(256), 0, st, indices, index_is_i64, N, C, d, nc, lv, wout, bout, (__nv_bfloat16*)quantized);
   else { set_error("bad dtype %d", dtype); return MV2_E_ARG; }
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }
 
-int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, float inv_temperature, float* avg_prob,
+int mv2_lfq_entropy_partials(const float* presign, int64_t N, int d, int num_codebooks, float inv_temperature, float* avg_prob,
                              float* stats, void* stream) {
-  MV2_CHECK_ARG(presign && avg_prob && stats && N > 0 && d > 0 && d <= 12);
+  MV2_CHECK_ARG(presign && avg_prob && stats && N > 0 && d > 0 && d <= 12 && num_codebooks > 0 && num_codebooks <= 65535);
   const int K = 1 << d;
   const int blocks = ceil_div(N, LE_TOK);
-  launch_k(lfq_entropy_kernel, dim3(blocks), dim3(256), K * sizeof(float), (cudaStream_t)stream, presign, N, d, inv_temperature, avg_prob, stats);
+  launch_k(lfq_entropy_kernel, dim3(dim3(blocks, num_codebooks)), dim3(256), K * sizeof(float), (cudaStream_t)stream, presign, N, d, num_codebooks,
+           inv_temperature, avg_prob, stats);
   MV2_CHECK_LAUNCH();
   return MV2_OK;
 }
@@ -2693,11 +2737,12 @@ int mv2_mse(const void* a, int a_dtype, const void* b, int b_dtype, int64_t n, v
 }
 size_t mv2_mse_workspace_bytes(void) { return (size_t)MSE_BLOCKS * sizeof(double); }
 
-int mv2_lfq_aux_finalize(const float* avg_prob_sum, const float* stats, int d, int64_t n_tokens, int64_t n_tokens_global,
+int mv2_lfq_aux_finalize(const float* avg_prob_sum, const float* stats, int d, int num_codebooks, int64_t n_tokens, int64_t n_tokens_global,
                          float diversity_gamma, float entropy_weight, float commitment_weight, float* out4, void* stream) {
-  MV2_CHECK_ARG(avg_prob_sum && stats && out4 && d > 0 && d <= 12 && n_tokens > 0 && n_tokens_global > 0);
-  launch_k(lfq_aux_final_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, avg_prob_sum, stats, 1 << d,
-           (float)(1.0 / (double)n_tokens_global), (float)(1.0 / (double)n_tokens), (float)(1.0 / ((double)n_tokens * d)),
+  const int nc = num_codebooks;
+  MV2_CHECK_ARG(avg_prob_sum && stats && out4 && d > 0 && d <= 12 && nc > 0 && n_tokens > 0 && n_tokens_global > 0);
+  launch_k(lfq_aux_final_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, avg_prob_sum, stats, 1 << d, nc,
+           (float)(1.0 / (double)n_tokens_global), (float)(1.0 / ((double)n_tokens * nc)), (float)(1.0 / ((double)n_tokens * nc * d)),
            diversity_gamma, entropy_weight, commitment_weight, out4);
   MV2_CHECK_LAUNCH();
   return MV2_OK;

@@ -58,8 +58,9 @@ class LfqBatchEntropy:
     all-reduce on a side stream.  start() launches; finish() returns
     (per_sample_entropy, batch_entropy, commitment, aux_loss) as 0-d tensors."""
 
-    def __init__(self, engine, inv_temperature: float = 100.0):
+    def __init__(self, engine, inv_temperature: float = 100.0, num_codebooks: int = 1):
         self.eng = engine
+        self.nc = int(num_codebooks)
         self.inv_temperature = inv_temperature
         self.side = torch.cuda.Stream(device=engine.device)
         self._pending = None
@@ -67,13 +68,14 @@ class LfqBatchEntropy:
     def start(self, presign: torch.Tensor, group=None):
         from ._lib import check
         eng = self.eng
-        N, d = presign.shape
+        N, D = presign.shape
+        d = D // self.nc                 # presign is [N][num_codebooks][d]
         K = 1 << d
-        avg = torch.zeros(K, device=presign.device, dtype=torch.float32)
+        avg = torch.zeros(self.nc * K, device=presign.device, dtype=torch.float32)
         stats = torch.zeros(2, device=presign.device, dtype=torch.float32)
         self.side.wait_stream(torch.cuda.current_stream(eng.device))
         with torch.cuda.stream(self.side):
-            check(eng.lib.mv2_lfq_entropy_partials(presign.data_ptr(), N, d, float(self.inv_temperature), avg.data_ptr(),
+            check(eng.lib.mv2_lfq_entropy_partials(presign.data_ptr(), N, d, self.nc, float(self.inv_temperature), avg.data_ptr(),
                                                    stats.data_ptr(), C.c_void_p(self.side.cuda_stream)),
                   "mv2_lfq_entropy_partials")
             eng.launches += 1
@@ -95,7 +97,7 @@ class LfqBatchEntropy:
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         out = torch.empty(4, device=avg.device, dtype=torch.float32)
         # avg is already a per-rank mean: "tokens_global" = number of ranks summed; per-rank terms use the local N
-        check(eng.lib.mv2_lfq_aux_finalize(avg.data_ptr(), stats.data_ptr(), d, N, world, float(diversity_gamma), float(entropy_w),
+        check(eng.lib.mv2_lfq_aux_finalize(avg.data_ptr(), stats.data_ptr(), d, self.nc, N, world, float(diversity_gamma), float(entropy_w),
                                            float(commit_w), out.data_ptr(), C.c_void_p(cur.cuda_stream)), "mv2_lfq_aux_finalize")
         eng.launches += 1
         self._pending = None

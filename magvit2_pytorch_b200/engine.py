@@ -746,46 +746,49 @@ class Engine:
         return self.to_channels_first(x, t_crop=tp)
 
     def quantize_cl(self, x, want_quantized=True, want_aux=False):
-        """x channels-last -> (quantized channels-last | None, indices (B,T,H,W), aux fp32 [N][d] | None)."""
+        """x channels-last -> (quantized channels-last | None, indices (B,T,H,W[,num_codebooks]), aux fp32 [N][D] | None)."""
         m = self.model
         B, T, H, W, Cc = x.shape
         N = B * T * H * W
         P = self._packs["quant"]
         q = self._new(x.shape) if want_quantized else None
-        d = m.quantizers.codebook_dim
-        aux = self._new((N, d), torch.float32) if want_aux else None
+        qz = m.quantizers
+        d, nc = qz.codebook_dim, qz.num_codebooks
+        ishape = (B, T, H, W) if nc == 1 else (B, T, H, W, nc)      # keep_num_codebooks_dim = num_codebooks > 1 (A.1 step 9)
+        aux = self._new((N, d * nc), torch.float32) if want_aux else None
         if m.use_fsq:
-            idx = torch.empty((B, T, H, W), device=self.device, dtype=torch.int32)
-            lv = (C.c_int32 * d)(*m.quantizers.levels)
-            check(self.lib.mv2_fsq_forward(_ptr(x), _dt(self.dtype), N, Cc, d, lv, _ptr(P["win"]), _ptr(P["bin"]),
+            idx = torch.empty(ishape, device=self.device, dtype=torch.int32)
+            lv = (C.c_int32 * d)(*qz.levels)
+            check(self.lib.mv2_fsq_forward(_ptr(x), _dt(self.dtype), N, Cc, d, nc, lv, _ptr(P["win"]), _ptr(P["bin"]),
                                            _ptr(P["wout"]), _ptr(P["bout"]), _ptr(idx), _ptr(q), _ptr(aux),
                                            self._stream()), "mv2_fsq_forward")
         else:
-            idx = torch.empty((B, T, H, W), device=self.device, dtype=torch.int64)
-            clamp = m.quantizers.soft_clamp_input_value
-            check(self.lib.mv2_lfq_forward(_ptr(x), _dt(self.dtype), N, Cc, d, _ptr(P["win"]), _ptr(P["bin"]),
-                                           _ptr(P["wout"]), _ptr(P["bout"]), float(clamp) if clamp else 0.0,
+            idx = torch.empty(ishape, device=self.device, dtype=torch.int64)
+            clamp = qz.soft_clamp_input_value
+            check(self.lib.mv2_lfq_forward(_ptr(x), _dt(self.dtype), N, Cc, d, nc, _ptr(P["win"]), _ptr(P["bin"]),
+                                           _ptr(P["wout"]), _ptr(P["bout"]), float(clamp) if clamp else 0.0, int(qz.spherical),
                                            _ptr(idx), _ptr(q), _ptr(aux), self._stream()), "mv2_lfq_forward")
         self.launches += 1
         return q, idx, aux
 
     def codes_to_quantized_cl(self, codes: torch.Tensor):
-        """indices (B,T,H,W) int64/int32 -> quantized channels-last.  LFQ/FSQ.indices_to_codes (M:1593)."""
+        """indices (B,T,H,W[,num_codebooks]) int64/int32 -> quantized channels-last.  LFQ/FSQ.indices_to_codes (M:1593)."""
         m = self.model
         codes = codes.contiguous()
-        B, T, H, W = codes.shape
-        Cc = m.quantizers.dim
+        B, T, H, W = codes.shape[:4]
+        qz = m.quantizers
+        Cc = qz.dim
         N = B * T * H * W
         P = self._packs["quant"]
-        d = m.quantizers.codebook_dim
+        d, nc = qz.codebook_dim, qz.num_codebooks
         q = self._new((B, T, H, W, Cc))
         is64 = int(codes.dtype == torch.int64)
         if m.use_fsq:
-            lv = (C.c_int32 * d)(*m.quantizers.levels)
-            check(self.lib.mv2_fsq_decode(_ptr(codes), is64, N, Cc, d, lv, _ptr(P["wout"]), _ptr(P["bout"]), _ptr(q),
+            lv = (C.c_int32 * d)(*qz.levels)
+            check(self.lib.mv2_fsq_decode(_ptr(codes), is64, N, Cc, d, nc, lv, _ptr(P["wout"]), _ptr(P["bout"]), _ptr(q),
                                           _dt(self.dtype), self._stream()), "mv2_fsq_decode")
         else:
-            check(self.lib.mv2_lfq_decode(_ptr(codes), is64, N, Cc, d, _ptr(P["wout"]), _ptr(P["bout"]), _ptr(q),
+            check(self.lib.mv2_lfq_decode(_ptr(codes), is64, N, Cc, d, nc, _ptr(P["wout"]), _ptr(P["bout"]), _ptr(q),
                                           _dt(self.dtype), self._stream()), "mv2_lfq_decode")
         self.launches += 1
         return q

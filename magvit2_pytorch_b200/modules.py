@@ -228,37 +228,47 @@ class FeedForward(_NoForward):
 
 class LFQ(_NoForward):
     """Parameter/buffer layout of vector_quantize_pytorch.LFQ:
-    persistent int64 ``mask``, Linear ``project_in`` / ``project_out`` (with bias)."""
+    persistent int64 ``mask``, Linear ``project_in`` / ``project_out`` (with bias) between ``dim`` and
+    ``log2(codebook_size) * num_codebooks`` channels."""
 
     def __init__(self, dim, codebook_size, entropy_loss_weight, commitment_loss_weight, diversity_gamma,
-                 soft_clamp_input_value):
+                 soft_clamp_input_value, num_codebooks=1, spherical=False):
         super().__init__()
         d = int(math.log2(codebook_size))
         assert 2 ** d == codebook_size, "codebook_size must be a power of two"
         self.dim, self.codebook_size, self.codebook_dim = dim, codebook_size, d
+        self.num_codebooks = int(num_codebooks)
+        self.spherical = bool(spherical)
         self.entropy_loss_weight = entropy_loss_weight
         self.commitment_loss_weight = commitment_loss_weight
         self.diversity_gamma = diversity_gamma
         self.soft_clamp_input_value = soft_clamp_input_value
-        if dim == d:
-            raise NotImplementedError("LFQ without projections (dim == log2(codebook_size)) is not supported")
-        self.project_in = nn.Linear(dim, d)
-        self.project_out = nn.Linear(d, dim)
+        cdims = d * self.num_codebooks
+        if dim == cdims:
+            raise NotImplementedError("LFQ without projections (dim == log2(codebook_size) * num_codebooks) is not supported")
+        if cdims > 16:
+            raise NotImplementedError("the quantiser kernels take at most 16 projected dims (log2(codebook_size) * num_codebooks)")
+        self.project_in = nn.Linear(dim, cdims)
+        self.project_out = nn.Linear(cdims, dim)
         self.register_buffer("mask", 2 ** torch.arange(d - 1, -1, -1))
 
 
 class FSQ(_NoForward):
     """Parameter layout of vector_quantize_pytorch.FSQ."""
 
-    def __init__(self, levels, dim):
+    def __init__(self, levels, dim, num_codebooks=1):
         super().__init__()
         self.levels = [int(l) for l in levels]
+        self.num_codebooks = int(num_codebooks)
         self.dim, self.codebook_dim = dim, len(levels)
         self.codebook_size = int(math.prod(self.levels))
-        if dim == len(levels):
+        cdims = len(levels) * self.num_codebooks
+        if dim == cdims:
             raise NotImplementedError("FSQ without projections is not supported")
-        self.project_in = nn.Linear(dim, len(levels))
-        self.project_out = nn.Linear(len(levels), dim)
+        if cdims > 16:
+            raise NotImplementedError("the quantiser kernels take at most 16 projected dims (len(levels) * num_codebooks)")
+        self.project_in = nn.Linear(dim, cdims)
+        self.project_out = nn.Linear(cdims, dim)
 
 
 class CausalConvTranspose3d(nn.Module):

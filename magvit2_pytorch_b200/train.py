@@ -158,29 +158,32 @@ def _lfq_train(x, qz, avg_global, inv_temperature=100.):
     `avg_global` is the cross-rank mean code probability of the forward pass; the local term enters as
     avg_local + (avg_global - avg_local).detach(), which reproduces the gradient of the reference's autograd-aware
     all-reduce (each rank back-propagates d H / d avg_global into its own tokens)."""
-    d = qz.codebook_dim
+    d, nc = qz.codebook_dim, qz.num_codebooks
     p = F.linear(x, qz.project_in.weight, qz.project_in.bias)
     cv = qz.soft_clamp_input_value
     if cv:
         p = (p / cv).tanh() * cv
+    p = p.reshape(-1, nc, d)
+    if qz.spherical:
+        p = F.normalize(p, dim=-1)
     p = p.float()
     qd = torch.where(p > 0, torch.ones_like(p), -torch.ones_like(p))
-    st = p + (qd - p).detach()
+    st = (p + (qd - p).detach()).reshape(*x.shape[:-1], nc * d)
     out = F.linear(st.to(x.dtype), qz.project_out.weight, qz.project_out.bias)
     mask = qz.mask.to(p.device)
     codebook = ((torch.arange(2 ** d, device=p.device)[:, None] & mask) != 0).float() * 2 - 1
-    prob = (2 * inv_temperature * (p.reshape(-1, d) @ codebook.t())).softmax(dim=-1)
+    prob = (2 * inv_temperature * torch.einsum("tcd,kd->tck", p, codebook)).softmax(dim=-1)      # (tokens, nc, K)
     per_sample = _entropy(prob).mean()
-    avg_local = prob.mean(dim=0)
-    avg = avg_local + (avg_global - avg_local).detach()
+    avg_local = prob.mean(dim=0)                                                                  # (nc, K)
+    avg = avg_local + (avg_global.reshape(nc, -1) - avg_local).detach()
     commit = ((p - qd) ** 2).mean()
-    aux = (per_sample - qz.diversity_gamma * _entropy(avg)) * qz.entropy_loss_weight + commit * qz.commitment_loss_weight
+    aux = (per_sample - qz.diversity_gamma * _entropy(avg).mean()) * qz.entropy_loss_weight + commit * qz.commitment_loss_weight
     return out, aux
 
 
 def _fsq_train(x, qz):
     """FSQ forward with the round() straight-through estimator."""
-    lv = torch.tensor(qz.levels, dtype=torch.int32, device=x.device)
+    lv = torch.tensor(qz.levels * qz.num_codebooks, dtype=torch.int32, device=x.device)     # the levels repeat per codebook
     z = F.linear(x, qz.project_in.weight, qz.project_in.bias).float()
     half_l = (lv - 1) * (1 + 1e-3) / 2
     offset = torch.where(lv % 2 == 0, 0.5, 0.0)
@@ -370,7 +373,7 @@ class TrainRunner:
         else:
             xq = x
             q, self.codes, pre = eng.quantize_cl(x, want_quantized=True, want_aux=True)
-            be = LfqBatchEntropy(eng)
+            be = LfqBatchEntropy(eng, num_codebooks=qz.num_codebooks)
             be.start(pre, group)
             avg_sum = be._pending[0]
             ps, bent, commit, aux = be.finish(qz.diversity_gamma, qz.entropy_loss_weight, qz.commitment_loss_weight, group)

@@ -17,7 +17,7 @@ factorisation in include/magvit2_b200.h; the other ``cond_*`` types raise in the
 ``forward(return_loss=True)`` (reconstruction + quantiser auxiliary loss; models built with ``use_gan=False,
 perceptual_loss_weight=0``) runs on the device; in ``model.train()`` with gradients enabled it returns a loss with a
 ``grad_fn`` (train.py: forward by the same kernels, backward by library code).
-Out of scope (raise at construction / call): ``num_codebooks > 1``, ``lfq_spherical``, the
+Out of scope (raise at construction / call): the
 GAN / perceptual training losses (``return_discr_loss``, ``return_loss`` with a discriminator or VGG).
 """
 from __future__ import annotations
@@ -128,10 +128,6 @@ class VideoTokenizer(nn.Module):
 
         if not isinstance(layers, tuple):
             raise TypeError("layers must be a tuple")
-        if num_codebooks != 1:
-            raise NotImplementedError("num_codebooks > 1 is not supported")
-        if lfq_spherical:
-            raise NotImplementedError("lfq_spherical is not supported")
         if pad_mode not in ("constant", "reflect", "replicate", "circular"):
             raise ValueError(f"unknown pad_mode {pad_mode!r}")
         if attn_dropout != 0.:
@@ -247,11 +243,11 @@ class VideoTokenizer(nn.Module):
             assert codebook_size is not None and fsq_levels is None, \
                 "if use_fsq is set to False, `codebook_size` must be set (and not `fsq_levels`)"
             self.quantizers = M.LFQ(dim, codebook_size, lfq_entropy_loss_weight, lfq_commitment_loss_weight,
-                                    lfq_diversity_gamma, lfq_soft_clamp_input_value)
+                                    lfq_diversity_gamma, lfq_soft_clamp_input_value, num_codebooks, lfq_spherical)   # M:1364-1373
         else:
             assert codebook_size is None and fsq_levels is not None, \
                 "if use_fsq is set to True, `fsq_levels` must be set (and not `codebook_size`)"
-            self.quantizers = M.FSQ(fsq_levels, dim)
+            self.quantizers = M.FSQ(fsq_levels, dim, num_codebooks)                        # M:1378-1382
         self.quantizer_aux_loss_weight = quantizer_aux_loss_weight
         self.register_buffer("zero", torch.tensor(0.), persistent=False)
 
@@ -475,7 +471,9 @@ class VideoTokenizer(nn.Module):
                 f"flattened video ids must have a length ({n}) that is divisible by the fmap size " \
                 f"({self.fmap_size}) squared ({self.fmap_size ** 2})"
             codes = codes.reshape(codes.shape[0], -1, self.fmap_size, self.fmap_size)
-        assert codes.ndim == 4, f"codes must be (B, T, H, W) or flat (B, N), got {tuple(codes.shape)}"
+        nc = self.quantizers.num_codebooks
+        assert codes.ndim == (4 if nc == 1 else 5) and (nc == 1 or codes.shape[-1] == nc), \
+            f"codes must be (B, T, H, W{'' if nc == 1 else ', num_codebooks'}) or flat (B, N), got {tuple(codes.shape)}"
         self._check_on_device(codes, "codes")
         eng = self.engine
         ff = bool(video_contains_first_frame)
@@ -500,7 +498,7 @@ class VideoTokenizer(nn.Module):
         x = eng.encode_cl(video)
         _, codes, pre = eng.quantize_cl(x, want_quantized=False, want_aux=True)
         q = self.quantizers
-        be = LfqBatchEntropy(eng)
+        be = LfqBatchEntropy(eng, num_codebooks=q.num_codebooks)
         be.start(pre, group)
         ps, bent, commit, aux = be.finish(q.diversity_gamma, q.entropy_loss_weight, q.commitment_loss_weight, group)
         return codes, (ps, bent, commit), aux
@@ -524,7 +522,7 @@ class VideoTokenizer(nn.Module):
         sfx = "" if ff else "_noff"
         res = self._graph_call(("train_enc_q" if need_recon else "train_enc") + sfx, enc, video)
         codes, pre = res[0], res[1]
-        be = LfqBatchEntropy(eng)
+        be = LfqBatchEntropy(eng, num_codebooks=qz.num_codebooks)
         be.start(pre, group)                                   # partial sums + all-reduce on the side stream ...
         recon = self._graph_call("train_dec" + sfx, lambda t: eng.decode_cl(t, ff), res[2]) if need_recon else None   # ... under the decoder
         ps, bent, commit, aux = be.finish(qz.diversity_gamma, qz.entropy_loss_weight, qz.commitment_loss_weight, group)

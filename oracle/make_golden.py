@@ -88,6 +88,13 @@ CONFIGS = {
     "mini_gateloop": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024,
                                       layers=("residual", "compress_space", "gateloop_time", "compress_time", "gateloop_time", "residual")),
                           video=(2, 3, 9, 32, 32), wseed=0, vseed=1237, full=True),
+    # num_codebooks > 1 (M:1057 -> M:1367 / M:1381) and lfq_spherical (M:1070 -> M:1372): indices keep a trailing codebook axis
+    "mini_mc": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=256, num_codebooks=2, lfq_spherical=True,
+                                layers=("residual", "compress_space", "compress_time", "residual")),
+                    video=(2, 3, 5, 32, 32), wseed=0, vseed=1238, full=True),
+    "mini_mc_fsq": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, use_fsq=True, fsq_levels=[8, 5, 5], num_codebooks=2,
+                                    layers=("residual", "compress_space", "compress_time", "residual")),
+                        video=(2, 3, 5, 32, 32), wseed=0, vseed=1238, full=True),
     "mini_sff": dict(kwargs=dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, separate_first_frame_encoding=True,
                                  layers=("residual", "compress_space", "compress_time", "residual")),
                      video=(2, 3, 5, 32, 32), wseed=0, vseed=1234, full=True),
@@ -164,6 +171,9 @@ def make(name: str):
         pre = proj   # raw project_in output; bounding is re-derived by the checker
     else:
         pre = (proj / 10.).tanh() * 10.
+        if kwargs.get("lfq_spherical"):
+            nc_ = kwargs.get("num_codebooks", 1)
+            pre = torch.nn.functional.normalize(pre.reshape(*pre.shape[:-1], nc_, -1), dim=-1).reshape(pre.shape)
     out = dict(
         name=name, kwargs=kwargs, video_shape=tuple(cfg["video"]), wseed=cfg["wseed"], vseed=cfg["vseed"],
         codes=codes.clone(), presign=pre.clone(),

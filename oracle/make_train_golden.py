@@ -66,3 +66,4 @@ def make(name="mini_train", base="mini", vseed=1234):
 
 if __name__ == "__main__":
     make()
+    make("mini_mc_train", base="mini_mc", vseed=1238)       # num_codebooks = 2, lfq_spherical

@@ -307,57 +307,65 @@ def feed_forward(x, sd, p):
 # quantisers (un-vendored dependency)
 # ----------------------------------------------------------------------------
 
-def lfq_presign(x, sd, clamp=10.):
-    """project_in + tanh soft clamp; returns fp32 (B, N, d) pre-sign values."""
+def lfq_presign(x, sd, clamp=10., nc=1, spherical=False):
+    """project_in + tanh soft clamp (+ per-codebook L2 normalisation when spherical, A.1 step 4);
+    returns fp32 (B, N, nc * d) pre-sign values."""
     b, c = x.shape[:2]
     tok = x.permute(0, 2, 3, 4, 1).reshape(b, -1, c)
     p = F.linear(tok, sd["quantizers.project_in.weight"], sd["quantizers.project_in.bias"])
     if clamp is not None:
         p = (p / clamp).tanh() * clamp
+    if spherical:
+        p = F.normalize(p.reshape(b, p.shape[1], nc, -1), dim=-1).reshape(p.shape)
     return p.float()
 
 
-def lfq_quantize(x, sd, clamp=10.):
-    """LFQ eval forward (A.1 steps 1-6, 9): returns (quantized (B,C,T,H,W), indices int64 (B,T,H,W), presign)."""
+def lfq_quantize(x, sd, clamp=10., nc=1, spherical=False):
+    """LFQ eval forward (A.1 steps 1-6, 9): returns (quantized (B,C,T,H,W), indices int64 (B,T,H,W[,nc]), presign)."""
     b, c, t, h, w = x.shape
-    p = lfq_presign(x, sd, clamp)
+    p = lfq_presign(x, sd, clamp, nc, spherical)
     q = torch.where(p > 0, torch.ones_like(p), -torch.ones_like(p))
     mask = sd["quantizers.mask"].to(torch.int32)
-    idx = ((q > 0).int() * mask).sum(dim=-1)                       # int64 (torch.sum promotes)
+    idx = ((q.reshape(b, -1, nc, mask.numel()) > 0).int() * mask).sum(dim=-1)      # int64 (torch.sum promotes)
     out = F.linear(q.to(x.dtype), sd["quantizers.project_out.weight"], sd["quantizers.project_out.bias"])
     out = out.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
-    return out, idx.reshape(b, t, h, w), p
+    idx = idx.reshape(b, t, h, w, nc)
+    return out, (idx[..., 0] if nc == 1 else idx), p                               # keep_num_codebooks_dim = nc > 1
 
 
-def lfq_indices_to_codes(idx, sd, dtype):
+def lfq_indices_to_codes(idx, sd, dtype, nc=1):
     """LFQ.indices_to_codes (A.1 last line): bits -> +-1 -> project_out -> channel first."""
     mask = sd["quantizers.mask"]
-    bits = ((idx[..., None].to(torch.int64) & mask) != 0).to(dtype)
-    codes = bits * 2 - 1
+    if nc == 1:
+        idx = idx[..., None]
+    bits = ((idx[..., None].to(torch.int64) & mask) != 0).to(dtype)                # (..., nc, d)
+    codes = (bits * 2 - 1).reshape(*idx.shape[:-1], -1)
     out = F.linear(codes, sd["quantizers.project_out.weight"].to(dtype), sd["quantizers.project_out.bias"].to(dtype))
     return out.movedim(-1, 1)
 
 
 def lfq_train_losses(p, d_bits, world_reduce=None, inv_temperature=100., diversity_gamma=2.5,
-                     entropy_w=0.1, commit_w=1.0):
-    """LFQ training-mode auxiliary terms (A.1 steps 7, 8, 10) from fp32 pre-sign values p (B, N, d).
-    ``world_reduce`` optionally maps the local avg_prob to the cross-rank mean (the 4 KiB all-reduce)."""
+                     entropy_w=0.1, commit_w=1.0, nc=1):
+    """LFQ training-mode auxiliary terms (A.1 steps 7, 8, 10) from fp32 pre-sign values p (B, N, nc * d).
+    ``world_reduce`` optionally maps the local avg_prob (nc, K) to the cross-rank mean (the 4 KiB all-reduce)."""
     K = 2 ** d_bits
     codes = torch.arange(K)
     mask = 2 ** torch.arange(d_bits - 1, -1, -1)
     codebook = ((codes[:, None] & mask) != 0).float() * 2 - 1
-    x = p.reshape(-1, d_bits).float()
-    logits = 2 * inv_temperature * (x @ codebook.t())
+    x = p.reshape(-1, nc, d_bits).float()
+    logits = 2 * inv_temperature * torch.einsum("tcd,kd->tck", x, codebook)
     prob = logits.softmax(dim=-1)
 
     def ent(pr):
         return (-pr * torch.log(pr.clamp(min=1e-5))).sum(dim=-1)
 
     per_sample = ent(prob).mean()
-    avg = prob.mean(dim=0)
+    avg = prob.mean(dim=0)                                            # (nc, K)
+    if nc == 1:
+        avg = avg[0]
     if world_reduce is not None:
         avg = world_reduce(avg)
-    batch_ent = ent(avg)
+    batch_ent = ent(avg).mean()
     q = torch.where(x > 0, torch.ones_like(x), -torch.ones_like(x))
     commit = ((x - q) ** 2).mean()
     aux = (per_sample - diversity_gamma * batch_ent) * entropy_w + commit * commit_w
@@ -370,30 +378,35 @@ def _fsq_consts(levels, dtype=torch.float32):
     return lv, basis
 
 
-def fsq_quantize(x, sd, levels):
-    """FSQ forward (A.2): project_in, tanh bound, round-half-even, mixed-radix int32 index, project_out."""
+def fsq_quantize(x, sd, levels, nc=1):
+    """FSQ forward (A.2): project_in, tanh bound, round-half-even, mixed-radix int32 index per codebook, project_out."""
     b, c, t, h, w = x.shape
     lv, basis = _fsq_consts(levels)
     tok = x.permute(0, 2, 3, 4, 1).reshape(b, -1, c)
     z = F.linear(tok, sd["quantizers.project_in.weight"], sd["quantizers.project_in.bias"])
     zf = z if z.dtype in (torch.float32, torch.float64) else z.float()
+    zf = zf.reshape(b, -1, nc, len(levels))
     half_l = (lv - 1) * (1 + 1e-3) / 2
     offset = torch.where(lv % 2 == 0, 0.5, 0.0)
     shift = (offset / half_l).atanh()
     bounded = (zf + shift).tanh() * half_l - offset
     half_w = lv // 2
     codes = bounded.round() / half_w
-    idx = ((codes * half_w + half_w) * basis).sum(dim=-1).to(torch.int32)
-    out = F.linear(codes.to(x.dtype), sd["quantizers.project_out.weight"], sd["quantizers.project_out.bias"])
+    idx = ((codes * half_w + half_w) * basis).sum(dim=-1).to(torch.int32)          # (b, n, nc)
+    out = F.linear(codes.reshape(b, -1, nc * len(levels)).to(x.dtype), sd["quantizers.project_out.weight"],
+                   sd["quantizers.project_out.bias"])
     out = out.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
-    return out, idx.reshape(b, t, h, w), bounded
+    idx = idx.reshape(b, t, h, w, nc)
+    return out, (idx[..., 0] if nc == 1 else idx), bounded.reshape(b, -1, nc * len(levels))
 
 
-def fsq_indices_to_codes(idx, sd, levels, dtype):
+def fsq_indices_to_codes(idx, sd, levels, dtype, nc=1):
     lv, basis = _fsq_consts(levels)
+    if nc == 1:
+        idx = idx[..., None]
     nonneg = (idx[..., None] // basis) % lv
     half_w = lv // 2
-    codes = ((nonneg - half_w) / half_w).to(dtype)
+    codes = ((nonneg - half_w) / half_w).to(dtype).reshape(*idx.shape[:-1], -1)
     out = F.linear(codes, sd["quantizers.project_out.weight"].to(dtype), sd["quantizers.project_out.bias"].to(dtype))
     return out.movedim(-1, 1)
 
@@ -410,7 +423,7 @@ class OracleTokenizer:
                  use_fsq=False, fsq_levels=None, attn_dim_head=32, attn_heads=8,
                  linear_attn_dim_head=8, linear_attn_heads=16, pad_mode="constant",
                  lfq_soft_clamp_input_value=10., dim_cond=None, dim_cond_expansion_factor=4.,
-                 separate_first_frame_encoding=False, dtype=torch.float32, **unused):
+                 separate_first_frame_encoding=False, num_codebooks=1, lfq_spherical=False, dtype=torch.float32, **unused):
         self.dtype = dtype
         self.sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in state_dict.items()
                    if not k.startswith("discr.")}
@@ -426,6 +439,7 @@ class OracleTokenizer:
         self.lin_heads, self.lin_dim_head = linear_attn_heads, linear_attn_dim_head
         self.pad_mode = pad_mode
         self.clamp = lfq_soft_clamp_input_value
+        self.nc, self.spherical = int(num_codebooks), bool(lfq_spherical)            # M:1057, M:1070
         self.channels = channels
         # conditioning (M:1134-1153, M:1318, M:1336-1352): ``has_cond`` is set by the first cond layer and never reset, so
         # every later layer is called with ``cond=`` too -- the reference's plain layers then raise TypeError.  Only specs
@@ -542,21 +556,23 @@ class OracleTokenizer:
         x = self._encode(video, video_contains_first_frame=ff)
         out = {}
         if self.use_fsq or not train:
-            q, idx, _ = (fsq_quantize if self.use_fsq else lfq_quantize)(x, self.sd, *( (self.fsq_levels,) if self.use_fsq else (self.clamp,) ))
+            q, idx, _ = self.quantize.__wrapped__(self, x)
             aux = torch.zeros((), dtype=video.dtype)
         else:
             b, c, t, h, w = x.shape
-            p = lfq_presign(x, self.sd, self.clamp)                          # (B, N, d) fp32, differentiable
+            p = lfq_presign(x, self.sd, self.clamp, self.nc, self.spherical)  # (B, N, nc d) fp32, differentiable
             qd = torch.where(p > 0, torch.ones_like(p), -torch.ones_like(p))
             st = p + (qd - p).detach()                                       # straight-through (A.1 step 6)
-            d_bits = p.shape[-1]
+            d_bits = p.shape[-1] // self.nc
             ps, be, cm, aux, _ = lfq_train_losses(p, d_bits, world_reduce, 100., lfq_diversity_gamma, lfq_entropy_loss_weight,
-                                                  lfq_commitment_loss_weight)
+                                                  lfq_commitment_loss_weight, self.nc)
             out.update(per_sample_entropy=ps, batch_entropy=be, commitment=cm)
             q = F.linear(st.to(x.dtype), self.sd["quantizers.project_out.weight"], self.sd["quantizers.project_out.bias"])
             q = q.reshape(b, t, h, w, c).permute(0, 4, 1, 2, 3)
             mask = self.sd["quantizers.mask"].to(torch.int32)
-            idx = ((qd > 0).int() * mask).sum(dim=-1).reshape(b, t, h, w)
+            idx = ((qd.reshape(b, -1, self.nc, d_bits) > 0).int() * mask).sum(dim=-1).reshape(b, t, h, w, self.nc)
+            if self.nc == 1:
+                idx = idx[..., 0]
         recon = self._decode(q, video_contains_first_frame=ff)
         recon_loss = F.mse_loss(video.to(recon.dtype), recon)                # M:1722
         out.update(codes=idx, recon=recon, recon_loss=recon_loss, aux=aux, total_loss=recon_loss + aux * quantizer_aux_loss_weight)
@@ -565,8 +581,8 @@ class OracleTokenizer:
     @torch.no_grad()
     def quantize(self, x):
         if self.use_fsq:
-            return fsq_quantize(x, self.sd, self.fsq_levels)
-        return lfq_quantize(x, self.sd, self.clamp)
+            return fsq_quantize(x, self.sd, self.fsq_levels, self.nc)
+        return lfq_quantize(x, self.sd, self.clamp, self.nc, self.spherical)
 
     def _check_video(self, video, video_contains_first_frame=True):
         assert video.ndim in (4, 5)                                            # M:1675
@@ -595,9 +611,9 @@ class OracleTokenizer:
             assert codes.shape[-1] % (self.fmap_size ** 2) == 0
             codes = codes.reshape(codes.shape[0], -1, self.fmap_size, self.fmap_size)
         if self.use_fsq:
-            q = fsq_indices_to_codes(codes, self.sd, self.fsq_levels, self.dtype)
+            q = fsq_indices_to_codes(codes, self.sd, self.fsq_levels, self.dtype, self.nc)
         else:
-            q = lfq_indices_to_codes(codes, self.sd, self.dtype)
+            q = lfq_indices_to_codes(codes, self.sd, self.dtype, self.nc)
         return self.decode(q, taps, cond=cond, video_contains_first_frame=video_contains_first_frame)
 
     @torch.no_grad()

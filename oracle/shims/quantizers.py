@@ -77,8 +77,9 @@ class LFQ(nn.Module):
         return self.codebook.dtype
 
     def indices_to_codes(self, indices, project_out=True):
-        is_img_or_video = indices.ndim >= 3
-        indices = indices[..., None]  # single-codebook axis
+        is_img_or_video = indices.ndim >= (3 + int(self.num_codebooks > 1))
+        if self.num_codebooks == 1:       # keep_num_codebooks_dim = num_codebooks > 1: otherwise add the codebook axis back
+            indices = indices[..., None]
         bits = ((indices[..., None].int() & self.mask) != 0).to(self.dtype)
         codes = bits * self.codebook_scale * 2 - self.codebook_scale
         codes = codes.reshape(*codes.shape[:-2], -1)
@@ -177,11 +178,14 @@ class FSQ(nn.Module):
         return (zhat * self._basis).sum(dim=-1).to(torch.int32)
 
     def indices_to_codes(self, indices):
-        is_img_or_video = indices.ndim >= 3
+        is_img_or_video = indices.ndim >= (3 + int(self.num_codebooks > 1))
+        if self.num_codebooks == 1:
+            indices = indices[..., None]
         ind = indices[..., None]
         nonneg = (ind // self._basis) % self._levels
         half_width = self._levels // 2
         codes = (nonneg - half_width) / half_width
+        codes = codes.reshape(*codes.shape[:-2], -1)
         codes = self.project_out(codes.to(self.project_out.weight.dtype) if isinstance(self.project_out, nn.Linear) else codes)
         if is_img_or_video:
             codes = codes.movedim(-1, 1)

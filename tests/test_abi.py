@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_load_and_version():
     lib = _lib.load()
-    assert lib.mv2_abi_version() == 2
+    assert lib.mv2_abi_version() == 3
     assert lib.mv2_se_workspace_bytes(2, 256, 64) == (2 * 8 * 66 + 2 * 80) * 4
     assert lib.mv2_linattn_workspace_bytes(3, 16, 1024) == 3 * 16 * 4 * 657 * 4 + 3 * 16 * 2 * 16 * 88 * 2
 

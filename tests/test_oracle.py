@@ -7,7 +7,7 @@ import torch
 from tests.util import (build_oracle, build_oracle_from_golden, build_product, golden_video, load_golden,
                         sample_like_golden)
 
-SMALL = ["cfg1", "mini", "mini_fsq", "mini_gateloop"]
+SMALL = ["cfg1", "mini", "mini_fsq", "mini_gateloop", "mini_mc", "mini_mc_fsq"]
 
 
 @pytest.mark.parametrize("name", SMALL)
@@ -248,11 +248,12 @@ def grad_digest_close(g, dg, rtol, what, atol=0.0):
     return max(n_err, s_err)
 
 
-def test_restated_loss_forward_and_gradients_match_reference_golden():
+@pytest.mark.parametrize("name", ["mini_train", "mini_mc_train"])
+def test_restated_loss_forward_and_gradients_match_reference_golden(name):
     """the differentiable restatement of forward(return_loss=True) reproduces the reference's loss values (eval and
     train mode) and, through autograd, the reference's gradient of every parameter (tests/golden/mini_train.pt, made by the
     unmodified reference: oracle/make_train_golden.py)."""
-    g = load_golden("mini_train")
+    g = load_golden(name)
     model = build_product(g["kwargs"], g["wseed"])
     video = golden_video(g)
     orc = build_oracle(model, g["kwargs"])

@@ -24,7 +24,7 @@ def _report(name, **kw):
         f.write(name + ": " + ", ".join(f"{k}={v}" for k, v in kw.items()) + "\n")
 
 
-@pytest.mark.parametrize("name", ["cfg1", "mini", "mini_fsq"])
+@pytest.mark.parametrize("name", ["cfg1", "mini", "mini_fsq", "mini_mc", "mini_mc_fsq"])
 def test_fp32_bit_exact_codes_and_recon_vs_golden(name):
     """fp32 storage + fp32 FMA: code indices bit-exact vs the reference golden, per-layer taps and recon
     within fp32 round-off."""
@@ -206,6 +206,27 @@ def test_lfq_training_aux_terms_vs_oracle():
     rps, rbe, rcm, raux, _ = lfq_train_losses(g["presign"], 10)
     for got, ref in ((ps, rps), (be, rbe), (cm, rcm), (aux, raux)):
         assert abs(got.item() - ref.item()) <= 2e-4 * max(1.0, abs(ref.item())), (got.item(), ref.item())
+
+
+def test_lfq_multi_codebook_spherical_aux_terms_vs_oracle():
+    """num_codebooks = 2 + lfq_spherical (M:1057, M:1070): per-(token, codebook) entropies, per-codebook mean probabilities,
+    commitment on the L2-normalised pre-sign values -- CUDA partial sums + finalize kernel against the oracle, fp32; plus the
+    train-mode return_loss forward against the value the reference produced (tests/golden/mini_mc_train.pt)."""
+    _require_cuda()
+    from oracle.restated import lfq_train_losses
+    g = load_golden("mini_mc")
+    model = build_product(g["kwargs"], g["wseed"]).cuda()
+    codes, (ps, be, cm), aux = model.lfq_loss_breakdown(golden_video(g).cuda())
+    assert codes.shape[-1] == 2 and torch.equal(codes.cpu(), g["codes"])
+    rps, rbe, rcm, raux, _ = lfq_train_losses(g["presign"], 8, nc=2)
+    for got, ref in ((ps, rps), (be, rbe), (cm, rcm), (aux, raux)):
+        assert abs(got.item() - ref.item()) <= 2e-4 * max(1.0, abs(ref.item())), (got.item(), ref.item())
+    gt = load_golden("mini_mc_train")
+    m2 = build_product(gt["kwargs"], gt["wseed"]).cuda().train()
+    with torch.no_grad():
+        total, bd = m2(golden_video(gt).cuda(), return_loss=True)
+    assert abs(total.item() - gt["train"]["total_loss"].item()) < 1e-5
+    assert abs(bd.lfq_aux_loss.item() - gt["train"]["aux"].item()) < 1e-5
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
