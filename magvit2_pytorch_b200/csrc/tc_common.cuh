@@ -349,6 +349,21 @@ __device__ __forceinline__ void epi_pack32_t(const uint32_t (&r)[32], const floa
     pk[2 * g + 1] = pack_bf16x2(act_ct<ACT>(__uint_as_float(r[4 * g + 2]) + b.z), act_ct<ACT>(__uint_as_float(r[4 * g + 3]) + b.w));
   }
 }
+// GEGLU of one packed 32-column chunk ([8 x | 8 gate] twice, M:466-469): 16 outputs -> 8 bf16x2 words
+__device__ __forceinline__ void epi_geglu_pack32(const uint32_t (&r)[32], const float* sb, uint32_t* pk) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float xv = __uint_as_float(r[g * 16 + q]) + sb[g * 16 + q];
+      const float gt = __uint_as_float(r[g * 16 + 8 + q]) + sb[g * 16 + 8 + q];
+      v[q] = 0.5f * gt * (1.f + erf_fast(gt * 0.70710678118654752440f)) * xv;
+    }
+    pk[4 * g] = pack_bf16x2(v[0], v[1]); pk[4 * g + 1] = pack_bf16x2(v[2], v[3]);
+    pk[4 * g + 2] = pack_bf16x2(v[4], v[5]); pk[4 * g + 3] = pack_bf16x2(v[6], v[7]);
+  }
+}
 // bias + activation of one 32-column chunk, kept in fp32 (for the fp32-staged residual epilogue)
 template <int ACT>
 __device__ __forceinline__ void epi_act32_t(uint32_t (&r)[32], const float* sb) {

@@ -664,6 +664,46 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
             }
             __syncwarp();
           }
+        } else if (MODE == EPI_GEGLU) {
+          // fc1 + GEGLU (M:466-469, M:492): 64 accumulator columns (packed [8 x | 8 gate] groups) give 32 outputs = 64 bytes per
+          // row, staged through the same transpose buffer as the plain epilogue so that every store instruction writes 8 rows x
+          // 64 contiguous bytes (the direct path wrote 32 scattered 16-byte pieces per instruction and was LSU bound: 12 k cycles
+          // per 128 x 256 tile against 2 k cycles of MMAs).  The two warps of a lane quarter alternate 64-column chunks
+          // (bn % 64 == 0: the packed width is a multiple of 128).
+          const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 2048;
+          const uint32_t wr = stg + lane * 64, wsw = (lane >> 1) & 3;
+          const int rl = lane >> 2, piece = lane & 3;
+          const int w2 = c.w0 + 8 * j + rl;
+          const uint32_t rd = stg + rl * 64;
+          const int h20 = c.h0 + sub * 4;
+          const int I = p.Co >> 1;
+          const int64_t row0 = ((((int64_t)c.b * p.T + c.t) * p.H + h20) * p.W + w2) * I + (c.n0 >> 1) + piece * 8;
+          const int64_t ks = (int64_t)p.W * I;
+          const int kmax = w2 < p.W ? p.H - h20 : 0;
+          for (int c0 = ((j + half) & 1) * 64; c0 < p.bn; c0 += 128) {
+            uint32_t r0[32], r1[32], pk[16];
+            tmem_ld_32x32b_x32(tl + c0, r0);
+            tmem_ld_32x32b_x32(tl + c0 + 32, r1);
+            tmem_ld_wait();
+            epi_geglu_pack32(r0, sbias + c.n0 + c0, pk);
+            epi_geglu_pack32(r1, sbias + c.n0 + c0 + 32, pk + 8);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wr + ((g ^ wsw) << 4)), "r"(pk[4 * g]),
+                           "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3]) : "memory");
+            __syncwarp();
+            const bool col_ok = c.n0 + c0 + piece * 16 < p.Co && c0 + piece * 16 < p.bn;
+            const int klim = col_ok ? kmax : 0;
+            __nv_bfloat16* yp = p.epi.y + row0 + (c0 >> 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint4 v;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(rd + k * 512 + ((piece ^ (((8 * k + rl) >> 1) & 3)) << 4)));
+              if (k < klim) *reinterpret_cast<uint4*>(yp + k * ks) = v;
+            }
+            __syncwarp();
+          }
         } else {
           for (int c0 = ((j + half) & 1) * 32; c0 < p.bn; c0 += 64) {
             uint32_t r[32];
@@ -760,7 +800,7 @@ extern "C" int mv2_tc_slab_supported(const mv2_tc_conv_args* a) {
   }
   if (a->Ci % 32 != 0 || a->Co > 4096) return 0;
   if (a->oscale && (a->epi_mode != 0 || a->shuffle != MV2_SHUFFLE_NONE)) return 0;   // demodulation: plain / ragged epilogues only
-  if (a->epi_mode == 1 && (a->Co % 32 != 0 || a->shuffle != MV2_SHUFFLE_NONE || a->res)) return 0;   // fused GEGLU
+  if (a->epi_mode == 1 && (a->Co % 64 != 0 || a->shuffle != MV2_SHUFFLE_NONE || a->res)) return 0;   // fused GEGLU (64-column epilogue chunks)
   if (a->epi_mode != 0 && a->epi_mode != 1) return 0;
   if (a->Co % 32 != 0 && a->Co > 32) return 0;           // ragged N only as a single (zero padded) 32-column tile
   if (a->Ci % 64 != 0 && a->kw != 1) return 0;           // 64-byte rows (32 channels): only h-shifted taps (1024 B multiples)
@@ -814,7 +854,7 @@ static int slab_fill_plan(const mv2_tc_conv_args* a, int n_sm, SlabParams& p, in
   if (const char* env = getenv("MV2_SLAB_CFG")) {   // debug / tuning override: "mw,bn"
     int emw = 0, ebn = 0;
     if (sscanf(env, "%d,%d", &emw, &ebn) == 2 && (emw == 1 || emw == 2 || emw == 4) && ebn >= 32 && ebn <= 256 && ebn % 16 == 0 &&
-        (co_pad % ebn == 0 || ragged_ok || (a->epi_mode == 1 && ebn % 32 == 0)) && emw * ebn <= 512 && !(emw >= 2 && a->Wo <= 8)) { best_mw = emw; best_bn = ebn; }
+        (a->epi_mode == 1 ? ebn % 64 == 0 : (co_pad % ebn == 0 || ragged_ok)) && emw * ebn <= 512 && !(emw >= 2 && a->Wo <= 8)) { best_mw = emw; best_bn = ebn; }
   }
   p.mw = best_mw; p.bn = best_bn;
   p.n_tiles_n = (co_pad + p.bn - 1) / p.bn;   // a ragged last tile reads zero-filled weight rows and stores nothing for them
