@@ -46,6 +46,7 @@ struct alignas(64) SlabParams {
   int slab_stages, w_stages, nbuf;
   int acc_stride;        // TMEM columns between the two accumulator buffers (256 when double buffered)
   int tpw;               // in-plane taps per weight stage (one 3-D TMA box {bk, bn, tpw})
+  int geglu_staged;      // EPI_GEGLU: 64-column chunks through the transpose buffers (1) or direct 16-byte row pieces (0)
   int cluster;           // 1, or 2: CTA pairs on neighbouring tiles multicast each other half of every weight tile
   TcEpi epi;
   // ---- EPI_FUSED_RU only (mv2_tc_ru_forward) ----
@@ -156,8 +157,14 @@ __device__ __forceinline__ void ru_second_gemm_issuer(const SlabParams& p, uint3
   }
 }
 
+// Epilogue warps per instantiation: 8 (two per TMEM lane quarter).  The fc1 + GEGLU flavour was also measured with 16 (its epilogue
+// is ~35 instructions per output and the kernel is bound by their issue: ncu 472 k warp instructions per SM at IPC 2.4, tensor pipe
+// 27 % active): no gain at C = 512, -8 % at C = 256 (profiles/r02_sweep_ff.json), so it stays at 8.
+template <int MODE> struct SlabEpiWarps { static constexpr int value = 8; };
+
 template <int MODE>
-__global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__ SlabParams p) {
+__global__ void __launch_bounds__(128 + 32 * SlabEpiWarps<MODE>::value, 1) tc_slab_kernel(const __grid_constant__ SlabParams p) {
+  constexpr int NEPI = SlabEpiWarps<MODE>::value;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.slab_stages; ++s) { mbar_init(slab_full + 8 * s, 1); mbar_init(slab_empty + 8 * s, 1); }
     for (int s = 0; s < p.w_stages; ++s) { mbar_init(w_full + 8 * s, 1); mbar_init(w_empty + 8 * s, p.cluster); }
-    for (int s = 0; s < 2; ++s) { mbar_init(t_full + 8 * s, 1); mbar_init(t_empty + 8 * s, 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(t_full + 8 * s, 1); mbar_init(t_empty + 8 * s, NEPI); }
     for (int s = 0; s < 4; ++s) { mbar_init(h_full + 8 * s, 8); mbar_init(m2_done + 8 * s, 1); }
     mbar_init(w1_full, 1);
     fence_barrier_init();
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
   if (warp == 1) tmem_alloc(tslot, 512);
   if (warp >= 4) {
     const int nb = p.n_tiles_n * p.bn;   // >= Co; padded columns read zeros
-    for (int i = threadIdx.x - 128; i < nb; i += 256) sbias[i] = (p.epi.bias && i < p.Co) ? p.epi.bias[i] : 0.f;
+    for (int i = threadIdx.x - 128; i < nb; i += 32 * NEPI) sbias[i] = (p.epi.bias && i < p.Co) ? p.epi.bias[i] : 0.f;
     if (MODE == EPI_FUSED_RU)
       for (int i = threadIdx.x - 128; i < nb; i += 256) {
         sbias[nb + i] = (p.bias1 && i < p.Co) ? p.bias1[i] : 0.f;
@@ -664,12 +671,12 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
             }
             __syncwarp();
           }
-        } else if (MODE == EPI_GEGLU) {
+        } else if (MODE == EPI_GEGLU && p.geglu_staged) {
           // fc1 + GEGLU (M:466-469, M:492): 64 accumulator columns (packed [8 x | 8 gate] groups) give 32 outputs = 64 bytes per
           // row, staged through the same transpose buffer as the plain epilogue so that every store instruction writes 8 rows x
-          // 64 contiguous bytes (the direct path wrote 32 scattered 16-byte pieces per instruction and was LSU bound: 12 k cycles
-          // per 128 x 256 tile against 2 k cycles of MMAs).  The two warps of a lane quarter alternate 64-column chunks
-          // (bn % 64 == 0: the packed width is a multiple of 128).
+          // 64 contiguous bytes instead of 32 scattered 16-byte pieces.  Opt-in (MV2_GEGLU_STAGED): measured 3 % slower than the
+          // direct path -- the kernel is bound by the instruction issue of the GELU math, not by the stores.  The two warps of a
+          // lane quarter alternate 64-column chunks (bn % 64 == 0: the packed width is a multiple of 128).
           const uint32_t stg = stage0 + (uint32_t)(warp - 4) * 2048;
           const uint32_t wr = stg + lane * 64, wsw = (lane >> 1) & 3;
           const int rl = lane >> 2, piece = lane & 3;
@@ -680,7 +687,9 @@ __global__ void __launch_bounds__(384, 1) tc_slab_kernel(const __grid_constant__
           const int64_t row0 = ((((int64_t)c.b * p.T + c.t) * p.H + h20) * p.W + w2) * I + (c.n0 >> 1) + piece * 8;
           const int64_t ks = (int64_t)p.W * I;
           const int kmax = w2 < p.W ? p.H - h20 : 0;
-          for (int c0 = ((j + half) & 1) * 64; c0 < p.bn; c0 += 128) {
+          const int nch = p.bn >> 6;                 // 64-column chunks per M-tile, dealt round-robin over the NEPI / 4 warps of a quarter
+          for (int c0 = 0; c0 < p.bn; c0 += 64) {
+            if (((j * nch + (c0 >> 6)) & (NEPI / 4 - 1)) != half) continue;
             uint32_t r0[32], r1[32], pk[16];
             tmem_ld_32x32b_x32(tl + c0, r0);
             tmem_ld_32x32b_x32(tl + c0 + 32, r1);
@@ -857,6 +866,9 @@ static int slab_fill_plan(const mv2_tc_conv_args* a, int n_sm, SlabParams& p, in
         (a->epi_mode == 1 ? ebn % 64 == 0 : (co_pad % ebn == 0 || ragged_ok)) && emw * ebn <= 512 && !(emw >= 2 && a->Wo <= 8)) { best_mw = emw; best_bn = ebn; }
   }
   p.mw = best_mw; p.bn = best_bn;
+  // measured inside a README step (profiles/r02_sweep_ff.json, CUPTI): fc1 + GEGLU 329 us with the direct row-piece stores, 339 us
+  // staged -- the epilogue is bound by the issue of its ~35 instructions per output, not by its stores -- so staged is opt-in
+  p.geglu_staged = (a->epi_mode == 1 && p.bn % 64 == 0 && getenv("MV2_GEGLU_STAGED")) ? 1 : 0;
   p.n_tiles_n = (co_pad + p.bn - 1) / p.bn;   // a ragged last tile reads zero-filled weight rows and stores nothing for them
   // weight multicast across CTA pairs: when one M-tile per CTA cannot amortise the weight stream (mw == 1, deep
   // layers) two CTAs on neighbouring tiles fetch half of every weight tile each and multicast it to both
@@ -882,8 +894,13 @@ static int slab_fill_plan(const mv2_tc_conv_args* a, int n_sm, SlabParams& p, in
   if (const char* env = getenv("MV2_SLAB_TPW")) { const int v = atoi(env); if (v >= 1 && taps2d % v == 0 && v * p.bn * p.row_bytes <= 64 * 1024) p.tpw = v; }
   int w_bytes = p.bn * p.row_bytes * p.tpw;
   const int nb_pad = p.n_tiles_n * p.bn;   // bias staging covers the padded column range
-  const int budget = 204 * 1024 - nb_pad * 4;   // 227 KB minus 16 KB epilogue transpose buffers, barriers, alignment slack
+  // 227 KB minus the epilogue transpose buffers (2 KB per epilogue warp: 16 KB, 32 KB for fc1 + GEGLU), barriers, alignment slack
+  const int budget = 204 * 1024 - nb_pad * 4 - (a->epi_mode == 1 ? (SlabEpiWarps<EPI_GEGLU>::value - 8) * 2048 : 0);
   p.slab_stages = p.slab_stride * 3 + w_bytes * 3 <= budget ? 3 : 2;
+  if (const char* env = getenv("MV2_SLAB_STAGES")) {   // tuning override: activation-slab ring depth
+    const int v = atoi(env);
+    if (v >= 2 && v <= 12 && v * p.slab_stride + 2 * w_bytes <= budget) p.slab_stages = v;
+  }
   p.w_stages = std::min(12, (budget - p.slab_stages * p.slab_stride) / w_bytes);
   if (p.w_stages < 2 && p.slab_stages > 2) { p.slab_stages = 2; p.w_stages = std::min(12, (budget - 2 * p.slab_stride) / w_bytes); }
   while (p.w_stages < 2 && p.tpw > 1) {   // wide slabs (mw = 4) + the fp32 residual staging: fall back to fewer taps per weight stage
@@ -978,7 +995,8 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights 2-D) failed: %d", (int)r); return MV2_E_CUDA; }
   }
-  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 32 + (size_t)nb_pad * 4 + 8 * 2048 + 1024;
+  const size_t smem = (size_t)p.slab_stages * p.slab_stride + (size_t)p.w_stages * w_bytes + 8 * (2 * p.slab_stages + 2 * p.w_stages + 4) + 32 + (size_t)nb_pad * 4 +
+                      (size_t)(a->epi_mode == 1 ? SlabEpiWarps<EPI_GEGLU>::value : 8) * 2048 + 1024;
   MV2_CHECK_ARG(smem <= 227 * 1024);
   static PerDeviceOnce attr_once;
   const cudaError_t attr_err = attr_once.run([] {
@@ -994,7 +1012,7 @@ extern "C" int mv2_tc_slab_forward(const mv2_tc_conv_args* a, void* stream) {
   if (attr_err != cudaSuccess) { set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err)); return MV2_E_CUDA; }
   int grid = std::min(p.total_tiles, n_sm);
   if (p.cluster > 1) grid &= ~1;
-  if (a->epi_mode == 1) launch_kc(tc_slab_kernel<EPI_GEGLU>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
+  if (a->epi_mode == 1) launch_kc(tc_slab_kernel<EPI_GEGLU>, dim3(grid), dim3(128 + 32 * SlabEpiWarps<EPI_GEGLU>::value), smem, (cudaStream_t)stream, p.cluster, p);
   else if (a->shuffle != MV2_SHUFFLE_NONE && (a->Co / (a->shuffle == MV2_SHUFFLE_SPACE ? 4 : 2)) % 32 == 0 && !getenv("MV2_NO_SHUFFLE_ST"))
     launch_kc(tc_slab_kernel<EPI_SHUFFLE_ST>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);
   else if (a->shuffle != MV2_SHUFFLE_NONE) launch_kc(tc_slab_kernel<EPI_SHUFFLE>, dim3(grid), dim3(384), smem, (cudaStream_t)stream, p.cluster, p);

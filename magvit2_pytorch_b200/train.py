@@ -403,6 +403,9 @@ class TrainRunner:
 
     def backward(self, g_recon, g_aux):
         """Runs the tape in reverse; returns {Parameter: grad}.  g_recon (B,C,T,H,W) or None, g_aux 0-d or None."""
+        if not self.tape:
+            raise RuntimeError("the tokenizer's backward ran already: the saved activations are released after one backward pass "
+                               "(call the forward again; retain_graph is not supported by this path)")
         if g_recon is None:
             g_recon = torch.zeros(self._recon_shape, device=self.eng.device, dtype=self.eng.dtype)
         g = g_recon.to(self.eng.dtype)
