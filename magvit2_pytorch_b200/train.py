@@ -7,12 +7,13 @@ Division of labour
   * FORWARD: the hand-written sm_100a kernels of the inference path (engine.Engine / libmagvit2_b200.so), with the
     ResidualUnit run unfused so that its intermediate activations exist.  The activations the backward needs are kept as
     they come out of the kernels (channels-last).
-  * BACKWARD: library code.  The convolutions that carry ~90 % of the FLOPs (conv_in, conv_out, the 3x3x3 and 1x1x1 convs of
-    every ResidualUnit, the strided down-samplers) call ``aten.convolution_backward`` (cuDNN) directly on those saved
-    activations -- no forward recomputation.  The light blocks (SqueezeExcite gating, attention / linear-attention /
+  * BACKWARD: the DATA gradient of the stride-1 causal convs (the 3x3x3 and 1x1x1 convs of every ResidualUnit, conv_out: about
+    half of the backward's conv FLOPs) runs on the engine's own conv kernels -- a transposed conv is the same implicit GEMM with
+    flipped / transposed weights.  The weight / bias gradients of all convs and the strided down-samplers call
+    ``aten.convolution_backward`` (cuDNN) directly on the saved activations -- no forward recomputation.  The light blocks (SqueezeExcite gating, attention / linear-attention /
     FeedForward blocks, the two up-samplers, the quantiser with its straight-through estimator and auxiliary losses) are
     differentiated by re-evaluating a torch restatement of the block on its saved input (``_vjp``).
-  There are no hand-written backward kernels yet; this slice makes the drop-in claim true for the trainer's generator step,
+  There are no dedicated backward kernels (wgrad, attention backward) yet; this slice makes the drop-in claim true for the trainer's generator step,
   it is not a speed claim for training.  Gradients are checked against the unmodified reference's autograd on the `mini`
   config (tests/golden/mini_train.pt, tests/test_train_gpu.py).
 
@@ -214,6 +215,8 @@ class TrainRunner:
         self.grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         self.codes = None
         self.breakdown = None
+        self.own_dgrad = True            # data gradient of the stride-1 convs through the engine's own conv kernels
+        self.own_dgrad_calls = 0
 
     # ---- gradient bookkeeping
     def _acc(self, param, g):
@@ -235,28 +238,44 @@ class TrainRunner:
         return gs[0]
 
     def _conv_bwd(self, g, x, weight, bias, k, stride=(1, 1, 1), pad=None, need_gx=True, x_is_cf=False):
-        """aten.convolution_backward for a conv the engine ran as  y = conv(x; leading pad (pt, ph, pw), stride).
+        """Backward of a conv the engine ran as  y = conv(x; leading pad (pt, ph, pw), stride).
         g: (B,To,Ho,Wo,Co) channels-last grad of the pre-activation output; x: the saved channels-last input (or, x_is_cf,
-        a (B,C,T,H,W) tensor).  The time axis is padded at the FRONT only (causal, M:913-928): those zero frames are
-        materialised; H / W use the symmetric padding natively.  Returns grad wrt x (channels-last) or None."""
+        a (B,C,T,H,W) tensor).  Returns grad wrt x (channels-last) or None.
+          * data gradient of the stride-1 causal convs (every ResidualUnit conv, conv_out): OUR conv kernels -- the transposed
+            conv is the same implicit GEMM with the weights flipped in (t, h, w) and transposed in (co, ci), no leading pad in
+            time (gx[t] = sum_e W'[e] g[t + e]; frames past the clip are the kernels' out-of-bounds zeros);
+          * weight / bias gradients, and the data gradient of the strided down-samplers: aten.convolution_backward (cuDNN).  The
+            time axis is padded at the FRONT only (causal, M:913-928): those zero frames are materialised; H / W use the
+            symmetric padding natively."""
         kt, kh, kw = k
+        causal_default = pad is None
         if pad is None:
             pad = (kt - 1, kh // 2, kw // 2)
         pt, ph, pw = pad
+        w5 = weight.reshape(weight.shape[0], weight.shape[1], kt, kh, kw)
+        gx = None
+        own_dgrad = need_gx and self.own_dgrad and causal_default and tuple(stride) == (1, 1, 1) and not x_is_cf
+        if own_dgrad:
+            from .engine import pack_conv
+            wt = w5.detach().flip(2, 3, 4).transpose(0, 1).contiguous()          # (Ci, Co, kt, kh, kw): dgrad weights
+            gx = self.eng.conv(g.contiguous(), pack_conv(wt, None, self.eng.dtype), pad=(0, ph, pw), out_spatial=tuple(x.shape[1:4]))
+            self.own_dgrad_calls += 1
         if x_is_cf:
             x_cf = F.pad(x, (0, 0, 0, 0, pt, 0)) if pt > 0 else x
         else:       # pad the (contiguous) channels-last tensor along T, then view it as (B,C,T,H,W) in channels_last_3d strides
             x_cf = (F.pad(x, (0, 0, 0, 0, 0, 0, pt, 0)) if pt > 0 else x).permute(0, 4, 1, 2, 3)
-        w5 = weight.reshape(weight.shape[0], weight.shape[1], kt, kh, kw)
-        gx, gw, gb = torch.ops.aten.convolution_backward(
+        lib_gx = need_gx and not own_dgrad
+        gxl, gw, gb = torch.ops.aten.convolution_backward(
             g.permute(0, 4, 1, 2, 3), x_cf, w5, [w5.shape[0]] if bias is not None else None, list(stride), [0, ph, pw],
-            [1, 1, 1], False, [0, 0, 0], 1, [need_gx, weight.requires_grad, bias is not None and bias.requires_grad])
+            [1, 1, 1], False, [0, 0, 0], 1, [lib_gx, weight.requires_grad, bias is not None and bias.requires_grad])
         self._acc(weight, gw)
         if bias is not None:
             self._acc(bias, gb)
         if not need_gx:
             return None
-        return gx[:, :, pt:].permute(0, 2, 3, 4, 1).contiguous()
+        if own_dgrad:
+            return gx
+        return gxl[:, :, pt:].permute(0, 2, 3, 4, 1).contiguous()
 
     # ---- forward pieces (engine kernels) that record their backward
     def _residual_unit(self, x, p, ru):

@@ -54,6 +54,35 @@ def test_fp32_losses_and_gradients_vs_reference_golden():
     print(f"{checked} parameter gradients checked, worst relative deviation vs the reference {worst:.2e}")
 
 
+def test_own_dgrad_kernels_agree_with_the_library_dgrad():
+    """The data gradient of the stride-1 causal convs runs on the engine's own conv kernels (flipped / transposed weights); with
+    TrainRunner.own_dgrad switched off the same gradients come from aten.convolution_backward: both agree to fp32 round-off."""
+    _require_cuda()
+    from magvit2_pytorch_b200 import train as T
+    g = load_golden("mini_train")
+    video = golden_video(g).cuda()
+    grads = []
+    for own in (True, False):
+        model = build_product(g["kwargs"], g["wseed"]).cuda()
+        orig = T.TrainRunner.__init__
+
+        def patched(self, m, _own=own, _orig=orig):
+            _orig(self, m)
+            self.own_dgrad = _own
+        T.TrainRunner.__init__ = patched
+        try:
+            _train_step(model, video)
+        finally:
+            T.TrainRunner.__init__ = orig
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    worst = 0.0
+    for k, a in grads[0].items():
+        b = grads[1][k]
+        worst = max(worst, float((a - b).abs().max()) / (float(b.abs().max()) + 1e-12))
+    print(f"own dgrad vs cuDNN dgrad: worst relative deviation {worst:.2e}")
+    assert worst < 2e-3, worst
+
+
 def test_optimizer_step_changes_the_loss_and_repacks_the_weights():
     """Trainer-shaped loop: backward, optimizer step, forward again -- the engine re-packs the updated parameters and the
     reconstruction loss goes down along the negative gradient by about lr * |grad|^2 (first-order prediction).  The quantiser's
