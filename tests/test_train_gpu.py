@@ -76,9 +76,11 @@ def test_own_dgrad_kernels_agree_with_the_library_dgrad():
             T.TrainRunner.__init__ = orig
         grads.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
     worst = 0.0
+    gnorm = sum(float(b.double().pow(2).sum()) for b in grads[1].values()) ** 0.5
     for k, a in grads[0].items():
         b = grads[1][k]
-        worst = max(worst, float((a - b).abs().max()) / (float(b.abs().max()) + 1e-12))
+        # gradients that are mathematically zero (bias of a softmax logit) hold only round-off noise: absolute floor
+        worst = max(worst, float((a - b).abs().max()) / (float(b.abs().max()) + 1e-6 * gnorm))
     print(f"own dgrad vs cuDNN dgrad: worst relative deviation {worst:.2e}")
     assert worst < 2e-3, worst
 
