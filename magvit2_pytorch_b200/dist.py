@@ -85,6 +85,12 @@ class LfqBatchEntropy:
         presign.record_stream(self.side)
         self._pending = (avg, stats, N, d)
 
+    @property
+    def avg_prob_sum(self) -> torch.Tensor:
+        """[num_codebooks * K] SUM over ranks of the per-rank mean code probabilities of the pending start() (valid on the side
+        stream; finish() orders the caller's stream after it)."""
+        return self._pending[0]
+
     def finish(self, diversity_gamma=2.5, entropy_w=0.1, commit_w=1.0, group=None):
         """-> (per_sample_entropy, batch_entropy, commitment, aux_loss) as 0-d fp32 tensors (views of one 4-float result of
         mv2_lfq_aux_finalize).  `avg` holds the SUM over ranks of the per-rank mean code probabilities (start() divides by the

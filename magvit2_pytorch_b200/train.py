@@ -21,13 +21,12 @@ Reference lines: M: = magvit2_pytorch/magvit2_pytorch.py, A: = attend.py.
 """
 from __future__ import annotations
 
-import ctypes as C
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Sequence
 
 import torch
 import torch.nn.functional as F
 
-from ._lib import ACT_ELU, ACT_NONE, check
+from ._lib import ACT_ELU, check
 from .engine import _dt, _ptr
 
 
@@ -394,7 +393,7 @@ class TrainRunner:
             q, self.codes, pre = eng.quantize_cl(x, want_quantized=True, want_aux=True)
             be = LfqBatchEntropy(eng, num_codebooks=qz.num_codebooks)
             be.start(pre, group)
-            avg_sum = be._pending[0]
+            avg_sum = be.avg_prob_sum
             ps, bent, commit, aux = be.finish(qz.diversity_gamma, qz.entropy_loss_weight, qz.commitment_loss_weight, group)
             world = torch.distributed.get_world_size(group) if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
             avg_global = avg_sum / world
