@@ -162,11 +162,12 @@ __device__ __forceinline__ void ru_second_gemm_issuer(const SlabParams& p, uint3
 // 27 % active): no gain at C = 512, -8 % at C = 256 (profiles/r02_sweep_ff.json), so it stays at 8.
 template <int MODE> struct SlabEpiWarps { static constexpr int value = 8; };
 
-// The fused ResidualUnit instantiation declares 512 threads per block (it is launched with 384): that caps it at 128 registers per
-// thread (ptxas: 128 registers, no spills, instead of 162), i.e. 48 k of the SM's 64 k registers, so that another stream lane's small
-// kernels can be co-resident during its 1.5 ms per step (measured alone: C = 64 310 -> 321 us, C = 128 unchanged).
+// Every instantiation declares 512 threads per block (they are launched with 384): that caps the kernel at 128 registers per
+// thread, i.e. 48 k of the SM's 64 k registers, so that another stream lane's small kernels can be co-resident with a persistent conv
+// CTA.  ptxas: no spills anywhere; fused ResidualUnit 162 -> 128, residual epilogue 164 -> 128, GEGLU 151 -> 127,
+// down-space 151 -> 123, staged shuffle 145 -> 123 registers.  Measured: the tcgen05 launches of a step 5.81 -> 5.73 ms.
 template <int MODE>
-__global__ void __launch_bounds__(MODE == EPI_FUSED_RU ? 512 : 128 + 32 * SlabEpiWarps<MODE>::value, 1) tc_slab_kernel(const __grid_constant__ SlabParams p) {
+__global__ void __launch_bounds__(512, 1) tc_slab_kernel(const __grid_constant__ SlabParams p) {
   constexpr int NEPI = SlabEpiWarps<MODE>::value;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
