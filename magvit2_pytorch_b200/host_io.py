@@ -45,6 +45,9 @@ class StreamLanes:
 
     def run_on(self, lane: int, fn, *args):
         s = self.streams[lane]
+        # (re)pack the parameters, if they changed, on the CALLER's stream: every lane is ordered after it below, so no lane
+        # can read packs that another lane's stream is still writing
+        _ = self.model.engine
         s.wait_stream(torch.cuda.current_stream(self.device))
         prev = self.model._lane
         self.model._lane = lane
@@ -122,6 +125,7 @@ class HostRoundTrip:
         lane = ((self.n - 1) % len(self.slots)) % len(self.lanes.streams) if self.lanes is not None else 0
         sc = self.lanes.streams[lane] if self.lanes is not None else cur
         if sc is not cur:
+            _ = self.model.engine                    # parameter (re)packing happens on `cur`, which every lane waits for
             sc.wait_stream(cur)                      # whatever the caller queued before this submit (weight updates, ...)
         sc.wait_event(slot.h2d)
         if slot.used:
