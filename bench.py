@@ -354,7 +354,7 @@ def main():
     # HostRoundTrip (the package's pinned-host front end) runs copy-in / kernels / copy-out on three streams, so the
     # copies of neighbouring steps overlap this step's kernels -- every step still copies its own input and results
     out_bufs = [(out_codes, out_video), (torch.empty_like(out_codes).pin_memory(), torch.empty_like(out_video).pin_memory())]
-    depth = max(2, 2 * nl)       # two staging slots per lane: the H2D copy of a lane's next input runs under its current step
+    depth = max(2, nl)           # one staging slot per lane (two per lane measured 2 % slower: profiles/README.md)
     out_bufs += [(torch.empty_like(out_codes).pin_memory(), torch.empty_like(out_video).pin_memory()) for _ in range(depth - 2)]
     hrt = HostRoundTrip(model, depth=depth, train_mode_forward=train_mode, lanes=nl)
     cur = torch.cuda.current_stream()
