@@ -49,10 +49,10 @@ def make(name="mini_train", base="mini", vseed=1234):
     grads = {k: (grad_digest(p.grad.detach()) if p.grad is not None else None) for k, p in model.named_parameters()}
     qlb = bd.quantizer_loss_breakdown
     out["train"] = dict(total_loss=total.detach().clone(), recon_loss=bd.recon_loss.detach().clone(),
-                        aux=bd.lfq_aux_loss.detach().clone(),
-                        per_sample_entropy=qlb.per_sample_entropy.detach().clone(),
-                        batch_entropy=qlb.batch_entropy.detach().clone(), commitment=qlb.commitment.detach().clone(),
-                        grads=grads)
+                        aux=torch.as_tensor(bd.lfq_aux_loss).detach().clone(), grads=grads)
+    if qlb is not None:           # LFQ only (FSQ has no auxiliary loss, M:1700-1703)
+        out["train"].update(per_sample_entropy=qlb.per_sample_entropy.detach().clone(),
+                            batch_entropy=qlb.batch_entropy.detach().clone(), commitment=qlb.commitment.detach().clone())
     out["reference_commit"] = "a00519fa (v0.5.1)"
     out["third_party"] = "oracle/shims (restated LFQ/TaylorSeriesLinearAttn; real packages unavailable)"
     path = os.path.join(GOLDEN_DIR, f"{name}.pt")
@@ -60,10 +60,12 @@ def make(name="mini_train", base="mini", vseed=1234):
     n_none = sum(g is None for g in grads.values())
     gn = sum(g["norm"] ** 2 for g in grads.values() if g is not None) ** 0.5
     print(f"[golden] {name}: eval total {out['eval']['total_loss'].item():.6f}; train total {out['train']['total_loss'].item():.6f} "
-          f"recon {out['train']['recon_loss'].item():.6f} aux {out['train']['aux'].item():.6f}; {len(grads)} params "
+          f"recon {out['train']['recon_loss'].item():.6f} aux {float(out['train']['aux']):.6f}; {len(grads)} params "
           f"({n_none} without grad), |grad| = {gn:.4e}; {os.path.getsize(path) / 1e3:.0f} KB")
 
 
 if __name__ == "__main__":
     make()
     make("mini_mc_train", base="mini_mc", vseed=1238)       # num_codebooks = 2, lfq_spherical
+    make("mini_fsq_train", base="mini_fsq", vseed=1234)     # FSQ: straight-through round, no auxiliary loss
+    make("mini_gateloop_train", base="mini_gateloop", vseed=1237)

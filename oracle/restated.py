@@ -391,7 +391,7 @@ def fsq_quantize(x, sd, levels, nc=1):
     shift = (offset / half_l).atanh()
     bounded = (zf + shift).tanh() * half_l - offset
     half_w = lv // 2
-    codes = bounded.round() / half_w
+    codes = (bounded + (bounded.round() - bounded).detach()) / half_w              # round with the straight-through gradient (A.2)
     idx = ((codes * half_w + half_w) * basis).sum(dim=-1).to(torch.int32)          # (b, n, nc)
     out = F.linear(codes.reshape(b, -1, nc * len(levels)).to(x.dtype), sd["quantizers.project_out.weight"],
                    sd["quantizers.project_out.bias"])

@@ -168,7 +168,8 @@ class FSQ(nn.Module):
         return (z + shift).tanh() * half_l - offset
 
     def quantize(self, z):
-        q = self.bound(z).round()
+        b = self.bound(z)
+        q = b + (b.round() - b).detach()        # round_ste (A.2: "straight-through"): the value is round(b) exactly
         half_width = self._levels // 2
         return q / half_width
 

@@ -25,18 +25,23 @@ def _train_step(model, video):
     return total, bd
 
 
-def test_fp32_losses_and_gradients_vs_reference_golden():
+@pytest.mark.parametrize("name", ["mini_train", "mini_mc_train", "mini_fsq_train", "mini_gateloop_train"])
+def test_fp32_losses_and_gradients_vs_reference_golden(name):
+    """LFQ (README-layer mini config), two spherical codebooks, FSQ (straight-through round) and gateloop_time layers."""
     _require_cuda()
-    g = load_golden("mini_train")
+    g = load_golden(name)
     gt = g["train"]
     model = build_product(g["kwargs"], g["wseed"]).cuda()
     total, bd = _train_step(model, golden_video(g).cuda())
     assert abs(total.item() - gt["total_loss"].item()) < 1e-5
     assert abs(bd.recon_loss.item() - gt["recon_loss"].item()) < 1e-5
-    assert abs(bd.lfq_aux_loss.item() - gt["aux"].item()) < 1e-5
-    ps, be, cm = bd.quantizer_loss_breakdown
-    for got, k in ((ps, "per_sample_entropy"), (be, "batch_entropy"), (cm, "commitment")):
-        assert abs(got.item() - gt[k].item()) < 1e-5, k
+    assert abs(float(bd.lfq_aux_loss) - float(gt["aux"])) < 1e-5
+    if "per_sample_entropy" in gt:
+        ps, be, cm = bd.quantizer_loss_breakdown
+        for got, k in ((ps, "per_sample_entropy"), (be, "batch_entropy"), (cm, "commitment")):
+            assert abs(got.item() - gt[k].item()) < 1e-5, k
+    else:
+        assert bd.quantizer_loss_breakdown is None
     named = dict(model.named_parameters())
     gnorm = sum(d["norm"] ** 2 for d in gt["grads"].values() if d is not None) ** 0.5
     worst, checked = 0.0, 0
@@ -50,8 +55,8 @@ def test_fp32_losses_and_gradients_vs_reference_golden():
         assert p.grad is not None, k
         worst = max(worst, grad_digest_close(p.grad, dg, 5e-3, k, atol=1e-7 * gnorm))
         checked += 1
-    assert checked >= 250, checked
-    print(f"{checked} parameter gradients checked, worst relative deviation vs the reference {worst:.2e}")
+    assert checked >= {"mini_train": 250, "mini_fsq_train": 250}.get(name, 50), checked
+    print(f"{name}: {checked} parameter gradients checked, worst relative deviation vs the reference {worst:.2e}")
 
 
 def test_own_dgrad_kernels_agree_with_the_library_dgrad():
