@@ -121,6 +121,22 @@ def _gateloop_block(x, gl):
     return torch.stack(outs, dim=1) + x
 
 
+def _residual_unit_mod(x, cond_e, mod):
+    """ResidualUnitMod (M:946-988) with Conv3DMod (M:718-753): per-clip weights w (cond + 1), demodulated by rsqrt(sum w_b^2),
+    one grouped causal conv over the batch; ELU; 1x1x1 conv; ELU; residual.  x (B,T,H,W,C), cond_e (B, dim_cond)."""
+    B, T, H, W, Cc = x.shape
+    c = F.linear(cond_e.to(x.dtype), mod.to_cond.weight, mod.to_cond.bias)
+    w = mod.conv.weights
+    o, i, kt, kh, kw = w.shape
+    wb = w[None] * (c[:, None, :, None, None, None] + 1.)
+    wb = wb * (wb ** 2).sum(dim=(2, 3, 4, 5), keepdim=True).clamp(min=mod.conv.eps).rsqrt()
+    xc = x.permute(0, 4, 1, 2, 3)
+    xg = F.pad(xc.reshape(1, B * i, T, H, W), (kw // 2, kw // 2, kh // 2, kh // 2, kt - 1, 0))
+    y = F.elu(F.conv3d(xg, wb.reshape(B * o, i, kt, kh, kw), groups=B).reshape(B, o, T, H, W))
+    y = F.elu(F.conv3d(y, mod.conv_out.weight, mod.conv_out.bias))
+    return (y + xc).permute(0, 2, 3, 4, 1)
+
+
 def _feed_forward_block(x, ff, shift):
     """Residual(FeedForward) / Residual(TokenShift(FeedForward)) (M:466-508, M:1191, M:1236)."""
     xs = _token_shift(x) if shift else x
@@ -205,9 +221,9 @@ class TrainRunner:
 
     def __init__(self, model):
         m = model
-        if m.has_cond or m.separate_first_frame_encoding or m.conv_in.pad_mode != "constant" or m.conv_out.pad_mode != "constant":
-            raise NotImplementedError("the training path covers unconditioned tokenizers with pad_mode='constant' and a shared "
-                                      "first-frame encoding (SURVEY.md 8f N2, first slice)")
+        if m.conv_in.pad_mode != "constant" or m.conv_out.pad_mode != "constant":
+            raise NotImplementedError("the training path covers tokenizers with pad_mode='constant' (SURVEY.md 8f N2, first slice)")
+        self.g_cond: Dict[str, torch.Tensor] = {}      # gradient wrt the cond stems' outputs, summed over the cond_residual stages
         self.m = m
         self.eng = m.engine
         self.tape: List[Callable] = []
@@ -224,16 +240,20 @@ class TrainRunner:
         g = g.reshape(param.shape).to(param.dtype)
         self.grads[param] = g if param not in self.grads else self.grads[param] + g
 
-    def _vjp(self, fn, x, params: Sequence[torch.nn.Parameter], gout):
-        """Gradient of the block fn at its saved input x: re-evaluates the torch restatement under autograd."""
+    def _vjp(self, fn, x, params: Sequence[torch.nn.Parameter], gout, extra=None):
+        """Gradient of the block fn at its saved input x: re-evaluates the torch restatement under autograd.  `extra`: further
+        leaf tensors (requires_grad) the block reads; their gradients are returned as the second element of a tuple."""
         x_ = x.detach().requires_grad_(True)
         params = [p for p in params if p.requires_grad]
+        extra = list(extra or [])
         with torch.enable_grad():
             out = fn(x_)
         outs, gouts = (list(out), list(gout)) if isinstance(out, (tuple, list)) else ([out], [gout])
-        gs = torch.autograd.grad(outs, [x_] + params, gouts, allow_unused=True)
-        for p, g in zip(params, gs[1:]):
+        gs = torch.autograd.grad(outs, [x_] + params + extra, gouts, allow_unused=True)
+        for p, g in zip(params, gs[1:1 + len(params)]):
             self._acc(p, g)
+        if extra:
+            return gs[0], gs[1 + len(params):]
         return gs[0]
 
     def _conv_bwd(self, g, x, weight, bias, k, stride=(1, 1, 1), pad=None, need_gx=True, x_is_cf=False):
@@ -312,10 +332,24 @@ class TrainRunner:
         self.tape.append(lambda g: self._vjp(fn, x, params, g))
         return out
 
-    def _stage(self, x, st, key, mod, decoder):
+    def _stage(self, x, st, key, mod, decoder, cond_e=None):
         eng = self.eng
         P = eng._packs
         B, T, H, W, Cc = x.shape
+        if st.kind == "cond_residual":
+            side = "dec" if decoder else "enc"
+            xin = x
+            out = eng._stage(x, st, key, decoder=decoder, cond_e=cond_e)
+
+            def bwd(g):
+                ce = cond_e.detach().requires_grad_(True)
+                gx, (gc,) = self._vjp(lambda t: _residual_unit_mod(t, ce, mod), xin, list(mod.parameters()), g, extra=[ce])
+                if gc is not None:
+                    self.g_cond[side] = gc if side not in self.g_cond else self.g_cond[side] + gc
+                return gx
+
+            self.tape.append(bwd)
+            return out
         if st.kind == "residual":
             units = list(mod) if st.nested else [mod]
             for j, ru in enumerate(units):
@@ -356,30 +390,53 @@ class TrainRunner:
                                lambda t: _feed_forward_block(t, ff, time_axis), list(ff.parameters()))
         raise NotImplementedError(f"no training path for layer type {st.kind!r}")
 
-    def forward(self, video, first_frame=True, group=None):
+    def forward(self, video, first_frame=True, group=None, cond=None):
         """-> (recon (B,C,T,H,W), aux_loss 0-d fp32); codes / the LFQ breakdown are left in .codes / .breakdown."""
         from .dist import LfqBatchEntropy
         m, eng = self.m, self.eng
         P = eng._packs
+        self.cond = cond
+        ce_enc = eng.cond_stem(cond, "enc") if m.has_cond else None            # M:1544-1548 (Linear + SiLU stems)
+        ce_dec = eng.cond_stem(cond, "dec") if m.has_cond else None            # M:1612-1616
         t_pad = m.time_padding if first_frame else 0
         cin, cout = m.conv_in.conv, m.conv_out.conv
         kin = tuple(cin.weight.shape[2:])
         pin = P.get("conv_in_tc")
-        if eng.dtype == torch.bfloat16 and eng.use_tc and pin is not None:
+        sff = bool(m.separate_first_frame_encoding and first_frame)
+        vid = video
+        if sff:
+            # M:1553-1561: the first frame through its own 2-D conv, frames 1.. through the causal conv_in on their own
+            Bv, _, Tv, Hv, Wv = video.shape
+            v_cl = eng.to_channels_last(video, 0)
+            first = eng.conv(eng.copy_frames(v_cl, 0, 1), P["conv_in_ff"])
+            x = eng._new((Bv, Tv + t_pad, Hv, Wv, first.shape[-1]))
+            eng.copy_frames(first, 0, 1, dst=x, dst_t0=t_pad, zero_front=True)
+            if Tv > 1:
+                rest = eng.conv(eng.copy_frames(v_cl, 1, Tv - 1), P["conv_in"])
+                eng.copy_frames(rest, 0, Tv - 1, dst=x, dst_t0=t_pad + 1)
+        elif eng.dtype == torch.bfloat16 and eng.use_tc and pin is not None:
             x = eng.conv(eng.ingest_kwpack(video, t_pad, pin), pin, pad=(pin.k_tc[0] - 1, pin.k_tc[1] // 2, 0))
         else:
             x = eng.conv(eng.to_channels_last(video, t_pad), P["conv_in"])
-        vid = video
 
         def bwd_conv_in(g):     # the video needs no gradient: weight / bias only
-            v = vid.float() / 255. if vid.dtype == torch.uint8 else vid
-            self._conv_bwd(g, v.to(eng.dtype), cin.weight, cin.bias, kin, pad=(t_pad + kin[0] - 1, kin[1] // 2, kin[2] // 2),
+            v = (vid.float() / 255. if vid.dtype == torch.uint8 else vid).to(eng.dtype)
+            if sff:
+                ff = m.conv_in_first_frame
+                kff = (1,) + tuple(ff.weight.shape[2:])
+                self._conv_bwd(g[:, t_pad:t_pad + 1].contiguous(), v[:, :, 0:1], ff.weight, ff.bias, kff, pad=(0, kff[1] // 2, kff[2] // 2),
+                               need_gx=False, x_is_cf=True)
+                if v.shape[2] > 1:
+                    self._conv_bwd(g[:, t_pad + 1:].contiguous(), v[:, :, 1:], cin.weight, cin.bias, kin,
+                                   pad=(kin[0] - 1, kin[1] // 2, kin[2] // 2), need_gx=False, x_is_cf=True)
+                return None
+            self._conv_bwd(g, v, cin.weight, cin.bias, kin, pad=(t_pad + kin[0] - 1, kin[1] // 2, kin[2] // 2),
                            need_gx=False, x_is_cf=True)
             return None
 
         self.tape.append(bwd_conv_in)
         for i, st in enumerate(m.stages):
-            x = self._stage(x, st, f"enc{i}", m.encoder_layers[i], decoder=False)
+            x = self._stage(x, st, f"enc{i}", m.encoder_layers[i], decoder=False, cond_e=ce_enc)
 
         qz = m.quantizers
         if m.use_fsq:
@@ -403,14 +460,33 @@ class TrainRunner:
 
         x = q
         for j, st in enumerate(reversed(m.stages)):
-            x = self._stage(x, st, f"dec{j}", m.decoder_layers[j], decoder=True)
+            x = self._stage(x, st, f"dec{j}", m.decoder_layers[j], decoder=True, cond_e=ce_dec)
         xo = x
         kout = tuple(cout.weight.shape[2:])
-        y = eng.conv(x, P["conv_out"])
-        recon = eng.to_channels_first(y, t_crop=t_pad)
+        if sff:
+            # M:1633-1639: conv_out_first_frame on frame t_pad, the causal conv_out on the frames after it, re-attached
+            Bx, Tx, Hx, Wx, _ = x.shape
+            first = eng.conv(eng.copy_frames(x, t_pad, 1), P["conv_out_ff"])
+            y = eng._new((Bx, Tx - t_pad, Hx, Wx, first.shape[-1]))
+            eng.copy_frames(first, 0, 1, dst=y, dst_t0=0)
+            if Tx - t_pad > 1:
+                eng.copy_frames(eng.conv(eng.copy_frames(x, t_pad + 1, Tx - t_pad - 1), P["conv_out"]), 0, Tx - t_pad - 1, dst=y, dst_t0=1)
+            recon = eng.to_channels_first(y)
+        else:
+            y = eng.conv(x, P["conv_out"])
+            recon = eng.to_channels_first(y, t_crop=t_pad)
 
         def bwd_conv_out(g_recon):    # (B,C,T,H,W) -> channels-last with zero gradient on the cropped time_padding frames
             g = g_recon.permute(0, 2, 3, 4, 1)
+            if sff:
+                off = m.conv_out_first_frame
+                kff = (1,) + tuple(off.weight.shape[2:])
+                gx = torch.zeros_like(xo)
+                gx[:, t_pad:t_pad + 1] = self._conv_bwd(g[:, 0:1].contiguous(), xo[:, t_pad:t_pad + 1].contiguous(), off.weight, off.bias, kff,
+                                                        pad=(0, kff[1] // 2, kff[2] // 2))
+                if xo.shape[1] - t_pad > 1:
+                    gx[:, t_pad + 1:] = self._conv_bwd(g[:, 1:].contiguous(), xo[:, t_pad + 1:].contiguous(), cout.weight, cout.bias, kout)
+                return gx
             if t_pad:
                 g = F.pad(g, (0, 0, 0, 0, 0, 0, t_pad, 0))
             return self._conv_bwd(g.contiguous(), xo, cout.weight, cout.bias, kout)
@@ -439,6 +515,11 @@ class TrainRunner:
                         g = self.tape[i]((g, ga.float()))
                 else:
                     g = self.tape[i](g)
+            for side, stem in (("enc", self.m.encoder_cond_in), ("dec", self.m.decoder_cond_in)):
+                if side in self.g_cond:       # cond stems (M:1344-1352): Linear + SiLU of the raw cond vector
+                    lin = stem[0]
+                    self._vjp(lambda t, lin=lin: F.silu(F.linear(t, lin.weight.float(), lin.bias.float())), self.cond.float(),
+                              list(lin.parameters()), self.g_cond[side].float())
         self.tape = []
         return self.grads
 
@@ -447,20 +528,20 @@ class _TokenizerTrainFn(torch.autograd.Function):
     """(video, *parameters) -> (recon, aux_loss): forward by the engine kernels, backward by TrainRunner's tape."""
 
     @staticmethod
-    def forward(ctx, runner, first_frame, video, *params):
-        recon, aux = runner.forward(video, first_frame)
+    def forward(ctx, runner, first_frame, cond, video, *params):
+        recon, aux = runner.forward(video, first_frame, cond=cond)
         ctx.runner, ctx.params = runner, params
         return recon, aux
 
     @staticmethod
     def backward(ctx, g_recon, g_aux):
         grads = ctx.runner.backward(g_recon, g_aux)
-        return (None, None, None) + tuple(grads.get(p) for p in ctx.params)
+        return (None, None, None, None) + tuple(grads.get(p) for p in ctx.params)
 
 
-def train_forward(model, video, first_frame=True):
+def train_forward(model, video, first_frame=True, cond=None):
     """-> (recon with grad_fn, aux_loss with grad_fn, codes, lfq breakdown | None)."""
     runner = TrainRunner(model)
     params = [p for p in model.parameters() if p.requires_grad]
-    recon, aux = _TokenizerTrainFn.apply(runner, first_frame, video, *params)
+    recon, aux = _TokenizerTrainFn.apply(runner, first_frame, cond, video, *params)
     return recon, aux, runner.codes, runner.breakdown

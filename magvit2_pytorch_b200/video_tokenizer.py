@@ -557,7 +557,7 @@ class VideoTokenizer(nn.Module):
         if return_loss and self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # the trainer's generator step (T:356-363): loss with a grad_fn.  Forward = the same kernels; backward = train.py
             from .train import train_forward
-            recon, aux, _, qlb = train_forward(self, video.contiguous(), ff)
+            recon, aux, _, qlb = train_forward(self, video.contiguous(), ff, cond)
             target = video.float() / 255. if video.dtype == torch.uint8 else video
             recon_loss = torch.nn.functional.mse_loss(target.to(recon.dtype), recon)          # M:1722
             self.quantizer_loss_breakdown, self.quantizer_aux_loss = qlb, aux.detach()

@@ -32,18 +32,24 @@ def make(name="mini_train", base="mini", vseed=1234):
     W.fill_state_dict_(model, cfg["wseed"])
     video = W.synth_video(*cfg["video"][:3], cfg["video"][3], seed=vseed)
     out = dict(name=name, kwargs=kwargs, video_shape=tuple(cfg["video"]), wseed=cfg["wseed"], vseed=vseed)
+    ckw = {}
+    if kwargs.get("dim_cond") is not None:          # conditioned layers (cond_residual): a (B, dim_cond) vector per clip
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(cfg["cseed"])
+        out["cond"] = torch.randn(cfg["video"][0], kwargs["dim_cond"], generator=gen)
+        ckw = dict(cond=out["cond"])
 
     model.eval()
     with torch.no_grad():
-        total, bd = model(video, return_loss=True)
-        rl, recon = model(video, return_recon_loss_only=True)
+        total, bd = model(video, return_loss=True, **ckw)
+        rl, recon = model(video, return_recon_loss_only=True, **ckw)
     out["eval"] = dict(total_loss=total.clone(), recon_loss=bd.recon_loss.clone(), aux=torch.as_tensor(bd.lfq_aux_loss).clone(),
                        recon_loss_only=rl.clone(), recon_mean=recon.mean(dim=(3, 4)).clone())
 
     model.train()
     for p in model.parameters():
         p.grad = None
-    total, bd = model(video, return_loss=True)
+    total, bd = model(video, return_loss=True, **ckw)
     total.backward()
     # per parameter: the gradient's L2 norm and a strided sample of at most ~1024 elements (the full set is 11 MB)
     grads = {k: (grad_digest(p.grad.detach()) if p.grad is not None else None) for k, p in model.named_parameters()}
@@ -69,3 +75,5 @@ if __name__ == "__main__":
     make("mini_mc_train", base="mini_mc", vseed=1238)       # num_codebooks = 2, lfq_spherical
     make("mini_fsq_train", base="mini_fsq", vseed=1234)     # FSQ: straight-through round, no auxiliary loss
     make("mini_gateloop_train", base="mini_gateloop", vseed=1237)
+    make("mini_cond_train", base="mini_cond", vseed=1249)   # cond_residual (ResidualUnitMod / Conv3DMod) + the cond stems
+    make("mini_sff_train", base="mini_sff", vseed=1234)     # separate_first_frame_encoding

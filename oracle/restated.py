@@ -546,14 +546,14 @@ class OracleTokenizer:
         return self._decode(*a, **k)
 
     def loss_forward(self, video, train: bool, world_reduce=None, lfq_entropy_loss_weight=0.1, lfq_commitment_loss_weight=1.,
-                     lfq_diversity_gamma=2.5, quantizer_aux_loss_weight=1.):
+                     lfq_diversity_gamma=2.5, quantizer_aux_loss_weight=1., cond=None):
         """forward(video, return_loss=True) of a tokenizer built with use_gan=False, perceptual_loss_weight=0 (M:1695-1727,
         M:1868-1896): total_loss = recon_loss + aux_loss * quantizer_aux_loss_weight.  Differentiable: with state_dict tensors
         that require grad, ``out["total_loss"].backward()`` yields the parameter gradients the trainer consumes (T:356-363).
         train=True is the LFQ training branch (M:1705; A.1 steps 6-8, 10: straight-through output, entropy + commitment terms);
         train=False (and FSQ) has zero auxiliary loss (M:1700-1703)."""
         video, ff = self._check_video(video, True)
-        x = self._encode(video, video_contains_first_frame=ff)
+        x = self._encode(video, cond=cond, video_contains_first_frame=ff)
         out = {}
         if self.use_fsq or not train:
             q, idx, _ = self.quantize.__wrapped__(self, x)
@@ -573,7 +573,7 @@ class OracleTokenizer:
             idx = ((qd.reshape(b, -1, self.nc, d_bits) > 0).int() * mask).sum(dim=-1).reshape(b, t, h, w, self.nc)
             if self.nc == 1:
                 idx = idx[..., 0]
-        recon = self._decode(q, video_contains_first_frame=ff)
+        recon = self._decode(q, cond=cond, video_contains_first_frame=ff)
         recon_loss = F.mse_loss(video.to(recon.dtype), recon)                # M:1722
         out.update(codes=idx, recon=recon, recon_loss=recon_loss, aux=aux, total_loss=recon_loss + aux * quantizer_aux_loss_weight)
         return out

@@ -248,7 +248,7 @@ def grad_digest_close(g, dg, rtol, what, atol=0.0):
     return max(n_err, s_err)
 
 
-@pytest.mark.parametrize("name", ["mini_train", "mini_mc_train", "mini_fsq_train", "mini_gateloop_train"])
+@pytest.mark.parametrize("name", ["mini_train", "mini_mc_train", "mini_fsq_train", "mini_gateloop_train", "mini_cond_train", "mini_sff_train"])
 def test_restated_loss_forward_and_gradients_match_reference_golden(name):
     """the differentiable restatement of forward(return_loss=True) reproduces the reference's loss values (eval and
     train mode) and, through autograd, the reference's gradient of every parameter (tests/golden/mini_train.pt, made by the
@@ -257,8 +257,9 @@ def test_restated_loss_forward_and_gradients_match_reference_golden(name):
     model = build_product(g["kwargs"], g["wseed"])
     video = golden_video(g)
     orc = build_oracle(model, g["kwargs"])
+    cond = g.get("cond")
     with torch.no_grad():
-        ev = orc.loss_forward(video, train=False)
+        ev = orc.loss_forward(video, train=False, cond=cond)
     assert abs(ev["total_loss"].item() - g["eval"]["total_loss"].item()) < 1e-6
     assert abs(ev["recon_loss"].item() - g["eval"]["recon_loss_only"].item()) < 1e-6
     assert ev["aux"].item() == 0.0 and g["eval"]["aux"].item() == 0.0
@@ -267,7 +268,7 @@ def test_restated_loss_forward_and_gradients_match_reference_golden(name):
     for v in orc.sd.values():
         if v.is_floating_point():
             v.requires_grad_(True)
-    tr = orc.loss_forward(video, train=True)
+    tr = orc.loss_forward(video, train=True, cond=cond)
     gt = g["train"]
     for k in ("total_loss", "recon_loss", "aux", "per_sample_entropy", "batch_entropy", "commitment"):
         if k in gt:                      # the three LFQ terms do not exist for FSQ

@@ -15,24 +15,26 @@ def _require_cuda():
         pytest.skip("needs a CUDA device")
 
 
-def _train_step(model, video):
+def _train_step(model, video, cond=None):
     model.train()
     for p in model.parameters():
         p.grad = None
-    total, bd = model(video, return_loss=True)
+    total, bd = model(video, return_loss=True) if cond is None else model(video, cond=cond, return_loss=True)
     assert total.requires_grad and total.grad_fn is not None
     total.backward()
     return total, bd
 
 
-@pytest.mark.parametrize("name", ["mini_train", "mini_mc_train", "mini_fsq_train", "mini_gateloop_train"])
+@pytest.mark.parametrize("name", ["mini_train", "mini_mc_train", "mini_fsq_train", "mini_gateloop_train", "mini_cond_train", "mini_sff_train"])
 def test_fp32_losses_and_gradients_vs_reference_golden(name):
-    """LFQ (README-layer mini config), two spherical codebooks, FSQ (straight-through round) and gateloop_time layers."""
+    """LFQ (README-layer mini config), two spherical codebooks, FSQ (straight-through round), gateloop_time layers, and
+    cond_residual layers (ResidualUnitMod / Conv3DMod + the cond stems)."""
     _require_cuda()
     g = load_golden(name)
     gt = g["train"]
     model = build_product(g["kwargs"], g["wseed"]).cuda()
-    total, bd = _train_step(model, golden_video(g).cuda())
+    cond = g["cond"].cuda() if g.get("cond") is not None else None
+    total, bd = _train_step(model, golden_video(g).cuda(), cond)
     assert abs(total.item() - gt["total_loss"].item()) < 1e-5
     assert abs(bd.recon_loss.item() - gt["recon_loss"].item()) < 1e-5
     assert abs(float(bd.lfq_aux_loss) - float(gt["aux"])) < 1e-5
