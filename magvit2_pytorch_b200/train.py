@@ -221,8 +221,6 @@ class TrainRunner:
 
     def __init__(self, model):
         m = model
-        if m.conv_in.pad_mode != "constant" or m.conv_out.pad_mode != "constant":
-            raise NotImplementedError("the training path covers tokenizers with pad_mode='constant' (SURVEY.md 8f N2, first slice)")
         self.g_cond: Dict[str, torch.Tensor] = {}      # gradient wrt the cond stems' outputs, summed over the cond_residual stages
         self.m = m
         self.eng = m.engine
@@ -295,6 +293,28 @@ class TrainRunner:
         if own_dgrad:
             return gx
         return gxl[:, :, pt:].permute(0, 2, 3, 4, 1).contiguous()
+
+    def _conv_bwd_padmode(self, g, x, weight, bias, k, pad_mode, need_gx=True):
+        """Backward of Engine.causal_conv_padded (CausalConv3d with pad_mode reflect / replicate / circular, M:925-927): the padding
+        is re-applied with F.pad under autograd, the conv backward runs without implicit padding on the padded tensor, and the
+        gradient is folded back through the padding.  Falls back to the zero-padded case like the forward (time_pad >= T)."""
+        kt, kh, kw = k
+        if pad_mode == "constant" or kt - 1 >= x.shape[1]:
+            return self._conv_bwd(g, x, weight, bias, k, need_gx=need_gx)
+        x_ = x.detach().permute(0, 4, 1, 2, 3).requires_grad_(need_gx)
+        with torch.enable_grad():
+            xp = F.pad(x_, (kw // 2, kw // 2, kh // 2, kh // 2, kt - 1, 0), mode=pad_mode)
+        w5 = weight.reshape(weight.shape[0], weight.shape[1], kt, kh, kw)
+        gxp, gw, gb = torch.ops.aten.convolution_backward(
+            g.permute(0, 4, 1, 2, 3), xp.detach(), w5, [w5.shape[0]] if bias is not None else None, [1, 1, 1], [0, 0, 0], [1, 1, 1],
+            False, [0, 0, 0], 1, [need_gx, weight.requires_grad, bias is not None and bias.requires_grad])
+        self._acc(weight, gw)
+        if bias is not None:
+            self._acc(bias, gb)
+        if not need_gx:
+            return None
+        gx, = torch.autograd.grad(xp, x_, gxp)
+        return gx.permute(0, 2, 3, 4, 1).contiguous()
 
     # ---- forward pieces (engine kernels) that record their backward
     def _residual_unit(self, x, p, ru):
@@ -403,6 +423,7 @@ class TrainRunner:
         kin = tuple(cin.weight.shape[2:])
         pin = P.get("conv_in_tc")
         sff = bool(m.separate_first_frame_encoding and first_frame)
+        mode_in, mode_out = m.conv_in.pad_mode, m.conv_out.pad_mode
         vid = video
         if sff:
             # M:1553-1561: the first frame through its own 2-D conv, frames 1.. through the causal conv_in on their own
@@ -411,9 +432,13 @@ class TrainRunner:
             first = eng.conv(eng.copy_frames(v_cl, 0, 1), P["conv_in_ff"])
             x = eng._new((Bv, Tv + t_pad, Hv, Wv, first.shape[-1]))
             eng.copy_frames(first, 0, 1, dst=x, dst_t0=t_pad, zero_front=True)
+            rest_in = eng.copy_frames(v_cl, 1, Tv - 1) if Tv > 1 else None
             if Tv > 1:
-                rest = eng.conv(eng.copy_frames(v_cl, 1, Tv - 1), P["conv_in"])
+                rest = eng.causal_conv_padded(rest_in, P["conv_in"], mode_in)
                 eng.copy_frames(rest, 0, Tv - 1, dst=x, dst_t0=t_pad + 1)
+        elif mode_in != "constant":
+            padded_in = eng.to_channels_last(video, t_pad)               # time_padding zero frames first (M:1537), then the mode's pad
+            x = eng.causal_conv_padded(padded_in, P["conv_in"], mode_in)
         elif eng.dtype == torch.bfloat16 and eng.use_tc and pin is not None:
             x = eng.conv(eng.ingest_kwpack(video, t_pad, pin), pin, pad=(pin.k_tc[0] - 1, pin.k_tc[1] // 2, 0))
         else:
@@ -427,8 +452,10 @@ class TrainRunner:
                 self._conv_bwd(g[:, t_pad:t_pad + 1].contiguous(), v[:, :, 0:1], ff.weight, ff.bias, kff, pad=(0, kff[1] // 2, kff[2] // 2),
                                need_gx=False, x_is_cf=True)
                 if v.shape[2] > 1:
-                    self._conv_bwd(g[:, t_pad + 1:].contiguous(), v[:, :, 1:], cin.weight, cin.bias, kin,
-                                   pad=(kin[0] - 1, kin[1] // 2, kin[2] // 2), need_gx=False, x_is_cf=True)
+                    self._conv_bwd_padmode(g[:, t_pad + 1:].contiguous(), rest_in, cin.weight, cin.bias, kin, mode_in, need_gx=False)
+                return None
+            if mode_in != "constant":
+                self._conv_bwd_padmode(g, padded_in, cin.weight, cin.bias, kin, mode_in, need_gx=False)
                 return None
             self._conv_bwd(g, v, cin.weight, cin.bias, kin, pad=(t_pad + kin[0] - 1, kin[1] // 2, kin[2] // 2),
                            need_gx=False, x_is_cf=True)
@@ -469,11 +496,12 @@ class TrainRunner:
             first = eng.conv(eng.copy_frames(x, t_pad, 1), P["conv_out_ff"])
             y = eng._new((Bx, Tx - t_pad, Hx, Wx, first.shape[-1]))
             eng.copy_frames(first, 0, 1, dst=y, dst_t0=0)
+            rest_out = eng.copy_frames(x, t_pad + 1, Tx - t_pad - 1) if Tx - t_pad > 1 else None
             if Tx - t_pad > 1:
-                eng.copy_frames(eng.conv(eng.copy_frames(x, t_pad + 1, Tx - t_pad - 1), P["conv_out"]), 0, Tx - t_pad - 1, dst=y, dst_t0=1)
+                eng.copy_frames(eng.causal_conv_padded(rest_out, P["conv_out"], mode_out), 0, Tx - t_pad - 1, dst=y, dst_t0=1)
             recon = eng.to_channels_first(y)
         else:
-            y = eng.conv(x, P["conv_out"])
+            y = eng.causal_conv_padded(x, P["conv_out"], mode_out)
             recon = eng.to_channels_first(y, t_crop=t_pad)
 
         def bwd_conv_out(g_recon):    # (B,C,T,H,W) -> channels-last with zero gradient on the cropped time_padding frames
@@ -485,11 +513,11 @@ class TrainRunner:
                 gx[:, t_pad:t_pad + 1] = self._conv_bwd(g[:, 0:1].contiguous(), xo[:, t_pad:t_pad + 1].contiguous(), off.weight, off.bias, kff,
                                                         pad=(0, kff[1] // 2, kff[2] // 2))
                 if xo.shape[1] - t_pad > 1:
-                    gx[:, t_pad + 1:] = self._conv_bwd(g[:, 1:].contiguous(), xo[:, t_pad + 1:].contiguous(), cout.weight, cout.bias, kout)
+                    gx[:, t_pad + 1:] = self._conv_bwd_padmode(g[:, 1:].contiguous(), rest_out, cout.weight, cout.bias, kout, mode_out)
                 return gx
             if t_pad:
                 g = F.pad(g, (0, 0, 0, 0, 0, 0, t_pad, 0))
-            return self._conv_bwd(g.contiguous(), xo, cout.weight, cout.bias, kout)
+            return self._conv_bwd_padmode(g.contiguous(), xo, cout.weight, cout.bias, kout, mode_out)
 
         self.tape.append(bwd_conv_out)
         self._recon_shape = tuple(recon.shape)

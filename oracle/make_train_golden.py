@@ -77,3 +77,5 @@ if __name__ == "__main__":
     make("mini_gateloop_train", base="mini_gateloop", vseed=1237)
     make("mini_cond_train", base="mini_cond", vseed=1249)   # cond_residual (ResidualUnitMod / Conv3DMod) + the cond stems
     make("mini_sff_train", base="mini_sff", vseed=1234)     # separate_first_frame_encoding
+    make("pad_reflect_train", base="pad_reflect", vseed=1236)       # pad_mode of conv_in / conv_out (M:925-927)
+    make("pad_circular_train", base="pad_circular", vseed=1236)

@@ -248,7 +248,7 @@ def grad_digest_close(g, dg, rtol, what, atol=0.0):
     return max(n_err, s_err)
 
 
-@pytest.mark.parametrize("name", ["mini_train", "mini_mc_train", "mini_fsq_train", "mini_gateloop_train", "mini_cond_train", "mini_sff_train"])
+@pytest.mark.parametrize("name", ["mini_train", "mini_mc_train", "mini_fsq_train", "mini_gateloop_train", "mini_cond_train", "mini_sff_train", "pad_reflect_train", "pad_circular_train"])
 def test_restated_loss_forward_and_gradients_match_reference_golden(name):
     """the differentiable restatement of forward(return_loss=True) reproduces the reference's loss values (eval and
     train mode) and, through autograd, the reference's gradient of every parameter (tests/golden/mini_train.pt, made by the

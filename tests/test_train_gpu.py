@@ -25,7 +25,7 @@ def _train_step(model, video, cond=None):
     return total, bd
 
 
-@pytest.mark.parametrize("name", ["mini_train", "mini_mc_train", "mini_fsq_train", "mini_gateloop_train", "mini_cond_train", "mini_sff_train"])
+@pytest.mark.parametrize("name", ["mini_train", "mini_mc_train", "mini_fsq_train", "mini_gateloop_train", "mini_cond_train", "mini_sff_train", "pad_reflect_train", "pad_circular_train"])
 def test_fp32_losses_and_gradients_vs_reference_golden(name):
     """LFQ (README-layer mini config), two spherical codebooks, FSQ (straight-through round), gateloop_time layers, and
     cond_residual layers (ResidualUnitMod / Conv3DMod + the cond stems)."""
