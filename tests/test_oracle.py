@@ -272,7 +272,7 @@ def test_restated_loss_forward_and_gradients_match_reference_golden(name):
     gt = g["train"]
     for k in ("total_loss", "recon_loss", "aux", "per_sample_entropy", "batch_entropy", "commitment"):
         if k in gt:                      # the three LFQ terms do not exist for FSQ
-            assert abs(float(tr[k]) - float(gt[k])) < 2e-6 * max(1.0, abs(float(gt[k]))), k
+            assert abs(float(tr[k].detach()) - float(gt[k])) < 2e-6 * max(1.0, abs(float(gt[k]))), k
     tr["total_loss"].backward()
     worst = 0.0
     gnorm = sum(d["norm"] ** 2 for d in gt["grads"].values() if d is not None) ** 0.5
