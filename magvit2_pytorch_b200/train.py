@@ -564,12 +564,25 @@ class _TokenizerTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_recon, g_aux):
         grads = ctx.runner.backward(g_recon, g_aux)
-        return (None, None, None, None) + tuple(grads.get(p) for p in ctx.params)
+        # every parameter handed to the Function gets a gradient tensor (zeros if this call did not touch it, e.g. conv_in of a
+        # one-frame clip with separate_first_frame_encoding): DistributedDataParallel waits for the hook of every parameter it can
+        # reach from the outputs
+        return (None, None, None, None) + tuple(grads[p] if p in grads else torch.zeros_like(p) for p in ctx.params)
+
+
+def live_parameters(model, first_frame=True):
+    """The parameters a forward can reach.  Left out, exactly like in the reference's graph (so DistributedDataParallel must be
+    built with find_unused_parameters=True there as here): the final LayerNorm of the encoder, which is constructed but never
+    executed (M:1322-1326, M:1565), and the first-frame convs unless separate_first_frame_encoding applies to this call."""
+    dead = {id(p) for p in model.encoder_layers[len(model.stages)].parameters()}
+    if not (model.separate_first_frame_encoding and first_frame):
+        dead |= {id(p) for mod in (model.conv_in_first_frame, model.conv_out_first_frame) for p in mod.parameters()}
+    return [p for p in model.parameters() if p.requires_grad and id(p) not in dead]
 
 
 def train_forward(model, video, first_frame=True, cond=None):
     """-> (recon with grad_fn, aux_loss with grad_fn, codes, lfq breakdown | None)."""
     runner = TrainRunner(model)
-    params = [p for p in model.parameters() if p.requires_grad]
+    params = live_parameters(model, first_frame)
     recon, aux = _TokenizerTrainFn.apply(runner, first_frame, cond, video, *params)
     return recon, aux, runner.codes, runner.breakdown

@@ -147,3 +147,37 @@ def test_bf16_gradients_agree_with_fp32():
     print(f"cosine(fp32 grads, bf16 grads): decoder side {cos_dec:.4f}, encoder side {cos_enc:.4f}")
     assert cos_dec > 0.95, cos_dec
     assert cos_enc > 0.5, cos_enc
+
+
+def test_generator_step_under_distributed_data_parallel():
+    """The trainer wraps the tokenizer in DistributedDataParallel (accelerate, find_unused_parameters=True as the reference's dead
+    final LayerNorm requires): the custom autograd Function spanning the model must feed DDP's reducer a gradient for every
+    parameter it reaches.  World size 1 (NCCL): gradients equal the plain run's, and a second step works (reducer finalised)."""
+    _require_cuda()
+    import socket
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    if dist.is_initialized():
+        pytest.skip("a process group is already initialised in this process")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    g = load_golden("mini_train")
+    video = golden_video(g).cuda()
+    plain = build_product(g["kwargs"], g["wseed"]).cuda()
+    _train_step(plain, video)
+    want = {k: p.grad.clone() for k, p in plain.named_parameters() if p.grad is not None}
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        model = build_product(g["kwargs"], g["wseed"]).cuda()
+        ddp = DDP(model, device_ids=[torch.cuda.current_device()], find_unused_parameters=True)
+        ddp.train()
+        for step in range(2):
+            for p in model.parameters():
+                p.grad = None
+            loss, bd = ddp(video, return_loss=True)
+            loss.backward()
+        got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        assert set(want) <= set(got)
+        for k, w in want.items():
+            assert torch.allclose(got[k], w, rtol=1e-4, atol=1e-6 * float(w.abs().max()) + 1e-12), k
+    finally:
+        dist.destroy_process_group()
