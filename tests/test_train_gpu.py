@@ -37,7 +37,7 @@ def test_fp32_losses_and_gradients_vs_reference_golden(name):
     total, bd = _train_step(model, golden_video(g).cuda(), cond)
     assert abs(total.item() - gt["total_loss"].item()) < 1e-5
     assert abs(bd.recon_loss.item() - gt["recon_loss"].item()) < 1e-5
-    assert abs(float(bd.lfq_aux_loss) - float(gt["aux"])) < 1e-5
+    assert abs(float(bd.lfq_aux_loss.detach()) - float(gt["aux"])) < 1e-5
     if "per_sample_entropy" in gt:
         ps, be, cm = bd.quantizer_loss_breakdown
         for got, k in ((ps, "per_sample_entropy"), (be, "batch_entropy"), (cm, "commitment")):
