@@ -156,3 +156,34 @@ def test_causal_conv_transpose3d_equivalent_causal_conv(kt, stride):
     assert set(m.state_dict()) == {"conv.weight", "conv.bias"}
     with pytest.raises(RuntimeError):
         m(x)                                                        # CPU-resident: no kernels to run, no eager fallback
+
+
+def test_stream_lanes_and_round_trip_refuse_cpu_models():
+    """The stream front ends are CUDA-only like the model itself: a CPU-resident tokenizer is refused up front."""
+    from magvit2_pytorch_b200 import HostRoundTrip, StreamLanes
+    m = build_product(dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, layers=("residual",)))
+    with pytest.raises(RuntimeError):
+        StreamLanes(m, 2)
+    with pytest.raises(RuntimeError):
+        HostRoundTrip(m, depth=2, lanes=2)
+    with pytest.raises(AssertionError):
+        HostRoundTrip.__init__(HostRoundTrip.__new__(HostRoundTrip), m, depth=2, lanes=3)     # more lanes than staging slots
+
+
+def test_live_parameters_leave_out_what_the_reference_graph_never_reaches():
+    """train.live_parameters: the dead final LayerNorm of the encoder (M:1322-1326, M:1565) and, unless
+    separate_first_frame_encoding applies, the first-frame convs are not handed to the autograd Function."""
+    from magvit2_pytorch_b200.train import live_parameters
+    kw = dict(image_size=32, init_dim=16, max_dim=64, codebook_size=1024, layers=("residual", "compress_time"))
+    m = build_product(kw)
+    live = {id(p) for p in live_parameters(m)}
+    named = dict(m.named_parameters())
+    dead = [k for k, p in named.items() if id(p) not in live]
+    assert sorted(dead) == ["encoder_layers.2.1.bias", "encoder_layers.2.1.weight"]
+    m2 = build_product(dict(kw, separate_first_frame_encoding=True))
+    named2 = dict(m2.named_parameters())
+    live_ff = {id(p) for p in live_parameters(m2, first_frame=True)}
+    live_noff = {id(p) for p in live_parameters(m2, first_frame=False)}
+    ff_keys = [k for k in named2 if "first_frame" in k]
+    assert len(ff_keys) == 4
+    assert all(id(named2[k]) in live_ff for k in ff_keys) and not any(id(named2[k]) in live_noff for k in ff_keys)
